@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""bench.py -- MMCTM E+M iterations/sec on synthetic Poisson counts (BASELINE.json metric).
+
+Workload (config.workload): configs[3] of BASELINE.json -- MMCTM 3-modality K=[10,8,6] on
+synthetic 1M samples (SNV96 / SV32 / ID83), FP64, total sample count fixed and sharded over the
+N ranks (strong scaling), one packed NCCL all-gather pair per iteration.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--samples D] [--impl reference]
+
+One JSON line on stdout (rank 0).  `value`: iterations/sec with counts and state resident in
+HBM; `e2e`: the same through the public API with host buffers (counts + state H2D, one
+iteration, state D2H inside the timed region); `roofline`: the dominant kernel against the
+measured HBM peak; `cpu_baseline`: the oracle on the host cores on a bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+K_CFG, V_CFG, ALPHA = [10, 8, 6], [96, 32, 83], [0.1, 0.1, 0.1]
+METRIC = "mmctm_em_iterations_per_sec"
+UNIT = "iterations/s"
+
+
+def algorithmic_bytes(nnz_total, D, MK, M):
+    """B_iter = 16 nnz + D (40 MK + 24 M)."""
+    return 16.0 * nnz_total + D * (40.0 * MK + 24.0 * M)
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, threading.Event(), []
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                p = [x.strip() for x in out.strip().split(",")]
+                if len(p) >= 6:
+                    self.rows.append(p)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def cpu_baseline(counts_fn, D_total, sample_D, nthreads, steps=1, warmup=0):
+    """Oracle (literal restatement of the reference) on the host cores, bounded sample."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import orc
+    import mmsig
+    counts = counts_fn(0, sample_D)
+    g0 = mmsig.synth.init_gamma(K_CFG, V_CFG)
+    m = orc.OracleMMCTM(K_CFG, ALPHA, V_CFG, counts, g0, arith=orc.ARITH_LITERAL, nthreads=nthreads)
+    for _ in range(warmup):
+        m.iterate()
+    t = time.perf_counter()
+    for _ in range(steps):
+        m.iterate()
+    dt = (time.perf_counter() - t) / steps
+    its = (1.0 / dt) * (sample_D / float(D_total))
+    return {"value": its, "unit": UNIT, "cores": nthreads, "kind": "port",
+            "sample": "oracle (C restatement of src/MMCTM.jl + NLopt LD_MMA; the Julia reference cannot run here), "
+                      "OpenMP over samples on %d threads, %d of the %d samples, %.2f s per iteration of the sample, "
+                      "scaled linearly in D" % (nthreads, sample_D, D_total, dt),
+            "seconds_per_sample_iteration": dt, "sample_D": sample_D}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import mmsig
+    D = args.samples
+    nthreads = os.cpu_count() or 1
+    sample_D = min(D, args.cpu_samples)
+    cb = cpu_baseline(lambda lo, hi: mmsig.synth.generate(D, K_CFG, V_CFG, lo=lo, hi=hi), D, sample_D, nthreads,
+                      steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(D, args.gpus), "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(D, n):
+    return {"workload": "MMCTM 3-modality K=[10,8,6], synthetic Poisson counts, D=%d samples "
+                        "(SNV96/SV32/ID83), FP64, exact LD_MMA E-step; BASELINE.json configs[3]" % D,
+            "samples": D, "K": K_CFG, "V": V_CFG, "parallelism": "samples sharded over %d rank(s)" % n,
+            "l2": "inputs per iteration (>= 2.6 GB at D=1e6) exceed the 126 MB L2; no flush needed"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--samples", type=int, default=1_000_000)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--cpu-samples", type=int, default=20_000)
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import mmsig
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dist = None
+    comm = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        uid = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            uid = torch.tensor(list(mmsig.capi.comm_unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(uid, 0)
+        comm = (bytes(uid.cpu().tolist()), rank, world)
+
+    D = args.samples
+    per = -(-D // world)
+    lo, hi = min(D, rank * per), min(D, (rank + 1) * per)
+    counts = mmsig.synth.generate(D, K_CFG, V_CFG, lo=lo, hi=hi)
+    Dl = hi - lo
+    nnz_local = sum(int(c[0][-1]) for c in counts)
+    MK, M = sum(K_CFG), len(K_CFG)
+    g0 = mmsig.synth.init_gamma(K_CFG, V_CFG)
+
+    # pinned host buffers (the e2e leg copies from / to these)
+    def pin(a):
+        t = torch.from_numpy(np.ascontiguousarray(a)).pin_memory()
+        return t.numpy(), t
+    keep = []
+    counts_p = []
+    for r, t, c in counts:
+        trip = []
+        for a in (r, t, c):
+            n, tt = pin(a)
+            keep.append(tt)
+            trip.append(n)
+        counts_p.append(tuple(trip))
+
+    stream = torch.cuda.Stream()
+    model = mmsig.MMCTM(K_CFG, ALPHA, counts_p, V=V_CFG, gamma0=g0, device=local, profile=True, comm=comm, D_total=D)
+    model.h.set_stream(stream.cuda_stream)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.cuda.stream(stream):
+        for _ in range(args.warmup):
+            model.iterate()
+        model.h.kernel_times(reset=True)
+        barrier()
+        sampler = ClockSampler(local)
+        sampler.start()
+        l0 = model.h.launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(args.steps):
+            ll = model.iterate()
+        e1.record(stream)
+        barrier()
+        sampler.stop_flag.set()
+        ms = e0.elapsed_time(e1)
+        launches = model.h.launch_count() - l0
+    ktimes = model.h.kernel_times(reset=True)
+    if dist is not None:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+        nz = torch.tensor([float(nnz_local)], dtype=torch.float64, device="cuda")
+        dist.all_reduce(nz)
+        nnz_total = float(nz.item())
+    else:
+        nnz_total = float(nnz_local)
+    ms_step = ms / args.steps
+    value = 1000.0 / ms_step
+
+    # ---- e2e: public API with host buffers; H2D of counts + state, one iteration, D2H of state ----
+    lam_h, t1 = pin(np.zeros((Dl, MK)))
+    nu_h, t2 = pin(np.ones((Dl, MK)))
+    keep += [t1, t2]
+    st = model.state()
+    mu_h, Sg_h, iS_h, gam_h = st["mu"], st["Sigma"], st["invSigma"], st["gamma"]
+    lam_h[:] = st["lam"]
+    nu_h[:] = st["nu"]
+    out = {k: pin(np.empty_like(v))[0] for k, v in st.items()}
+    h2d = sum(a.nbytes for trip in counts_p for a in trip) + lam_h.nbytes + nu_h.nbytes + mu_h.nbytes + \
+        Sg_h.nbytes + iS_h.nbytes + gam_h.nbytes + 8 * M
+    d2h = sum(v.nbytes for v in out.values()) + 8 * M
+    order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
+
+    def e2e_step():
+        model._set_data(counts_p, D)                                          # counts H2D (+ row packing)
+        model.set_state(gam_h, lam=lam_h, nu=nu_h, mu=mu_h, Sigma=Sg_h, invSigma=iS_h)   # state H2D
+        ll_ = model.iterate()                                                 # one E+M iteration, LL D2H
+        model.h.check(model.h.lib.mmsig_mmctm_get_state(model.h.h, *[mmsig.capi.dp(out[k]) for k in order]))
+        return ll_
+    e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.e2e_steps):
+        e2e_step()
+    barrier()
+    e2e_ms = (time.perf_counter() - t0) * 1000.0 / args.e2e_steps
+    if dist is not None:
+        t = torch.tensor([e2e_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_ms = float(t.item())
+    model.h.kernel_times(reset=True)
+
+    if rank != 0:
+        model.close()
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel ----
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    per_kernel = {k: {"ms_per_step": v[0] / args.steps, "launches_per_step": v[1] / args.steps}
+                  for k, v in ktimes.items() if v[1] > 0}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
+    alg_local = algorithmic_bytes(nnz_local, Dl, MK, M)
+    roof = None
+    if dom:
+        dms = per_kernel[dom]["ms_per_step"] / max(per_kernel[dom]["launches_per_step"], 1)
+        ach = alg_local / (dms * 1e-3) / 1e9
+        roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
+                "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_local, "kernel_ms_per_launch": dms,
+                "iteration_gbs_all_kernels": algorithmic_bytes(nnz_total, D, MK, M) / (ms_step * 1e-3) / 1e9,
+                "note": "exact-LD_MMA FP64 mode is FP64-pipe bound, not HBM bound (DESIGN.md); see profiles/"}
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(D, world),
+            "samples_iterations_per_sec": value * D,
+            "nnz_per_sample": nnz_total / D,
+            "ll": [float(x) for x in ll],
+            "clocks": sampler.summary(),
+            "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "ms_per_step": e2e_ms, "what": "set_data + set_state (pinned host -> device), iterate, get_state (device -> pinned host)"},
+            "gpu_launches": int(launches),
+            "kernels": per_kernel,
+            "roofline": roof}
+    if not args.no_cpu and world >= 1:
+        nthreads = os.cpu_count() or 1
+        sample_D = min(D, args.cpu_samples)
+        line["cpu_baseline"] = cpu_baseline(lambda a, b: mmsig.synth.generate(D, K_CFG, V_CFG, lo=a, hi=b), D, sample_D, nthreads)
+    print(json.dumps(line), flush=True)
+    model.close()
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

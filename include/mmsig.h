@@ -1,0 +1,134 @@
+/*
+ * mmsig.h -- C ABI of libmmsig.so: the B200-native (sm_100a) variational-EM inner loop of the
+ * MMCTM / CTM / LDA topic models of shahcompbio/MultiModalMuSig.jl.
+ *
+ * The reference has no FFI of its own (it is pure Julia); the boundary this library replaces
+ * is the Julia method level
+ *     fit!(model::MMCTM; maxiter, tol, verbose, autoα, updateΣ)      reference src/MMCTM.jl:457-494
+ *     fit!(model::LDA;   maxiter, tol, verbose)                      reference src/LDA.jl:198-224
+ * and, underneath, fitdoc!/update_*!/calculate_* (src/MMCTM.jl:110-455, src/LDA.jl:69-196).
+ * julia/MMSigB200.jl `ccall`s these entry points; tests and bench.py bind them with ctypes.
+ *
+ * Conventions
+ *   - every call blocks and returns 0 on success, a negative MMSIG_E* code otherwise; the
+ *     message is at mmsig_last_error(h).  No exceptions / longjmp cross the boundary.
+ *   - the caller owns every host buffer; the library never keeps a host pointer after return.
+ *     Device memory lives behind the opaque handle.  A handle is not thread-safe; distinct
+ *     handles are independent.
+ *   - any output pointer may be NULL (= not wanted).
+ *   - flat layouts (the Julia shim flattens / scatters the nested vectors):
+ *       counts, modality m : CSR  rowptr[m][0..D] int64, term[m][w] int32 0-BASED, count[m][w] int32 > 0
+ *       lambda, nu, props  : D x MK row-major (MK = sum K[m]; block m of row d = model.λ[d][off_m+1 : off_m+K_m])
+ *       zeta               : D x M
+ *       gamma/Elnphi/phi   : concatenated [m][k][v] row-major
+ *       mu MK ; Sigma, invSigma MK x MK row-major
+ *       LDA lambda/Elnbeta/beta : [k][v] (= Julia's V x K column-major) ; gamma/theta : [d][k] (= K x D column-major)
+ *   - there is NO CPU fallback: without a CUDA device mmsig_create fails with MMSIG_ENODEV.
+ */
+#ifndef MMSIG_H
+#define MMSIG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMSIG_OK        0
+#define MMSIG_EINVAL   -1   /* bad argument / call order                  */
+#define MMSIG_ENODEV   -2   /* no usable CUDA device                      */
+#define MMSIG_ECUDA    -3   /* CUDA runtime error                         */
+#define MMSIG_ENOMEM   -4
+#define MMSIG_ENCCL    -5   /* NCCL missing or failed                     */
+#define MMSIG_ELIMIT   -6   /* unsupported size (see mmsig_limits)        */
+
+#define MMSIG_STOP_NLOPT27 0   /* NLopt >= 2.7 x-tolerance rule (default)  */
+#define MMSIG_STOP_NLOPT26 1   /* NLopt <= 2.6 rule                         */
+
+#define MMSIG_FLAG_UPDATE_SIGMA 1u   /* fit!'s updateΣ=true (src/MMCTM.jl:468-470) */
+
+typedef struct mmsig_handle mmsig_handle;
+
+typedef struct {
+    int32_t device;        /* CUDA device ordinal                                          */
+    int32_t stop_rule;     /* MMSIG_STOP_*: which NLopt x-tolerance rule LD_MMA follows    */
+    int32_t profile;       /* != 0: time every kernel with CUDA events (mmsig_kernel_times) */
+    int32_t reserved[5];   /* must be 0                                                    */
+} mmsig_config;
+
+int32_t     mmsig_version(void);
+int32_t     mmsig_create(const mmsig_config *cfg, mmsig_handle **out);
+int32_t     mmsig_destroy(mmsig_handle *h);
+const char *mmsig_last_error(const mmsig_handle *h);           /* h may be NULL: last create error */
+/* run every kernel of this handle on an existing CUDA stream (a cudaStream_t, e.g. torch's) */
+int32_t     mmsig_set_stream(mmsig_handle *h, void *cuda_stream);
+int32_t     mmsig_synchronize(mmsig_handle *h);
+
+/* ---- multi-GPU: one handle (process) per GPU, samples sharded over ranks -----------------
+ * Per iteration the ranks exchange one small packed buffer of double-double partial sums
+ * (topic-term statistics, Σλ, Σν, then ΣΔΔᵀ and the LL numerators) with ncclAllGather and
+ * each rank reduces it in rank order, so all ranks hold bit-identical globals. */
+int32_t mmsig_comm_unique_id(uint8_t id_out[128]);
+int32_t mmsig_comm_init(mmsig_handle *h, const uint8_t id[128], int32_t rank, int32_t nranks);
+
+/* ---- MMCTM / CTM  (reference src/MMCTM.jl) -------------------------------------------- */
+/* model.X, K, V (src/MMCTM.jl:29-40); with mmsig_comm_init, D and the CSR are this rank's shard
+ * and D_total is the global sample count (else pass D_total = D). */
+int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
+                             const int32_t *K, const int32_t *V,
+                             const int64_t *const *rowptr, const int32_t *const *term,
+                             const int32_t *const *count);
+/* model.α, γ, λ, ν, μ, Σ, invΣ.  NULL => the constructor's value (src/MMCTM.jl:44-46,82-83):
+ * λ=0, ν=1, μ=0, Σ=invΣ=I.  alpha and gamma are required.  Elnϕ is derived (src/MMCTM.jl:78-79). */
+int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, const double *gamma,
+                              const double *lambda, const double *nu, const double *mu,
+                              const double *Sigma, const double *invSigma);
+/* one body of fit!'s loop (src/MMCTM.jl:463-479): E-step over all samples, μ, [Σ, invΣ], γ, Elnϕ,
+ * props, ϕ, per-modality log-likelihoods -> ll_out[M]. */
+int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *ll_out);
+/* fit! (src/MMCTM.jl:457-494): loop + `length(ll) > 10 && check_convergence` (src/common.jl:48-51);
+ * ll_hist is maxiter x M.  The ELBO of :490 is mmsig_mmctm_elbo. */
+int32_t mmsig_mmctm_fit(mmsig_handle *h, int32_t maxiter, double tol, uint32_t flags,
+                        double *ll_hist, int32_t *n_iter, int32_t *converged);
+/* calculate_elbo (src/MMCTM.jl:271-382) with the staleness of :490: θ, ζ, sumθ from the last
+ * E-step, everything else current.  terms[7] = ElnPϕ, ElnPη, ElnPZ, ElnPX, ElnQϕ, ElnQη, ElnQZ. */
+int32_t mmsig_mmctm_elbo(mmsig_handle *h, double *elbo, double *terms);
+int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double *nu, double *zeta,
+                              double *mu, double *Sigma, double *invSigma, double *gamma,
+                              double *Elnphi, double *phi, double *props);
+/* model.θ[d][m] for all d of modality m, nnz_m x K_m row-major ([w][k]); recomputed lazily from
+ * the λ / Elnϕ the last E-step used (the library never stores θ). */
+int32_t mmsig_mmctm_get_theta(mmsig_handle *h, int32_t m, double *theta_out);
+/* diagnostics: objective evaluations LD_MMA spent per sample in the last E-step */
+int32_t mmsig_mmctm_get_evals(mmsig_handle *h, int32_t *nev_nu, int32_t *nev_lambda);
+
+/* ---- LDA  (reference src/LDA.jl) -------------------------------------------------------- */
+int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
+                           const int64_t *rowptr, const int32_t *term, const int32_t *count);
+/* model.α, η, λ (required, [k][v]); gamma [d][k] or NULL => constructor state (γ=1, ϕ=1/K,
+ * src/LDA.jl:41-49), i.e. the first update_γ! gives α + N_d/K. */
+int32_t mmsig_lda_set_state(mmsig_handle *h, double alpha, double eta, const double *lambda,
+                            const double *gamma_next);
+/* one body of fit!'s loop (src/LDA.jl:202-209) -> *ll_out */
+int32_t mmsig_lda_iterate(mmsig_handle *h, double *ll_out);
+int32_t mmsig_lda_fit(mmsig_handle *h, int32_t maxiter, double tol, double *ll_hist,
+                      int32_t *n_iter, int32_t *converged);
+/* calculate_elbo (src/LDA.jl:114-172); terms[7] = ElnPβ, ElnPθ, ElnPZ, ElnPX, ElnQβ, ElnQθ, ElnQZ */
+int32_t mmsig_lda_elbo(mmsig_handle *h, double *elbo, double *terms);
+int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, double *beta,
+                            double *gamma, double *Elntheta, double *theta);
+/* model.ϕ[d] for all d, nnz x K row-major ([w][k]), recomputed lazily */
+int32_t mmsig_lda_get_phi(mmsig_handle *h, double *phi_out);
+
+/* ---- instrumentation ---------------------------------------------------------------------- */
+/* kernels launched by this handle since creation (bench.py's gpu_launches) */
+int64_t mmsig_launch_count(const mmsig_handle *h);
+/* with cfg.profile: per-kernel accumulated device time.  names_out: n_max pointers to static
+ * strings; returns the number of kernels filled.  reset != 0 clears the accumulators. */
+int32_t mmsig_kernel_times(mmsig_handle *h, int32_t n_max, const char **names_out,
+                           double *ms_total_out, int64_t *launches_out, int32_t reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMSIG_H */

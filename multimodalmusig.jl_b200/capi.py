@@ -1,0 +1,149 @@
+"""ctypes binding of libmmsig.so (include/mmsig.h).  No torch types cross this boundary:
+plain pointers and sizes only.  There is no CPU fallback: a missing library or device raises."""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmmsig.so")
+
+c_dp = C.POINTER(C.c_double)
+c_i32p = C.POINTER(C.c_int32)
+c_i64p = C.POINTER(C.c_int64)
+c_u8p = C.POINTER(C.c_uint8)
+
+FLAG_UPDATE_SIGMA = 1
+STOP_NLOPT27, STOP_NLOPT26 = 0, 1
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("stop_rule", C.c_int32), ("profile", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
+
+
+class MmsigError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("libmmsig error %d: %s" % (code, msg))
+        self.code = code
+
+
+_SIGS = {
+    "mmsig_version": (C.c_int32, []),
+    "mmsig_create": (C.c_int32, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
+    "mmsig_destroy": (C.c_int32, [C.c_void_p]),
+    "mmsig_last_error": (C.c_char_p, [C.c_void_p]),
+    "mmsig_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
+    "mmsig_synchronize": (C.c_int32, [C.c_void_p]),
+    "mmsig_comm_unique_id": (C.c_int32, [c_u8p]),
+    "mmsig_comm_init": (C.c_int32, [C.c_void_p, c_u8p, C.c_int32, C.c_int32]),
+    "mmsig_mmctm_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
+                                         C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)]),
+    "mmsig_mmctm_set_state": (C.c_int32, [C.c_void_p] + [c_dp] * 7),
+    "mmsig_mmctm_iterate": (C.c_int32, [C.c_void_p, C.c_uint32, c_dp]),
+    "mmsig_mmctm_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p]),
+    "mmsig_mmctm_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
+    "mmsig_mmctm_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 10),
+    "mmsig_mmctm_get_theta": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
+    "mmsig_mmctm_get_evals": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
+    "mmsig_lda_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p]),
+    "mmsig_lda_set_state": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, c_dp, c_dp]),
+    "mmsig_lda_iterate": (C.c_int32, [C.c_void_p, c_dp]),
+    "mmsig_lda_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, c_dp, c_i32p, c_i32p]),
+    "mmsig_lda_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
+    "mmsig_lda_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 6),
+    "mmsig_lda_get_phi": (C.c_int32, [C.c_void_p, c_dp]),
+    "mmsig_launch_count": (C.c_int64, [C.c_void_p]),
+    "mmsig_kernel_times": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), c_dp, c_i64p, C.c_int32]),
+}
+EXPORTS = sorted(_SIGS)
+_LIB = None
+
+
+def load():
+    """dlopen libmmsig.so and declare every entry point of include/mmsig.h."""
+    global _LIB
+    if _LIB is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "(make -C multimodalmusig.jl_b200/csrc); there is no CPU fallback" % LIB_PATH)
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            f = getattr(lib, name)
+            f.restype = res
+            f.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def dp(a):
+    return None if a is None else a.ctypes.data_as(c_dp)
+
+
+def f64(a, n=None):
+    if a is None:
+        return None
+    a = np.ascontiguousarray(a, dtype=np.float64)
+    if n is not None and a.size != n:
+        raise ValueError("expected %d values, got %d" % (n, a.size))
+    return a
+
+
+class Handle:
+    """Owns one mmsig_handle (one GPU)."""
+
+    def __init__(self, device=0, stop_rule=STOP_NLOPT27, profile=False):
+        self.lib = load()
+        cfg = Config(device=device, stop_rule=stop_rule, profile=int(profile))
+        hp = C.c_void_p()
+        rc = self.lib.mmsig_create(C.byref(cfg), C.byref(hp))
+        if rc != 0:
+            raise MmsigError(rc, (self.lib.mmsig_last_error(None) or b"").decode())
+        self.h = hp
+
+    def check(self, rc):
+        if rc != 0:
+            raise MmsigError(rc, (self.lib.mmsig_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mmsig_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def set_stream(self, cuda_stream_ptr):
+        self.check(self.lib.mmsig_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
+
+    def synchronize(self):
+        self.check(self.lib.mmsig_synchronize(self.h))
+
+    def comm_init(self, uid_bytes, rank, nranks):
+        buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid_bytes))
+        self.check(self.lib.mmsig_comm_init(self.h, buf, rank, nranks))
+
+    def launch_count(self):
+        return int(self.lib.mmsig_launch_count(self.h))
+
+    def kernel_times(self, reset=False):
+        n = 64
+        names = (C.c_char_p * n)()
+        ms = np.zeros(n)
+        cnt = np.zeros(n, dtype=np.int64)
+        k = self.lib.mmsig_kernel_times(self.h, n, names, dp(ms), cnt.ctypes.data_as(c_i64p), int(reset))
+        if k < 0:
+            self.check(k)
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
+
+
+def comm_unique_id():
+    lib = load()
+    buf = (C.c_uint8 * 128)()
+    rc = lib.mmsig_comm_unique_id(buf)
+    if rc != 0:
+        raise MmsigError(rc, (lib.mmsig_last_error(None) or b"").decode())
+    return bytes(buf)

@@ -1,0 +1,657 @@
+// mmctm_kernels.cuh -- sm_100a kernels for one MMCTM / CTM variational-EM iteration
+// (reference src/MMCTM.jl:450-479; dataflow in DESIGN.md).  FP64, pinned arithmetic.
+//
+//   k_theta_stats   responsibilities θ over the sparse [term,count] rows of one modality:
+//                   exact Σ_w n θ (sumθ, per sample) and exact Σ_d n θ (K x V statistics)
+//   k_solve         per-sample ζ, then LD_MMA for ν and for λ (one warp per sample,
+//                   lane j = coordinate j), Σλ / Σν partials
+//   k_combine       block partials -> one double-double vector
+//   k_mstep1        γ, Elnϕ, ϕ, μ
+//   k_post          ΣΔΔᵀ partials, softmax props and the per-modality log-likelihood pass
+//   k_mstep2        Σ, invΣ (LU with partial pivoting, one warp), LL
+#pragma once
+#include "det_math.cuh"
+
+namespace mmsig {
+
+constexpr int MAXM = 8;          // modalities
+constexpr int MAXMK = 32;        // ΣK_m: one coordinate per lane
+constexpr int MMA_MAXEVAL = 10000;
+
+struct MmctmDev {
+    int M, MK;
+    long long D, D_total;
+    int K[MAXM], V[MAXM], koff[MAXM + 1], goff[MAXM + 1];
+    const long long *rowptr[MAXM];
+    const int2 *rec[MAXM];        // (term, count) per nonzero
+    const double *N;              // D x M
+    double Ntot[MAXM];            // Σ_d N_dm over ALL ranks
+    double *lam, *lam_prev, *nu, *zeta, *sumtheta;
+    double *gamma, *Elnphi, *Elnphi_prev, *phi, *stats, *alpha;
+    double *mu, *Sigma, *invSigma;
+    double2 *nusum;               // MK, rank-summed Σ_d ν (dd) from mstep1 for mstep2
+    int *nev_nu, *nev_lam;
+    int stop_rule;
+};
+
+// ------------------------------------------------------------------------------------------
+// θ pass of one modality (src/MMCTM.jl:183-198, :110-117, :224-240).  One warp per sample,
+// lane <-> nonzero w.  Per nonzero: e_k = exp(λ_k + Elnϕ[k][v]), Z = Σ_k e_k (index order),
+// θ_k = e_k / Z, addend a = θ_k n.  Σ_w a -> sumθ[d][k]; Σ_d a -> this warp's private
+// double-double K x V table in shared memory (a row's terms are distinct, so lanes never
+// collide).  Nothing of size K x nnz is ever stored.
+// ------------------------------------------------------------------------------------------
+template <int KP, int NP>
+__global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 *partial, int nwarps_blk) {
+    extern __shared__ double smem[];
+    const int K = p.K[m], V = p.V[m], KV = K * V, off = p.koff[m];
+    double *Eln = smem;                       // KV
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *thi = smem + KV + (size_t)warp * 2 * KV;
+    double *tlo = thi + KV;
+    const double *Eg = p.Elnphi + p.goff[m];
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = Eg[i];
+    for (int i = lane; i < 2 * KV; i += 32) thi[i] = 0.0;
+    __syncthreads();
+
+    const long long *rowptr = p.rowptr[m];
+    const int2 *rec = p.rec[m];
+    const long long nw = (long long)gridDim.x * nwarps_blk;
+    for (long long d = (long long)blockIdx.x * nwarps_blk + warp; d < p.D; d += nw) {
+        double lamk[KP];
+        {
+            double mine = (lane < K) ? p.lam_prev[d * p.MK + off + lane] : 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
+        }
+        double shi[NP], slo[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) { shi[k] = 0.0; slo[k] = 0.0; }
+        const long long beg = rowptr[d], end = rowptr[d + 1];
+        for (long long w = beg + lane; w < end; w += 32) {
+            const int2 r = rec[w];
+            const int v = r.x;
+            const double n = (double)r.y;
+            double e[KP];
+            double Z = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) {
+                    e[k] = det_exp(lamk[k] + Eln[k * V + v]);
+                    Z += e[k];
+                }
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) {
+                    const double a = (e[k] / Z) * n;
+                    dd_add(thi[k * V + v], tlo[k * V + v], a);
+                    dd_add(shi[k], slo[k], a);
+                }
+        }
+        __syncwarp();
+        warp_multi_reduce_dd<NP>(shi, slo, lane);
+        const int idx = warp_multi_index<NP>(lane);
+        constexpr int GROUP = 32 / NP;            // lanes sharing one index
+        if (idx < K && (lane & (GROUP - 1)) == 0)
+            p.sumtheta[d * p.MK + off + idx] = dd_round(shi[0], slo[0]);
+    }
+    __syncthreads();
+    // block partial: warps' tables merged in warp order
+    double2 *out = partial + (size_t)blockIdx.x * KV;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        double hi = 0.0, lo = 0.0;
+        for (int wv = 0; wv < nwarps_blk; ++wv) {
+            const double *t = smem + KV + (size_t)wv * 2 * KV;
+            dd_merge(hi, lo, t[i], t[KV + i]);
+        }
+        out[i] = make_double2(hi, lo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// NLopt LD_MMA with zero constraints, one warp per problem, lane j = coordinate j.
+// Restates the recurrence of the oracle's orc_mma_minimize (ORC_ARITH_DET) op for op.
+// ------------------------------------------------------------------------------------------
+struct SolveCtx {
+    double Sjj;        // invΣ[j][j]
+    double muj;        // μ[j]
+    double c;          // N_dm / ζ_dm of this lane's modality
+    double s;          // sumθ[j]
+    double other;      // ν solve: λ_j ; λ solve: 0.5 ν_j
+    bool active;       // lane < MK
+};
+
+template <int MKP, bool IS_NU>
+__device__ __forceinline__ void mma_eval(double x, const SolveCtx &c, const double (&Srow)[MKP],
+                                         double *dsh, int lane, double &f, double &g) {
+    double t, grad;
+    if (IS_NU) {
+        // src/common.jl:25-36, maximised; fused per-coordinate term (DET)
+        const double e = det_exp(c.other + 0.5 * x);
+        grad = (-0.5 * c.Sjj - (c.c / 2) * e) + (1.0 / (2 * x));
+        t = (-0.5 * (x * c.Sjj) - c.c * e) + det_log(x) / 2;
+    } else {
+        // src/common.jl:11-23
+        const double diff = x - c.muj;
+        const double e = det_exp(x + c.other);
+        if (lane < MKP) dsh[lane] = diff;
+        __syncwarp();
+        double q = 0.0;
+#pragma unroll
+        for (int i = 0; i < MKP; i += 2) {
+            const double2 dv = *reinterpret_cast<const double2 *>(dsh + i);
+            q = fma(Srow[i], dv.x, q);
+            q = fma(Srow[i + 1], dv.y, q);
+        }
+        __syncwarp();
+        const double ce = c.c * e;
+        grad = (-q + c.s) - ce;
+        const double a = q * diff, b = x * c.s;
+        t = (b - 0.5 * a) - ce;
+    }
+    if (!c.active) { t = 0.0; grad = 0.0; }
+    f = -warp_tree_sum(t);          // NLopt minimises the negated objective
+    g = -grad;
+}
+
+template <int MKP, bool IS_NU>
+__device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const double (&Srow)[MKP],
+                                         double *dsh, int lane, int stop_rule) {
+    const double lb = IS_NU ? 1e-7 : -__longlong_as_double(0x7ff0000000000000LL);
+    const double xtol_rel = 1e-4, xtol_abs = 1e-4;
+    double sigma = 1.0;              // a bound is infinite -> sigma = 1
+    double rho = 1.0;
+    double g, fmin, fcur, gcur;
+    mma_eval<MKP, IS_NU>(x, c, Srow, dsh, lane, fmin, g);
+    int nev = 1;
+    double xcur = x, xprev = x, xprevprev = x;
+    int k = 0;
+    while (true) {
+        if (++k > 1) xprevprev = xprev;
+        xprev = xcur;
+        while (true) {
+            double u = g;
+            const double v = fabs(g) * sigma + 0.5 * rho;
+            const double sigma2 = sigma * sigma;
+            u *= sigma2;
+            const double r = u / (v * sigma);
+            double dx = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
+            double xc = x + dx;
+            if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
+            else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
+            if (xc < lb) xc = lb;
+            dx = xc - x;
+            const double dx2 = dx * dx;
+            const double denominv = 1.0 / (sigma2 - dx2);
+            const double cc = sigma2 * dx;
+            double gterm = (g * cc + (fabs(g) * sigma + 0.5 * rho) * dx2) * denominv;
+            double wterm = 0.5 * dx2 * denominv;
+            warp_tree_sum2(gterm, wterm);
+            const double gval = fmin + gterm, wval = wterm;
+            xcur = xc;
+            mma_eval<MKP, IS_NU>(xcur, c, Srow, dsh, lane, fcur, gcur);
+            ++nev;
+            const bool inner_done = gval >= fcur;
+            if (fcur < fmin) { fmin = fcur; x = xcur; g = gcur; }
+            if (nev >= MMA_MAXEVAL) return nev;
+            if (inner_done) break;
+            if (fcur > gval) {
+                const double r1 = 10 * rho, r2 = 1.1 * (rho + (fcur - gval) / wval);
+                rho = r1 < r2 ? r1 : r2;
+            }
+        }
+        // x-tolerance (NLopt stop.c) on (xcur, xprev)
+        const double ad = c.active ? fabs(xcur - xprev) : 0.0;
+        bool stop;
+        if (stop_rule == 1) {       // NLopt <= 2.6: per coordinate
+            const bool ok = ad < xtol_abs || ad < xtol_rel * (fabs(xcur) + fabs(xprev)) * 0.5 || xcur == xprev;
+            stop = __all_sync(FULLMASK, ok || !c.active);
+        } else {                    // NLopt >= 2.7: L1 norms, else all |dx| <= xtol_abs
+            double dn = ad, xn = c.active ? fabs(xcur) : 0.0;
+            warp_tree_sum2(dn, xn);
+            stop = (dn <= xtol_rel * xn) || __all_sync(FULLMASK, !(ad > xtol_abs));
+        }
+        if (stop) break;
+        rho = 0.1 * rho > 1e-5 ? 0.1 * rho : 1e-5;
+        if (k > 1) {
+            const double s2 = (xcur - xprev) * (xprev - xprevprev);
+            const double gam = s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
+            sigma *= gam;
+        }
+    }
+    return nev;
+}
+
+// sequential sum over this lane's modality block [lo, hi) of a per-lane value
+__device__ __forceinline__ double block_sum_seq(double e, int lo, int hi, int MK) {
+    double s = 0.0;
+    for (int i = 0; i < MK; ++i) {
+        const double v = shfl_d(e, i);
+        if (i >= lo && i < hi) s += v;
+    }
+    return s;
+}
+
+// ------------------------------------------------------------------------------------------
+// fitdoc! minus the θ pass (src/MMCTM.jl:450-455): ζ from the old λ, ν (:172-181), then
+// update_ν! (:156-170) and update_λ! (:127-143, with the new ν, old ζ, old sumθ).
+// partial: [gridDim.x][2*MK] dd of Σ_d λ_new and Σ_d ν_new.
+// ------------------------------------------------------------------------------------------
+template <int MKP>
+__global__ void __launch_bounds__(256) k_solve(MmctmDev p, double2 *partial) {
+    __shared__ double dsh_all[8][MKP];
+    __shared__ double2 red[8][2][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MK = p.MK, M = p.M;
+    double *dsh = dsh_all[warp];
+    if (lane < MKP) dsh[lane] = 0.0;
+    const bool active = lane < MK;
+    int mod = 0;
+    for (int m = 0; m < M; ++m)
+        if (lane >= p.koff[m]) mod = m;
+    const int blo = p.koff[mod], bhi = p.koff[mod + 1];
+
+    double Srow[MKP];
+#pragma unroll
+    for (int i = 0; i < MKP; ++i) Srow[i] = (active && i < MK) ? p.invSigma[lane * MK + i] : 0.0;
+    SolveCtx c;
+    c.active = active;
+    c.Sjj = active ? p.invSigma[lane * MK + lane] : 0.0;
+    c.muj = active ? p.mu[lane] : 0.0;
+
+    double lsh = 0.0, lsl = 0.0, nsh = 0.0, nsl = 0.0;
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const long long base = d * MK + lane;
+        double lam = active ? p.lam_prev[base] : 0.0;
+        double nu = active ? p.nu[base] : 1.0;
+        c.s = active ? p.sumtheta[base] : 0.0;
+        // ζ_dm = Σ_{k in block m} exp(λ + ν/2), index order
+        const double e0 = active ? det_exp(lam + 0.5 * nu) : 0.0;
+        const double zeta = block_sum_seq(e0, blo, bhi, MK);
+        const double Ndm = active ? p.N[d * M + mod] : 0.0;
+        c.c = active ? Ndm / zeta : 0.0;
+        if (active && lane == blo) p.zeta[d * M + mod] = zeta;
+        // ν
+        c.other = lam;
+        const int nev_nu = mma_solve<MKP, true>(nu, c, Srow, dsh, lane, p.stop_rule);
+        // λ (new ν, old ζ)
+        c.other = 0.5 * nu;
+        const int nev_lam = mma_solve<MKP, false>(lam, c, Srow, dsh, lane, p.stop_rule);
+        if (active) {
+            p.lam[base] = lam;
+            p.nu[base] = nu;
+            dd_add(lsh, lsl, lam);
+            dd_add(nsh, nsl, nu);
+        }
+        if (lane == 0) { p.nev_nu[d] = nev_nu; p.nev_lam[d] = nev_lam; }
+    }
+    red[warp][0][lane] = make_double2(lsh, lsl);
+    red[warp][1][lane] = make_double2(nsh, nsl);
+    __syncthreads();
+    if (threadIdx.x < 64) {
+        const int which = threadIdx.x >> 5;
+        double hi = 0.0, lo = 0.0;
+        for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv][which][lane].x, red[wv][which][lane].y);
+        if (lane < MK) partial[(size_t)blockIdx.x * 2 * MK + which * MK + lane] = make_double2(hi, lo);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// block partials -> one dd vector.  Segment s: dst[dst_off + i] = Σ_part src[part*n + i].
+// ------------------------------------------------------------------------------------------
+struct CombineSegs {
+    int nseg;
+    const double2 *src[MAXM + 2];
+    int nparts[MAXM + 2], n[MAXM + 2], dst_off[MAXM + 2];
+};
+__global__ void k_combine(CombineSegs s, double2 *dst) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int base = 0;
+    for (int g = 0; g < s.nseg; ++g) {
+        if (t < base + s.n[g]) {
+            const int i = t - base;
+            double hi = 0.0, lo = 0.0;
+            for (int part = 0; part < s.nparts[g]; ++part) {
+                const double2 v = s.src[g][(size_t)part * s.n[g] + i];
+                dd_merge(hi, lo, v.x, v.y);
+            }
+            dst[s.dst_off[g] + i] = make_double2(hi, lo);
+            return;
+        }
+        base += s.n[g];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// M-step, part 1 (single block).  gathered: [nranks][G + 2 MK] dd.
+// γ = exact_round(α + Σ n θ) (src/MMCTM.jl:224-240), Elnϕ = ψ(γ) - ψ(Σ_v γ) (:214-222),
+// ϕ = γ / Σ_v γ (:244-250), μ = exact_round(Σ_d λ) / D (:200-202).
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gathered, int nranks) {
+    __shared__ double rowsum[MAXMK], rowdig[MAXMK];
+    const int G = p.goff[p.M], MK = p.MK, P1 = G + 2 * MK;
+    for (int i = threadIdx.x; i < P1; i += blockDim.x) {
+        double hi = 0.0, lo = 0.0;
+        for (int r = 0; r < nranks; ++r) {
+            const double2 v = gathered[(size_t)r * P1 + i];
+            dd_merge(hi, lo, v.x, v.y);
+        }
+        if (i < G) {
+            int m = 0;
+            while (i >= p.goff[m + 1]) ++m;
+            p.stats[i] = dd_round(hi, lo);
+            dd_add(hi, lo, p.alpha[m]);
+            p.gamma[i] = dd_round(hi, lo);
+            p.Elnphi_prev[i] = p.Elnphi[i];
+        } else if (i < G + MK) {
+            p.mu[i - G] = dd_round(hi, lo) / (double)p.D_total;
+        } else {
+            p.nusum[i - G - MK] = make_double2(hi, lo);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < MK) {
+        int m = 0;
+        while ((int)threadIdx.x >= p.koff[m + 1]) ++m;
+        const int k = threadIdx.x - p.koff[m];
+        const double *g = p.gamma + p.goff[m] + k * p.V[m];
+        double s = 0.0;
+        for (int v = 0; v < p.V[m]; ++v) s += g[v];
+        rowsum[threadIdx.x] = s;
+        rowdig[threadIdx.x] = det_digamma(s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        int m = 0;
+        while (i >= p.goff[m + 1]) ++m;
+        const int row = p.koff[m] + (i - p.goff[m]) / p.V[m];
+        const double gv = p.gamma[i];
+        p.Elnphi[i] = det_digamma(gv) - rowdig[row];
+        p.phi[i] = gv / rowsum[row];
+    }
+}
+
+// Elnϕ from γ only (constructor, src/MMCTM.jl:78-79)
+__global__ void __launch_bounds__(1024) k_elnphi(MmctmDev p) {
+    __shared__ double rowdig[MAXMK];
+    const int G = p.goff[p.M], MK = p.MK;
+    if (threadIdx.x < MK) {
+        int m = 0;
+        while ((int)threadIdx.x >= p.koff[m + 1]) ++m;
+        const int k = threadIdx.x - p.koff[m];
+        const double *g = p.gamma + p.goff[m] + k * p.V[m];
+        double s = 0.0;
+        for (int v = 0; v < p.V[m]; ++v) s += g[v];
+        rowdig[threadIdx.x] = det_digamma(s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        int m = 0;
+        while (i >= p.goff[m + 1]) ++m;
+        const int row = p.koff[m] + (i - p.goff[m]) / p.V[m];
+        p.Elnphi[i] = det_digamma(p.gamma[i]) - rowdig[row];
+        p.Elnphi_prev[i] = p.Elnphi[i];
+        p.phi[i] = p.gamma[i];                  // model.ϕ = deepcopy(model.γ), src/MMCTM.jl:80
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// Post pass: ΣΔΔᵀ partials with the new μ (src/MMCTM.jl:204-210), props = softmax(λ block)
+// (:145-154) and the per-modality log-likelihood (:384-448), lane <-> nonzero.
+// partial: [gridDim.x][MK*MK + M] dd.
+// ------------------------------------------------------------------------------------------
+template <int MKP>
+__global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int do_moments, double *props_out) {
+    extern __shared__ double smem[];
+    const int G = p.goff[p.M], MK = p.MK, M = p.M;
+    double2 *red = reinterpret_cast<double2 *>(smem);      // 256 double2 = 512 doubles
+    double *phi = smem + 512;                             // G
+    double *psh_all = phi + G;                            // 8 x 32
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *psh = psh_all + warp * 32;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) phi[i] = p.phi[i];
+    __syncthreads();
+    const bool active = lane < MK;
+    int mod = 0;
+    for (int m = 0; m < M; ++m)
+        if (lane >= p.koff[m]) mod = m;
+    const int blo = p.koff[mod], bhi = p.koff[mod + 1];
+    const double muj = active ? p.mu[lane] : 0.0;
+
+    double mhi[MKP], mlo[MKP];
+#pragma unroll
+    for (int i = 0; i < MKP; ++i) { mhi[i] = 0.0; mlo[i] = 0.0; }
+    double llh[MAXM], lll[MAXM];
+#pragma unroll
+    for (int m = 0; m < MAXM; ++m) { llh[m] = 0.0; lll[m] = 0.0; }
+
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const double lam = active ? p.lam[d * MK + lane] : 0.0;
+        if (do_moments) {
+            const double diff = lam - muj;
+#pragma unroll
+            for (int i = 0; i < MKP; ++i) {
+                const double di = shfl_d(diff, i);
+                if (i < MK) dd_add(mhi[i], mlo[i], diff * di);
+            }
+        }
+        // props
+        const double e = active ? det_exp(lam) : 0.0;
+        const double s = block_sum_seq(e, blo, bhi, MK);
+        const double pr = active ? e / s : 0.0;
+        if (props_out && active) props_out[d * MK + lane] = pr;
+        __syncwarp();
+        psh[lane] = pr;
+        __syncwarp();
+#pragma unroll
+        for (int m = 0; m < MAXM; ++m) {
+            if (m < M) {
+                const double docN = p.N[d * M + m];
+                if (docN > 0) {
+                    const int K = p.K[m], V = p.V[m], ko = p.koff[m];
+                    const double *ph = phi + p.goff[m];
+                    const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
+                    double hi = 0.0, lo = 0.0;
+                    for (long long w = beg + lane; w < end; w += 32) {
+                        const int2 r = p.rec[m][w];
+                        double pw = 0.0;
+                        for (int k = 0; k < K; ++k) pw += psh[ko + k] * ph[k * V + r.x];
+                        dd_add(hi, lo, (double)r.y * det_log(pw));
+                    }
+                    __syncwarp();
+                    warp_dd_allreduce(hi, lo);
+                    double dl = dd_round(hi, lo);
+                    dl = dl / docN;
+                    dd_add(llh[m], lll[m], dl * docN);     // identical in every lane
+                }
+            }
+        }
+    }
+    // block combine through shared memory, one moment column at a time
+    __syncthreads();
+    double2 *out = partial + (size_t)blockIdx.x * (MK * MK + M);
+#pragma unroll
+    for (int i = 0; i < MKP; ++i) {
+        red[warp * 32 + lane] = make_double2(mhi[i], mlo[i]);
+        __syncthreads();
+        if (warp == 0 && active && i < MK) {
+            double hi = 0.0, lo = 0.0;
+            for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv * 32 + lane].x, red[wv * 32 + lane].y);
+            out[lane * MK + i] = make_double2(hi, lo);          // Σ_d diff_lane * diff_i
+        }
+        __syncthreads();
+    }
+    for (int m = 0; m < M; ++m) {
+        if (lane == 0) red[warp] = make_double2(llh[m], lll[m]);
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double hi = 0.0, lo = 0.0;
+            for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv].x, red[wv].y);
+            out[MK * MK + m] = make_double2(hi, lo);
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// LU with partial pivoting + inverse, one warp, n <= 32; restates the oracle's lu_factor /
+// orc_inv (LAPACK getrf/getri as used by Julia's inv, src/MMCTM.jl:211) op for op.
+// A: n x n row-major in shared memory (destroyed); B: n x n scratch; out: global row-major.
+// returns log|det A| via *logabsdet if not null (plain sum of det_log |u_ii|).
+// ------------------------------------------------------------------------------------------
+__device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, double *out, double *logabsdet) {
+    const int lane = threadIdx.x & 31;
+    for (int k = 0; k < n; ++k) {
+        // first index of the maximum |A[i][k]|, i >= k
+        double best = (lane >= k && lane < n) ? fabs(A[lane * n + k]) : -1.0;
+        int bi = lane;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ob = shfl_xor_d(best, off);
+            const int oi = __shfl_xor_sync(FULLMASK, bi, off);
+            if (ob > best || (ob == best && oi < bi)) { best = ob; bi = oi; }
+        }
+        if (lane == 0) piv[k] = bi;
+        if (best == 0.0) return false;
+        __syncwarp();
+        if (bi != k && lane < n) {
+            const double t = A[k * n + lane];
+            A[k * n + lane] = A[bi * n + lane];
+            A[bi * n + lane] = t;
+        }
+        __syncwarp();
+        const double inv = 1.0 / A[k * n + k];
+        __syncwarp();
+        if (lane > k && lane < n) A[lane * n + k] = A[lane * n + k] * inv;
+        __syncwarp();
+        if (lane > k && lane < n)
+            for (int i = k + 1; i < n; ++i) A[i * n + lane] -= A[i * n + k] * A[k * n + lane];
+        __syncwarp();
+    }
+    if (logabsdet) {
+        double r = 0.0;
+        for (int i = 0; i < n; ++i) r += det_log(fabs(A[i * n + i]));
+        *logabsdet = r;
+    }
+    if (out && lane < n) {
+        const int c = lane;
+        for (int i = 0; i < n; ++i) B[i * n + c] = (i == c) ? 1.0 : 0.0;
+        for (int k = 0; k < n; ++k)
+            if (piv[k] != k) {
+                const double t = B[k * n + c];
+                B[k * n + c] = B[piv[k] * n + c];
+                B[piv[k] * n + c] = t;
+            }
+        for (int i = 0; i < n; ++i) {
+            double s = B[i * n + c];
+            for (int j = 0; j < i; ++j) s -= A[i * n + j] * B[j * n + c];
+            B[i * n + c] = s;
+        }
+        for (int i = n - 1; i >= 0; --i) {
+            double s = B[i * n + c];
+            for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * B[j * n + c];
+            B[i * n + c] = s / A[i * n + i];
+        }
+        for (int i = 0; i < n; ++i) out[i * n + c] = B[i * n + c];
+    }
+    __syncwarp();
+    return true;
+}
+
+// M-step, part 2 (one warp).  gathered: [nranks][MK*MK + M] dd.
+// Σ = exact_round(diag Σ_d ν + Σ_d ΔΔᵀ) / D, invΣ = inv(Σ) (src/MMCTM.jl:204-212); ll_m (:417).
+__global__ void __launch_bounds__(32) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
+                                               double *ll_out, int *status) {
+    __shared__ double A[MAXMK * MAXMK], B[MAXMK * MAXMK];
+    __shared__ int piv[MAXMK];
+    const int MK = p.MK, M = p.M, P2 = MK * MK + M, lane = threadIdx.x;
+    for (int i = lane; i < P2; i += 32) {
+        double hi = 0.0, lo = 0.0;
+        for (int r = 0; r < nranks; ++r) {
+            const double2 v = gathered[(size_t)r * P2 + i];
+            dd_merge(hi, lo, v.x, v.y);
+        }
+        if (i < MK * MK) {
+            if (do_sigma) {
+                const int a = i / MK, b = i % MK;
+                if (a == b) dd_merge(hi, lo, p.nusum[a].x, p.nusum[a].y);
+                const double sv = dd_round(hi, lo) / (double)p.D_total;
+                p.Sigma[i] = sv;
+                A[i] = sv;
+            }
+        } else {
+            const int m = i - MK * MK;
+            ll_out[m] = dd_round(hi, lo) / p.Ntot[m];
+        }
+    }
+    __syncwarp();
+    if (do_sigma) {
+        const bool ok = warp_lu_inverse(MK, A, B, piv, p.invSigma, nullptr);
+        if (lane == 0) *status = ok ? 0 : 1;
+    }
+}
+
+// props only (get_state): softmax of each λ block
+__global__ void __launch_bounds__(256) k_props(MmctmDev p, double *props_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MK = p.MK;
+    const bool active = lane < MK;
+    int mod = 0;
+    for (int m = 0; m < p.M; ++m)
+        if (lane >= p.koff[m]) mod = m;
+    const int blo = p.koff[mod], bhi = p.koff[mod + 1];
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const double lam = active ? p.lam[d * MK + lane] : 0.0;
+        const double e = active ? det_exp(lam) : 0.0;
+        const double s = block_sum_seq(e, blo, bhi, MK);
+        if (active) props_out[d * MK + lane] = e / s;
+    }
+}
+
+// ζ from the current λ, ν (constructor, src/MMCTM.jl:85-86)
+__global__ void __launch_bounds__(256) k_zeta(MmctmDev p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int MK = p.MK;
+    const bool active = lane < MK;
+    int mod = 0;
+    for (int m = 0; m < p.M; ++m)
+        if (lane >= p.koff[m]) mod = m;
+    const int blo = p.koff[mod], bhi = p.koff[mod + 1];
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const double e = active ? det_exp(p.lam[d * MK + lane] + 0.5 * p.nu[d * MK + lane]) : 0.0;
+        const double s = block_sum_seq(e, blo, bhi, MK);
+        if (active && lane == blo) p.zeta[d * p.M + mod] = s;
+    }
+}
+
+// θ of one modality, materialised on request (model.θ[d][m]); uses the λ / Elnϕ of the last
+// E-step (lam_prev, Elnphi_prev).  out: nnz x K.
+__global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *out) {
+    extern __shared__ double smem[];
+    const int K = p.K[m], V = p.V[m], KV = K * V, off = p.koff[m];
+    double *Eln = smem;
+    const double *Eg = p.Elnphi_prev + p.goff[m];
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = Eg[i];
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
+        for (long long w = beg + lane; w < end; w += 32) {
+            const int v = p.rec[m][w].x;
+            double Z = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double e = det_exp(p.lam_prev[d * p.MK + off + k] + Eln[k * V + v]);
+                out[w * K + k] = e;
+                Z += e;
+            }
+            for (int k = 0; k < K; ++k) out[w * K + k] = out[w * K + k] / Z;
+        }
+    }
+}
+
+}  // namespace mmsig

@@ -1,0 +1,788 @@
+// mmsig_api.cu -- the C ABI of libmmsig.so (include/mmsig.h): handle, device memory, launch
+// plans, NCCL exchange, fit loops.  Host side of the MMCTM / CTM / LDA variational-EM path.
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <dlfcn.h>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/mmsig.h"
+#include "det_math.cuh"
+#include "mmctm_kernels.cuh"
+#include "elbo_kernels.cuh"
+#include "lda_kernels.cuh"
+
+using namespace mmsig;
+
+// ---- NCCL, bound at run time (dlopen) so that a process that already holds torch's libnccl
+// shares it and single-GPU users need no NCCL at all ---------------------------------------
+typedef struct ncclComm *ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId_t;
+typedef int (*pfn_ncclGetUniqueId)(ncclUniqueId_t *);
+typedef int (*pfn_ncclCommInitRank)(ncclComm_t *, int, ncclUniqueId_t, int);
+typedef int (*pfn_ncclCommDestroy)(ncclComm_t);
+typedef int (*pfn_ncclAllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t);
+typedef const char *(*pfn_ncclGetErrorString)(int);
+static const int kNcclInt8 = 0, kNcclFloat64 = 8;
+
+struct NcclApi {
+    void *lib = nullptr;
+    pfn_ncclGetUniqueId GetUniqueId = nullptr;
+    pfn_ncclCommInitRank CommInitRank = nullptr;
+    pfn_ncclCommDestroy CommDestroy = nullptr;
+    pfn_ncclAllGather AllGather = nullptr;
+    pfn_ncclGetErrorString GetErrorString = nullptr;
+};
+static NcclApi g_nccl;
+static std::string g_last_error;
+
+static bool load_nccl(std::string &err) {
+    if (g_nccl.lib) return true;
+    void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!lib) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+    g_nccl.GetUniqueId = (pfn_ncclGetUniqueId)dlsym(lib, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (pfn_ncclCommInitRank)dlsym(lib, "ncclCommInitRank");
+    g_nccl.CommDestroy = (pfn_ncclCommDestroy)dlsym(lib, "ncclCommDestroy");
+    g_nccl.AllGather = (pfn_ncclAllGather)dlsym(lib, "ncclAllGather");
+    g_nccl.GetErrorString = (pfn_ncclGetErrorString)dlsym(lib, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.AllGather || !g_nccl.CommDestroy) {
+        err = "libnccl lacks a required symbol";
+        return false;
+    }
+    g_nccl.lib = lib;
+    return true;
+}
+
+// ---- handle -------------------------------------------------------------------------------
+struct KernelTime { const char *name; double ms; int64_t n; };
+struct PendingEvent { int idx; cudaEvent_t a, b; };
+
+struct MmctmHost {
+    bool has_data = false, has_state = false, estep_done = false;
+    MmctmDev p{};
+    int G = 0;
+    std::vector<long long> nnz;
+    int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0};
+    size_t smem_theta[MAXM] = {0};
+    int grid_solve = 0, grid_post = 0;
+    size_t smem_post = 0;
+    double2 *part_theta[MAXM] = {nullptr};
+    double2 *part_solve = nullptr, *part_post = nullptr, *part_elbo = nullptr;
+    double2 *rank_p1 = nullptr, *gath_p1 = nullptr, *rank_p2 = nullptr, *gath_p2 = nullptr;
+    double *d_ll = nullptr;
+    int *d_status = nullptr;
+    double *lamA = nullptr, *lamB = nullptr;
+};
+
+struct LdaHost {
+    bool has_data = false, has_state = false, iterated = false;
+    LdaDev p{};
+    long long nnz = 0;
+    int grid = 0, W = 0;
+    size_t smem = 0;
+    double2 *part = nullptr, *rank_p = nullptr, *gath_p = nullptr;
+    double *d_ll = nullptr;
+    double *gamA = nullptr, *gamB = nullptr;
+};
+
+struct mmsig_handle {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    bool own_stream = false;
+    std::string err;
+    int stop_rule = 0;
+    bool profile = false;
+    int numSM = 0;
+    size_t smem_optin = 0;
+    ncclComm_t comm = nullptr;
+    int rank = 0, nranks = 1;
+    int64_t launches = 0;
+    std::vector<KernelTime> kt;
+    std::vector<PendingEvent> pending;
+    std::vector<void *> allocs_mm, allocs_lda;
+    MmctmHost mm;
+    LdaHost lda;
+};
+
+static int fail(mmsig_handle *h, int code, const std::string &msg) {
+    if (h) h->err = msg;
+    g_last_error = msg;
+    return code;
+}
+#define CU(call)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e_ = (call);                                                                   \
+        if (e_ != cudaSuccess)                                                                     \
+            return fail(h, MMSIG_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));       \
+    } while (0)
+#define NEED(cond, msg)                                                                            \
+    do {                                                                                           \
+        if (!(cond)) return fail(h, MMSIG_EINVAL, msg);                                            \
+    } while (0)
+
+template <typename T>
+static int dev_alloc(mmsig_handle *h, std::vector<void *> &pool, T **out, size_t count) {
+    void *ptr = nullptr;
+    cudaError_t e = cudaMalloc(&ptr, std::max<size_t>(count, 1) * sizeof(T));
+    if (e != cudaSuccess) return fail(h, MMSIG_ENOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    pool.push_back(ptr);
+    *out = (T *)ptr;
+    return 0;
+}
+static void free_pool(std::vector<void *> &pool) {
+    for (void *p : pool) cudaFree(p);
+    pool.clear();
+}
+
+// kernel launch bookkeeping: count, optional event timing
+static int kt_index(mmsig_handle *h, const char *name) {
+    for (size_t i = 0; i < h->kt.size(); ++i)
+        if (h->kt[i].name == name || !strcmp(h->kt[i].name, name)) return (int)i;
+    h->kt.push_back({name, 0.0, 0});
+    return (int)h->kt.size() - 1;
+}
+struct LaunchScope {
+    mmsig_handle *h;
+    PendingEvent pe{};
+    bool timed;
+    LaunchScope(mmsig_handle *h_, const char *name) : h(h_), timed(h_->profile) {
+        h->launches++;
+        if (timed) {
+            pe.idx = kt_index(h, name);
+            cudaEventCreate(&pe.a);
+            cudaEventCreate(&pe.b);
+            cudaEventRecord(pe.a, h->stream);
+        }
+    }
+    ~LaunchScope() {
+        if (timed) {
+            cudaEventRecord(pe.b, h->stream);
+            h->pending.push_back(pe);
+        }
+    }
+};
+static void resolve_pending(mmsig_handle *h) {
+    for (auto &pe : h->pending) {
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, pe.a, pe.b) == cudaSuccess) {
+            h->kt[pe.idx].ms += ms;
+            h->kt[pe.idx].n += 1;
+        }
+        cudaEventDestroy(pe.a);
+        cudaEventDestroy(pe.b);
+    }
+    h->pending.clear();
+}
+
+static int gather(mmsig_handle *h, const double2 *rank_buf, double2 *gath_buf, size_t n, const double2 **out) {
+    if (h->nranks == 1) { *out = rank_buf; return 0; }
+    LaunchScope ls(h, "ncclAllGather");
+    int rc = g_nccl.AllGather(rank_buf, gath_buf, n * 2, kNcclFloat64, h->comm, h->stream);
+    if (rc != 0)
+        return fail(h, MMSIG_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    *out = gath_buf;
+    return 0;
+}
+
+
+// opt a kernel in to the largest dynamic shared memory the device allows (minus its static part)
+template <typename F>
+static cudaError_t allow_max_smem(mmsig_handle *h, F kernel) {
+    cudaFuncAttributes fa;
+    cudaError_t e = cudaFuncGetAttributes(&fa, kernel);
+    if (e != cudaSuccess) return e;
+    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(h->smem_optin - fa.sharedSizeBytes));
+}
+
+// ---- generic ------------------------------------------------------------------------------
+extern "C" int32_t mmsig_version(void) { return 100; }
+
+extern "C" const char *mmsig_last_error(const mmsig_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
+
+extern "C" int32_t mmsig_create(const mmsig_config *cfg, mmsig_handle **out) {
+    mmsig_handle *h = nullptr;
+    if (!cfg || !out) return fail(nullptr, MMSIG_EINVAL, "mmsig_create: null argument");
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(nullptr, MMSIG_ENODEV, std::string("no CUDA device (there is no CPU fallback): ") +
+                                               (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MMSIG_EINVAL, "mmsig_create: bad device ordinal");
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, MMSIG_ECUDA, "cudaGetDeviceProperties failed");
+    if (prop.major < 10)
+        return fail(nullptr, MMSIG_ENODEV, "device is not sm_100 class; libmmsig carries sm_100a code only");
+    h = new mmsig_handle();
+    h->device = cfg->device;
+    h->stop_rule = cfg->stop_rule == MMSIG_STOP_NLOPT26 ? 1 : 0;
+    h->profile = cfg->profile != 0;
+    h->numSM = prop.multiProcessorCount;
+    h->smem_optin = prop.sharedMemPerBlockOptin;
+    if (cudaSetDevice(h->device) != cudaSuccess || cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, MMSIG_ECUDA, "cannot create stream");
+    }
+    h->own_stream = true;
+    *out = h;
+    return 0;
+}
+
+extern "C" int32_t mmsig_destroy(mmsig_handle *h) {
+    if (!h) return 0;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    resolve_pending(h);
+    free_pool(h->allocs_mm);
+    free_pool(h->allocs_lda);
+    if (h->comm) g_nccl.CommDestroy(h->comm);
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+    return 0;
+}
+
+extern "C" int32_t mmsig_set_stream(mmsig_handle *h, void *cuda_stream) {
+    NEED(h, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->own_stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    return 0;
+}
+
+extern "C" int32_t mmsig_synchronize(mmsig_handle *h) {
+    NEED(h, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int32_t mmsig_comm_unique_id(uint8_t id_out[128]) {
+    mmsig_handle *h = nullptr;
+    std::string err;
+    if (!load_nccl(err)) return fail(h, MMSIG_ENCCL, err);
+    ncclUniqueId_t id;
+    int rc = g_nccl.GetUniqueId(&id);
+    if (rc != 0) return fail(h, MMSIG_ENCCL, "ncclGetUniqueId failed");
+    memcpy(id_out, id.internal, 128);
+    return 0;
+}
+
+extern "C" int32_t mmsig_comm_init(mmsig_handle *h, const uint8_t id[128], int32_t rank, int32_t nranks) {
+    NEED(h && id, "null argument");
+    NEED(nranks >= 1 && rank >= 0 && rank < nranks, "bad rank / nranks");
+    NEED(!h->mm.has_data && !h->lda.has_data, "mmsig_comm_init must precede set_data");
+    std::string err;
+    if (!load_nccl(err)) return fail(h, MMSIG_ENCCL, err);
+    CU(cudaSetDevice(h->device));
+    ncclUniqueId_t uid;
+    memcpy(uid.internal, id, 128);
+    int rc = g_nccl.CommInitRank(&h->comm, nranks, uid, rank);
+    if (rc != 0) return fail(h, MMSIG_ENCCL, std::string("ncclCommInitRank: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
+    h->rank = rank;
+    h->nranks = nranks;
+    return 0;
+}
+
+extern "C" int64_t mmsig_launch_count(const mmsig_handle *h) { return h ? h->launches : 0; }
+
+extern "C" int32_t mmsig_kernel_times(mmsig_handle *h, int32_t n_max, const char **names_out, double *ms_total_out,
+                                      int64_t *launches_out, int32_t reset) {
+    NEED(h, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    resolve_pending(h);
+    int n = std::min<int>(n_max, (int)h->kt.size());
+    for (int i = 0; i < n; ++i) {
+        if (names_out) names_out[i] = h->kt[i].name;
+        if (ms_total_out) ms_total_out[i] = h->kt[i].ms;
+        if (launches_out) launches_out[i] = h->kt[i].n;
+    }
+    if (reset)
+        for (auto &k : h->kt) { k.ms = 0.0; k.n = 0; }
+    return n;
+}
+
+// sum of per-rank int64 totals (Σ_d N_dm) over ranks, on the host
+static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
+    if (h->nranks == 1) return 0;
+    long long *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, n * sizeof(long long)));
+    CU(cudaMalloc(&d_out, (size_t)n * h->nranks * sizeof(long long)));
+    CU(cudaMemcpyAsync(d_in, vals, n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    int rc = g_nccl.AllGather(d_in, d_out, (size_t)n * sizeof(long long), kNcclInt8, h->comm, h->stream);
+    if (rc != 0) return fail(h, MMSIG_ENCCL, "ncclAllGather (totals) failed");
+    std::vector<long long> all((size_t)n * h->nranks);
+    CU(cudaMemcpyAsync(all.data(), d_out, all.size() * sizeof(long long), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int i = 0; i < n; ++i) {
+        long long s = 0;
+        for (int r = 0; r < h->nranks; ++r) s += all[(size_t)r * n + i];
+        vals[i] = s;
+    }
+    cudaFree(d_in);
+    cudaFree(d_out);
+    return 0;
+}
+
+// ---- count ingest: (term, count) -> packed records, row totals, validation ------------------
+// flags: bit0 term out of range, bit1 count <= 0, bit2 terms of a row not strictly ascending
+__global__ void k_pack_rows(const long long *rowptr, const int *term, const int *count, long long D, int V,
+                            int2 *rec, double *N, int M, int m, int *flags) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
+    int bad = 0;
+    for (long long d = (long long)blockIdx.x * (blockDim.x >> 5) + warp; d < D; d += nw) {
+        const long long beg = rowptr[d], end = rowptr[d + 1];
+        long long s = 0;
+        for (long long w = beg + lane; w < end; w += 32) {
+            const int t = term[w], c = count[w];
+            if (t < 0 || t >= V) bad |= 1;
+            if (c <= 0) bad |= 2;
+            if (w > beg && term[w - 1] >= t) bad |= 4;
+            rec[w] = make_int2(t, c);
+            s += c;
+        }
+        for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(FULLMASK, s, off);
+        if (lane == 0) N[d * M + m] = (double)s;
+    }
+    if (bad) atomicOr(flags, bad);
+}
+
+static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, long long D, int V, int M, int m,
+                         const int64_t *rowptr, const int32_t *term, const int32_t *count,
+                         const long long **d_rowptr, const int2 **d_rec, double *d_N, long long *nnz_out,
+                         long long *ntot_out) {
+    NEED(rowptr && rowptr[0] == 0, "rowptr[0] must be 0");
+    const long long nnz = rowptr[D];
+    NEED(nnz >= 0, "rowptr[D] < 0");
+    NEED(nnz == 0 || (term && count), "null term / count");
+    long long *drp = nullptr;
+    int2 *drec = nullptr;
+    int *dterm = nullptr, *dcount = nullptr, *dflags = nullptr;
+    int rc;
+    if ((rc = dev_alloc(h, pool, &drp, D + 1))) return rc;
+    if ((rc = dev_alloc(h, pool, &drec, nnz))) return rc;
+    CU(cudaMalloc(&dterm, std::max<long long>(nnz, 1) * sizeof(int)));
+    CU(cudaMalloc(&dcount, std::max<long long>(nnz, 1) * sizeof(int)));
+    CU(cudaMalloc(&dflags, sizeof(int)));
+    CU(cudaMemsetAsync(dflags, 0, sizeof(int), h->stream));
+    CU(cudaMemcpyAsync(drp, rowptr, (D + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (nnz) {
+        CU(cudaMemcpyAsync(dterm, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(dcount, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    {
+        LaunchScope ls(h, "k_pack_rows");
+        int grid = (int)std::min<long long>((D + 7) / 8, (long long)h->numSM * 8);
+        k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(drp, dterm, dcount, D, V, drec, d_N, M, m, dflags);
+    }
+    int flags = 0;
+    CU(cudaMemcpyAsync(&flags, dflags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dterm);
+    cudaFree(dcount);
+    cudaFree(dflags);
+    CU(cudaGetLastError());
+    // monotone rowptr is implied by non-negative row lengths; check on the host (cheap, D+1 ints)
+    for (long long d = 0; d < D; ++d)
+        if (rowptr[d + 1] < rowptr[d]) return fail(h, MMSIG_EINVAL, "rowptr not monotone");
+    if (flags & 1) return fail(h, MMSIG_EINVAL, "term index out of range [0, V)");
+    if (flags & 2) return fail(h, MMSIG_EINVAL, "count must be > 0 (zeros are dropped by format_counts_*)");
+    if (flags & 4) return fail(h, MMSIG_EINVAL, "terms of a row must be strictly ascending (as format_counts_* produces)");
+    long long ntot = 0;
+    for (long long w = 0; w < nnz; ++w) ntot += count[w];
+    *d_rowptr = drp;
+    *d_rec = drec;
+    *nnz_out = nnz;
+    *ntot_out = ntot;
+    return 0;
+}
+
+// ===========================================================================================
+// MMCTM
+// ===========================================================================================
+template <typename F>
+static int pick_theta_plan(mmsig_handle *h, F kernel, int KV, int D, int *W_out, int *grid_out, size_t *smem_out) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kernel));
+    // one template instance can serve several modalities: always opt in to the device maximum
+    CU(allow_max_smem(h, kernel));
+    int bestW = 0, best_warps = 0, best_blocks = 0;
+    size_t best_smem = 0;
+    for (int W : {8, 4, 2, 1}) {
+        size_t smem = (size_t)(1 + 2 * W) * KV * sizeof(double);
+        if (smem > h->smem_optin) continue;
+        if (W * 32 * fa.numRegs > 65536) continue;
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, W * 32, smem));
+        if (nb * W > best_warps) { best_warps = nb * W; bestW = W; best_blocks = nb; best_smem = smem; }
+    }
+    if (!bestW) return fail(h, MMSIG_ELIMIT, "K*V topic-term table does not fit in shared memory");
+    *W_out = bestW;
+    *smem_out = best_smem;
+    long long want = (long long)h->numSM * best_blocks;
+    long long cap = ((long long)D + bestW - 1) / bestW;
+    *grid_out = (int)std::max<long long>(1, std::min(want, cap));
+    return 0;
+}
+
+#define THETA_DISPATCH(K, EXPR)                                   \
+    do {                                                          \
+        if ((K) <= 8) { constexpr int KP = 8, NP = 8; EXPR; }     \
+        else if ((K) <= 12) { constexpr int KP = 12, NP = 16; EXPR; } \
+        else if ((K) <= 16) { constexpr int KP = 16, NP = 16; EXPR; } \
+        else if ((K) <= 20) { constexpr int KP = 20, NP = 32; EXPR; } \
+        else if ((K) <= 24) { constexpr int KP = 24, NP = 32; EXPR; } \
+        else { constexpr int KP = 32, NP = 32; EXPR; }            \
+    } while (0)
+#define MK_DISPATCH(MK, EXPR)                                     \
+    do {                                                          \
+        if ((MK) <= 8) { constexpr int MKP = 8; EXPR; }           \
+        else if ((MK) <= 16) { constexpr int MKP = 16; EXPR; }    \
+        else if ((MK) <= 24) { constexpr int MKP = 24; EXPR; }    \
+        else { constexpr int MKP = 32; EXPR; }                    \
+    } while (0)
+
+extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                        const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
+                                        const int32_t *const *count) {
+    NEED(h, "null handle");
+    NEED(K && V && rowptr && term && count, "null argument");
+    NEED(D >= 1 && D_total >= D, "need 1 <= D <= D_total");
+    NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
+    if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
+    CU(cudaSetDevice(h->device));
+    free_pool(h->allocs_mm);
+    h->mm = MmctmHost();
+    MmctmHost &mm = h->mm;
+    MmctmDev &p = mm.p;
+    p.M = M;
+    p.D = D;
+    p.D_total = D_total;
+    p.stop_rule = h->stop_rule;
+    p.koff[0] = 0;
+    p.goff[0] = 0;
+    for (int m = 0; m < M; ++m) {
+        NEED(K[m] >= 1 && V[m] >= 1, "K[m], V[m] must be >= 1");
+        if (K[m] > 32) return fail(h, MMSIG_ELIMIT, "K[m] <= 32 supported");
+        p.K[m] = K[m];
+        p.V[m] = V[m];
+        p.koff[m + 1] = p.koff[m] + K[m];
+        p.goff[m + 1] = p.goff[m] + K[m] * V[m];
+    }
+    p.MK = p.koff[M];
+    mm.G = p.goff[M];
+    if (p.MK > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 32 supported (one coordinate per lane)");
+    int rc;
+    double *dN = nullptr;
+    if ((rc = dev_alloc(h, h->allocs_mm, &dN, (size_t)D * M))) return rc;
+    p.N = dN;
+    long long ntot[MAXM];
+    mm.nnz.resize(M);
+    for (int m = 0; m < M; ++m)
+        if ((rc = upload_counts(h, h->allocs_mm, D, V[m], M, m, rowptr[m], term[m], count[m], &p.rowptr[m], &p.rec[m],
+                                dN, &mm.nnz[m], &ntot[m])))
+            return rc;
+    if ((rc = allsum_ll(h, ntot, M))) return rc;
+    for (int m = 0; m < M; ++m) p.Ntot[m] = (double)ntot[m];
+
+    const size_t DMK = (size_t)D * p.MK;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.lamA, DMK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.lamB, DMK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.nu, DMK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.sumtheta, DMK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.zeta, (size_t)D * M))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_nu, (size_t)D))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_lam, (size_t)D))) return rc;
+    p.lam = mm.lamA;
+    p.lam_prev = mm.lamB;
+    for (double **t : {&p.gamma, &p.Elnphi, &p.Elnphi_prev, &p.phi, &p.stats})
+        if ((rc = dev_alloc(h, h->allocs_mm, t, (size_t)mm.G))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.alpha, (size_t)M))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.mu, (size_t)p.MK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.Sigma, (size_t)p.MK * p.MK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.invSigma, (size_t)p.MK * p.MK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.nusum, (size_t)p.MK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.d_ll, (size_t)M + 16))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.d_status, (size_t)1))) return rc;
+    CU(cudaMemsetAsync(mm.d_status, 0, sizeof(int), h->stream));
+    CU(cudaMemsetAsync(p.nev_nu, 0, D * sizeof(int), h->stream));
+    CU(cudaMemsetAsync(p.nev_lam, 0, D * sizeof(int), h->stream));
+    CU(cudaMemsetAsync(p.sumtheta, 0, DMK * sizeof(double), h->stream));
+
+    // launch plans
+    for (int m = 0; m < M; ++m) {
+        const int KV = K[m] * V[m];
+        THETA_DISPATCH(K[m], rc = pick_theta_plan(h, k_theta_stats<KP, NP>, KV, (int)std::min<int64_t>(D, 1 << 30),
+                                                   &mm.W_theta[m], &mm.grid_theta[m], &mm.smem_theta[m]));
+        if (rc) return rc;
+        if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
+    }
+    {
+        int nb = 0;
+        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
+        mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+        mm.smem_post = (size_t)(512 + mm.G + 256) * sizeof(double);
+        if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
+        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP>)));
+        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP>, 256, mm.smem_post)));
+        mm.grid_post = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+    }
+    const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + M;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_solve, (size_t)mm.grid_solve * 2 * p.MK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_post, (size_t)mm.grid_post * P2))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_elbo, (size_t)mm.grid_post * 8))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.rank_p1, (size_t)P1))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.gath_p1, (size_t)P1 * h->nranks))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.rank_p2, (size_t)P2 + 16))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.gath_p2, (size_t)(P2 + 16) * h->nranks))) return rc;
+    mm.has_data = true;
+    return 0;
+}
+
+__global__ void k_fill(double *x, size_t n, double v) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) x[i] = v;
+}
+static void fill(mmsig_handle *h, double *x, size_t n, double v) {
+    LaunchScope ls(h, "k_fill");
+    int grid = (int)std::min<size_t>((n + 255) / 256, (size_t)h->numSM * 8);
+    k_fill<<<std::max(grid, 1), 256, 0, h->stream>>>(x, n, v);
+}
+
+extern "C" int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, const double *gamma, const double *lambda,
+                                         const double *nu, const double *mu, const double *Sigma, const double *invSigma) {
+    NEED(h, "null handle");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_data, "mmsig_mmctm_set_data first");
+    NEED(alpha && gamma, "alpha and gamma are required");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    const size_t DMK = (size_t)p.D * p.MK, MK2 = (size_t)p.MK * p.MK;
+    for (int m = 0; m < p.M; ++m) NEED(alpha[m] > 0, "alpha must be > 0");
+    CU(cudaMemcpyAsync(p.alpha, alpha, p.M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(p.gamma, gamma, mm.G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (lambda) CU(cudaMemcpyAsync(p.lam, lambda, DMK * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CU(cudaMemsetAsync(p.lam, 0, DMK * sizeof(double), h->stream));
+    CU(cudaMemcpyAsync(p.lam_prev, p.lam, DMK * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+    if (nu) CU(cudaMemcpyAsync(p.nu, nu, DMK * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else fill(h, p.nu, DMK, 1.0);
+    if (mu) CU(cudaMemcpyAsync(p.mu, mu, p.MK * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CU(cudaMemsetAsync(p.mu, 0, p.MK * sizeof(double), h->stream));
+    std::vector<double> eye(MK2, 0.0);
+    for (int j = 0; j < p.MK; ++j) eye[(size_t)j * p.MK + j] = 1.0;
+    CU(cudaMemcpyAsync(p.Sigma, Sigma ? Sigma : eye.data(), MK2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(p.invSigma, invSigma ? invSigma : eye.data(), MK2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, "k_elnphi");
+        k_elnphi<<<1, 1024, 0, h->stream>>>(p);
+    }
+    {
+        LaunchScope ls(h, "k_zeta");
+        k_zeta<<<mm.grid_solve, 256, 0, h->stream>>>(p);
+    }
+    CU(cudaMemsetAsync(p.stats, 0, mm.G * sizeof(double), h->stream));
+    CU(cudaStreamSynchronize(h->stream));      // eye / caller buffers may go away
+    CU(cudaGetLastError());
+    mm.has_state = true;
+    mm.estep_done = false;
+    return 0;
+}
+
+static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
+    MmctmHost &mm = h->mm;
+    MmctmDev &p = mm.p;
+    const int do_sigma = (flags & MMSIG_FLAG_UPDATE_SIGMA) ? 1 : 0;
+    std::swap(p.lam, p.lam_prev);              // lam_prev = λ of the previous iteration (what θ uses)
+    for (int m = 0; m < p.M; ++m) {
+        LaunchScope ls(h, "k_theta_stats");
+        THETA_DISPATCH(p.K[m], (k_theta_stats<KP, NP><<<mm.grid_theta[m], mm.W_theta[m] * 32, mm.smem_theta[m], h->stream>>>(
+                                   p, m, mm.part_theta[m], mm.W_theta[m])));
+    }
+    {
+        LaunchScope ls(h, "k_solve");
+        MK_DISPATCH(p.MK, (k_solve<MKP><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve)));
+    }
+    const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + p.M;
+    {
+        CombineSegs s{};
+        s.nseg = p.M + 1;
+        for (int m = 0; m < p.M; ++m) {
+            s.src[m] = mm.part_theta[m];
+            s.nparts[m] = mm.grid_theta[m];
+            s.n[m] = p.K[m] * p.V[m];
+            s.dst_off[m] = p.goff[m];
+        }
+        s.src[p.M] = mm.part_solve;
+        s.nparts[p.M] = mm.grid_solve;
+        s.n[p.M] = 2 * p.MK;
+        s.dst_off[p.M] = mm.G;
+        LaunchScope ls(h, "k_combine");
+        k_combine<<<(P1 + 127) / 128, 128, 0, h->stream>>>(s, mm.rank_p1);
+    }
+    const double2 *g1 = nullptr;
+    int rc;
+    if ((rc = gather(h, mm.rank_p1, mm.gath_p1, P1, &g1))) return rc;
+    {
+        LaunchScope ls(h, "k_mstep1");
+        k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks);
+    }
+    {
+        LaunchScope ls(h, "k_post");
+        MK_DISPATCH(p.MK, (k_post<MKP><<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post, do_sigma, nullptr)));
+    }
+    {
+        CombineSegs s{};
+        s.nseg = 1;
+        s.src[0] = mm.part_post;
+        s.nparts[0] = mm.grid_post;
+        s.n[0] = P2;
+        s.dst_off[0] = 0;
+        LaunchScope ls(h, "k_combine");
+        k_combine<<<(P2 + 127) / 128, 128, 0, h->stream>>>(s, mm.rank_p2);
+    }
+    const double2 *g2 = nullptr;
+    if ((rc = gather(h, mm.rank_p2, mm.gath_p2, P2, &g2))) return rc;
+    {
+        LaunchScope ls(h, "k_mstep2");
+        k_mstep2<<<1, 32, 0, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
+    }
+    mm.estep_done = true;
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *ll_out) {
+    NEED(h, "null handle");
+    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    CU(cudaSetDevice(h->device));
+    int rc = mmctm_iterate_async(h, flags);
+    if (rc) return rc;
+    double ll[MAXM];
+    int status = 0;
+    CU(cudaMemcpyAsync(ll, h->mm.d_ll, h->mm.p.M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(&status, h->mm.d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (status) return fail(h, MMSIG_EINVAL, "Sigma is singular (inv failed)");
+    if (ll_out) memcpy(ll_out, ll, h->mm.p.M * sizeof(double));
+    return 0;
+}
+
+// src/common.jl:48-51 on the last two LL vectors
+static bool converged_vec(const double *prev, const double *cur, int M, double tol) {
+    double r = 0.0;
+    for (int i = 0; i < M; ++i) {
+        double v = std::fabs(prev[i] - cur[i]) / std::fabs(cur[i]);
+        if (v > r || v != v) r = v;
+    }
+    return r < tol;
+}
+
+extern "C" int32_t mmsig_mmctm_fit(mmsig_handle *h, int32_t maxiter, double tol, uint32_t flags, double *ll_hist,
+                                   int32_t *n_iter, int32_t *converged) {
+    NEED(h, "null handle");
+    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
+    const int M = h->mm.p.M;
+    int it = 0, conv = 0;
+    for (int iter = 1; iter <= maxiter; ++iter) {
+        double *ll = ll_hist + (size_t)(iter - 1) * M;
+        int rc = mmsig_mmctm_iterate(h, flags, ll);
+        if (rc) return rc;
+        it = iter;
+        if (iter > 10 && converged_vec(ll - M, ll, M, tol)) { conv = 1; break; }   // src/MMCTM.jl:485
+    }
+    if (n_iter) *n_iter = it;
+    if (converged) *converged = conv;
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double *nu, double *zeta, double *mu,
+                                         double *Sigma, double *invSigma, double *gamma, double *Elnphi, double *phi,
+                                         double *props) {
+    NEED(h, "null handle");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_state, "mmsig_mmctm_set_state first");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    const size_t DMK = (size_t)p.D * p.MK, MK2 = (size_t)p.MK * p.MK;
+    auto d2h = [&](double *dst, const double *src, size_t n) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+    };
+    CU(d2h(lambda, p.lam, DMK));
+    CU(d2h(nu, p.nu, DMK));
+    CU(d2h(zeta, p.zeta, (size_t)p.D * p.M));
+    CU(d2h(mu, p.mu, p.MK));
+    CU(d2h(Sigma, p.Sigma, MK2));
+    CU(d2h(invSigma, p.invSigma, MK2));
+    CU(d2h(gamma, p.gamma, mm.G));
+    CU(d2h(Elnphi, p.Elnphi, mm.G));
+    CU(d2h(phi, p.phi, mm.G));
+    if (props) {
+        // sumtheta is not needed once the iteration is over only if the ELBO is not wanted: use a scratch
+        double *scratch = nullptr;
+        CU(cudaMalloc(&scratch, DMK * sizeof(double)));
+        {
+            LaunchScope ls(h, "k_props");
+            k_props<<<mm.grid_solve, 256, 0, h->stream>>>(p, scratch);
+        }
+        CU(cudaMemcpyAsync(props, scratch, DMK * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(scratch);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_get_theta(mmsig_handle *h, int32_t m, double *theta_out) {
+    NEED(h && theta_out, "null argument");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_state, "mmsig_mmctm_set_state first");
+    NEED(m >= 0 && m < mm.p.M, "bad modality");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    const size_t n = (size_t)mm.nnz[m] * p.K[m];
+    double *d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(double)));
+    const size_t smem = (size_t)p.K[m] * p.V[m] * sizeof(double);
+    CU(allow_max_smem(h, k_theta_out));
+    {
+        LaunchScope ls(h, "k_theta_out");
+        k_theta_out<<<mm.grid_solve, 256, smem, h->stream>>>(p, m, d);
+    }
+    CU(cudaMemcpyAsync(theta_out, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_get_evals(mmsig_handle *h, int32_t *nev_nu, int32_t *nev_lambda) {
+    NEED(h, "null handle");
+    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = h->mm.p;
+    if (nev_nu) CU(cudaMemcpyAsync(nev_nu, p.nev_nu, p.D * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    if (nev_lambda) CU(cudaMemcpyAsync(nev_lambda, p.nev_lam, p.D * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+#include "elbo_api.inl"
+
+extern "C" int32_t mmsig_mmctm_elbo(mmsig_handle *h, double *elbo, double *terms) {
+    NEED(h, "null handle");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_state, "mmsig_mmctm_set_state first");
+    CU(cudaSetDevice(h->device));
+    return mmctm_elbo_impl(h, elbo, terms);
+}
+
+#include "lda_api.inl"

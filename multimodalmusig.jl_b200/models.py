@@ -1,0 +1,258 @@
+"""Host-side mirror of the reference's model API for the hot path, over the C ABI.
+
+    reference (Julia)                              here
+    MMCTM(K, α, X) / MMCTM(K, α, V, X)             MMCTM(K, alpha, counts, V=None, gamma0=...)
+    fit!(model; maxiter, tol, verbose, updateΣ)    model.fit(maxiter=100, tol=1e-4, verbose=True, updateSigma=True)
+    model.ϕ / .props / .λ / .ν / .μ / .Σ / .γ      model.phi / .props / .lam / .nu / .mu / .Sigma / .gamma
+    model.elbo / .ll / .converged                  same names
+    LDA(K, α, η, X) / fit! / .β / .θ               LDA(K, alpha, eta, counts) / .fit / .beta / .theta
+
+Model construction (including the random γ₀ / λ₀, src/MMCTM.jl:59-63, src/LDA.jl:36) stays on the
+host, as it does in Julia; the library receives state and runs the iterations.  All state lives
+on the GPU between calls; the properties download it.
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import capi
+from .counts import infer_V
+
+
+class MMCTM:
+    """src/MMCTM.jl:1-108.  counts: list over modalities of (rowptr, term0, count)."""
+
+    def __init__(self, K, alpha, counts, V=None, gamma0=None, rng=None, device=0,
+                 stop_rule=capi.STOP_NLOPT27, profile=False, comm=None, D_total=None):
+        self.K = [int(k) for k in K]
+        self.M = len(self.K)
+        self.alpha = np.asarray(alpha, dtype=np.float64).copy()
+        if len(counts) != self.M or self.alpha.size != self.M:
+            raise ValueError("K, alpha and counts must have one entry per modality")
+        self.V = infer_V(counts) if V is None else [int(v) for v in V]      # src/MMCTM.jl:94-108
+        self.D = len(counts[0][0]) - 1
+        self.MK = sum(self.K)
+        self.G = sum(k * v for k, v in zip(self.K, self.V))
+        if gamma0 is None:                                                  # init=:random, :59-63
+            rng = np.random.default_rng() if rng is None else rng
+            gamma0 = rng.integers(1, 101, size=self.G).astype(np.float64)
+        self.h = capi.Handle(device=device, stop_rule=stop_rule, profile=profile)
+        if comm is not None:
+            uid, rank, nranks = comm
+            self.h.comm_init(uid, rank, nranks)
+        self._set_data(counts, self.D if D_total is None else D_total)
+        self.set_state(gamma=gamma0)
+        self.converged = False
+        self.elbo = float("nan")
+        self.ll = None
+
+    def _set_data(self, counts, D_total):
+        lib = self.h.lib
+        keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32),
+                 np.ascontiguousarray(c, np.int32)) for r, t, c in counts]
+        M = self.M
+        rp = (capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep])
+        tp = (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep])
+        cp = (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep])
+        K = np.asarray(self.K, np.int32)
+        V = np.asarray(self.V, np.int32)
+        self.h.check(lib.mmsig_mmctm_set_data(self.h.h, self.D, D_total, M, K.ctypes.data_as(capi.c_i32p),
+                                              V.ctypes.data_as(capi.c_i32p), rp, tp, cp))
+        self.nnz = [int(k[0][-1]) for k in keep]
+
+    def set_state(self, gamma, lam=None, nu=None, mu=None, Sigma=None, invSigma=None, alpha=None):
+        """Upload variational state; None -> the constructor's value (src/MMCTM.jl:44-46,82-83)."""
+        if alpha is not None:
+            self.alpha = np.asarray(alpha, dtype=np.float64).copy()
+        D, MK = self.D, self.MK
+        a = [capi.f64(self.alpha, self.M), capi.f64(gamma, self.G), capi.f64(lam, D * MK), capi.f64(nu, D * MK),
+             capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
+        self.h.check(self.h.lib.mmsig_mmctm_set_state(self.h.h, *[capi.dp(x) for x in a]))
+
+    def iterate(self, updateSigma=True):
+        """One body of fit!'s loop (src/MMCTM.jl:463-479); returns the M log-likelihoods."""
+        ll = np.zeros(self.M)
+        self.h.check(self.h.lib.mmsig_mmctm_iterate(self.h.h, capi.FLAG_UPDATE_SIGMA if updateSigma else 0,
+                                                    capi.dp(ll)))
+        return ll
+
+    def fit(self, maxiter=100, tol=1e-4, verbose=True, autoalpha=False, updateSigma=True):
+        """fit!(model; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true), src/MMCTM.jl:457-494."""
+        if autoalpha:
+            raise NotImplementedError("autoα=true (update_α!, src/MMCTM.jl:252-269) is outside the hot path built here")
+        flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        if verbose:
+            hist = []
+            for it in range(1, maxiter + 1):
+                ll = self.iterate(updateSigma)
+                hist.append(ll)
+                print("%d\tLog-likelihoods: %s" % (it, ", ".join(repr(float(x)) for x in ll)))   # :482
+                if len(hist) > 10 and _converged(hist[-2], hist[-1], tol):
+                    self.converged = True
+                    break
+            hist = np.asarray(hist)
+        else:
+            buf = np.zeros((maxiter, self.M))
+            n, conv = C.c_int32(), C.c_int32()
+            self.h.check(self.h.lib.mmsig_mmctm_fit(self.h.h, maxiter, tol, flags, capi.dp(buf),
+                                                    C.byref(n), C.byref(conv)))
+            hist = buf[:n.value].copy()
+            self.converged = bool(conv.value)
+        self.elbo = self.calculate_elbo()[0]          # :490
+        self.ll = hist[-1].copy()                     # :491
+        return hist
+
+    def calculate_elbo(self):
+        e = C.c_double()
+        t = np.zeros(7)
+        self.h.check(self.h.lib.mmsig_mmctm_elbo(self.h.h, C.byref(e), capi.dp(t)))
+        return e.value, t
+
+    def state(self, props=True):
+        D, MK, M, G = self.D, self.MK, self.M, self.G
+        out = dict(lam=np.empty((D, MK)), nu=np.empty((D, MK)), zeta=np.empty((D, M)), mu=np.empty(MK),
+                   Sigma=np.empty((MK, MK)), invSigma=np.empty((MK, MK)), gamma=np.empty(G), Elnphi=np.empty(G),
+                   phi=np.empty(G), props=np.empty((D, MK)) if props else None)
+        order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
+        self.h.check(self.h.lib.mmsig_mmctm_get_state(self.h.h, *[capi.dp(out[k]) for k in order]))
+        return out
+
+    def _get(self, name):
+        return self.state(props=(name == "props"))[name]
+
+    lam = property(lambda s: s._get("lam"))
+    nu = property(lambda s: s._get("nu"))
+    zeta = property(lambda s: s._get("zeta"))
+    mu = property(lambda s: s._get("mu"))
+    Sigma = property(lambda s: s._get("Sigma"))
+    invSigma = property(lambda s: s._get("invSigma"))
+    gamma = property(lambda s: s._get("gamma"))
+    Elnphi = property(lambda s: s._get("Elnphi"))
+
+    def _split(self, flat):
+        out, o = [], 0
+        for k, v in zip(self.K, self.V):
+            out.append(flat[o:o + k * v].reshape(k, v))
+            o += k * v
+        return out
+
+    @property
+    def phi(self):
+        """model.ϕ[m][k] -> list over m of (K_m, V_m) arrays."""
+        return self._split(self._get("phi"))
+
+    @property
+    def props(self):
+        """model.props[d][m] -> list over m of (D, K_m) arrays."""
+        p = self._get("props")
+        o = np.cumsum([0] + self.K)
+        return [p[:, o[m]:o[m + 1]] for m in range(self.M)]
+
+    def theta(self, m):
+        """model.θ[d][m] for all d: (nnz_m, K_m), recomputed from the last E-step's inputs."""
+        out = np.empty((self.nnz[m], self.K[m]))
+        self.h.check(self.h.lib.mmsig_mmctm_get_theta(self.h.h, m, capi.dp(out)))
+        return out
+
+    def evals(self):
+        a = np.zeros(self.D, np.int32)
+        b = np.zeros(self.D, np.int32)
+        self.h.check(self.h.lib.mmsig_mmctm_get_evals(self.h.h, a.ctypes.data_as(capi.c_i32p),
+                                                      b.ctypes.data_as(capi.c_i32p)))
+        return a, b
+
+    def close(self):
+        self.h.close()
+
+
+def _converged(prev, cur, tol):
+    """check_convergence, src/common.jl:48-51."""
+    with np.errstate(all="ignore"):
+        r = np.max(np.abs(np.asarray(prev) - np.asarray(cur)) / np.abs(np.asarray(cur)))
+    return bool(r < tol)
+
+
+class LDA:
+    """src/LDA.jl:1-67.  counts: (rowptr, term0, count)."""
+
+    def __init__(self, K, alpha, eta, counts, V=None, lambda0=None, rng=None, device=0, profile=False,
+                 comm=None, D_total=None):
+        self.K = int(K)
+        self.alpha, self.eta = float(alpha), float(eta)
+        r, t, c = counts
+        self.V = (int(np.max(t)) + 1 if len(t) else 0) if V is None else int(V)   # src/LDA.jl:57-67
+        self.D = len(r) - 1
+        self.nnz = int(r[-1])
+        if lambda0 is None:                                                       # src/LDA.jl:36
+            rng = np.random.default_rng() if rng is None else rng
+            lambda0 = rng.integers(1, 101, size=self.K * self.V).astype(np.float64)
+        self.h = capi.Handle(device=device, profile=profile)
+        if comm is not None:
+            uid, rank, nranks = comm
+            self.h.comm_init(uid, rank, nranks)
+        keep = (np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32), np.ascontiguousarray(c, np.int32))
+        self.h.check(self.h.lib.mmsig_lda_set_data(self.h.h, self.D, self.D if D_total is None else D_total,
+                                                   self.K, self.V, keep[0].ctypes.data_as(capi.c_i64p),
+                                                   keep[1].ctypes.data_as(capi.c_i32p), keep[2].ctypes.data_as(capi.c_i32p)))
+        self.set_state(lambda0)
+        self.converged = False
+        self.elbo = float("nan")
+        self.ll = float("nan")
+
+    def set_state(self, lam, gamma_next=None):
+        self.h.check(self.h.lib.mmsig_lda_set_state(self.h.h, self.alpha, self.eta,
+                                                    capi.dp(capi.f64(lam, self.K * self.V)),
+                                                    capi.dp(capi.f64(gamma_next, self.D * self.K))))
+
+    def iterate(self):
+        ll = C.c_double()
+        self.h.check(self.h.lib.mmsig_lda_iterate(self.h.h, C.byref(ll)))
+        return ll.value
+
+    def fit(self, maxiter=1000, tol=1e-4, verbose=True):
+        """fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true), src/LDA.jl:198-224."""
+        if verbose:
+            hist = []
+            for it in range(1, maxiter + 1):
+                hist.append(self.iterate())
+                print("%d\tLog-likelihood: %r" % (it, hist[-1]))               # :212
+                if len(hist) > 10 and _converged([hist[-2]], [hist[-1]], tol):
+                    self.converged = True
+                    break
+            hist = np.asarray(hist)
+        else:
+            buf = np.zeros(maxiter)
+            n, conv = C.c_int32(), C.c_int32()
+            self.h.check(self.h.lib.mmsig_lda_fit(self.h.h, maxiter, tol, capi.dp(buf), C.byref(n), C.byref(conv)))
+            hist = buf[:n.value].copy()
+            self.converged = bool(conv.value)
+        self.elbo = self.calculate_elbo()[0]
+        self.ll = float(hist[-1])
+        return hist
+
+    def calculate_elbo(self):
+        e = C.c_double()
+        t = np.zeros(7)
+        self.h.check(self.h.lib.mmsig_lda_elbo(self.h.h, C.byref(e), capi.dp(t)))
+        return e.value, t
+
+    def state(self):
+        K, V, D = self.K, self.V, self.D
+        out = dict(lam=np.empty((K, V)), Elnbeta=np.empty((K, V)), beta=np.empty((K, V)),
+                   gamma=np.empty((D, K)), Elntheta=np.empty((D, K)), theta=np.empty((D, K)))
+        order = ("lam", "Elnbeta", "beta", "gamma", "Elntheta", "theta")
+        self.h.check(self.h.lib.mmsig_lda_get_state(self.h.h, *[capi.dp(out[k]) for k in order]))
+        return out
+
+    beta = property(lambda s: s.state()["beta"])       # [k][v] (Julia: V x K)
+    theta = property(lambda s: s.state()["theta"])     # [d][k] (Julia: K x D)
+    lam = property(lambda s: s.state()["lam"])
+    gamma = property(lambda s: s.state()["gamma"])
+
+    def phi(self):
+        out = np.empty((self.nnz, self.K))
+        self.h.check(self.h.lib.mmsig_lda_get_phi(self.h.h, capi.dp(out)))
+        return out
+
+    def close(self):
+        self.h.close()

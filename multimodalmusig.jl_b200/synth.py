@@ -1,8 +1,13 @@
 """Synthetic Poisson counts from a generative MMCTM (BASELINE.json north_star).
 
-Data: numpy Generator(Philox(key=20261018)); init: Philox(key=42).
-phi*_{mk} ~ Dirichlet(0.1); A ~ N(0,1)^{MKxMK}, Sigma* = A A^T / MK + 0.1 I, mu* = 0;
-eta_d ~ N(mu*, Sigma*); p_dm = softmax(eta_d[block m]); count_dmv ~ Poisson(R_m sum_k p_dmk phi*_mkv).
+Truth:  phi*_{mk} ~ Dirichlet(0.1 1_V);  A ~ N(0,1)^{MKxMK}, Sigma* = A A^T / MK + 0.1 I, mu* = 0;
+        eta_d ~ N(mu*, Sigma*);  p_dm = softmax(eta_d[block m]);
+        count_dmv ~ Poisson(R_m sum_k p_dmk phi*_mkv),  R = 3500 (SNV96) / 85 (SV32, SV48) / 300 (ID83).
+RNG:    numpy Generator(Philox).  The truth uses key DATA_KEY; samples are drawn in chunks of CHUNK
+        samples, chunk i from Philox(key=DATA_KEY + 1 + i), so any contiguous range of samples can be
+        generated on its own (each rank generates only its shard) and the union does not depend on
+        the number of ranks.  Init state: Philox(key=INIT_KEY), gamma0 = integers U{1..100}
+        (src/MMCTM.jl:61), lambda0 likewise (src/LDA.jl:36).
 """
 import numpy as np
 
@@ -10,35 +15,42 @@ from .counts import make_count_csr
 
 DATA_KEY = 20261018
 INIT_KEY = 42
+CHUNK = 50_000
 RATES = {96: 3500.0, 32: 85.0, 83: 300.0, 48: 85.0}
 
 
-def generate(D, K, V, rates=None, key=DATA_KEY, chunk=200_000):
+def truth(K, V, key=DATA_KEY):
     rng = np.random.Generator(np.random.Philox(key=key))
-    M = len(K)
     MK = int(sum(K))
-    rates = [RATES.get(v, 300.0) for v in V] if rates is None else rates
-    phis = [rng.dirichlet(np.full(V[m], 0.1), size=K[m]) for m in range(M)]
+    phis = [rng.dirichlet(np.full(V[m], 0.1), size=K[m]) for m in range(len(K))]
     A = rng.standard_normal((MK, MK))
     Sig = A @ A.T / MK + 0.1 * np.eye(MK)
+    return phis, Sig
+
+
+def generate(D, K, V, rates=None, key=DATA_KEY, lo=0, hi=None):
+    """CSR counts of samples lo:hi (default all D) of the D-sample synthetic corpus."""
+    hi = D if hi is None else hi
+    M = len(K)
+    rates = [RATES.get(v, 300.0) for v in V] if rates is None else rates
+    phis, Sig = truth(K, V, key)
     Lc = np.linalg.cholesky(Sig)
+    MK = int(sum(K))
     parts = [[] for _ in range(M)]
-    for lo in range(0, D, chunk):
-        n = min(chunk, D - lo)
-        eta = rng.standard_normal((n, MK)) @ Lc.T
+    for ci in range(lo // CHUNK, (max(hi, 1) - 1) // CHUNK + 1):
+        c0, c1 = ci * CHUNK, min((ci + 1) * CHUNK, D)
+        rng = np.random.Generator(np.random.Philox(key=key + 1 + ci))
+        eta = rng.standard_normal((c1 - c0, MK)) @ Lc.T
+        a, b = max(lo, c0) - c0, min(hi, c1) - c0
         off = 0
         for m in range(M):
             e = eta[:, off:off + K[m]]
             e = np.exp(e - e.max(axis=1, keepdims=True))
             p = e / e.sum(axis=1, keepdims=True)
-            mean = rates[m] * (p @ phis[m])
-            parts[m].append(rng.poisson(mean).astype(np.int32))
+            cnt = rng.poisson(rates[m] * (p @ phis[m])).astype(np.int32)
+            parts[m].append(cnt[a:b])
             off += K[m]
-    counts = []
-    for m in range(M):
-        dense = np.concatenate(parts[m], axis=0)       # (D, V)
-        counts.append(make_count_csr(dense.T))
-    return counts
+    return [make_count_csr(np.concatenate(parts[m], axis=0).T) for m in range(M)]
 
 
 def init_gamma(K, V, key=INIT_KEY):

@@ -239,7 +239,7 @@ double orc_logmvbeta(const double *vals, int n)
  * ===================================================================== */
 
 #define ORC_MMA_RHOMIN 1e-5
-#define ORC_MMA_MAXEVAL 100000   /* guard only; NLopt has no limit here */
+#define ORC_MMA_MAXEVAL 10000    /* guard only; NLopt has no limit here */
 
 static int orc_isinf(double x) { return fabs(x) >= HUGE_VAL * 0.99 || isinf(x); }
 

@@ -1,0 +1,44 @@
+"""CPU-side checks of the drop-in boundary: libmmsig.so loads, exports every symbol that
+include/mmsig.h declares, and refuses to run without a GPU (no CPU fallback)."""
+import os
+import re
+
+import pytest
+
+import mmsig
+from conftest import ROOT
+
+
+def _declared():
+    src = open(os.path.join(ROOT, "include", "mmsig.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(mmsig_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = mmsig.capi.load()
+    names = _declared()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "libmmsig.so does not export %s" % n
+    assert sorted(mmsig.capi.EXPORTS) == names, "capi.py and mmsig.h disagree"
+    assert lib.mmsig_version() >= 100
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(mmsig.capi.MmsigError) as e:
+        mmsig.capi.Handle()
+    assert e.value.code == -2 and "no CPU fallback" in str(e.value)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "multimodalmusig.jl_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+                txt = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in txt.lower() or f in ("det_math.cuh", "mmctm_kernels.cuh", "lda_kernels.cuh"), f
+                assert "import orc" not in txt and "liboracle" not in txt, f

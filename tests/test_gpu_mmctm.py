@@ -1,0 +1,173 @@
+"""CUDA path (through the C ABI) against the oracle: MMCTM / CTM.
+
+Tolerances (north_star): one E+M iteration from an identical state within 1e-12 relative on
+ϕ, λ, ν, μ, Σ, ELBO; a fixed-iteration fit within 1e-8 relative ELBO.  Against the oracle's
+pinned arithmetic (ORC_ARITH_DET) the per-sample results are required to be BIT-EXACT, because
+anything looser lets MMA's branch decisions diverge."""
+import numpy as np
+import pytest
+
+import orc
+import mmsig
+from mmsig.counts import from_nested
+from util import oracle_mmctm, small_synth, rel_err, norm_err
+
+pytestmark = pytest.mark.gpu
+
+TOL_ITER = 1e-12
+TOL_FIT_ELBO = 1e-8
+
+
+def _pair(K, alpha, V, counts, gamma0, stop_rule=0):
+    o = oracle_mmctm(K, alpha, V, counts, gamma0, stop_rule=stop_rule)
+    g = mmsig.MMCTM(K, alpha, counts, V=V, gamma0=gamma0, stop_rule=stop_rule)
+    return o, g
+
+
+def _check_iteration(o, g, ll_o, ll_g, exact=True):
+    s = g.state()
+    nn, nl = g.evals()
+    assert np.array_equal(nn, o.nev_nu) and np.array_equal(nl, o.nev_lambda), "MMA evaluation counts differ"
+    if exact:
+        assert np.array_equal(s["lam"], o.lam), "lambda not bit-exact: max abs %.3e" % np.abs(s["lam"] - o.lam).max()
+        assert np.array_equal(s["nu"], o.nu), "nu not bit-exact"
+        assert np.array_equal(s["zeta"], o.zeta), "zeta not bit-exact"
+        assert np.array_equal(s["gamma"], o.gamma), "gamma not bit-exact: rel %.3e" % rel_err(s["gamma"], o.gamma)
+        assert np.array_equal(s["mu"], o.mu), "mu not bit-exact"
+        assert np.array_equal(s["Sigma"], o.Sigma), "Sigma not bit-exact"
+        assert np.array_equal(s["invSigma"], o.invSigma), "invSigma not bit-exact"
+        assert np.array_equal(s["Elnphi"], o.Elnphi) and np.array_equal(s["phi"], o.phi)
+        assert np.array_equal(s["props"], o.props)
+        assert np.array_equal(ll_g, ll_o), "log-likelihoods not bit-exact"
+    assert rel_err(s["lam"], o.lam) <= TOL_ITER or norm_err(s["lam"], o.lam) <= TOL_ITER
+    assert rel_err(s["nu"], o.nu) <= TOL_ITER
+    assert rel_err(s["phi"], o.phi) <= TOL_ITER
+    assert norm_err(s["mu"], o.mu) <= TOL_ITER
+    assert norm_err(s["Sigma"], o.Sigma) <= TOL_ITER
+    assert rel_err(ll_g, ll_o) <= TOL_ITER
+
+
+def test_toy_corpus_one_iteration(golden):
+    t = golden["mmctm_toy"]
+    counts = from_nested(t["X"], 2)
+    g0 = np.random.default_rng(1).integers(1, 101, 20).astype(float)
+    o, g = _pair(t["K"], t["alpha"], [4, 4], counts, g0)
+    # constructor state: Elnphi, zeta (src/MMCTM.jl:78-86)
+    s = g.state(props=False)
+    assert np.array_equal(s["Elnphi"], o.Elnphi) and np.array_equal(s["zeta"], o.zeta)
+    ll_o, ll_g = o.iterate(), g.iterate()
+    _check_iteration(o, g, ll_o, ll_g)
+    eo, to = o.elbo()
+    eg, tg = g.calculate_elbo()
+    assert rel_err(tg, to) <= TOL_ITER and abs(eg - eo) <= TOL_ITER * abs(eo)
+    g.close()
+
+
+def test_brca_one_iteration_and_elbo(brca):
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    o, g = _pair(K, alpha, V, brca, g0)
+    ll_o, ll_g = o.iterate(), g.iterate()
+    _check_iteration(o, g, ll_o, ll_g)
+    eo, to = o.elbo()
+    eg, tg = g.calculate_elbo()
+    assert rel_err(tg, to) <= TOL_ITER, (tg, to)
+    assert abs(eg - eo) <= TOL_ITER * abs(eo)
+    for m in range(2):
+        np.testing.assert_allclose(g.theta(m), o.theta(m), rtol=1e-13)
+    g.close()
+
+
+def test_brca_fit_config1(brca):
+    """config 1: MMCTM([7,7],[0.1,0.1]) on brca-eu, fit!(tol=1e-5) (README.md:18-26)."""
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    o, g = _pair(K, alpha, V, brca, g0)
+    ho = o.fit(maxiter=30, tol=1e-5)
+    hg = g.fit(maxiter=30, tol=1e-5, verbose=False)
+    assert hg.shape == ho.shape and g.converged == o.converged
+    assert np.array_equal(hg, ho), "LL history differs: %.3e" % rel_err(hg, ho)
+    _check_iteration(o, g, ho[-1], hg[-1])
+    eo, _ = o.elbo()
+    assert abs(g.elbo - eo) <= TOL_FIT_ELBO * abs(eo)
+    assert abs(g.elbo - eo) <= TOL_ITER * abs(eo)
+    assert np.array_equal(g.ll, ho[-1])
+    g.close()
+
+
+@pytest.mark.parametrize("K,V,D,empty", [([10, 8, 6], [96, 32, 83], 1500, 0.05),     # config 4 shape
+                                         ([10], [96], 1200, 0.0),                    # config 3: CTM
+                                         ([7, 7], [96, 32], 800, 0.1),               # config 5 shape
+                                         ([1, 2], [5, 3], 64, 0.3),                  # degenerate sizes
+                                         ([16, 16], [40, 7], 300, 0.0)])             # MK = 32
+def test_synthetic_three_iterations(K, V, D, empty):
+    counts = small_synth(D, K, V, empty_frac=empty)
+    alpha = [0.1] * len(K)
+    g0 = mmsig.synth.init_gamma(K, V)
+    o, g = _pair(K, alpha, V, counts, g0)
+    for it in range(3):
+        ll_o, ll_g = o.iterate(), g.iterate()
+        _check_iteration(o, g, ll_o, ll_g)
+    eo, to = o.elbo()
+    eg, tg = g.calculate_elbo()
+    assert abs(eg - eo) <= TOL_ITER * abs(eo), (tg, to)
+    g.close()
+
+
+def test_stop_rule_nlopt26_and_no_sigma_update(brca):
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    o, g = _pair(K, alpha, V, brca, g0, stop_rule=1)
+    for it in range(2):
+        ll_o, ll_g = o.iterate(updateSigma=(it == 0)), g.iterate(updateSigma=(it == 0))
+        _check_iteration(o, g, ll_o, ll_g)
+    g.close()
+
+
+def test_set_state_continues_a_fit(brca):
+    """fit! is re-entrant: state downloaded from one handle and uploaded into another continues
+    identically (src/MMCTM.jl: all state lives in the struct)."""
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    a = mmsig.MMCTM(K, alpha, brca, V=V, gamma0=g0)
+    a.iterate(); a.iterate()
+    s = a.state()
+    b = mmsig.MMCTM(K, alpha, brca, V=V, gamma0=s["gamma"])
+    b.set_state(s["gamma"], lam=s["lam"], nu=s["nu"], mu=s["mu"], Sigma=s["Sigma"], invSigma=s["invSigma"])
+    la, lb = a.iterate(), b.iterate()
+    assert np.array_equal(la, lb)
+    sa, sb = a.state(), b.state()
+    for k in ("lam", "nu", "gamma", "mu", "Sigma"):
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close(); b.close()
+
+
+def test_against_literal_oracle_statistics(brca):
+    """The literal oracle (glibc exp/log, sequential sums) differs from the pinned arithmetic by
+    rounding only; where MMA takes the same number of evaluations the results agree closely, and the
+    aggregate quantities agree to the level the flipped samples allow."""
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    o = oracle_mmctm(K, alpha, V, brca, g0, arith=orc.ARITH_LITERAL)
+    g = mmsig.MMCTM(K, alpha, brca, V=V, gamma0=g0)
+    ll_o, ll_g = o.iterate(), g.iterate()
+    nn, nl = g.evals()
+    same = (nn == o.nev_nu) & (nl == o.nev_lambda)
+    assert same.mean() > 0.9
+    s = g.state()
+    assert np.abs(s["lam"] - o.lam)[same].max() < 1e-6
+    assert rel_err(ll_g, ll_o) < 1e-6
+    assert rel_err(s["phi"], o.phi) < 1e-5
+    g.close()
+
+
+def test_bad_input_is_rejected():
+    rp = np.array([0, 2, 3], np.int64)
+    with pytest.raises(mmsig.capi.MmsigError):          # term out of range
+        mmsig.MMCTM([2], [0.1], [(rp, np.array([0, 9, 1], np.int32), np.array([1, 1, 1], np.int32))], V=[4])
+    with pytest.raises(mmsig.capi.MmsigError):          # unsorted row
+        mmsig.MMCTM([2], [0.1], [(rp, np.array([3, 1, 1], np.int32), np.array([1, 1, 1], np.int32))], V=[4])
+    with pytest.raises(mmsig.capi.MmsigError):          # zero count
+        mmsig.MMCTM([2], [0.1], [(rp, np.array([0, 1, 1], np.int32), np.array([1, 0, 1], np.int32))], V=[4])
+    with pytest.raises(mmsig.capi.MmsigError):          # sum(K) > 32
+        mmsig.MMCTM([20, 20], [0.1, 0.1], [(rp, np.array([0, 1, 1], np.int32), np.array([1, 1, 1], np.int32))] * 2, V=[4, 4])
