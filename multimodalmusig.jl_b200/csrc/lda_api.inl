@@ -1,9 +1,312 @@
 // lda_api.inl -- host side of the LDA entry points (included by mmsig_api.cu)
-#define LDA_TODO return fail(h, MMSIG_EINVAL, "LDA path not built yet")
-extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t, int64_t, int32_t, int32_t, const int64_t *, const int32_t *, const int32_t *) { LDA_TODO; }
-extern "C" int32_t mmsig_lda_set_state(mmsig_handle *h, double, double, const double *, const double *) { LDA_TODO; }
-extern "C" int32_t mmsig_lda_iterate(mmsig_handle *h, double *) { LDA_TODO; }
-extern "C" int32_t mmsig_lda_fit(mmsig_handle *h, int32_t, double, double *, int32_t *, int32_t *) { LDA_TODO; }
-extern "C" int32_t mmsig_lda_elbo(mmsig_handle *h, double *, double *) { LDA_TODO; }
-extern "C" int32_t mmsig_lda_get_state(mmsig_handle *h, double *, double *, double *, double *, double *, double *) { LDA_TODO; }
-extern "C" int32_t mmsig_lda_get_phi(mmsig_handle *h, double *) { LDA_TODO; }
+
+template <typename F>
+static int pick_lda_plan(mmsig_handle *h, F kernel, int KV, long long D, int *W_out, int *grid_out, size_t *smem_out) {
+    cudaFuncAttributes fa;
+    CU(cudaFuncGetAttributes(&fa, kernel));
+    CU(allow_max_smem(h, kernel));
+    int bestW = 0, best_warps = 0, best_blocks = 0;
+    size_t best_smem = 0;
+    for (int W : {8, 4, 2, 1}) {
+        size_t smem = (size_t)(1 + W) * KV * sizeof(double);
+        if (smem + fa.sharedSizeBytes > h->smem_optin) continue;
+        int nb = 0;
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, W * 32, smem));
+        if (nb * W > best_warps) { best_warps = nb * W; bestW = W; best_blocks = nb; best_smem = smem; }
+    }
+    if (!bestW) return fail(h, MMSIG_ELIMIT, "K*V topic-term table does not fit in shared memory");
+    *W_out = bestW;
+    *smem_out = best_smem;
+    long long want = (long long)h->numSM * best_blocks, cap = (D + bestW - 1) / bestW;
+    *grid_out = (int)std::max<long long>(1, std::min(want, cap));
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
+                                      const int64_t *rowptr, const int32_t *term, const int32_t *count) {
+    NEED(h, "null handle");
+    NEED(rowptr, "null rowptr");
+    NEED(D >= 1 && D_total >= D, "need 1 <= D <= D_total");
+    NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
+    NEED(K >= 1 && V >= 1, "K, V must be >= 1");
+    if (K > 32) return fail(h, MMSIG_ELIMIT, "K <= 32 supported");
+    CU(cudaSetDevice(h->device));
+    free_pool(h->allocs_lda);
+    h->lda = LdaHost();
+    LdaHost &L = h->lda;
+    LdaDev &p = L.p;
+    p.K = K;
+    p.V = V;
+    p.D = D;
+    p.D_total = D_total;
+    int rc;
+    double *dN = nullptr;
+    if ((rc = dev_alloc(h, h->allocs_lda, &dN, (size_t)D))) return rc;
+    p.N = dN;
+    long long ntot = 0;
+    if ((rc = upload_counts(h, h->allocs_lda, D, V, 1, 0, rowptr, term, count, &p.rowptr, &p.rec, dN, &L.nnz, &ntot)))
+        return rc;
+    if ((rc = allsum_ll(h, &ntot, 1))) return rc;
+    p.Ntot = (double)ntot;
+    const size_t KV = (size_t)K * V, DK = (size_t)D * K;
+    for (double **t : {&p.lam, &p.Elnbeta, &p.Elnbeta_prev, &p.beta, &p.expElnbeta, &p.expElnbeta_prev})
+        if ((rc = dev_alloc(h, h->allocs_lda, t, KV))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.gamA, DK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.gamB, DK))) return rc;
+    p.gamma = L.gamA;
+    p.gamma_next = L.gamB;
+    THETA_DISPATCH(K, rc = pick_lda_plan(h, k_lda_estep<KP, NP>, (int)KV, D, &L.W, &L.grid, &L.smem));
+    if (rc) return rc;
+    {
+        int nb = 0;
+        L.smem_ll = (KV + 256) * sizeof(double);
+        L.smem_elbo = (2 * KV + 512) * sizeof(double);
+        CU(allow_max_smem(h, k_lda_ll));
+        CU(allow_max_smem(h, k_lda_elbo));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_ll, 256, L.smem_ll));
+        L.grid_ll = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+    }
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.part, (size_t)L.grid * KV))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.part_ll, (size_t)L.grid_ll * 8))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.rank_p, KV + 16))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.gath_p, (KV + 16) * h->nranks))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.rank_ll, (size_t)16))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.gath_ll, (size_t)16 * h->nranks))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.d_ll, (size_t)8))) return rc;
+    L.has_data = true;
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_set_state(mmsig_handle *h, double alpha, double eta, const double *lambda,
+                                       const double *gamma_next) {
+    NEED(h, "null handle");
+    LdaHost &L = h->lda;
+    NEED(L.has_data, "mmsig_lda_set_data first");
+    NEED(lambda, "lambda is required");
+    NEED(alpha > 0 && eta > 0, "alpha, eta must be > 0");
+    CU(cudaSetDevice(h->device));
+    LdaDev &p = L.p;
+    p.alpha = alpha;
+    p.eta = eta;
+    const size_t KV = (size_t)p.K * p.V, DK = (size_t)p.D * p.K;
+    CU(cudaMemcpyAsync(p.lam, lambda, KV * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, "k_lda_elnbeta");
+        k_lda_elnbeta<<<1, 1024, 0, h->stream>>>(p);
+    }
+    if (gamma_next) CU(cudaMemcpyAsync(p.gamma_next, gamma_next, DK * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else {
+        LaunchScope ls(h, "k_lda_gamma_init");
+        k_lda_gamma_init<<<L.grid_ll, 256, 0, h->stream>>>(p);
+    }
+    fill(h, p.gamma, DK, 1.0);                       // model.γ = 1 (src/LDA.jl:41)
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    L.has_state = true;
+    L.iterated = false;
+    return 0;
+}
+
+static int lda_iterate_async(mmsig_handle *h) {
+    LdaHost &L = h->lda;
+    LdaDev &p = L.p;
+    const int KV = p.K * p.V;
+    std::swap(p.gamma, p.gamma_next);               // γ_t <- what the previous pass (or init) produced
+    {
+        LaunchScope ls(h, "k_lda_estep");
+        THETA_DISPATCH(p.K, (k_lda_estep<KP, NP><<<L.grid, L.W * 32, L.smem, h->stream>>>(p, L.part, L.W)));
+    }
+    {
+        CombineSegs s{};
+        s.nseg = 1;
+        s.src[0] = L.part;
+        s.nparts[0] = L.grid;
+        s.n[0] = KV;
+        s.dst_off[0] = 0;
+        LaunchScope ls(h, "k_combine");
+        k_combine<<<(KV + 127) / 128, 128, 0, h->stream>>>(s, L.rank_p);
+    }
+    const double2 *g = nullptr;
+    int rc;
+    if ((rc = gather(h, L.rank_p, L.gath_p, KV, &g))) return rc;
+    {
+        LaunchScope ls(h, "k_lda_mstep");
+        k_lda_mstep<<<1, 1024, 0, h->stream>>>(p, g, h->nranks);
+    }
+    {
+        LaunchScope ls(h, "k_lda_ll");
+        k_lda_ll<<<L.grid_ll, 256, L.smem_ll, h->stream>>>(p, L.part_ll);
+    }
+    {
+        CombineSegs s{};
+        s.nseg = 1;
+        s.src[0] = L.part_ll;
+        s.nparts[0] = L.grid_ll;
+        s.n[0] = 1;
+        s.dst_off[0] = 0;
+        LaunchScope ls(h, "k_combine");
+        k_combine<<<1, 128, 0, h->stream>>>(s, L.rank_ll);
+    }
+    if ((rc = gather(h, L.rank_ll, L.gath_ll, 1, &g))) return rc;
+    {
+        LaunchScope ls(h, "k_lda_ll_final");
+        k_lda_ll_final<<<1, 32, 0, h->stream>>>(g, h->nranks, p.Ntot, L.d_ll);
+    }
+    L.iterated = true;
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_iterate(mmsig_handle *h, double *ll_out) {
+    NEED(h, "null handle");
+    NEED(h->lda.has_state, "mmsig_lda_set_state first");
+    CU(cudaSetDevice(h->device));
+    int rc = lda_iterate_async(h);
+    if (rc) return rc;
+    double ll = 0.0;
+    CU(cudaMemcpyAsync(&ll, h->lda.d_ll, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    if (ll_out) *ll_out = ll;
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_fit(mmsig_handle *h, int32_t maxiter, double tol, double *ll_hist, int32_t *n_iter,
+                                 int32_t *converged) {
+    NEED(h, "null handle");
+    NEED(h->lda.has_state, "mmsig_lda_set_state first");
+    NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
+    int it = 0, conv = 0;
+    for (int iter = 1; iter <= maxiter; ++iter) {
+        int rc = mmsig_lda_iterate(h, &ll_hist[iter - 1]);
+        if (rc) return rc;
+        it = iter;
+        if (iter > 10) {                                       // src/LDA.jl:215, src/common.jl:53-56
+            double r = std::fabs(ll_hist[iter - 2] - ll_hist[iter - 1]) / std::fabs(ll_hist[iter - 1]);
+            if (r < tol) { conv = 1; break; }
+        }
+    }
+    if (n_iter) *n_iter = it;
+    if (converged) *converged = conv;
+    return 0;
+}
+
+static int lda_elbo_pass(mmsig_handle *h, double *phi_dev, double2 *host_parts /*[7]*/, double *tab /*[4]*/) {
+    LdaHost &L = h->lda;
+    LdaDev &p = L.p;
+    const int nb = L.grid_ll;
+    double2 *parts = nullptr;
+    double *d_tab = nullptr;
+    CU(cudaMalloc(&parts, (size_t)nb * 8 * sizeof(double2)));
+    CU(cudaMalloc(&d_tab, 4 * sizeof(double)));
+    CU(cudaMemsetAsync(parts, 0, (size_t)nb * 8 * sizeof(double2), h->stream));
+    {
+        LaunchScope ls(h, "k_lda_elbo");
+        k_lda_elbo<<<nb, 256, L.smem_elbo, h->stream>>>(p, parts, phi_dev);
+    }
+    {
+        LaunchScope ls(h, "k_lda_elbo_tables");
+        k_lda_elbo_tables<<<1, 256, 0, h->stream>>>(p, d_tab);
+    }
+    {
+        CombineSegs s{};
+        s.nseg = 1;
+        s.src[0] = parts;
+        s.nparts[0] = nb;
+        s.n[0] = 8;
+        s.dst_off[0] = 0;
+        LaunchScope ls(h, "k_combine");
+        k_combine<<<1, 128, 0, h->stream>>>(s, L.rank_ll);
+    }
+    const double2 *g = nullptr;
+    int rc = gather(h, L.rank_ll, L.gath_ll, 8, &g);
+    if (rc) return rc;
+    std::vector<double2> hp((size_t)8 * h->nranks);
+    CU(cudaMemcpyAsync(hp.data(), g, hp.size() * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaMemcpyAsync(tab, d_tab, 4 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(parts);
+    cudaFree(d_tab);
+    CU(cudaGetLastError());
+    for (int i = 0; i < 7; ++i) {
+        long double s = 0;
+        for (int r = 0; r < h->nranks; ++r) s += (long double)hp[(size_t)r * 8 + i].x + (long double)hp[(size_t)r * 8 + i].y;
+        host_parts[i] = make_double2((double)s, 0.0);
+    }
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_elbo(mmsig_handle *h, double *elbo, double *terms) {
+    NEED(h, "null handle");
+    LdaHost &L = h->lda;
+    NEED(L.has_state && L.iterated, "mmsig_lda_elbo needs at least one iteration");
+    CU(cudaSetDevice(h->device));
+    LdaDev &p = L.p;
+    double2 s[7];
+    double tab[4];
+    int rc = lda_elbo_pass(h, nullptr, s, tab);
+    if (rc) return rc;
+    const double K = p.K, V = p.V, Dt = (double)p.D_total;
+    double t[7];
+    t[0] = K * (std::lgamma(V * p.eta) - V * std::lgamma(p.eta)) + (p.eta - 1) * tab[0];          // :114-118
+    t[1] = Dt * (std::lgamma(K * p.alpha) - K * std::lgamma(p.alpha)) + (p.alpha - 1) * s[0].x;   // :120-124
+    t[2] = s[1].x;                                                                               // :126-132
+    t[3] = s[2].x;                                                                               // :134-140
+    t[4] = tab[1] - tab[2] - tab[3];                                                             // :142-146
+    t[5] = s[4].x - s[5].x - s[6].x;                                                             // :148-152
+    t[6] = s[3].x;                                                                               // :154-160
+    if (terms) memcpy(terms, t, sizeof(t));
+    if (elbo) *elbo = t[0] + t[1] + t[2] + t[3] - t[4] - t[5] - t[6];
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, double *beta, double *gamma,
+                                       double *Elntheta, double *theta) {
+    NEED(h, "null handle");
+    LdaHost &L = h->lda;
+    NEED(L.has_state, "mmsig_lda_set_state first");
+    CU(cudaSetDevice(h->device));
+    LdaDev &p = L.p;
+    const size_t KV = (size_t)p.K * p.V, DK = (size_t)p.D * p.K;
+    auto d2h = [&](double *dst, const double *src, size_t n) -> cudaError_t {
+        return dst ? cudaMemcpyAsync(dst, src, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream) : cudaSuccess;
+    };
+    CU(d2h(lambda, p.lam, KV));
+    CU(d2h(Elnbeta, p.Elnbeta, KV));
+    CU(d2h(beta, p.beta, KV));
+    CU(d2h(gamma, p.gamma, DK));
+    if (Elntheta || theta) {
+        double *dE = nullptr, *dT = nullptr;
+        CU(cudaMalloc(&dE, DK * sizeof(double)));
+        CU(cudaMalloc(&dT, DK * sizeof(double)));
+        {
+            LaunchScope ls(h, "k_lda_theta_out");
+            k_lda_theta_out<<<L.grid_ll, 256, 0, h->stream>>>(p, dE, dT);
+        }
+        CU(d2h(Elntheta, dE, DK));
+        CU(d2h(theta, dT, DK));
+        CU(cudaStreamSynchronize(h->stream));
+        cudaFree(dE);
+        cudaFree(dT);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_get_phi(mmsig_handle *h, double *phi_out) {
+    NEED(h && phi_out, "null argument");
+    LdaHost &L = h->lda;
+    NEED(L.has_state && L.iterated, "mmsig_lda_get_phi needs at least one iteration");
+    CU(cudaSetDevice(h->device));
+    const size_t n = (size_t)L.nnz * L.p.K;
+    double *d = nullptr;
+    CU(cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(double)));
+    double2 s[7];
+    double tab[4];
+    int rc = lda_elbo_pass(h, d, s, tab);
+    if (rc) { cudaFree(d); return rc; }
+    CU(cudaMemcpyAsync(phi_out, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(d);
+    return 0;
+}

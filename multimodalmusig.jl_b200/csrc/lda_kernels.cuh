@@ -1,10 +1,333 @@
-// lda_kernels.cuh -- LDA variational-EM iteration (reference src/LDA.jl:69-224).
+// lda_kernels.cuh -- LDA variational-EM iteration (reference src/LDA.jl:69-224), FP64.
+//
+// Iteration t of fit! (src/LDA.jl:201-209):
+//   γ_t = α + Σ_w n ϕ_{t-1}   (update_γ!, :82-90; ϕ_0 = 1/K)      <- produced by pass t-1 (γ_next)
+//   Elnθ_t = ψ(γ_t) - ψ(Σ_k γ_t)                                   (:78-80)
+//   ϕ_t[k,w] ∝ exp(Elnθ_t[k] + Elnβ_{t-1}[v_w,k])                  (update_ϕ!, :69-76)
+//   λ_t = η + Σ_d n ϕ_t ; Elnβ_t ; β_t ; θ_t                       (:92-112)
+//   ll_t = Σ n log(θ_t[:,d]·β_t[v,:]) / N                          (:174-188)
+// ϕ (K x nnz) is never stored: one pass computes ϕ_t on the fly, adds n ϕ_t into the K x V
+// statistics and emits γ_{t+1}.  LDA has no data-dependent branches, so its tolerance is the
+// plain 1e-12 of north_star and the exponentials are hoisted: ϕ ∝ e^{Elnθ_k} · e^{Elnβ_kv}
+// (K exps per sample + a K x V table instead of K·nnz exps).
 #pragma once
 #include "det_math.cuh"
 
 namespace mmsig {
+
 struct LdaDev {
     int K, V;
     long long D, D_total;
+    const long long *rowptr;
+    const int2 *rec;
+    const double *N;             // D
+    double Ntot;                 // Σ_d N_d over all ranks
+    double alpha, eta;
+    double *lam, *Elnbeta, *Elnbeta_prev, *beta, *expElnbeta, *expElnbeta_prev;   // K x V, [k][v]
+    double *gamma, *gamma_next;  // D x K, [d][k]
 };
+
+template <int N>
+__device__ __forceinline__ void warp_multi_reduce(double (&v)[N], int lane) {
+    int off = 16;
+#pragma unroll
+    for (int half = N / 2; half >= 1; half >>= 1, off >>= 1) {
+        const bool upper = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < half; ++i) {
+            const double send = upper ? v[i] : v[i + half];
+            const double keep = upper ? v[i + half] : v[i];
+            v[i] = keep + shfl_xor_d(send, off);
+        }
+    }
+    for (; off >= 1; off >>= 1) v[0] = v[0] + shfl_xor_d(v[0], off);
+}
+
+// Elnθ of one sample on lanes k < K (all lanes get ψ(Σγ) consistently)
+__device__ __forceinline__ double lda_elntheta(double gk, int K, int lane) {
+    double s = 0.0;
+    for (int k = 0; k < K; ++k) s += shfl_d(gk, k);
+    const double ds = det_digamma(s);
+    return (lane < K) ? det_digamma(gk) - ds : 0.0;
+}
+
+// γ_1 = α + Σ_w (1/K) n_w  (update_γ! on the constructor's ϕ = 1/K, src/LDA.jl:46-49,82-90)
+__global__ void __launch_bounds__(256) k_lda_gamma_init(LdaDev p) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long nw = (long long)gridDim.x * 8;
+    const double invK = 1.0 / p.K;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        double s = 0.0;
+        for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) s += invK * (double)p.rec[w].y;
+        s = warp_tree_sum(s);
+        if (lane < p.K) p.gamma_next[d * p.K + lane] = p.alpha + s;
+    }
+}
+
+// One E pass.  partial: [gridDim.x][K*V] (as double2 {sum, 0} so that k_combine can be shared).
+template <int KP, int NP>
+__global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, int nwarps_blk) {
+    extern __shared__ double smem[];
+    const int K = p.K, V = p.V, KV = K * V;
+    double *E = smem;                                  // e^{Elnβ}, KV
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *tab = smem + KV + (size_t)warp * KV;       // this warp's statistics
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) E[i] = p.expElnbeta[i];
+    for (int i = lane; i < KV; i += 32) tab[i] = 0.0;
+    __syncthreads();
+    const long long nw = (long long)gridDim.x * nwarps_blk;
+    for (long long d = (long long)blockIdx.x * nwarps_blk + warp; d < p.D; d += nw) {
+        const double gk = (lane < K) ? p.gamma[d * K + lane] : 0.0;
+        const double elt = lda_elntheta(gk, K, lane);
+        const double mine = (lane < K) ? det_exp(elt) : 0.0;
+        double et[KP];
+#pragma unroll
+        for (int k = 0; k < KP; ++k) et[k] = shfl_d(mine, k);
+        double g[NP];
+#pragma unroll
+        for (int k = 0; k < NP; ++k) g[k] = 0.0;
+        for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) {
+            const int2 r = p.rec[w];
+            const int v = r.x;
+            double pk[KP];
+            double Z = 0.0;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) {
+                    pk[k] = et[k] * E[k * V + v];
+                    Z += pk[k];
+                }
+            const double scale = (double)r.y / Z;
+#pragma unroll
+            for (int k = 0; k < KP; ++k)
+                if (k < K) {
+                    const double a = pk[k] * scale;
+                    tab[k * V + v] += a;
+                    g[k] += a;
+                }
+        }
+        __syncwarp();
+        warp_multi_reduce<NP>(g, lane);
+        const int idx = warp_multi_index<NP>(lane);
+        constexpr int GROUP = 32 / NP;
+        if (idx < K && (lane & (GROUP - 1)) == 0) p.gamma_next[d * K + idx] = p.alpha + g[0];
+    }
+    __syncthreads();
+    double2 *out = partial + (size_t)blockIdx.x * KV;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        double s = 0.0;
+        for (int wv = 0; wv < nwarps_blk; ++wv) s += smem[KV + (size_t)wv * KV + i];
+        out[i] = make_double2(s, 0.0);
+    }
+}
+
+// M-step (single block): λ = η + Σ n ϕ (:100-105), Elnβ (:96-98), β (:110-112), e^{Elnβ}.
+__global__ void __launch_bounds__(1024) k_lda_mstep(LdaDev p, const double2 *gathered, int nranks) {
+    __shared__ double rowsum[32], rowdig[32];
+    const int K = p.K, V = p.V, KV = K * V;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        double hi = 0.0, lo = 0.0;
+        for (int r = 0; r < nranks; ++r) dd_merge(hi, lo, gathered[(size_t)r * KV + i].x, gathered[(size_t)r * KV + i].y);
+        dd_add(hi, lo, p.eta);
+        p.lam[i] = dd_round(hi, lo);
+        p.Elnbeta_prev[i] = p.Elnbeta[i];
+        p.expElnbeta_prev[i] = p.expElnbeta[i];
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < K) {
+        double s = 0.0;
+        for (int v = 0; v < V; ++v) s += p.lam[threadIdx.x * V + v];
+        rowsum[threadIdx.x] = s;
+        rowdig[threadIdx.x] = det_digamma(s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        const int k = i / V;
+        const double l = p.lam[i];
+        const double e = det_digamma(l) - rowdig[k];
+        p.Elnbeta[i] = e;
+        p.expElnbeta[i] = det_exp(e);
+        p.beta[i] = l / rowsum[k];
+    }
+}
+
+// constructor: Elnβ, e^{Elnβ} from λ (src/LDA.jl:36-39)
+__global__ void __launch_bounds__(1024) k_lda_elnbeta(LdaDev p) {
+    __shared__ double rowdig[32];
+    const int K = p.K, V = p.V, KV = K * V;
+    if ((int)threadIdx.x < K) {
+        double s = 0.0;
+        for (int v = 0; v < V; ++v) s += p.lam[threadIdx.x * V + v];
+        rowdig[threadIdx.x] = det_digamma(s);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        const double e = det_digamma(p.lam[i]) - rowdig[i / V];
+        p.Elnbeta[i] = e;
+        p.Elnbeta_prev[i] = e;
+        p.expElnbeta[i] = det_exp(e);
+        p.expElnbeta_prev[i] = p.expElnbeta[i];
+        p.beta[i] = 0.0;
+    }
+}
+
+// log-likelihood pass (src/LDA.jl:174-188) with θ_t = γ_t / Σγ_t and the new β.
+// partial: [gridDim.x] double2.
+__global__ void __launch_bounds__(256) k_lda_ll(LdaDev p, double2 *partial) {
+    extern __shared__ double smem[];
+    __shared__ double2 red[8];
+    const int K = p.K, V = p.V, KV = K * V;
+    double *beta = smem;                 // KV
+    double *thsh = smem + KV;            // 8 x 32
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *th = thsh + warp * 32;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) beta[i] = p.beta[i];
+    __syncthreads();
+    double hi = 0.0, lo = 0.0;
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const double gk = (lane < K) ? p.gamma[d * K + lane] : 0.0;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += shfl_d(gk, k);
+        __syncwarp();
+        th[lane] = gk / s;
+        __syncwarp();
+        for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) {
+            const int2 r = p.rec[w];
+            double dot = 0.0;
+            for (int k = 0; k < K; ++k) dot += th[k] * beta[k * V + r.x];
+            dd_add(hi, lo, (double)r.y * det_log(dot));
+        }
+    }
+    __syncwarp();
+    warp_dd_allreduce(hi, lo);
+    if (lane == 0) red[warp] = make_double2(hi, lo);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double h = 0.0, l = 0.0;
+        for (int wv = 0; wv < 8; ++wv) dd_merge(h, l, red[wv].x, red[wv].y);
+        partial[blockIdx.x] = make_double2(h, l);
+    }
+}
+
+__global__ void k_lda_ll_final(const double2 *gathered, int nranks, double Ntot, double *ll_out) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) {
+        double hi = 0.0, lo = 0.0;
+        for (int r = 0; r < nranks; ++r) dd_merge(hi, lo, gathered[r].x, gathered[r].y);
+        *ll_out = dd_round(hi, lo) / Ntot;
+    }
+}
+
+// θ, Elnθ of the current γ (get_state)
+__global__ void __launch_bounds__(256) k_lda_theta_out(LdaDev p, double *Elntheta, double *theta) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, K = p.K;
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const double gk = (lane < K) ? p.gamma[d * K + lane] : 0.0;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += shfl_d(gk, k);
+        const double elt = lda_elntheta(gk, K, lane);
+        if (lane < K) {
+            if (Elntheta) Elntheta[d * K + lane] = elt;
+            if (theta) theta[d * K + lane] = gk / s;
+        }
+    }
+}
+
+// ELBO data terms (src/LDA.jl:120-160) and optional ϕ output; ϕ_T is recomputed from γ_T and the
+// Elnβ the last E pass used.  partial: [gridDim.x][8] dd:
+//  [0] Σ Elnθ   [1] ElnPZ = Σ ϕ Elnθ n   [2] ElnPX = Σ ϕ Elnβ_T n   [3] ElnQZ = Σ ϕ log ϕ (no n, as :154-160)
+//  [4] Σ lgamma(γ)   [5] Σ_d lgamma(Σ_k γ)   [6] Σ (γ-1) Elnθ
+__global__ void __launch_bounds__(256) k_lda_elbo(LdaDev p, double2 *partial, double *phi_out) {
+    extern __shared__ double smem[];
+    __shared__ double2 red[8 * 7];
+    const int K = p.K, V = p.V, KV = K * V;
+    double *Eprev = smem;              // e^{Elnβ_{T-1}}
+    double *Eln = smem + KV;           // Elnβ_T
+    double *sh = smem + 2 * KV;        // 8 x 64 : e^{Elnθ}, Elnθ per warp
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double *et = sh + warp * 64, *el = et + 32;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) { Eprev[i] = p.expElnbeta_prev[i]; Eln[i] = p.Elnbeta[i]; }
+    __syncthreads();
+    double hi[7] = {0, 0, 0, 0, 0, 0, 0}, lo[7] = {0, 0, 0, 0, 0, 0, 0};
+    const long long nw = (long long)gridDim.x * 8;
+    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+        const double gk = (lane < K) ? p.gamma[d * K + lane] : 0.0;
+        double s = 0.0;
+        for (int k = 0; k < K; ++k) s += shfl_d(gk, k);
+        const double elt = lda_elntheta(gk, K, lane);
+        __syncwarp();
+        et[lane] = (lane < K) ? det_exp(elt) : 0.0;
+        el[lane] = elt;
+        __syncwarp();
+        if (lane < K) {
+            dd_add(hi[0], lo[0], elt);
+            dd_add(hi[4], lo[4], lgamma(gk));
+            dd_add(hi[6], lo[6], (gk - 1) * elt);
+        }
+        if (lane == 0) dd_add(hi[5], lo[5], lgamma(s));
+        for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) {
+            const int2 r = p.rec[w];
+            const double n = (double)r.y;
+            double Z = 0.0;
+            for (int k = 0; k < K; ++k) Z += et[k] * Eprev[k * V + r.x];
+            double a = 0.0, b = 0.0, c = 0.0;
+            for (int k = 0; k < K; ++k) {
+                const double ph = et[k] * Eprev[k * V + r.x] / Z;
+                if (phi_out) phi_out[w * K + k] = ph;
+                a += ph * el[k] * n;
+                b += ph * Eln[k * V + r.x] * n;
+                if (ph > 0.0) c += ph * det_log(ph);
+            }
+            dd_add(hi[1], lo[1], a);
+            dd_add(hi[2], lo[2], b);
+            dd_add(hi[3], lo[3], c);
+        }
+    }
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 7; ++i) warp_dd_allreduce(hi[i], lo[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 7; ++i) red[warp * 7 + i] = make_double2(hi[i], lo[i]);
+    __syncthreads();
+    if (threadIdx.x < 7) {
+        double h = 0.0, l = 0.0;
+        for (int wv = 0; wv < 8; ++wv) dd_merge(h, l, red[wv * 7 + threadIdx.x].x, red[wv * 7 + threadIdx.x].y);
+        partial[(size_t)blockIdx.x * 8 + threadIdx.x] = make_double2(h, l);
+    }
+}
+
+// table terms of the LDA ELBO (single block): out[0] = ΣElnβ, out[1] = Σ lgamma(λ),
+// out[2] = Σ_k lgamma(Σ_v λ), out[3] = Σ (λ-1) Elnβ
+__global__ void __launch_bounds__(256) k_lda_elbo_tables(LdaDev p, double *out) {
+    __shared__ double2 red[8 * 4];
+    __shared__ double2 res[4];
+    const int K = p.K, V = p.V, KV = K * V;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    double hi[4] = {0, 0, 0, 0}, lo[4] = {0, 0, 0, 0};
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        dd_add(hi[0], lo[0], p.Elnbeta[i]);
+        dd_add(hi[1], lo[1], lgamma(p.lam[i]));
+        dd_add(hi[3], lo[3], (p.lam[i] - 1) * p.Elnbeta[i]);
+    }
+    if ((int)threadIdx.x < K) {
+        double s = 0.0;
+        for (int v = 0; v < V; ++v) s += p.lam[threadIdx.x * V + v];
+        dd_add(hi[2], lo[2], lgamma(s));
+    }
+#pragma unroll
+    for (int i = 0; i < 4; ++i) warp_dd_allreduce(hi[i], lo[i]);
+    if (lane == 0)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) red[warp * 4 + i] = make_double2(hi[i], lo[i]);
+    __syncthreads();
+    if (threadIdx.x < 4) {
+        double h = 0.0, l = 0.0;
+        for (int wv = 0; wv < 8; ++wv) dd_merge(h, l, red[wv * 4 + threadIdx.x].x, red[wv * 4 + threadIdx.x].y);
+        res[threadIdx.x] = make_double2(h, l);
+        out[threadIdx.x] = dd_round(h, l);
+    }
+}
+
 }  // namespace mmsig

@@ -83,9 +83,9 @@ struct LdaHost {
     bool has_data = false, has_state = false, iterated = false;
     LdaDev p{};
     long long nnz = 0;
-    int grid = 0, W = 0;
-    size_t smem = 0;
-    double2 *part = nullptr, *rank_p = nullptr, *gath_p = nullptr;
+    int grid = 0, W = 0, grid_ll = 0;
+    size_t smem = 0, smem_ll = 0, smem_elbo = 0;
+    double2 *part = nullptr, *part_ll = nullptr, *rank_p = nullptr, *gath_p = nullptr, *rank_ll = nullptr, *gath_ll = nullptr;
     double *d_ll = nullptr;
     double *gamA = nullptr, *gamB = nullptr;
 };
