@@ -1,0 +1,173 @@
+# MMSigB200.jl -- drop-in GPU `fit!` for MultiModalMuSig.jl's MMCTM / CTM / LDA.
+#
+# The Julia API stays as it is: format_counts_mmctm/ctm/lda, MMCTM(K, α, X), LDA(K, α, η, X),
+# fit!(model; tol), model.ϕ / model.props / model.β / model.θ.  Loading this file after
+# `using MultiModalMuSig` replaces the two `fit!` methods (reference src/MMCTM.jl:457-494,
+# src/LDA.jl:198-224) by thin wrappers that flatten the model state, `ccall` libmmsig.so
+# (include/mmsig.h) and scatter the results back into the nested vectors.  Model construction,
+# including the random γ / λ initialisation (src/MMCTM.jl:59-63, src/LDA.jl:36), is untouched.
+#
+# NOTE: written against the C ABI but NOT executed in the build environment (no Julia there);
+# the same entry points are exercised by tests/ through ctypes.
+module MMSigB200
+
+using MultiModalMuSig
+import MultiModalMuSig: fit!, MMCTM, LDA, check_convergence
+
+const LIB = get(ENV, "MMSIG_LIB", joinpath(@__DIR__, "..", "multimodalmusig.jl_b200", "libmmsig.so"))
+
+struct MmsigConfig
+    device::Int32
+    stop_rule::Int32
+    profile::Int32
+    reserved::NTuple{5,Int32}
+end
+
+function check(h::Ptr{Cvoid}, rc::Int32)
+    if rc != 0
+        msg = unsafe_string(ccall((:mmsig_last_error, LIB), Cstring, (Ptr{Cvoid},), h))
+        error("libmmsig error $rc: $msg")
+    end
+end
+
+function create(; device=0, stop_rule=0)
+    cfg = Ref(MmsigConfig(Int32(device), Int32(stop_rule), Int32(0), ntuple(_ -> Int32(0), 5)))
+    h = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mmsig_create, LIB), Int32, (Ref{MmsigConfig}, Ref{Ptr{Cvoid}}), cfg, h)
+    check(C_NULL, rc)
+    return h[]
+end
+
+destroy(h) = ccall((:mmsig_destroy, LIB), Int32, (Ptr{Cvoid},), h)
+
+# X[d][m] (nnz x 2 Int, 1-based terms) -> CSR per modality (int64 rowptr, int32 0-based term, int32 count)
+function flatten_counts(X::Vector{Vector{Matrix{Int}}}, M::Int)
+    D = length(X)
+    rowptr = [zeros(Int64, D + 1) for m in 1:M]
+    for m in 1:M, d in 1:D
+        rowptr[m][d + 1] = rowptr[m][d] + size(X[d][m], 1)
+    end
+    term = [Vector{Int32}(undef, rowptr[m][end]) for m in 1:M]
+    count = [Vector{Int32}(undef, rowptr[m][end]) for m in 1:M]
+    for m in 1:M, d in 1:D
+        r = (rowptr[m][d] + 1):rowptr[m][d + 1]
+        term[m][r] .= X[d][m][:, 1] .- 1
+        count[m][r] .= X[d][m][:, 2]
+    end
+    return rowptr, term, count
+end
+
+flat_rows(v::Vector{Vector{Float64}}) = collect(reduce(vcat, v))                         # [d][j] -> D*MK row-major
+flat_tables(t::Vector{Vector{Vector{Float64}}}) = collect(reduce(vcat, [reduce(vcat, tm) for tm in t]))   # [m][k][v]
+
+function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true,
+              device=0, stop_rule=0)
+    autoα && error("autoα=true is not on the GPU path; use the CPU fit!")
+    D, M, MK = model.D, model.M, sum(model.K)
+    rowptr, term, count = flatten_counts(model.X, M)
+    K32, V32 = Int32.(model.K), Int32.(model.V)
+    λ, ν = flat_rows(model.λ), flat_rows(model.ν)
+    γ = flat_tables(model.γ)
+    Σ, invΣ = collect(transpose(model.Σ)), collect(transpose(model.invΣ))               # row-major
+    h = create(device=device, stop_rule=stop_rule)
+    ll = Vector{Float64}[]
+    try
+        GC.@preserve rowptr term count begin
+            rp = [pointer(r) for r in rowptr]; tp = [pointer(t) for t in term]; cp = [pointer(c) for c in count]
+            check(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                h, D, D, M, K32, V32, rp, tp, cp))
+        end
+        check(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
+        flags = UInt32(updateΣ ? 1 : 0)
+        llbuf = zeros(M)
+        for iter in 1:maxiter                                   # src/MMCTM.jl:462-489
+            check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+            push!(ll, copy(llbuf))
+            verbose && println("$iter\tLog-likelihoods: ", join(ll[end], ", "))
+            if length(ll) > 10 && check_convergence(ll, tol=tol)
+                model.converged = true
+                break
+            end
+        end
+        elbo = Ref(0.0)
+        check(h, ccall((:mmsig_mmctm_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
+        ζ = zeros(D * M); μ = zeros(MK); Elnϕ = similar(γ); ϕ = similar(γ); props = zeros(D * MK)
+        check(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+        # scatter back into the nested vectors (shapes preserved)
+        for d in 1:D
+            model.λ[d] .= @view λ[(d - 1) * MK + 1:d * MK]
+            model.ν[d] .= @view ν[(d - 1) * MK + 1:d * MK]
+            model.ζ[d] .= @view ζ[(d - 1) * M + 1:d * M]
+            off = 0
+            for m in 1:M
+                model.props[d][m] .= @view props[(d - 1) * MK + off + 1:(d - 1) * MK + off + model.K[m]]
+                off += model.K[m]
+            end
+        end
+        model.μ .= μ
+        model.Σ .= transpose(reshape(Σ, MK, MK)); model.invΣ .= transpose(reshape(invΣ, MK, MK))
+        o = 0
+        for m in 1:M, k in 1:model.K[m]
+            r = (o + 1):(o + model.V[m])
+            model.γ[m][k] .= @view γ[r]; model.Elnϕ[m][k] .= @view Elnϕ[r]; model.ϕ[m][k] .= @view ϕ[r]
+            o += model.V[m]
+        end
+        # model.θ is materialised lazily: materialize_theta!(model, h) before destroy if wanted
+        model.elbo = elbo[]
+        model.ll = ll[end]
+    finally
+        destroy(h)
+    end
+    return ll
+end
+
+function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
+    D, K, V = model.D, model.K, model.V
+    rowptr = zeros(Int64, D + 1)
+    for d in 1:D rowptr[d + 1] = rowptr[d] + size(model.X[d], 1) end
+    term = Vector{Int32}(undef, rowptr[end]); count = Vector{Int32}(undef, rowptr[end])
+    for d in 1:D
+        r = (rowptr[d] + 1):rowptr[d + 1]
+        term[r] .= model.X[d][:, 1] .- 1; count[r] .= model.X[d][:, 2]
+    end
+    λ = Float64.(vec(model.λ))            # V x K column-major == [k][v]
+    h = create(device=device)
+    ll = Float64[]
+    try
+        check(h, ccall((:mmsig_lda_set_data, LIB), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}), h, D, D, K, V, rowptr, term, count))
+        check(h, ccall((:mmsig_lda_set_state, LIB), Int32, (Ptr{Cvoid}, Float64, Float64, Ptr{Float64}, Ptr{Float64}),
+            h, model.α, model.η, λ, C_NULL))
+        l = Ref(0.0)
+        for iter in 1:maxiter                                   # src/LDA.jl:201-219
+            check(h, ccall((:mmsig_lda_iterate, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}), h, l))
+            push!(ll, l[])
+            verbose && println("$iter\tLog-likelihood: ", ll[end])
+            if length(ll) > 10 && check_convergence(ll, tol=tol)
+                model.converged = true
+                break
+            end
+        end
+        elbo = Ref(0.0)
+        check(h, ccall((:mmsig_lda_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
+        Elnβ = similar(λ); β = similar(λ); γ = zeros(K * D); Elnθ = zeros(K * D); θ = zeros(K * D)
+        check(h, ccall((:mmsig_lda_get_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, λ, Elnβ, β, γ, Elnθ, θ))
+        model.λ .= reshape(λ, V, K); model.Elnβ .= reshape(Elnβ, V, K); model.β .= reshape(β, V, K)
+        model.γ .= reshape(γ, K, D); model.Elnθ .= reshape(Elnθ, K, D); model.θ .= reshape(θ, K, D)
+        model.elbo = elbo[]
+        model.ll = ll[end]
+    finally
+        destroy(h)
+    end
+    return ll
+end
+
+end # module

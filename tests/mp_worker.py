@@ -1,0 +1,83 @@
+"""Multi-rank parity worker (launched by torchrun from test_gpu_multi.py / by hand):
+every rank owns a contiguous shard of the samples on its own GPU; rank 0 checks the gathered
+result against the full-data oracle -- bit-exactly, because every cross-sample sum is exactly
+rounded and therefore independent of the sharding."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import mmsig  # noqa: E402
+
+
+def main():
+    mode = sys.argv[1] if len(sys.argv) > 1 else "mmctm"
+    D = int(sys.argv[2]) if len(sys.argv) > 2 else 3000
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("cpu:gloo,cuda:nccl")
+    uid = [mmsig.capi.comm_unique_id() if rank == 0 else None]
+    dist.broadcast_object_list(uid, 0)
+    comm = (uid[0], rank, world)
+    if mode == "mmctm":
+        K, V = [10, 8, 6], [96, 32, 83]
+        full = mmsig.synth.generate(D, K, V, key=5)
+        b = mmsig.counts.shard_rows([c[0] for c in full], world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        shard = [mmsig.counts.slice_csr(c, lo, hi) for c in full]
+        g0 = mmsig.synth.init_gamma(K, V)
+        m = mmsig.MMCTM(K, [0.1] * 3, shard, V=V, gamma0=g0, device=local, comm=comm, D_total=D)
+        lls = [m.iterate() for _ in range(3)]
+        s = m.state()
+        elbo = m.calculate_elbo()[0]
+        parts = [None] * world
+        dist.gather_object((lo, hi, s["lam"], s["nu"], s["props"]), parts if rank == 0 else None, 0)
+        if rank == 0:
+            import orc
+            o = orc.OracleMMCTM(K, [0.1] * 3, V, full, g0, arith=orc.ARITH_DET, nthreads=os.cpu_count() or 1)
+            llo = [o.iterate() for _ in range(3)]
+            lam = np.concatenate([p[2] for p in parts]); nu = np.concatenate([p[3] for p in parts])
+            props = np.concatenate([p[4] for p in parts])
+            assert [p[0] for p in parts] == [int(x) for x in b[:-1]]
+            assert np.array_equal(lam, o.lam) and np.array_equal(nu, o.nu) and np.array_equal(props, o.props)
+            for k in ("gamma", "mu", "Sigma", "invSigma", "phi"):
+                assert np.array_equal(s[k], getattr(o, k)), k
+            assert np.array_equal(np.asarray(lls), np.asarray(llo))
+            eo = o.elbo()[0]
+            assert abs(elbo - eo) <= 1e-12 * abs(eo), (elbo, eo)
+            print("MULTI-RANK PARITY OK mmctm world=%d D=%d shards=%s" % (world, D, b.tolist()), flush=True)
+        m.close()
+    else:
+        K, V = 20, 96
+        full = mmsig.synth.generate(D, [K], [V], key=5)[0]
+        b = mmsig.counts.shard_rows([full[0]], world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        lam0 = mmsig.synth.init_lda_lambda(K, V)
+        m = mmsig.LDA(K, 0.1, 0.1, mmsig.counts.slice_csr(full, lo, hi), V=V, lambda0=lam0, device=local, comm=comm, D_total=D)
+        lls = [m.iterate() for _ in range(3)]
+        s = m.state()
+        elbo = m.calculate_elbo()[0]
+        parts = [None] * world
+        dist.gather_object((lo, hi, s["gamma"]), parts if rank == 0 else None, 0)
+        if rank == 0:
+            import orc
+            o = orc.OracleLDA(K, 0.1, 0.1, V, full, lam0, nthreads=os.cpu_count() or 1)
+            llo = [o.iterate() for _ in range(3)]
+            gam = np.concatenate([p[2] for p in parts])
+            rel = lambda a, c: float(np.max(np.abs(a - c) / np.abs(c)))
+            assert rel(gam, o.gamma) < 1e-12 and rel(s["lam"], o.lam) < 1e-12 and rel(np.asarray(lls), np.asarray(llo)) < 1e-12
+            eo = o.elbo()[0]
+            assert abs(elbo - eo) <= 1e-11 * abs(eo), (elbo, eo)
+            print("MULTI-RANK PARITY OK lda world=%d D=%d" % (world, D), flush=True)
+        m.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
