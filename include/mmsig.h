@@ -99,6 +99,15 @@ int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double *nu, doubl
 /* model.θ[d][m] for all d of modality m, nnz_m x K_m row-major ([w][k]); recomputed lazily from
  * the λ / Elnϕ the last E-step used (the library never stores θ). */
 int32_t mmsig_mmctm_get_theta(mmsig_handle *h, int32_t m, double *theta_out);
+/* Independent random restarts on the resident counts (README.md:42 "fit many models and pick the
+ * best one"; scripts/run_mmctm.jl:77-111): for r < R, reset the state to the constructor's with
+ * gamma0[r] (R x sum K_m V_m), run mmsig_mmctm_fit, take the ELBO.  elbo_out[R], ll_out[R x M],
+ * n_iter_out[R]; *best = argmax ELBO and the handle is left holding that restart's final state.
+ * Restarts need no communication: with several GPUs give each handle its own slice of restarts
+ * (each handle holds the full counts) and take the arg-max of the returned ELBOs on the host. */
+int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double *gamma0, int32_t maxiter, double tol,
+                             uint32_t flags, double *elbo_out, double *ll_out, int32_t *n_iter_out,
+                             int32_t *best);
 /* diagnostics: objective evaluations LD_MMA spent per sample in the last E-step */
 int32_t mmsig_mmctm_get_evals(mmsig_handle *h, int32_t *nev_nu, int32_t *nev_lambda);
 
@@ -119,6 +128,9 @@ int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, do
                             double *gamma, double *Elntheta, double *theta);
 /* model.ϕ[d] for all d, nnz x K row-major ([w][k]), recomputed lazily */
 int32_t mmsig_lda_get_phi(mmsig_handle *h, double *phi_out);
+
+/* ---- test hook: the pinned device math on arrays (fn 0 = exp, 1 = log, 2 = digamma) ---------- */
+int32_t mmsig_debug_math(mmsig_handle *h, int32_t fn, int64_t n, const double *x, double *y);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */
 /* kernels launched by this handle since creation (bench.py's gpu_launches) */

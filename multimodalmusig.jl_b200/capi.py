@@ -45,6 +45,8 @@ _SIGS = {
     "mmsig_mmctm_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_mmctm_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 10),
     "mmsig_mmctm_get_theta": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
+    "mmsig_mmctm_restarts": (C.c_int32, [C.c_void_p, C.c_int32, c_dp, C.c_int32, C.c_double, C.c_uint32, c_dp, c_dp,
+                                         c_i32p, c_i32p]),
     "mmsig_mmctm_get_evals": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
     "mmsig_lda_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p]),
     "mmsig_lda_set_state": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, c_dp, c_dp]),
@@ -53,6 +55,7 @@ _SIGS = {
     "mmsig_lda_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_lda_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 6),
     "mmsig_lda_get_phi": (C.c_int32, [C.c_void_p, c_dp]),
+    "mmsig_debug_math": (C.c_int32, [C.c_void_p, C.c_int32, C.c_int64, c_dp, c_dp]),
     "mmsig_launch_count": (C.c_int64, [C.c_void_p]),
     "mmsig_kernel_times": (C.c_int32, [C.c_void_p, C.c_int32, C.POINTER(C.c_char_p), c_dp, c_i64p, C.c_int32]),
 }

@@ -44,8 +44,10 @@ extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_tota
     if ((rc = dev_alloc(h, h->allocs_lda, &dN, (size_t)D))) return rc;
     p.N = dN;
     long long ntot = 0;
-    if ((rc = upload_counts(h, h->allocs_lda, D, V, 1, 0, rowptr, term, count, &p.rowptr, &p.rec, dN, &L.nnz, &ntot)))
-        return rc;
+    if ((rc = upload_counts(h, h->allocs_lda, L.cb, D, V, 1, 0, rowptr, term, count, dN, &ntot))) return rc;
+    p.rowptr = L.cb.rowptr;
+    p.rec = L.cb.rec;
+    L.nnz = L.cb.nnz;
     if ((rc = allsum_ll(h, &ntot, 1))) return rc;
     p.Ntot = (double)ntot;
     const size_t KV = (size_t)K * V, DK = (size_t)D * K;

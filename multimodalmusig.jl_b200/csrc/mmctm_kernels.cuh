@@ -121,10 +121,15 @@ struct SolveCtx {
     bool active;       // lane < MK
 };
 
+// Lane-local part of one objective evaluation: the per-coordinate term t (to be tree-summed
+// into the maximised objective) and the gradient.  Inactive lanes (>= MK) carry a dummy
+// problem with a non-zero gradient so that no division ever sees a zero numerator (IEEE double
+// division takes a ~65-instruction slow path for zero / subnormal operands, and a warp pays
+// for it if any lane does); their terms are masked out of every reduction.
 template <int MKP, bool IS_NU>
-__device__ __forceinline__ void mma_eval(double x, const SolveCtx &c, const double (&Srow)[MKP],
-                                         double *dsh, int lane, double &f, double &g) {
-    double t, grad;
+__device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, const double (&Srow)[MKP],
+                                               double *dsh, int lane, double &t, double &g) {
+    double grad;
     if (IS_NU) {
         // src/common.jl:25-36, maximised; fused per-coordinate term (DET)
         const double e = det_exp(c.other + 0.5 * x);
@@ -134,7 +139,7 @@ __device__ __forceinline__ void mma_eval(double x, const SolveCtx &c, const doub
         // src/common.jl:11-23
         const double diff = x - c.muj;
         const double e = det_exp(x + c.other);
-        if (lane < MKP) dsh[lane] = diff;
+        if (lane < MKP) dsh[lane] = c.active ? diff : 0.0;
         __syncwarp();
         double q = 0.0;
 #pragma unroll
@@ -149,9 +154,8 @@ __device__ __forceinline__ void mma_eval(double x, const SolveCtx &c, const doub
         const double a = q * diff, b = x * c.s;
         t = (b - 0.5 * a) - ce;
     }
-    if (!c.active) { t = 0.0; grad = 0.0; }
-    f = -warp_tree_sum(t);          // NLopt minimises the negated objective
-    g = -grad;
+    if (!c.active) { t = 0.0; grad = -1.0; }
+    g = -grad;                       // NLopt minimises the negated objective
 }
 
 template <int MKP, bool IS_NU>
@@ -162,7 +166,11 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
     double sigma = 1.0;              // a bound is infinite -> sigma = 1
     double rho = 1.0;
     double g, fmin, fcur, gcur;
-    mma_eval<MKP, IS_NU>(x, c, Srow, dsh, lane, fmin, g);
+    {
+        double t;
+        mma_eval_local<MKP, IS_NU>(x, c, Srow, dsh, lane, t, g);
+        fmin = -warp_tree_sum(t);
+    }
     int nev = 1;
     double xcur = x, xprev = x, xprevprev = x;
     int k = 0;
@@ -180,16 +188,20 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
             else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
             if (xc < lb) xc = lb;
+            if (!c.active) xc = x;                   // dummy lanes stay put
             dx = xc - x;
             const double dx2 = dx * dx;
             const double denominv = 1.0 / (sigma2 - dx2);
             const double cc = sigma2 * dx;
             double gterm = (g * cc + (fabs(g) * sigma + 0.5 * rho) * dx2) * denominv;
             double wterm = 0.5 * dx2 * denominv;
-            warp_tree_sum2(gterm, wterm);
-            const double gval = fmin + gterm, wval = wterm;
             xcur = xc;
-            mma_eval<MKP, IS_NU>(xcur, c, Srow, dsh, lane, fcur, gcur);
+            // the new point's lane-local work first, then ONE 3-way butterfly for gval, wval, f
+            double t;
+            mma_eval_local<MKP, IS_NU>(xcur, c, Srow, dsh, lane, t, gcur);
+            warp_tree_sum3(gterm, wterm, t);
+            const double gval = fmin + gterm, wval = wterm;
+            fcur = -t;
             ++nev;
             const bool inner_done = gval >= fcur;
             if (fcur < fmin) { fmin = fcur; x = xcur; g = gcur; }
@@ -264,7 +276,7 @@ __global__ void __launch_bounds__(256) k_solve(MmctmDev p, double2 *partial) {
     for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
         const long long base = d * MK + lane;
         double lam = active ? p.lam_prev[base] : 0.0;
-        double nu = active ? p.nu[base] : 1.0;
+        double nu = active ? p.nu[base] : 1.5;
         c.s = active ? p.sumtheta[base] : 0.0;
         // ζ_dm = Σ_{k in block m} exp(λ + ν/2), index order
         const double e0 = active ? det_exp(lam + 0.5 * nu) : 0.0;

@@ -62,8 +62,19 @@ static bool load_nccl(std::string &err) {
 struct KernelTime { const char *name; double ms; int64_t n; };
 struct PendingEvent { int idx; cudaEvent_t a, b; };
 
+// device-side storage of one modality's counts; reused across set_data calls of the same shape
+struct CountBuf {
+    long long D = -1, nnz = -1;
+    long long *rowptr = nullptr;
+    int2 *rec = nullptr;
+    int *term = nullptr, *count = nullptr;      // staging for the packing kernel
+    int *flags = nullptr;                       // [0] flags, [2..3] 8 bytes: sum of counts
+};
+
 struct MmctmHost {
     bool has_data = false, has_state = false, estep_done = false;
+    CountBuf cb[MAXM];
+    double *props_scratch = nullptr;
     MmctmDev p{};
     int G = 0;
     std::vector<long long> nnz;
@@ -77,10 +88,12 @@ struct MmctmHost {
     double *d_ll = nullptr;
     int *d_status = nullptr;
     double *lamA = nullptr, *lamB = nullptr;
+    std::vector<double> alpha_host;
 };
 
 struct LdaHost {
     bool has_data = false, has_state = false, iterated = false;
+    CountBuf cb;
     LdaDev p{};
     long long nnz = 0;
     int grid = 0, W = 0, grid_ll = 0;
@@ -334,10 +347,11 @@ static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
 // ---- count ingest: (term, count) -> packed records, row totals, validation ------------------
 // flags: bit0 term out of range, bit1 count <= 0, bit2 terms of a row not strictly ascending
 __global__ void k_pack_rows(const long long *rowptr, const int *term, const int *count, long long D, int V,
-                            int2 *rec, double *N, int M, int m, int *flags) {
+                            int2 *rec, double *N, int M, int m, int *flags, unsigned long long *ntot) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     int bad = 0;
+    unsigned long long tot = 0;
     for (long long d = (long long)blockIdx.x * (blockDim.x >> 5) + warp; d < D; d += nw) {
         const long long beg = rowptr[d], end = rowptr[d + 1];
         long long s = 0;
@@ -350,58 +364,52 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
             s += c;
         }
         for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(FULLMASK, s, off);
-        if (lane == 0) N[d * M + m] = (double)s;
+        if (lane == 0) { N[d * M + m] = (double)s; tot += (unsigned long long)s; }
     }
     if (bad) atomicOr(flags, bad);
+    if (lane == 0 && tot) atomicAdd(ntot, tot);
 }
 
-static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, long long D, int V, int M, int m,
-                         const int64_t *rowptr, const int32_t *term, const int32_t *count,
-                         const long long **d_rowptr, const int2 **d_rec, double *d_N, long long *nnz_out,
+static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, int V, int M, int m,
+                         const int64_t *rowptr, const int32_t *term, const int32_t *count, double *d_N,
                          long long *ntot_out) {
     NEED(rowptr && rowptr[0] == 0, "rowptr[0] must be 0");
+    for (long long d = 0; d < D; ++d)
+        if (rowptr[d + 1] < rowptr[d]) return fail(h, MMSIG_EINVAL, "rowptr not monotone");
     const long long nnz = rowptr[D];
-    NEED(nnz >= 0, "rowptr[D] < 0");
     NEED(nnz == 0 || (term && count), "null term / count");
-    long long *drp = nullptr;
-    int2 *drec = nullptr;
-    int *dterm = nullptr, *dcount = nullptr, *dflags = nullptr;
     int rc;
-    if ((rc = dev_alloc(h, pool, &drp, D + 1))) return rc;
-    if ((rc = dev_alloc(h, pool, &drec, nnz))) return rc;
-    CU(cudaMalloc(&dterm, std::max<long long>(nnz, 1) * sizeof(int)));
-    CU(cudaMalloc(&dcount, std::max<long long>(nnz, 1) * sizeof(int)));
-    CU(cudaMalloc(&dflags, sizeof(int)));
-    CU(cudaMemsetAsync(dflags, 0, sizeof(int), h->stream));
-    CU(cudaMemcpyAsync(drp, rowptr, (D + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (cb.D != D || cb.nnz != nnz) {
+        if ((rc = dev_alloc(h, pool, &cb.rowptr, D + 1))) return rc;
+        if ((rc = dev_alloc(h, pool, &cb.rec, nnz))) return rc;
+        if ((rc = dev_alloc(h, pool, &cb.term, nnz))) return rc;
+        if ((rc = dev_alloc(h, pool, &cb.count, nnz))) return rc;
+        if ((rc = dev_alloc(h, pool, &cb.flags, (size_t)4))) return rc;
+        cb.D = D;
+        cb.nnz = nnz;
+    }
+    CU(cudaMemsetAsync(cb.flags, 0, 4 * sizeof(int), h->stream));
+    CU(cudaMemcpyAsync(cb.rowptr, rowptr, (D + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     if (nnz) {
-        CU(cudaMemcpyAsync(dterm, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(dcount, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(cb.term, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(cb.count, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
     {
         LaunchScope ls(h, "k_pack_rows");
         int grid = (int)std::min<long long>((D + 7) / 8, (long long)h->numSM * 8);
-        k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(drp, dterm, dcount, D, V, drec, d_N, M, m, dflags);
+        k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr, cb.term, cb.count, D, V, cb.rec, d_N, M, m,
+                                                               cb.flags, (unsigned long long *)(cb.flags + 2));
     }
-    int flags = 0;
-    CU(cudaMemcpyAsync(&flags, dflags, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+    int hf[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(hf, cb.flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(dterm);
-    cudaFree(dcount);
-    cudaFree(dflags);
     CU(cudaGetLastError());
-    // monotone rowptr is implied by non-negative row lengths; check on the host (cheap, D+1 ints)
-    for (long long d = 0; d < D; ++d)
-        if (rowptr[d + 1] < rowptr[d]) return fail(h, MMSIG_EINVAL, "rowptr not monotone");
-    if (flags & 1) return fail(h, MMSIG_EINVAL, "term index out of range [0, V)");
-    if (flags & 2) return fail(h, MMSIG_EINVAL, "count must be > 0 (zeros are dropped by format_counts_*)");
-    if (flags & 4) return fail(h, MMSIG_EINVAL, "terms of a row must be strictly ascending (as format_counts_* produces)");
-    long long ntot = 0;
-    for (long long w = 0; w < nnz; ++w) ntot += count[w];
-    *d_rowptr = drp;
-    *d_rec = drec;
-    *nnz_out = nnz;
-    *ntot_out = ntot;
+    if (hf[0] & 1) return fail(h, MMSIG_EINVAL, "term index out of range [0, V)");
+    if (hf[0] & 2) return fail(h, MMSIG_EINVAL, "count must be > 0 (zeros are dropped by format_counts_*)");
+    if (hf[0] & 4) return fail(h, MMSIG_EINVAL, "terms of a row must be strictly ascending (as format_counts_* produces)");
+    unsigned long long nt;
+    memcpy(&nt, hf + 2, 8);
+    *ntot_out = (long long)nt;
     return 0;
 }
 
@@ -459,6 +467,34 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
     if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
     CU(cudaSetDevice(h->device));
+    int MKsum = 0;
+    for (int m = 0; m < M; ++m) {
+        NEED(K[m] >= 1 && V[m] >= 1, "K[m], V[m] must be >= 1");
+        if (K[m] > 32) return fail(h, MMSIG_ELIMIT, "K[m] <= 32 supported");
+        NEED(rowptr[m], "null rowptr");
+        MKsum += K[m];
+    }
+    if (MKsum > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 32 supported (one coordinate per lane)");
+    // same shape as what is already resident (a repeated fit! on the same corpus): keep every
+    // allocation and launch plan, only refresh the counts
+    bool same = h->mm.has_data && h->mm.p.M == M && h->mm.p.D == D && h->mm.p.D_total == D_total;
+    for (int m = 0; same && m < M; ++m)
+        same = h->mm.p.K[m] == K[m] && h->mm.p.V[m] == V[m] && h->mm.cb[m].nnz == rowptr[m][D];
+    int rc;
+    long long ntot[MAXM];
+    if (same) {
+        MmctmHost &mm = h->mm;
+        mm.has_state = false;
+        for (int m = 0; m < M; ++m)
+            if ((rc = upload_counts(h, h->allocs_mm, mm.cb[m], D, V[m], M, m, rowptr[m], term[m], count[m],
+                                    const_cast<double *>(mm.p.N), &ntot[m]))) {
+                mm.has_data = false;
+                return rc;
+            }
+        if ((rc = allsum_ll(h, ntot, M))) return rc;
+        for (int m = 0; m < M; ++m) mm.p.Ntot[m] = (double)ntot[m];
+        return 0;
+    }
     free_pool(h->allocs_mm);
     h->mm = MmctmHost();
     MmctmHost &mm = h->mm;
@@ -470,8 +506,6 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     p.koff[0] = 0;
     p.goff[0] = 0;
     for (int m = 0; m < M; ++m) {
-        NEED(K[m] >= 1 && V[m] >= 1, "K[m], V[m] must be >= 1");
-        if (K[m] > 32) return fail(h, MMSIG_ELIMIT, "K[m] <= 32 supported");
         p.K[m] = K[m];
         p.V[m] = V[m];
         p.koff[m + 1] = p.koff[m] + K[m];
@@ -479,17 +513,17 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     }
     p.MK = p.koff[M];
     mm.G = p.goff[M];
-    if (p.MK > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 32 supported (one coordinate per lane)");
-    int rc;
     double *dN = nullptr;
     if ((rc = dev_alloc(h, h->allocs_mm, &dN, (size_t)D * M))) return rc;
     p.N = dN;
-    long long ntot[MAXM];
     mm.nnz.resize(M);
-    for (int m = 0; m < M; ++m)
-        if ((rc = upload_counts(h, h->allocs_mm, D, V[m], M, m, rowptr[m], term[m], count[m], &p.rowptr[m], &p.rec[m],
-                                dN, &mm.nnz[m], &ntot[m])))
+    for (int m = 0; m < M; ++m) {
+        if ((rc = upload_counts(h, h->allocs_mm, mm.cb[m], D, V[m], M, m, rowptr[m], term[m], count[m], dN, &ntot[m])))
             return rc;
+        p.rowptr[m] = mm.cb[m].rowptr;
+        p.rec[m] = mm.cb[m].rec;
+        mm.nnz[m] = mm.cb[m].nnz;
+    }
     if ((rc = allsum_ll(h, ntot, M))) return rc;
     for (int m = 0; m < M; ++m) p.Ntot[m] = (double)ntot[m];
 
@@ -566,6 +600,7 @@ extern "C" int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, c
     MmctmDev &p = mm.p;
     const size_t DMK = (size_t)p.D * p.MK, MK2 = (size_t)p.MK * p.MK;
     for (int m = 0; m < p.M; ++m) NEED(alpha[m] > 0, "alpha must be > 0");
+    mm.alpha_host.assign(alpha, alpha + p.M);
     CU(cudaMemcpyAsync(p.alpha, alpha, p.M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(p.gamma, gamma, mm.G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     if (lambda) CU(cudaMemcpyAsync(p.lam, lambda, DMK * sizeof(double), cudaMemcpyHostToDevice, h->stream));
@@ -725,16 +760,15 @@ extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double
     CU(d2h(Elnphi, p.Elnphi, mm.G));
     CU(d2h(phi, p.phi, mm.G));
     if (props) {
-        // sumtheta is not needed once the iteration is over only if the ELBO is not wanted: use a scratch
-        double *scratch = nullptr;
-        CU(cudaMalloc(&scratch, DMK * sizeof(double)));
+        if (!mm.props_scratch) {
+            int rc = dev_alloc(h, h->allocs_mm, &mm.props_scratch, DMK);
+            if (rc) return rc;
+        }
         {
             LaunchScope ls(h, "k_props");
-            k_props<<<mm.grid_solve, 256, 0, h->stream>>>(p, scratch);
+            k_props<<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.props_scratch);
         }
-        CU(cudaMemcpyAsync(props, scratch, DMK * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
-        cudaFree(scratch);
+        CU(cudaMemcpyAsync(props, mm.props_scratch, DMK * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
@@ -783,6 +817,90 @@ extern "C" int32_t mmsig_mmctm_elbo(mmsig_handle *h, double *elbo, double *terms
     NEED(mm.has_state, "mmsig_mmctm_set_state first");
     CU(cudaSetDevice(h->device));
     return mmctm_elbo_impl(h, elbo, terms);
+}
+
+// ---- test hook -----------------------------------------------------------------------------------
+__global__ void k_debug_math(int fn, long long n, const double *x, double *y) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        y[i] = fn == 0 ? det_exp(x[i]) : fn == 1 ? det_log(x[i]) : det_digamma(x[i]);
+}
+extern "C" int32_t mmsig_debug_math(mmsig_handle *h, int32_t fn, int64_t n, const double *x, double *y) {
+    NEED(h && x && y && n >= 0 && fn >= 0 && fn <= 2, "bad argument");
+    CU(cudaSetDevice(h->device));
+    double *dx = nullptr, *dy = nullptr;
+    CU(cudaMalloc(&dx, std::max<int64_t>(n, 1) * sizeof(double)));
+    CU(cudaMalloc(&dy, std::max<int64_t>(n, 1) * sizeof(double)));
+    CU(cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, "k_debug_math");
+        k_debug_math<<<h->numSM, 256, 0, h->stream>>>(fn, n, dx, dy);
+    }
+    CU(cudaMemcpyAsync(y, dy, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaFree(dx);
+    cudaFree(dy);
+    CU(cudaGetLastError());
+    return 0;
+}
+
+// ---- restarts (config 5) ----------------------------------------------------------------------
+extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double *gamma0, int32_t maxiter, double tol,
+                                        uint32_t flags, double *elbo_out, double *ll_out, int32_t *n_iter_out,
+                                        int32_t *best) {
+    NEED(h, "null handle");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_state, "mmsig_mmctm_set_state first (it provides alpha)");
+    NEED(R >= 1 && gamma0 && maxiter >= 1, "R >= 1, gamma0 and maxiter >= 1 required");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    const size_t DMK = (size_t)p.D * p.MK, G = mm.G, MK2 = (size_t)p.MK * p.MK, DM = (size_t)p.D * p.M;
+    // snapshot buffers for the best restart
+    struct Snap { double **live; size_t n; double *copy; };
+    std::vector<Snap> snaps = {{&p.lam, DMK, nullptr}, {&p.lam_prev, DMK, nullptr}, {&p.nu, DMK, nullptr},
+                               {&p.sumtheta, DMK, nullptr}, {&p.zeta, DM, nullptr}, {&p.gamma, G, nullptr},
+                               {&p.Elnphi, G, nullptr}, {&p.Elnphi_prev, G, nullptr}, {&p.phi, G, nullptr},
+                               {&p.stats, G, nullptr}, {&p.mu, (size_t)p.MK, nullptr}, {&p.Sigma, MK2, nullptr},
+                               {&p.invSigma, MK2, nullptr}};
+    auto free_snaps = [&]() { for (auto &s : snaps) if (s.copy) cudaFree(s.copy); };
+    if (R > 1)
+        for (auto &s : snaps)
+            if (cudaMalloc(&s.copy, std::max<size_t>(s.n, 1) * sizeof(double)) != cudaSuccess) {
+                free_snaps();
+                return fail(h, MMSIG_ENOMEM, "cudaMalloc (restart snapshot)");
+            }
+    std::vector<double> hist((size_t)maxiter * p.M);
+    std::vector<double> alpha = mm.alpha_host;
+    int best_r = -1;
+    double best_e = 0.0;
+    int rc = 0;
+    for (int r = 0; r < R && !rc; ++r) {
+        rc = mmsig_mmctm_set_state(h, alpha.data(), gamma0 + (size_t)r * G, nullptr, nullptr, nullptr, nullptr, nullptr);
+        if (rc) break;
+        int nit = 0, conv = 0;
+        rc = mmsig_mmctm_fit(h, maxiter, tol, flags, hist.data(), &nit, &conv);
+        if (rc) break;
+        double e = 0.0;
+        rc = mmsig_mmctm_elbo(h, &e, nullptr);
+        if (rc) break;
+        if (elbo_out) elbo_out[r] = e;
+        if (n_iter_out) n_iter_out[r] = nit;
+        if (ll_out) memcpy(ll_out + (size_t)r * p.M, hist.data() + (size_t)(nit - 1) * p.M, p.M * sizeof(double));
+        if (best_r < 0 || e > best_e || best_e != best_e) {           // arg-max ELBO, first wins ties
+            best_r = r;
+            best_e = e;
+            if (R > 1)
+                for (auto &s : snaps)
+                    cudaMemcpyAsync(s.copy, *s.live, s.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        }
+    }
+    if (!rc && R > 1 && best_r != R - 1)
+        for (auto &s : snaps) cudaMemcpyAsync(*s.live, s.copy, s.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+    cudaStreamSynchronize(h->stream);
+    free_snaps();
+    if (rc) return rc;
+    CU(cudaGetLastError());
+    if (best) *best = best_r;
+    return 0;
 }
 
 #include "lda_api.inl"

@@ -102,6 +102,20 @@ class MMCTM:
         self.ll = hist[-1].copy()                     # :491
         return hist
 
+    def fit_restarts(self, gamma0s, maxiter=100, tol=1e-4, updateSigma=True):
+        """R independent restarts from the constructor state with gamma0s[r] on the resident counts;
+        keeps the best-ELBO fit in the model (README.md:42; scripts/run_mmctm.jl:77-111).
+        Returns (elbo[R], ll[R, M], n_iter[R], best)."""
+        g = capi.f64(np.asarray(gamma0s, dtype=np.float64).reshape(-1, self.G))
+        R = g.shape[0]
+        elbo, ll = np.zeros(R), np.zeros((R, self.M))
+        nit, best = np.zeros(R, np.int32), C.c_int32()
+        self.h.check(self.h.lib.mmsig_mmctm_restarts(
+            self.h.h, R, capi.dp(g), maxiter, tol, capi.FLAG_UPDATE_SIGMA if updateSigma else 0,
+            capi.dp(elbo), capi.dp(ll), nit.ctypes.data_as(capi.c_i32p), C.byref(best)))
+        self.elbo, self.ll = float(elbo[best.value]), ll[best.value].copy()
+        return elbo, ll, nit, best.value
+
     def calculate_elbo(self):
         e = C.c_double()
         t = np.zeros(7)

@@ -171,3 +171,29 @@ def test_bad_input_is_rejected():
         mmsig.MMCTM([2], [0.1], [(rp, np.array([0, 1, 1], np.int32), np.array([1, 0, 1], np.int32))], V=[4])
     with pytest.raises(mmsig.capi.MmsigError):          # sum(K) > 32
         mmsig.MMCTM([20, 20], [0.1, 0.1], [(rp, np.array([0, 1, 1], np.int32), np.array([1, 1, 1], np.int32))] * 2, V=[4, 4])
+
+
+def test_restarts_config5_shape():
+    """config 5 (shape): independent restarts on resident counts, arg-max ELBO; the handle ends up
+    holding the best restart's state."""
+    K, V, D, R = [7, 7], [96, 32], 400, 4
+    counts = small_synth(D, K, V)
+    rng = np.random.default_rng(5)
+    g0s = rng.integers(1, 101, size=(R, sum(k * v for k, v in zip(K, V)))).astype(float)
+    g = mmsig.MMCTM(K, [0.1, 0.1], counts, V=V, gamma0=g0s[0])
+    elbo, ll, nit, best = g.fit_restarts(g0s, maxiter=12, tol=1e-4)
+    eo, states = [], []
+    for r in range(R):
+        o = oracle_mmctm(K, [0.1, 0.1], V, counts, g0s[r])
+        h = o.fit(maxiter=12, tol=1e-4)
+        eo.append(o.elbo()[0])
+        states.append((o.lam.copy(), o.phi.copy(), h[-1].copy(), len(h)))
+    eo = np.asarray(eo)
+    assert rel_err(elbo, eo) <= TOL_ITER
+    assert best == int(np.argmax(eo))
+    assert np.array_equal(nit, [s[3] for s in states])
+    s = g.state()
+    assert np.array_equal(s["lam"], states[best][0]) and np.array_equal(s["phi"], states[best][1])
+    assert np.array_equal(ll[best], states[best][2]) and np.array_equal(g.ll, states[best][2])
+    assert abs(g.calculate_elbo()[0] - eo[best]) <= TOL_ITER * abs(eo[best])
+    g.close()
