@@ -135,8 +135,9 @@ __global__ void __launch_bounds__(256) k_elbo_qz(MmctmDev p, int m, double2 *par
             double Z = 0.0;
             for (int k = 0; k < K; ++k) Z += det_exp(p.lam_prev[d * p.MK + off + k] + Eln[k * V + r.x]);
             double s = 0.0;
+            const double rz = 1.0 / Z;
             for (int k = 0; k < K; ++k) {
-                const double th = det_exp(p.lam_prev[d * p.MK + off + k] + Eln[k * V + r.x]) / Z;
+                const double th = det_exp(p.lam_prev[d * p.MK + off + k] + Eln[k * V + r.x]) * rz;
                 if (th > 0.0) s += th * det_log(th);
             }
             dd_add(hi[0], lo[0], (double)r.y * s);

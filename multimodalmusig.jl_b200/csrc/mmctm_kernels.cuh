@@ -17,6 +17,13 @@ namespace mmsig {
 constexpr int MAXM = 8;          // modalities
 constexpr int MAXMK = 32;        // ΣK_m: one coordinate per lane
 constexpr int MMA_MAXEVAL = 10000;
+#ifndef MATVEC_UNROLL
+#define MATVEC_UNROLL 4
+#endif
+constexpr int kMatvecUnroll = MATVEC_UNROLL;
+#ifndef SOLVE_MIN_BLOCKS
+#define SOLVE_MIN_BLOCKS 4
+#endif
 
 struct MmctmDev {
     int M, MK;
@@ -37,7 +44,7 @@ struct MmctmDev {
 // ------------------------------------------------------------------------------------------
 // θ pass of one modality (src/MMCTM.jl:183-198, :110-117, :224-240).  One warp per sample,
 // lane <-> nonzero w.  Per nonzero: e_k = exp(λ_k + Elnϕ[k][v]), Z = Σ_k e_k (index order),
-// θ_k = e_k / Z, addend a = θ_k n.  Σ_w a -> sumθ[d][k]; Σ_d a -> this warp's private
+// θ_k = e_k (1/Z), addend a = θ_k n.  Σ_w a -> sumθ[d][k]; Σ_d a -> this warp's private
 // double-double K x V table in shared memory (a row's terms are distinct, so lanes never
 // collide).  Nothing of size K x nnz is ever stored.
 // ------------------------------------------------------------------------------------------
@@ -80,10 +87,11 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
                     e[k] = det_exp(lamk[k] + Eln[k * V + v]);
                     Z += e[k];
                 }
+            const double rz = 1.0 / Z;                 // DET: θ_k = e_k * (1/Z), one division per nonzero
 #pragma unroll
             for (int k = 0; k < KP; ++k)
                 if (k < K) {
-                    const double a = (e[k] / Z) * n;
+                    const double a = (e[k] * rz) * n;
                     dd_add(thi[k * V + v], tlo[k * V + v], a);
                     dd_add(shi[k], slo[k], a);
                 }
@@ -127,7 +135,7 @@ struct SolveCtx {
 // division takes a ~65-instruction slow path for zero / subnormal operands, and a warp pays
 // for it if any lane does); their terms are masked out of every reduction.
 template <int MKP, bool IS_NU>
-__device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, const double (&Srow)[MKP],
+__device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, const double *__restrict__ ST,
                                                double *dsh, int lane, double &t, double &g) {
     double grad;
     if (IS_NU) {
@@ -142,11 +150,11 @@ __device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, cons
         if (lane < MKP) dsh[lane] = c.active ? diff : 0.0;
         __syncwarp();
         double q = 0.0;
-#pragma unroll
+#pragma unroll kMatvecUnroll
         for (int i = 0; i < MKP; i += 2) {
             const double2 dv = *reinterpret_cast<const double2 *>(dsh + i);
-            q = fma(Srow[i], dv.x, q);
-            q = fma(Srow[i + 1], dv.y, q);
+            q = fma(ST[i * 32 + lane], dv.x, q);          // ST[i][j] = invΣ[j][i]: conflict-free
+            q = fma(ST[(i + 1) * 32 + lane], dv.y, q);
         }
         __syncwarp();
         const double ce = c.c * e;
@@ -159,7 +167,7 @@ __device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, cons
 }
 
 template <int MKP, bool IS_NU>
-__device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const double (&Srow)[MKP],
+__device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const double *__restrict__ ST,
                                          double *dsh, int lane, int stop_rule) {
     const double lb = IS_NU ? 1e-7 : -__longlong_as_double(0x7ff0000000000000LL);
     const double xtol_rel = 1e-4, xtol_abs = 1e-4;
@@ -168,7 +176,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
     double g, fmin, fcur, gcur;
     {
         double t;
-        mma_eval_local<MKP, IS_NU>(x, c, Srow, dsh, lane, t, g);
+        mma_eval_local<MKP, IS_NU>(x, c, ST, dsh, lane, t, g);
         fmin = -warp_tree_sum(t);
     }
     int nev = 1;
@@ -198,7 +206,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             xcur = xc;
             // the new point's lane-local work first, then ONE 3-way butterfly for gval, wval, f
             double t;
-            mma_eval_local<MKP, IS_NU>(xcur, c, Srow, dsh, lane, t, gcur);
+            mma_eval_local<MKP, IS_NU>(xcur, c, ST, dsh, lane, t, gcur);
             warp_tree_sum3(gterm, wterm, t);
             const double gval = fmin + gterm, wval = wterm;
             fcur = -t;
@@ -250,9 +258,10 @@ __device__ __forceinline__ double block_sum_seq(double e, int lo, int hi, int MK
 // partial: [gridDim.x][2*MK] dd of Σ_d λ_new and Σ_d ν_new.
 // ------------------------------------------------------------------------------------------
 template <int MKP>
-__global__ void __launch_bounds__(256) k_solve(MmctmDev p, double2 *partial) {
+__global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, double2 *partial) {
     __shared__ double dsh_all[8][MKP];
     __shared__ double2 red[8][2][32];
+    __shared__ double ST[MKP * 32];          // invΣ transposed, zero padded: ST[i*32+j] = invΣ[j][i]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MK = p.MK, M = p.M;
     double *dsh = dsh_all[warp];
@@ -263,9 +272,11 @@ __global__ void __launch_bounds__(256) k_solve(MmctmDev p, double2 *partial) {
         if (lane >= p.koff[m]) mod = m;
     const int blo = p.koff[mod], bhi = p.koff[mod + 1];
 
-    double Srow[MKP];
-#pragma unroll
-    for (int i = 0; i < MKP; ++i) Srow[i] = (active && i < MK) ? p.invSigma[lane * MK + i] : 0.0;
+    for (int t = threadIdx.x; t < MKP * 32; t += blockDim.x) {
+        const int i = t >> 5, j = t & 31;
+        ST[t] = (i < MK && j < MK) ? p.invSigma[j * MK + i] : 0.0;
+    }
+    __syncthreads();
     SolveCtx c;
     c.active = active;
     c.Sjj = active ? p.invSigma[lane * MK + lane] : 0.0;
@@ -286,10 +297,10 @@ __global__ void __launch_bounds__(256) k_solve(MmctmDev p, double2 *partial) {
         if (active && lane == blo) p.zeta[d * M + mod] = zeta;
         // ν
         c.other = lam;
-        const int nev_nu = mma_solve<MKP, true>(nu, c, Srow, dsh, lane, p.stop_rule);
+        const int nev_nu = mma_solve<MKP, true>(nu, c, ST, dsh, lane, p.stop_rule);
         // λ (new ν, old ζ)
         c.other = 0.5 * nu;
-        const int nev_lam = mma_solve<MKP, false>(lam, c, Srow, dsh, lane, p.stop_rule);
+        const int nev_lam = mma_solve<MKP, false>(lam, c, ST, dsh, lane, p.stop_rule);
         if (active) {
             p.lam[base] = lam;
             p.nu[base] = nu;
@@ -316,6 +327,7 @@ struct CombineSegs {
     int nseg;
     const double2 *src[MAXM + 2];
     int nparts[MAXM + 2], n[MAXM + 2], dst_off[MAXM + 2];
+    int stride[MAXM + 2];        // distance between parts in src (0 = n)
 };
 __global__ void k_combine(CombineSegs s, double2 *dst) {
     const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -324,8 +336,9 @@ __global__ void k_combine(CombineSegs s, double2 *dst) {
         if (t < base + s.n[g]) {
             const int i = t - base;
             double hi = 0.0, lo = 0.0;
+            const int stride = s.stride[g] ? s.stride[g] : s.n[g];
             for (int part = 0; part < s.nparts[g]; ++part) {
-                const double2 v = s.src[g][(size_t)part * s.n[g] + i];
+                const double2 v = s.src[g][(size_t)part * stride + i];
                 dd_merge(hi, lo, v.x, v.y);
             }
             dst[s.dst_off[g] + i] = make_double2(hi, lo);
@@ -413,8 +426,8 @@ __global__ void __launch_bounds__(1024) k_elnphi(MmctmDev p) {
 // (:145-154) and the per-modality log-likelihood (:384-448), lane <-> nonzero.
 // partial: [gridDim.x][MK*MK + M] dd.
 // ------------------------------------------------------------------------------------------
-template <int MKP>
-__global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int do_moments, double *props_out) {
+template <int MKP, bool DO_MOMENTS, bool DO_LL>
+__global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, double *props_out) {
     extern __shared__ double smem[];
     const int G = p.goff[p.M], MK = p.MK, M = p.M;
     double2 *red = reinterpret_cast<double2 *>(smem);      // 256 double2 = 512 doubles
@@ -422,7 +435,8 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int 
     double *psh_all = phi + G;                            // 8 x 32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *psh = psh_all + warp * 32;
-    for (int i = threadIdx.x; i < G; i += blockDim.x) phi[i] = p.phi[i];
+    if (DO_LL)
+        for (int i = threadIdx.x; i < G; i += blockDim.x) phi[i] = p.phi[i];
     __syncthreads();
     const bool active = lane < MK;
     int mod = 0;
@@ -431,9 +445,10 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int 
     const int blo = p.koff[mod], bhi = p.koff[mod + 1];
     const double muj = active ? p.mu[lane] : 0.0;
 
-    double mhi[MKP], mlo[MKP];
+    constexpr int NM = DO_MOMENTS ? MKP : 1;
+    double mhi[NM], mlo[NM];
 #pragma unroll
-    for (int i = 0; i < MKP; ++i) { mhi[i] = 0.0; mlo[i] = 0.0; }
+    for (int i = 0; i < NM; ++i) { mhi[i] = 0.0; mlo[i] = 0.0; }
     double llh[MAXM], lll[MAXM];
 #pragma unroll
     for (int m = 0; m < MAXM; ++m) { llh[m] = 0.0; lll[m] = 0.0; }
@@ -441,14 +456,15 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int 
     const long long nw = (long long)gridDim.x * 8;
     for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
         const double lam = active ? p.lam[d * MK + lane] : 0.0;
-        if (do_moments) {
+        if (DO_MOMENTS) {
             const double diff = lam - muj;
 #pragma unroll
-            for (int i = 0; i < MKP; ++i) {
+            for (int i = 0; i < NM; ++i) {
                 const double di = shfl_d(diff, i);
                 if (i < MK) dd_add(mhi[i], mlo[i], diff * di);
             }
         }
+        if (!DO_LL) continue;
         // props
         const double e = active ? det_exp(lam) : 0.0;
         const double s = block_sum_seq(e, blo, bhi, MK);
@@ -485,7 +501,7 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int 
     __syncthreads();
     double2 *out = partial + (size_t)blockIdx.x * (MK * MK + M);
 #pragma unroll
-    for (int i = 0; i < MKP; ++i) {
+    for (int i = 0; i < (DO_MOMENTS ? MKP : 0); ++i) {
         red[warp * 32 + lane] = make_double2(mhi[i], mlo[i]);
         __syncthreads();
         if (warp == 0 && active && i < MK) {
@@ -495,7 +511,7 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, int 
         }
         __syncthreads();
     }
-    for (int m = 0; m < M; ++m) {
+    for (int m = 0; m < (DO_LL ? M : 0); ++m) {
         if (lane == 0) red[warp] = make_double2(llh[m], lll[m]);
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -661,7 +677,8 @@ __global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *ou
                 out[w * K + k] = e;
                 Z += e;
             }
-            for (int k = 0; k < K; ++k) out[w * K + k] = out[w * K + k] / Z;
+            const double rz = 1.0 / Z;
+            for (int k = 0; k < K; ++k) out[w * K + k] = out[w * K + k] * rz;
         }
     }
 }

@@ -80,7 +80,8 @@ struct MmctmHost {
     std::vector<long long> nnz;
     int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0};
     size_t smem_theta[MAXM] = {0};
-    int grid_solve = 0, grid_post = 0;
+    int grid_solve = 0, grid_post = 0, grid_mom = 0;
+    double2 *part_mom = nullptr;
     size_t smem_post = 0;
     double2 *part_theta[MAXM] = {nullptr};
     double2 *part_solve = nullptr, *part_post = nullptr, *part_elbo = nullptr;
@@ -565,13 +566,19 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
         mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
         mm.smem_post = (size_t)(512 + mm.G + 256) * sizeof(double);
         if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
-        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP>)));
-        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP>, 256, mm.smem_post)));
+        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, true, false>)));
+        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, false, true>)));
+        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP, false, true>, 256, mm.smem_post)));
         mm.grid_post = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP, true, false>, 256, mm.smem_post)));
+        mm.grid_mom = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
     }
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + M;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_solve, (size_t)mm.grid_solve * 2 * p.MK))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_post, (size_t)mm.grid_post * P2))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_mom, (size_t)mm.grid_mom * P2))) return rc;
+    CU(cudaMemsetAsync(mm.part_post, 0, (size_t)mm.grid_post * P2 * sizeof(double2), h->stream));
+    CU(cudaMemsetAsync(mm.part_mom, 0, (size_t)mm.grid_mom * P2 * sizeof(double2), h->stream));
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_elbo, (size_t)mm.grid_post * 8))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.rank_p1, (size_t)P1))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.gath_p1, (size_t)P1 * h->nranks))) return rc;
@@ -668,17 +675,28 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
         LaunchScope ls(h, "k_mstep1");
         k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks);
     }
-    {
-        LaunchScope ls(h, "k_post");
-        MK_DISPATCH(p.MK, (k_post<MKP><<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post, do_sigma, nullptr)));
+    if (do_sigma) {
+        LaunchScope ls(h, "k_moments");
+        MK_DISPATCH(p.MK, (k_post<MKP, true, false><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom, nullptr)));
     }
     {
+        LaunchScope ls(h, "k_loglik");
+        MK_DISPATCH(p.MK, (k_post<MKP, false, true><<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post, nullptr)));
+    }
+    {
+        // moments (first MK*MK entries) from the moments pass, LL (last M) from the LL pass
         CombineSegs s{};
-        s.nseg = 1;
-        s.src[0] = mm.part_post;
-        s.nparts[0] = mm.grid_post;
-        s.n[0] = P2;
+        s.nseg = 2;
+        s.src[0] = mm.part_mom;
+        s.nparts[0] = do_sigma ? mm.grid_mom : 0;
+        s.n[0] = p.MK * p.MK;
         s.dst_off[0] = 0;
+        s.stride[0] = P2;
+        s.src[1] = mm.part_post + p.MK * p.MK;
+        s.nparts[1] = mm.grid_post;
+        s.n[1] = p.M;
+        s.dst_off[1] = p.MK * p.MK;
+        s.stride[1] = P2;
         LaunchScope ls(h, "k_combine");
         k_combine<<<(P2 + 127) / 128, 128, 0, h->stream>>>(s, mm.rank_p2);
     }

@@ -44,9 +44,10 @@
  *         gval / wval, the x-tolerance norms): a fixed 32-leaf binary tree
  *         (tree_sum32); mat-vec rows: one fma chain in index order;
  *     (3) sums over data items (nonzeros w of a row, samples d): the
- *         EXACTLY ROUNDED sum of the same addends the literal code adds --
- *         order independent by definition, so it is also independent of how
- *         samples are sharded over warps, blocks or GPUs.
+ *         EXACTLY ROUNDED sum of the addends -- order independent by
+ *         definition, so it is also independent of how samples are sharded
+ *         over warps, blocks or GPUs;
+ *     (4) theta_k = e_k * (1/Z) (one division per nonzero) instead of e_k / Z.
  *   Nothing else changes.  tests/ check LITERAL against the reference's
  *   known-answer tests, DET against LITERAL (agreement to ~1e-13 wherever no
  *   MMA branch flips), and the CUDA path against DET.
@@ -690,7 +691,11 @@ void orc_mmctm_update_theta(orc_mmctm *m, int64_t d)
                 th[k] = xexp(m->arith, lam[off + k] + Eln[(size_t)k * V + v]);
                 s += th[k];
             }
-            for (int k = 0; k < K; ++k) th[k] /= s;
+            if (m->arith) {     /* DET: theta_k = e_k * (1/Z), one division per nonzero */
+                double rz = 1.0 / s;
+                for (int k = 0; k < K; ++k) th[k] = th[k] * rz;
+            } else
+                for (int k = 0; k < K; ++k) th[k] /= s;
         }
     }
 }
