@@ -27,22 +27,6 @@ struct LdaDev {
     double *gamma, *gamma_next;  // D x K, [d][k]
 };
 
-template <int N>
-__device__ __forceinline__ void warp_multi_reduce(double (&v)[N], int lane) {
-    int off = 16;
-#pragma unroll
-    for (int half = N / 2; half >= 1; half >>= 1, off >>= 1) {
-        const bool upper = (lane & off) != 0;
-#pragma unroll
-        for (int i = 0; i < half; ++i) {
-            const double send = upper ? v[i] : v[i + half];
-            const double keep = upper ? v[i + half] : v[i];
-            v[i] = keep + shfl_xor_d(send, off);
-        }
-    }
-    for (; off >= 1; off >>= 1) v[0] = v[0] + shfl_xor_d(v[0], off);
-}
-
 // Elnθ of one sample on lanes k < K (all lanes get ψ(Σγ) consistently)
 __device__ __forceinline__ double lda_elntheta(double gk, int K, int lane) {
     double s = 0.0;

@@ -71,9 +71,9 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
 #pragma unroll
             for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
         }
-        double shi[NP], slo[NP];
+        double sth[NP];                     // Σ_w a_kw of this lane's nonzeros (w ≡ lane mod 32)
 #pragma unroll
-        for (int k = 0; k < NP; ++k) { shi[k] = 0.0; slo[k] = 0.0; }
+        for (int k = 0; k < NP; ++k) sth[k] = 0.0;
         const long long beg = rowptr[d], end = rowptr[d + 1];
         for (long long w = beg + lane; w < end; w += 32) {
             const int2 r = rec[w];
@@ -93,15 +93,15 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
                 if (k < K) {
                     const double a = (e[k] * rz) * n;
                     dd_add(thi[k * V + v], tlo[k * V + v], a);
-                    dd_add(shi[k], slo[k], a);
+                    sth[k] += a;
                 }
         }
         __syncwarp();
-        warp_multi_reduce_dd<NP>(shi, slo, lane);
+        // the butterfly tree over lanes (recursive halving computes exactly its partial sums)
+        warp_multi_reduce<NP>(sth, lane);
         const int idx = warp_multi_index<NP>(lane);
         constexpr int GROUP = 32 / NP;            // lanes sharing one index
-        if (idx < K && (lane & (GROUP - 1)) == 0)
-            p.sumtheta[d * p.MK + off + idx] = dd_round(shi[0], slo[0]);
+        if (idx < K && (lane & (GROUP - 1)) == 0) p.sumtheta[d * p.MK + off + idx] = sth[0];
     }
     __syncthreads();
     // block partial: warps' tables merged in warp order
@@ -207,15 +207,15 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             // the new point's lane-local work first, then ONE 3-way butterfly for gval, wval, f
             double t;
             mma_eval_local<MKP, IS_NU>(xcur, c, ST, dsh, lane, t, gcur);
-            warp_tree_sum3(gterm, wterm, t);
+            warp_tree_sum3h(gterm, wterm, t, lane);
             const double gval = fmin + gterm, wval = wterm;
             fcur = -t;
             ++nev;
-            const bool inner_done = gval >= fcur;
+            const bool inner_done = __all_sync(FULLMASK, gval >= fcur);   // identical in all lanes; the vote tells the compiler so
             if (fcur < fmin) { fmin = fcur; x = xcur; g = gcur; }
-            if (nev >= MMA_MAXEVAL) return nev;
+            if (nev >= MMA_MAXEVAL) return nev;           // nev is lane-invariant
             if (inner_done) break;
-            if (fcur > gval) {
+            if (__all_sync(FULLMASK, fcur > gval)) {
                 const double r1 = 10 * rho, r2 = 1.1 * (rho + (fcur - gval) / wval);
                 rho = r1 < r2 ? r1 : r2;
             }
@@ -229,7 +229,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
         } else {                    // NLopt >= 2.7: L1 norms, else all |dx| <= xtol_abs
             double dn = ad, xn = c.active ? fabs(xcur) : 0.0;
             warp_tree_sum2(dn, xn);
-            stop = (dn <= xtol_rel * xn) || __all_sync(FULLMASK, !(ad > xtol_abs));
+            stop = __all_sync(FULLMASK, dn <= xtol_rel * xn) || __all_sync(FULLMASK, !(ad > xtol_abs));
         }
         if (stop) break;
         rho = 0.1 * rho > 1e-5 ? 0.1 * rho : 1e-5;
@@ -481,16 +481,15 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, doub
                     const int K = p.K[m], V = p.V[m], ko = p.koff[m];
                     const double *ph = phi + p.goff[m];
                     const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
-                    double hi = 0.0, lo = 0.0;
+                    double rs = 0.0;
                     for (long long w = beg + lane; w < end; w += 32) {
                         const int2 r = p.rec[m][w];
                         double pw = 0.0;
                         for (int k = 0; k < K; ++k) pw += psh[ko + k] * ph[k * V + r.x];
-                        dd_add(hi, lo, (double)r.y * det_log(pw));
+                        rs += (double)r.y * det_log(pw);
                     }
                     __syncwarp();
-                    warp_dd_allreduce(hi, lo);
-                    double dl = dd_round(hi, lo);
+                    double dl = warp_tree_sum(rs);             // row sum: leaf = w mod 32, butterfly
                     dl = dl / docN;
                     dd_add(llh[m], lll[m], dl * docN);     // identical in every lane
                 }

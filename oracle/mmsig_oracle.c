@@ -43,10 +43,12 @@
  *     (2) sums over the MK coordinates of one sample (objective values, MMA's
  *         gval / wval, the x-tolerance norms): a fixed 32-leaf binary tree
  *         (tree_sum32); mat-vec rows: one fma chain in index order;
- *     (3) sums over data items (nonzeros w of a row, samples d): the
- *         EXACTLY ROUNDED sum of the addends -- order independent by
- *         definition, so it is also independent of how samples are sharded
- *         over warps, blocks or GPUs;
+ *     (3) sums over the nonzeros w of ONE row (sum-theta, the row's
+ *         log-likelihood): the same tree, leaf = w mod 32;
+ *         sums over SAMPLES d (topic-term statistics, sum lambda, sum nu,
+ *         the covariance moments, the LL totals): the EXACTLY ROUNDED sum
+ *         of the addends -- order independent by definition, so independent
+ *         of how samples are sharded over warps, blocks or GPUs;
  *     (4) theta_k = e_k * (1/Z) (one division per nonzero) instead of e_k / Z.
  *   Nothing else changes.  tests/ check LITERAL against the reference's
  *   known-answer tests, DET against LITERAL (agreement to ~1e-13 wherever no
@@ -706,11 +708,12 @@ void orc_mmctm_calc_sumtheta(const orc_mmctm *m, int64_t d, double *out)
     for (int i = 0; i < m->M; ++i) {
         int K = m->K[i], off = m->koff[i];
         for (int k = 0; k < K; ++k) {
-            if (m->arith) {     /* DET: exactly rounded sum of the same addends */
-                dd_t a = {0.0, 0.0};
-                for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w)
-                    dd_add(&a, m->theta[i][(size_t)w * K + k] * (double)m->cnt[i][w]);
-                out[off + k] = dd_round(a);
+            if (m->arith) {     /* DET: the row's addends through the fixed tree (leaf = w mod 32) */
+                int64_t b = m->rowptr[i][d], n = m->rowptr[i][d + 1] - b;
+                double t[n ? n : 1];
+                for (int64_t w = 0; w < n; ++w)
+                    t[w] = m->theta[i][(size_t)(b + w) * K + k] * (double)m->cnt[i][b + w];
+                out[off + k] = tree_sum32(t, (int)n);
                 continue;
             }
             double s = 0.0;
@@ -965,15 +968,16 @@ void orc_mmctm_loglikelihoods(const orc_mmctm *m, double *ll)
             if (docN > 0) {
                 const double *p = m->props + (size_t)d * m->MK + m->koff[i];
                 double dl = 0.0;
-                dd_t dl_dd = {0.0, 0.0};
+                int64_t rb = m->rowptr[i][d], rn = m->rowptr[i][d + 1] - rb;
+                double tl[rn ? rn : 1];
                 for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w) {
                     int v = m->term[i][w];
                     double pw = 0.0;
                     for (int k = 0; k < K; ++k) pw += p[k] * phi[(size_t)k * V + v];
-                    if (m->arith) dd_add(&dl_dd, (double)m->cnt[i][w] * det_log(pw));
+                    if (m->arith) tl[w - rb] = (double)m->cnt[i][w] * det_log(pw);
                     else dl += (double)m->cnt[i][w] * log(pw);
                 }
-                if (m->arith) dl = dd_round(dl_dd);           /* DET: exact row sum */
+                if (m->arith) dl = tree_sum32(tl, (int)rn);   /* DET: row sum through the fixed tree */
                 dl = dl / (double)docN;                       /* :399 */
                 if (m->arith) dd_add(&tot_dd, dl * (double)docN);
                 else tot += dl * (double)docN;                /* :412 */
