@@ -39,6 +39,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index):
         super().__init__(daemon=True)
         self.index, self.stop_flag, self.rows = index, threading.Event(), []
+        self.t0 = self.t1 = None            # the timed region, set by the caller
 
     def run(self):
         q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -49,7 +50,7 @@ class ClockSampler(threading.Thread):
                                       "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
                 p = [x.strip() for x in out.strip().split(",")]
                 if len(p) >= 6:
-                    self.rows.append(p)
+                    self.rows.append([time.perf_counter()] + p)
             except Exception:
                 pass
             self.stop_flag.wait(0.2)
@@ -57,11 +58,14 @@ class ClockSampler(threading.Thread):
     def summary(self):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        sm = sorted(float(r[0]) for r in self.rows)
+        rows, window = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= self.t1], "timed region"
+        if not rows:                        # region shorter than one nvidia-smi call: use the loaded warm-up too
+            rows, window = self.rows, "warm-up + timed region (timed region shorter than one sample)"
+        sm = sorted(float(r[1]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
-                "samples": len(self.rows)}
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(rows[0][2]), "reasons": reasons,
+                "samples": len(rows), "window": window}
 
 
 def cpu_baseline(counts_fn, D_total, sample_D, nthreads, steps=1, warmup=0):
@@ -178,13 +182,14 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local)
+    sampler.start()
     with torch.cuda.stream(stream):
         for _ in range(args.warmup):
             model.iterate()
         model.h.kernel_times(reset=True)
         barrier()
-        sampler = ClockSampler(local)
-        sampler.start()
+        sampler.t0 = time.perf_counter()
         l0 = model.h.launch_count()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record(stream)
@@ -192,6 +197,7 @@ def main():
             ll = model.iterate()
         e1.record(stream)
         barrier()
+        sampler.t1 = time.perf_counter()
         sampler.stop_flag.set()
         ms = e0.elapsed_time(e1)
         launches = model.h.launch_count() - l0

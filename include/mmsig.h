@@ -45,7 +45,10 @@ extern "C" {
 #define MMSIG_STOP_NLOPT27 0   /* NLopt >= 2.7 x-tolerance rule (default)  */
 #define MMSIG_STOP_NLOPT26 1   /* NLopt <= 2.6 rule                         */
 
-#define MMSIG_FLAG_UPDATE_SIGMA 1u   /* fit!'s updateΣ=true (src/MMCTM.jl:468-470) */
+#define MMSIG_FLAG_UPDATE_SIGMA  1u  /* fit!'s updateΣ=true (src/MMCTM.jl:468-470)                        */
+#define MMSIG_FLAG_FREEZE_TOPICS 2u  /* keep γ, Elnϕ, ϕ (LDA: λ, Elnβ, β): fit_heldout / transform / predict */
+#define MMSIG_FLAG_FREEZE_MU     4u  /* keep μ (with UPDATE_SIGMA clear: the Gaussian prior is frozen)     */
+#define MMSIG_FLAG_UNSMOOTHED    8u  /* θ ∝ exp(λ)·ϕ (unsmoothed_update_θ!, src/MMCTM.jl:496-509); LDA: ϕ ∝ exp(Elnθ)·β (src/LDA.jl:226-231) */
 
 typedef struct mmsig_handle mmsig_handle;
 
@@ -83,8 +86,12 @@ int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_
 int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, const double *gamma,
                               const double *lambda, const double *nu, const double *mu,
                               const double *Sigma, const double *invSigma);
+/* model.ϕ override (fit_heldout / transform copy the fitted model's ϕ, src/MMCTM.jl:515,563) */
+int32_t mmsig_mmctm_set_phi(mmsig_handle *h, const double *phi);
 /* one body of fit!'s loop (src/MMCTM.jl:463-479): E-step over all samples, μ, [Σ, invΣ], γ, Elnϕ,
- * props, ϕ, per-modality log-likelihoods -> ll_out[M]. */
+ * props, ϕ, per-modality log-likelihoods -> ll_out[M].  flags = MMSIG_FLAG_UPDATE_SIGMA for fit!;
+ * FREEZE_TOPICS|FREEZE_MU is the loop body of fit_heldout (src/MMCTM.jl:566-573) and
+ * predict_modality_η (:604-609); adding UNSMOOTHED gives transform's (:523-538). */
 int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *ll_out);
 /* fit! (src/MMCTM.jl:457-494): loop + `length(ll) > 10 && check_convergence` (src/common.jl:48-51);
  * ll_hist is maxiter x M.  The ELBO of :490 is mmsig_mmctm_elbo. */
@@ -120,6 +127,10 @@ int32_t mmsig_lda_set_state(mmsig_handle *h, double alpha, double eta, const dou
                             const double *gamma_next);
 /* one body of fit!'s loop (src/LDA.jl:202-209) -> *ll_out */
 int32_t mmsig_lda_iterate(mmsig_handle *h, double *ll_out);
+/* model.β override, and the loop bodies of fit_heldout (src/LDA.jl:275-280: FREEZE_TOPICS) and
+ * transform (:242-246: FREEZE_TOPICS | UNSMOOTHED) */
+int32_t mmsig_lda_set_beta(mmsig_handle *h, const double *beta);
+int32_t mmsig_lda_iterate_flags(mmsig_handle *h, uint32_t flags, double *ll_out);
 int32_t mmsig_lda_fit(mmsig_handle *h, int32_t maxiter, double tol, double *ll_hist,
                       int32_t *n_iter, int32_t *converged);
 /* calculate_elbo (src/LDA.jl:114-172); terms[7] = ElnPβ, ElnPθ, ElnPZ, ElnPX, ElnQβ, ElnQθ, ElnQZ */

@@ -109,29 +109,33 @@ extern "C" int32_t mmsig_lda_set_state(mmsig_handle *h, double alpha, double eta
     return 0;
 }
 
-static int lda_iterate_async(mmsig_handle *h) {
+static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     LdaHost &L = h->lda;
     LdaDev &p = L.p;
     const int KV = p.K * p.V;
+    const bool freeze = (flags & MMSIG_FLAG_FREEZE_TOPICS) != 0, unsm = (flags & MMSIG_FLAG_UNSMOOTHED) != 0;
+    L.last_unsmoothed = unsm;
+    L.last_frozen = freeze;
     std::swap(p.gamma, p.gamma_next);               // γ_t <- what the previous pass (or init) produced
     {
         LaunchScope ls(h, "k_lda_estep");
-        THETA_DISPATCH(p.K, (k_lda_estep<KP, NP><<<L.grid, L.W * 32, L.smem, h->stream>>>(p, L.part, L.W)));
-    }
-    {
-        CombineSegs s{};
-        s.nseg = 1;
-        s.src[0] = L.part;
-        s.nparts[0] = L.grid;
-        s.n[0] = KV;
-        s.dst_off[0] = 0;
-        LaunchScope ls(h, "k_combine");
-        k_combine<<<(KV + 127) / 128, 128, 0, h->stream>>>(s, L.rank_p);
+        THETA_DISPATCH(p.K, (k_lda_estep<KP, NP><<<L.grid, L.W * 32, L.smem, h->stream>>>(p, L.part, L.W,
+                                                                                         unsm ? p.beta : p.expElnbeta, !freeze)));
     }
     const double2 *g = nullptr;
     int rc;
-    if ((rc = gather(h, L.rank_p, L.gath_p, KV, &g))) return rc;
-    {
+    if (!freeze) {
+        {
+            CombineSegs s{};
+            s.nseg = 1;
+            s.src[0] = L.part;
+            s.nparts[0] = L.grid;
+            s.n[0] = KV;
+            s.dst_off[0] = 0;
+            LaunchScope ls(h, "k_combine");
+            k_combine<<<(KV + 7) / 8, 256, 0, h->stream>>>(s, L.rank_p);
+        }
+        if ((rc = gather(h, L.rank_p, L.gath_p, KV, &g))) return rc;
         LaunchScope ls(h, "k_lda_mstep");
         k_lda_mstep<<<1, 1024, 0, h->stream>>>(p, g, h->nranks);
     }
@@ -147,7 +151,7 @@ static int lda_iterate_async(mmsig_handle *h) {
         s.n[0] = 1;
         s.dst_off[0] = 0;
         LaunchScope ls(h, "k_combine");
-        k_combine<<<1, 128, 0, h->stream>>>(s, L.rank_ll);
+        k_combine<<<1, 256, 0, h->stream>>>(s, L.rank_ll);
     }
     if ((rc = gather(h, L.rank_ll, L.gath_ll, 1, &g))) return rc;
     {
@@ -158,11 +162,22 @@ static int lda_iterate_async(mmsig_handle *h) {
     return 0;
 }
 
-extern "C" int32_t mmsig_lda_iterate(mmsig_handle *h, double *ll_out) {
+extern "C" int32_t mmsig_lda_set_beta(mmsig_handle *h, const double *beta) {
+    NEED(h && beta, "null argument");
+    NEED(h->lda.has_state, "mmsig_lda_set_state first");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->lda.p.beta, beta, (size_t)h->lda.p.K * h->lda.p.V * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int32_t mmsig_lda_iterate(mmsig_handle *h, double *ll_out) { return mmsig_lda_iterate_flags(h, 0, ll_out); }
+
+extern "C" int32_t mmsig_lda_iterate_flags(mmsig_handle *h, uint32_t flags, double *ll_out) {
     NEED(h, "null handle");
     NEED(h->lda.has_state, "mmsig_lda_set_state first");
     CU(cudaSetDevice(h->device));
-    int rc = lda_iterate_async(h);
+    int rc = lda_iterate_async(h, flags);
     if (rc) return rc;
     double ll = 0.0;
     CU(cudaMemcpyAsync(&ll, h->lda.d_ll, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -203,7 +218,10 @@ static int lda_elbo_pass(mmsig_handle *h, double *phi_dev, double2 *host_parts /
     CU(cudaMemsetAsync(parts, 0, (size_t)nb * 8 * sizeof(double2), h->stream));
     {
         LaunchScope ls(h, "k_lda_elbo");
-        k_lda_elbo<<<nb, 256, L.smem_elbo, h->stream>>>(p, parts, phi_dev);
+        // ϕ_T as the last E pass computed it: from β (unsmoothed), the current e^{Elnβ} (topics frozen)
+        // or the e^{Elnβ} that preceded the last M-step
+        const double *Etab = L.last_unsmoothed ? p.beta : (L.last_frozen ? p.expElnbeta : p.expElnbeta_prev);
+        k_lda_elbo<<<nb, 256, L.smem_elbo, h->stream>>>(p, parts, phi_dev, Etab);
     }
     {
         LaunchScope ls(h, "k_lda_elbo_tables");
@@ -217,7 +235,7 @@ static int lda_elbo_pass(mmsig_handle *h, double *phi_dev, double2 *host_parts /
         s.n[0] = 8;
         s.dst_off[0] = 0;
         LaunchScope ls(h, "k_combine");
-        k_combine<<<1, 128, 0, h->stream>>>(s, L.rank_ll);
+        k_combine<<<1, 256, 0, h->stream>>>(s, L.rank_ll);
     }
     const double2 *g = nullptr;
     int rc = gather(h, L.rank_ll, L.gath_ll, 8, &g);

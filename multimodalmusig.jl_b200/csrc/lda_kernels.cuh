@@ -50,13 +50,14 @@ __global__ void __launch_bounds__(256) k_lda_gamma_init(LdaDev p) {
 
 // One E pass.  partial: [gridDim.x][K*V] (as double2 {sum, 0} so that k_combine can be shared).
 template <int KP, int NP>
-__global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, int nwarps_blk) {
+__global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, int nwarps_blk, const double *Etab,
+                                                   int want_stats) {
     extern __shared__ double smem[];
     const int K = p.K, V = p.V, KV = K * V;
     double *E = smem;                                  // e^{Elnβ}, KV
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *tab = smem + KV + (size_t)warp * KV;       // this warp's statistics
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) E[i] = p.expElnbeta[i];
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) E[i] = Etab[i];     // e^{Elnβ}, or β (unsmoothed)
     for (int i = lane; i < KV; i += 32) tab[i] = 0.0;
     __syncthreads();
     const long long nw = (long long)gridDim.x * nwarps_blk;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, i
             for (int k = 0; k < KP; ++k)
                 if (k < K) {
                     const double a = pk[k] * scale;
-                    tab[k * V + v] += a;
+                    if (want_stats) tab[k * V + v] += a;
                     g[k] += a;
                 }
         }
@@ -222,7 +223,7 @@ __global__ void __launch_bounds__(256) k_lda_theta_out(LdaDev p, double *Elnthet
 // Elnβ the last E pass used.  partial: [gridDim.x][8] dd:
 //  [0] Σ Elnθ   [1] ElnPZ = Σ ϕ Elnθ n   [2] ElnPX = Σ ϕ Elnβ_T n   [3] ElnQZ = Σ ϕ log ϕ (no n, as :154-160)
 //  [4] Σ lgamma(γ)   [5] Σ_d lgamma(Σ_k γ)   [6] Σ (γ-1) Elnθ
-__global__ void __launch_bounds__(256) k_lda_elbo(LdaDev p, double2 *partial, double *phi_out) {
+__global__ void __launch_bounds__(256) k_lda_elbo(LdaDev p, double2 *partial, double *phi_out, const double *Etab) {
     extern __shared__ double smem[];
     __shared__ double2 red[8 * 7];
     const int K = p.K, V = p.V, KV = K * V;
@@ -231,7 +232,7 @@ __global__ void __launch_bounds__(256) k_lda_elbo(LdaDev p, double2 *partial, do
     double *sh = smem + 2 * KV;        // 8 x 64 : e^{Elnθ}, Elnθ per warp
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *et = sh + warp * 64, *el = et + 32;
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) { Eprev[i] = p.expElnbeta_prev[i]; Eln[i] = p.Elnbeta[i]; }
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) { Eprev[i] = Etab[i]; Eln[i] = p.Elnbeta[i]; }
     __syncthreads();
     double hi[7] = {0, 0, 0, 0, 0, 0, 0}, lo[7] = {0, 0, 0, 0, 0, 0, 0};
     const long long nw = (long long)gridDim.x * 8;

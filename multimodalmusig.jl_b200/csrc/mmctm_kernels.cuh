@@ -49,14 +49,17 @@ struct MmctmDev {
 // collide).  Nothing of size K x nnz is ever stored.
 // ------------------------------------------------------------------------------------------
 template <int KP, int NP>
-__global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 *partial, int nwarps_blk) {
+__global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 *partial, int nwarps_blk, int unsmoothed,
+                                                     int want_stats) {
     extern __shared__ double smem[];
     const int K = p.K[m], V = p.V[m], KV = K * V, off = p.koff[m];
     double *Eln = smem;                       // KV
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *thi = smem + KV + (size_t)warp * 2 * KV;
     double *tlo = thi + KV;
-    const double *Eg = p.Elnphi + p.goff[m];
+    // smoothed (update_θ!, :183-198): table = Elnϕ, e = exp(λ + Elnϕ);
+    // unsmoothed (unsmoothed_update_θ!, :496-509): table = ϕ, e = exp(λ) ϕ
+    const double *Eg = (unsmoothed ? p.phi : p.Elnphi) + p.goff[m];
     for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = Eg[i];
     for (int i = lane; i < 2 * KV; i += 32) thi[i] = 0.0;
     __syncthreads();
@@ -68,6 +71,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
         double lamk[KP];
         {
             double mine = (lane < K) ? p.lam_prev[d * p.MK + off + lane] : 0.0;
+            if (unsmoothed) mine = det_exp(mine);
 #pragma unroll
             for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
         }
@@ -84,7 +88,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
 #pragma unroll
             for (int k = 0; k < KP; ++k)
                 if (k < K) {
-                    e[k] = det_exp(lamk[k] + Eln[k * V + v]);
+                    e[k] = unsmoothed ? lamk[k] * Eln[k * V + v] : det_exp(lamk[k] + Eln[k * V + v]);
                     Z += e[k];
                 }
             const double rz = 1.0 / Z;                 // DET: θ_k = e_k * (1/Z), one division per nonzero
@@ -92,7 +96,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
             for (int k = 0; k < KP; ++k)
                 if (k < K) {
                     const double a = (e[k] * rz) * n;
-                    dd_add(thi[k * V + v], tlo[k * V + v], a);
+                    if (want_stats) dd_add(thi[k * V + v], tlo[k * V + v], a);
                     sth[k] += a;
                 }
         }
@@ -329,19 +333,21 @@ struct CombineSegs {
     int nparts[MAXM + 2], n[MAXM + 2], dst_off[MAXM + 2];
     int stride[MAXM + 2];        // distance between parts in src (0 = n)
 };
-__global__ void k_combine(CombineSegs s, double2 *dst) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+__global__ void __launch_bounds__(256) k_combine(CombineSegs s, double2 *dst) {
+    // one warp per output entry; lanes stride over the parts, then a dd butterfly
+    const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     int base = 0;
     for (int g = 0; g < s.nseg; ++g) {
         if (t < base + s.n[g]) {
             const int i = t - base;
-            double hi = 0.0, lo = 0.0;
             const int stride = s.stride[g] ? s.stride[g] : s.n[g];
-            for (int part = 0; part < s.nparts[g]; ++part) {
+            double hi = 0.0, lo = 0.0;
+            for (int part = lane; part < s.nparts[g]; part += 32) {
                 const double2 v = s.src[g][(size_t)part * stride + i];
                 dd_merge(hi, lo, v.x, v.y);
             }
-            dst[s.dst_off[g] + i] = make_double2(hi, lo);
+            warp_dd_allreduce(hi, lo);
+            if (lane == 0) dst[s.dst_off[g] + i] = make_double2(hi, lo);
             return;
         }
         base += s.n[g];
@@ -353,7 +359,8 @@ __global__ void k_combine(CombineSegs s, double2 *dst) {
 // γ = exact_round(α + Σ n θ) (src/MMCTM.jl:224-240), Elnϕ = ψ(γ) - ψ(Σ_v γ) (:214-222),
 // ϕ = γ / Σ_v γ (:244-250), μ = exact_round(Σ_d λ) / D (:200-202).
 // ------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gathered, int nranks) {
+__global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gathered, int nranks, int freeze_topics,
+                                                 int freeze_mu) {
     __shared__ double rowsum[MAXMK], rowdig[MAXMK];
     const int G = p.goff[p.M], MK = p.MK, P1 = G + 2 * MK;
     for (int i = threadIdx.x; i < P1; i += blockDim.x) {
@@ -363,6 +370,7 @@ __global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gath
             dd_merge(hi, lo, v.x, v.y);
         }
         if (i < G) {
+            if (freeze_topics) continue;
             int m = 0;
             while (i >= p.goff[m + 1]) ++m;
             p.stats[i] = dd_round(hi, lo);
@@ -370,11 +378,12 @@ __global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gath
             p.gamma[i] = dd_round(hi, lo);
             p.Elnphi_prev[i] = p.Elnphi[i];
         } else if (i < G + MK) {
-            p.mu[i - G] = dd_round(hi, lo) / (double)p.D_total;
+            if (!freeze_mu) p.mu[i - G] = dd_round(hi, lo) / (double)p.D_total;
         } else {
             p.nusum[i - G - MK] = make_double2(hi, lo);
         }
     }
+    if (freeze_topics) return;
     __syncthreads();
     if (threadIdx.x < MK) {
         int m = 0;
@@ -657,11 +666,11 @@ __global__ void __launch_bounds__(256) k_zeta(MmctmDev p) {
 
 // θ of one modality, materialised on request (model.θ[d][m]); uses the λ / Elnϕ of the last
 // E-step (lam_prev, Elnphi_prev).  out: nnz x K.
-__global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *out) {
+__global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *out, int unsmoothed) {
     extern __shared__ double smem[];
     const int K = p.K[m], V = p.V[m], KV = K * V, off = p.koff[m];
     double *Eln = smem;
-    const double *Eg = p.Elnphi_prev + p.goff[m];
+    const double *Eg = (unsmoothed ? p.phi : p.Elnphi_prev) + p.goff[m];
     for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = Eg[i];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -672,7 +681,8 @@ __global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *ou
             const int v = p.rec[m][w].x;
             double Z = 0.0;
             for (int k = 0; k < K; ++k) {
-                const double e = det_exp(p.lam_prev[d * p.MK + off + k] + Eln[k * V + v]);
+                const double lk = p.lam_prev[d * p.MK + off + k];
+                const double e = unsmoothed ? det_exp(lk) * Eln[k * V + v] : det_exp(lk + Eln[k * V + v]);
                 out[w * K + k] = e;
                 Z += e;
             }

@@ -72,7 +72,7 @@ struct CountBuf {
 };
 
 struct MmctmHost {
-    bool has_data = false, has_state = false, estep_done = false;
+    bool has_data = false, has_state = false, estep_done = false, last_unsmoothed = false;
     CountBuf cb[MAXM];
     double *props_scratch = nullptr;
     MmctmDev p{};
@@ -93,7 +93,7 @@ struct MmctmHost {
 };
 
 struct LdaHost {
-    bool has_data = false, has_state = false, iterated = false;
+    bool has_data = false, has_state = false, iterated = false, last_unsmoothed = false, last_frozen = false;
     CountBuf cb;
     LdaDev p{};
     long long nnz = 0;
@@ -637,15 +637,27 @@ extern "C" int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, c
     return 0;
 }
 
+extern "C" int32_t mmsig_mmctm_set_phi(mmsig_handle *h, const double *phi) {
+    NEED(h && phi, "null argument");
+    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    CU(cudaSetDevice(h->device));
+    CU(cudaMemcpyAsync(h->mm.p.phi, phi, h->mm.G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
 static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     const int do_sigma = (flags & MMSIG_FLAG_UPDATE_SIGMA) ? 1 : 0;
+    const int freeze_topics = (flags & MMSIG_FLAG_FREEZE_TOPICS) ? 1 : 0, freeze_mu = (flags & MMSIG_FLAG_FREEZE_MU) ? 1 : 0;
+    const int unsm = (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0;
+    mm.last_unsmoothed = unsm != 0;
     std::swap(p.lam, p.lam_prev);              // lam_prev = λ of the previous iteration (what θ uses)
     for (int m = 0; m < p.M; ++m) {
         LaunchScope ls(h, "k_theta_stats");
         THETA_DISPATCH(p.K[m], (k_theta_stats<KP, NP><<<mm.grid_theta[m], mm.W_theta[m] * 32, mm.smem_theta[m], h->stream>>>(
-                                   p, m, mm.part_theta[m], mm.W_theta[m])));
+                                   p, m, mm.part_theta[m], mm.W_theta[m], unsm, !freeze_topics)));
     }
     {
         LaunchScope ls(h, "k_solve");
@@ -666,14 +678,14 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
         s.n[p.M] = 2 * p.MK;
         s.dst_off[p.M] = mm.G;
         LaunchScope ls(h, "k_combine");
-        k_combine<<<(P1 + 127) / 128, 128, 0, h->stream>>>(s, mm.rank_p1);
+        k_combine<<<(P1 + 7) / 8, 256, 0, h->stream>>>(s, mm.rank_p1);
     }
     const double2 *g1 = nullptr;
     int rc;
     if ((rc = gather(h, mm.rank_p1, mm.gath_p1, P1, &g1))) return rc;
     {
         LaunchScope ls(h, "k_mstep1");
-        k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks);
+        k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu);
     }
     if (do_sigma) {
         LaunchScope ls(h, "k_moments");
@@ -698,7 +710,7 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
         s.dst_off[1] = p.MK * p.MK;
         s.stride[1] = P2;
         LaunchScope ls(h, "k_combine");
-        k_combine<<<(P2 + 127) / 128, 128, 0, h->stream>>>(s, mm.rank_p2);
+        k_combine<<<(P2 + 7) / 8, 256, 0, h->stream>>>(s, mm.rank_p2);
     }
     const double2 *g2 = nullptr;
     if ((rc = gather(h, mm.rank_p2, mm.gath_p2, P2, &g2))) return rc;
@@ -807,7 +819,7 @@ extern "C" int32_t mmsig_mmctm_get_theta(mmsig_handle *h, int32_t m, double *the
     CU(allow_max_smem(h, k_theta_out));
     {
         LaunchScope ls(h, "k_theta_out");
-        k_theta_out<<<mm.grid_solve, 256, smem, h->stream>>>(p, m, d);
+        k_theta_out<<<mm.grid_solve, 256, smem, h->stream>>>(p, m, d, mm.last_unsmoothed ? 1 : 0);
     }
     CU(cudaMemcpyAsync(theta_out, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -921,4 +933,5 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
     return 0;
 }
 
+extern "C" int32_t mmsig_lda_iterate_flags(mmsig_handle *h, uint32_t flags, double *ll_out);
 #include "lda_api.inl"

@@ -69,12 +69,77 @@ class MMCTM:
              capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
         self.h.check(self.h.lib.mmsig_mmctm_set_state(self.h.h, *[capi.dp(x) for x in a]))
 
-    def iterate(self, updateSigma=True):
-        """One body of fit!'s loop (src/MMCTM.jl:463-479); returns the M log-likelihoods."""
+    def iterate(self, updateSigma=True, flags=None):
+        """One body of fit!'s loop (src/MMCTM.jl:463-479); returns the M log-likelihoods.
+        flags (capi.FLAG_*) selects the frozen / unsmoothed loop bodies of fit_heldout / transform."""
         ll = np.zeros(self.M)
-        self.h.check(self.h.lib.mmsig_mmctm_iterate(self.h.h, capi.FLAG_UPDATE_SIGMA if updateSigma else 0,
-                                                    capi.dp(ll)))
+        if flags is None:
+            flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        self.h.check(self.h.lib.mmsig_mmctm_iterate(self.h.h, flags, capi.dp(ll)))
         return ll
+
+    def set_phi(self, phi_flat):
+        self.h.check(self.h.lib.mmsig_mmctm_set_phi(self.h.h, capi.dp(capi.f64(phi_flat, self.G))))
+
+    def _loop(self, flags, maxiter, tol, verbose):
+        hist = []
+        for it in range(1, maxiter + 1):
+            hist.append(self.iterate(flags=flags))
+            if verbose:
+                print("%d\tLog-likelihoods: %s" % (it, ", ".join(repr(float(x)) for x in hist[-1])))
+            if len(hist) > 10 and _converged(hist[-2], hist[-1], tol):
+                self.converged = True
+                break
+        self.ll = hist[-1].copy()
+        return np.asarray(hist)
+
+    def fit_heldout(self, counts_heldout, maxiter=100, verbose=False, device=0):
+        """fit_heldout(Xheldout, model; maxiter=100) (src/MMCTM.jl:554-586): a model on the held-out
+        samples with μ, Σ, invΣ, γ, Elnϕ, ϕ of this one; per iteration E-step, props, LL."""
+        s = self.state(props=False)
+        new = MMCTM(self.K, self.alpha, counts_heldout, V=self.V, gamma0=s["gamma"], device=device)
+        new.set_state(s["gamma"], mu=s["mu"], Sigma=s["Sigma"], invSigma=s["invSigma"])
+        new.set_phi(s["phi"])
+        new.ll_history = new._loop(capi.FLAG_FREEZE_TOPICS | capi.FLAG_FREEZE_MU, maxiter, 1e-4, verbose)
+        return new
+
+    def transform(self, counts, maxiter=1000, tol=1e4, fit_gaussian=False, verbose=False, device=0, rng=None):
+        """transform(model, X; maxiter=1000, tol=1e4, fit_gaussian=false) (src/MMCTM.jl:511-552):
+        unsmoothed θ ∝ exp(λ)·ϕ with this model's ϕ; μ, Σ copied unless fit_gaussian -- and, as in
+        the reference, invΣ is NOT copied (it stays the constructor's identity, :517-520)."""
+        s = self.state(props=False)
+        rng = np.random.default_rng() if rng is None else rng
+        g0 = rng.integers(1, 101, size=self.G).astype(np.float64)       # the fresh model's γ (unused by θ)
+        new = MMCTM(self.K, self.alpha, counts, V=self.V, gamma0=g0, device=device)
+        if not fit_gaussian:
+            new.set_state(g0, mu=s["mu"], Sigma=s["Sigma"])
+        new.set_phi(s["phi"])
+        flags = capi.FLAG_FREEZE_TOPICS | capi.FLAG_UNSMOOTHED | \
+            (capi.FLAG_UPDATE_SIGMA if fit_gaussian else capi.FLAG_FREEZE_MU)
+        new.ll_history = new._loop(flags, maxiter, tol, verbose)
+        return new
+
+    def predict_modality_eta(self, counts_obs, m, maxiter=100, device=0):
+        """predict_modality_η(Xobs, m, model; maxiter=100) (src/MMCTM.jl:588-634): fit λ on the observed
+        modalities with everything else frozen, then η_u = μ_u + Σ_uo invΣ[o,o] (λ - μ_o).
+        The reference's stopping test reads `props` it never computes (undefined values, :609-618),
+        so this runs exactly `maxiter` E-steps."""
+        s = self.state(props=False)
+        obsM = [i for i in range(self.M) if i != m]
+        ko = np.cumsum([0] + self.K)
+        go = np.cumsum([0] + [k * v for k, v in zip(self.K, self.V)])
+        un = np.arange(ko[m], ko[m + 1])
+        ob = np.concatenate([np.arange(ko[i], ko[i + 1]) for i in obsM])
+        g_obs = np.concatenate([s["gamma"][go[i]:go[i + 1]] for i in obsM])
+        om = MMCTM([self.K[i] for i in obsM], self.alpha[obsM], counts_obs, V=[self.V[i] for i in obsM],
+                   gamma0=g_obs, device=device)
+        om.set_state(g_obs, mu=s["mu"][ob], Sigma=s["Sigma"][np.ix_(ob, ob)], invSigma=s["invSigma"][np.ix_(ob, ob)])
+        for _ in range(maxiter):
+            om.iterate(flags=capi.FLAG_FREEZE_TOPICS | capi.FLAG_FREEZE_MU)
+        lam = om.lam
+        om.close()
+        A = s["Sigma"][np.ix_(un, ob)] @ s["invSigma"][np.ix_(ob, ob)]
+        return s["mu"][un] + (lam - s["mu"][ob]) @ A.T
 
     def fit(self, maxiter=100, tol=1e-4, verbose=True, autoalpha=False, updateSigma=True):
         """fit!(model; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true), src/MMCTM.jl:457-494."""
@@ -218,10 +283,45 @@ class LDA:
                                                     capi.dp(capi.f64(lam, self.K * self.V)),
                                                     capi.dp(capi.f64(gamma_next, self.D * self.K))))
 
-    def iterate(self):
+    def iterate(self, flags=0):
         ll = C.c_double()
-        self.h.check(self.h.lib.mmsig_lda_iterate(self.h.h, C.byref(ll)))
+        self.h.check(self.h.lib.mmsig_lda_iterate_flags(self.h.h, flags, C.byref(ll)))
         return ll.value
+
+    def set_beta(self, beta):
+        self.h.check(self.h.lib.mmsig_lda_set_beta(self.h.h, capi.dp(capi.f64(beta, self.K * self.V))))
+
+    def _loop(self, flags, maxiter, tol, verbose):
+        hist = []
+        for it in range(1, maxiter + 1):
+            hist.append(self.iterate(flags))
+            if verbose:
+                print("%d\tLog-likelihood: %r" % (it, hist[-1]))
+            if len(hist) > 10 and _converged([hist[-2]], [hist[-1]], tol):
+                self.converged = True
+                break
+        self.ll = float(hist[-1])
+        return np.asarray(hist)
+
+    def transform(self, counts, maxiter=1000, tol=1e-4, verbose=False, device=0):
+        """transform(model, X) (src/LDA.jl:233-263): θ of new samples under this model's β
+        (unsmoothed ϕ ∝ exp(Elnθ)·β); returns θ as (D, K)."""
+        s = self.state()
+        new = LDA(self.K, self.alpha, self.eta, counts, V=self.V, lambda0=np.ones(self.K * self.V), device=device)
+        new.set_beta(s["beta"])
+        new._loop(capi.FLAG_FREEZE_TOPICS | capi.FLAG_UNSMOOTHED, maxiter, tol, verbose)
+        th = new.theta
+        new.close()
+        return th
+
+    def fit_heldout(self, counts_heldout, maxiter=100, verbose=False, device=0):
+        """fit_heldout(Xheldout, model; maxiter=100) (src/LDA.jl:265-295): λ, β, Elnβ frozen."""
+        s = self.state()
+        new = LDA(self.K, self.alpha, self.eta, counts_heldout, V=self.V, lambda0=s["lam"], device=device)
+        new.set_beta(s["beta"])
+        new.ll_history = new._loop(capi.FLAG_FREEZE_TOPICS, maxiter, 1e-4, verbose)
+        new.elbo = new.calculate_elbo()[0]
+        return new
 
     def fit(self, maxiter=1000, tol=1e-4, verbose=True):
         """fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true), src/LDA.jl:198-224."""

@@ -702,6 +702,30 @@ void orc_mmctm_update_theta(orc_mmctm *m, int64_t d)
     }
 }
 
+/* src/MMCTM.jl:496-509 : theta ∝ exp(lambda) * phi (phi, not exp(Elnphi)) */
+void orc_mmctm_unsmoothed_update_theta(orc_mmctm *m, int64_t d)
+{
+    const double *lam = m->lambda + (size_t)d * m->MK;
+    for (int i = 0; i < m->M; ++i) {
+        int K = m->K[i], V = m->V[i], off = m->koff[i];
+        const double *phi = m->phi + m->goff[i];
+        for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w) {
+            int v = m->term[i][w];
+            double *th = m->theta[i] + (size_t)w * K;
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) {
+                th[k] = xexp(m->arith, lam[off + k]) * phi[(size_t)k * V + v];
+                s += th[k];
+            }
+            if (m->arith) {
+                double rz = 1.0 / s;
+                for (int k = 0; k < K; ++k) th[k] = th[k] * rz;
+            } else
+                for (int k = 0; k < K; ++k) th[k] /= s;
+        }
+    }
+}
+
 /* src/MMCTM.jl:110-117 */
 void orc_mmctm_calc_sumtheta(const orc_mmctm *m, int64_t d, double *out)
 {
@@ -1097,6 +1121,30 @@ void orc_mmctm_iterate(orc_mmctm *m, int updateSigma, int autoalpha, double *ll)
     orc_mmctm_loglikelihoods(m, ll);
 }
 
+/* The loop bodies of fit_heldout (src/MMCTM.jl:566-573: E-step, props, LL), transform
+ * (:523-538: E-step with unsmoothed theta, [mu, Sigma], props, LL) and predict_modality_eta
+ * (:604-609) as flag combinations of one iteration. */
+void orc_mmctm_iterate_flags(orc_mmctm *m, unsigned flags, double *ll)
+{
+    const int unsm = (flags & ORC_FLAG_UNSMOOTHED) != 0;
+#ifdef _OPENMP
+    #pragma omp parallel for schedule(dynamic, 16) num_threads(m->nthreads > 0 ? m->nthreads : 1)
+#endif
+    for (int64_t d = 0; d < m->D; ++d) {
+        orc_mmctm_update_zeta(m, d);
+        if (unsm) orc_mmctm_unsmoothed_update_theta(m, d);
+        else orc_mmctm_update_theta(m, d);
+        orc_mmctm_update_nu(m, d);
+        orc_mmctm_update_lambda(m, d);
+    }
+    if (!(flags & ORC_FLAG_FREEZE_MU)) orc_mmctm_update_mu(m);
+    if (flags & ORC_FLAG_UPDATE_SIGMA) orc_mmctm_update_Sigma(m);
+    if (!(flags & ORC_FLAG_FREEZE_TOPICS)) { orc_mmctm_update_gamma(m); }
+    orc_mmctm_update_props(m);
+    if (!(flags & ORC_FLAG_FREEZE_TOPICS)) orc_mmctm_update_phi(m);
+    orc_mmctm_loglikelihoods(m, ll);
+}
+
 /* src/common.jl:48-51 */
 static int check_convergence_vec(const double *prev, const double *cur, int M, double tol)
 {
@@ -1221,6 +1269,34 @@ void orc_lda_update_phi(orc_lda *m)
             }
             for (int k = 0; k < K; ++k) p[k] /= s;
         }
+}
+
+/* src/LDA.jl:226-231 : phi ∝ exp(Elntheta) * beta */
+void orc_lda_unsmoothed_update_phi(orc_lda *m)
+{
+    int K = m->K, V = m->V;
+    for (int64_t d = 0; d < m->D; ++d)
+        for (int64_t w = m->rowptr[d]; w < m->rowptr[d + 1]; ++w) {
+            int v = m->term[w];
+            double *p = m->phi + (size_t)w * K;
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) {
+                p[k] = xexp(m->arith, m->Elntheta[(size_t)d * K + k]) * m->beta[(size_t)k * V + v];
+                s += p[k];
+            }
+            for (int k = 0; k < K; ++k) p[k] /= s;
+        }
+}
+
+/* loop bodies of LDA fit_heldout (src/LDA.jl:275-280) and transform (:242-246) */
+double orc_lda_iterate_flags(orc_lda *m, unsigned flags)
+{
+    orc_lda_update_gamma(m);
+    if (flags & ORC_FLAG_UNSMOOTHED) orc_lda_unsmoothed_update_phi(m);
+    else orc_lda_update_phi(m);
+    if (!(flags & ORC_FLAG_FREEZE_TOPICS)) { orc_lda_update_lambda(m); orc_lda_update_beta(m); }
+    orc_lda_update_theta(m);
+    return orc_lda_loglikelihood(m);
 }
 
 /* src/LDA.jl:96-98 */

@@ -61,6 +61,12 @@ typedef double (*orc_func)(unsigned n, const double *x, double *grad, void *data
 #define ORC_ARITH_LITERAL 0  /* reference operation order, glibc exp/log      */
 #define ORC_ARITH_DET     1  /* same addends, every rounding pinned            */
 
+/* iteration flags (same values as MMSIG_FLAG_*) */
+#define ORC_FLAG_UPDATE_SIGMA   1u
+#define ORC_FLAG_FREEZE_TOPICS  2u
+#define ORC_FLAG_FREEZE_MU      4u
+#define ORC_FLAG_UNSMOOTHED     8u
+
 #define ORC_STOP_NLOPT27 0   /* NLopt >= 2.7 x-tolerance rule (default) */
 #define ORC_STOP_NLOPT26 1   /* NLopt <= 2.6 x-tolerance rule           */
 
@@ -118,6 +124,8 @@ void orc_mmctm_free(orc_mmctm *m);
 
 void orc_mmctm_update_zeta(orc_mmctm *m, int64_t d);       /* :172-181 */
 void orc_mmctm_update_theta(orc_mmctm *m, int64_t d);      /* :183-198 */
+void orc_mmctm_unsmoothed_update_theta(orc_mmctm *m, int64_t d); /* :496-509 */
+void orc_mmctm_iterate_flags(orc_mmctm *m, unsigned flags, double *ll); /* fit_heldout :566-573, transform :523-538 */
 void orc_mmctm_calc_sumtheta(const orc_mmctm *m, int64_t d, double *out); /* :110-117 */
 void orc_mmctm_calc_Ndivzeta(const orc_mmctm *m, int64_t d, double *out); /* :119-125 */
 void orc_mmctm_update_nu(orc_mmctm *m, int64_t d);         /* :156-170 */
@@ -169,6 +177,8 @@ void orc_lda_update_theta(orc_lda *m);      /* :92-94  */
 double orc_lda_loglikelihood(const orc_lda *m); /* :174-188 */
 double orc_lda_elbo(const orc_lda *m, double *terms); /* :114-172; PBeta,PTheta,PZ,PX,QBeta,QTheta,QZ */
 double orc_lda_iterate(orc_lda *m);         /* :202-209 */
+void orc_lda_unsmoothed_update_phi(orc_lda *m);               /* :226-231 */
+double orc_lda_iterate_flags(orc_lda *m, unsigned flags);     /* fit_heldout :275-280, transform :242-246 */
 int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist); /* :198-224 */
 
 #ifdef __cplusplus

@@ -95,6 +95,10 @@ def lib():
     sig("orc_mmctm_elbo", d, pm, c_dp)
     sig("orc_mmctm_iterate", None, pm, i, i, c_dp)
     sig("orc_mmctm_fit", i, pm, i, d, i, i, c_dp)
+    sig("orc_mmctm_iterate_flags", None, pm, C.c_uint, c_dp)
+    sig("orc_mmctm_unsmoothed_update_theta", None, pm, i64)
+    sig("orc_lda_iterate_flags", d, pl, C.c_uint)
+    sig("orc_lda_unsmoothed_update_phi", None, pl)
     sig("orc_lda_new", pl, i, i, i64, c_i64p, c_i32p, c_i32p, d, d, c_dp)
     sig("orc_lda_free", None, pl)
     for n in ("Elntheta", "gamma", "phi", "Elnbeta", "lambda", "beta", "theta"):
@@ -119,6 +123,7 @@ def _view(ptr, shape):
 
 
 ARITH_LITERAL, ARITH_DET = 0, 1
+FLAG_UPDATE_SIGMA, FLAG_FREEZE_TOPICS, FLAG_FREEZE_MU, FLAG_UNSMOOTHED = 1, 2, 4, 8
 STOP_NLOPT27, STOP_NLOPT26 = 0, 1
 
 
@@ -194,6 +199,11 @@ class OracleMMCTM:
         self.L.orc_mmctm_iterate(self.p, int(updateSigma), int(autoalpha), _dp(ll))
         return ll
 
+    def iterate_flags(self, flags):
+        ll = np.zeros(self.M)
+        self.L.orc_mmctm_iterate_flags(self.p, int(flags), _dp(ll))
+        return ll
+
     def fit(self, maxiter=100, tol=1e-4, updateSigma=True, autoalpha=False):
         hist = np.zeros((maxiter, self.M))
         n = self.L.orc_mmctm_fit(self.p, maxiter, tol, int(updateSigma), int(autoalpha), _dp(hist))
@@ -253,6 +263,9 @@ class OracleLDA:
 
     def iterate(self):
         return self.L.orc_lda_iterate(self.p)
+
+    def iterate_flags(self, flags):
+        return self.L.orc_lda_iterate_flags(self.p, int(flags))
 
     def fit(self, maxiter=1000, tol=1e-4):
         hist = np.zeros(maxiter)
