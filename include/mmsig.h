@@ -48,6 +48,7 @@ extern "C" {
 #define MMSIG_FLAG_UPDATE_SIGMA  1u  /* fit!'s updateΣ=true (src/MMCTM.jl:468-470)                        */
 #define MMSIG_FLAG_FREEZE_TOPICS 2u  /* keep γ, Elnϕ, ϕ (LDA: λ, Elnβ, β): fit_heldout / transform / predict */
 #define MMSIG_FLAG_FREEZE_MU     4u  /* keep μ (with UPDATE_SIGMA clear: the Gaussian prior is frozen)     */
+#define MMSIG_FLAG_AUTO_ALPHA   16u  /* fit!'s autoα=true: update_α! after update_γ! (src/MMCTM.jl:252-269,472-474), on the host */
 #define MMSIG_FLAG_UNSMOOTHED    8u  /* θ ∝ exp(λ)·ϕ (unsmoothed_update_θ!, src/MMCTM.jl:496-509); LDA: ϕ ∝ exp(Elnθ)·β (src/LDA.jl:226-231) */
 
 typedef struct mmsig_handle mmsig_handle;
@@ -86,6 +87,8 @@ int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_
 int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, const double *gamma,
                               const double *lambda, const double *nu, const double *mu,
                               const double *Sigma, const double *invSigma);
+/* model.α as update_α! left it */
+int32_t mmsig_mmctm_get_alpha(mmsig_handle *h, double *alpha_out);
 /* model.ϕ override (fit_heldout / transform copy the fitted model's ϕ, src/MMCTM.jl:515,563) */
 int32_t mmsig_mmctm_set_phi(mmsig_handle *h, const double *phi);
 /* one body of fit!'s loop (src/MMCTM.jl:463-479): E-step over all samples, μ, [Σ, invΣ], γ, Elnϕ,

@@ -62,7 +62,6 @@ flat_tables(t::Vector{Vector{Vector{Float64}}}) = collect(reduce(vcat, [reduce(v
 
 function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true,
               device=0, stop_rule=0)
-    autoα && error("autoα=true is not on the GPU path; use the CPU fit!")
     D, M, MK = model.D, model.M, sum(model.K)
     rowptr, term, count = flatten_counts(model.X, M)
     K32, V32 = Int32.(model.K), Int32.(model.V)
@@ -81,7 +80,7 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
         check(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
             (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
             h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
-        flags = UInt32(updateΣ ? 1 : 0)
+        flags = UInt32((updateΣ ? 1 : 0) | (autoα ? 16 : 0))
         llbuf = zeros(M)
         for iter in 1:maxiter                                   # src/MMCTM.jl:462-489
             check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
@@ -119,6 +118,7 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
             o += model.V[m]
         end
         # model.θ is materialised lazily: materialize_theta!(model, h) before destroy if wanted
+        autoα && check(h, ccall((:mmsig_mmctm_get_alpha, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, model.α))
         model.elbo = elbo[]
         model.ll = ll[end]
     finally

@@ -13,7 +13,7 @@ c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_u8p = C.POINTER(C.c_uint8)
 
-FLAG_UPDATE_SIGMA, FLAG_FREEZE_TOPICS, FLAG_FREEZE_MU, FLAG_UNSMOOTHED = 1, 2, 4, 8
+FLAG_UPDATE_SIGMA, FLAG_FREEZE_TOPICS, FLAG_FREEZE_MU, FLAG_UNSMOOTHED, FLAG_AUTO_ALPHA = 1, 2, 4, 8, 16
 STOP_NLOPT27, STOP_NLOPT26 = 0, 1
 
 
@@ -40,6 +40,7 @@ _SIGS = {
     "mmsig_mmctm_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
                                          C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)]),
     "mmsig_mmctm_set_state": (C.c_int32, [C.c_void_p] + [c_dp] * 7),
+    "mmsig_mmctm_get_alpha": (C.c_int32, [C.c_void_p, c_dp]),
     "mmsig_mmctm_set_phi": (C.c_int32, [C.c_void_p, c_dp]),
     "mmsig_mmctm_iterate": (C.c_int32, [C.c_void_p, C.c_uint32, c_dp]),
     "mmsig_mmctm_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p]),

@@ -646,6 +646,103 @@ extern "C" int32_t mmsig_mmctm_set_phi(mmsig_handle *h, const double *phi) {
     return 0;
 }
 
+// ---- update_α! (src/MMCTM.jl:252-269): a 1-D LD_MMA per modality on table sums, on the host.
+// Plain libm arithmetic in the reference's operation order (α_objective, src/common.jl:38-46;
+// digamma per SpecialFunctions.jl; NLopt LD_MMA with lb = 1e-7, xtol_rel = xtol_abs = 1e-5).
+static double host_digamma(double x) {
+    double psi = 0.0;
+    if (x <= 0.0) { psi = -M_PI / std::tan(M_PI * x); x = 1.0 - x; }
+    if (x < 7.0) {
+        int n = 7 - (int)std::floor(x);
+        for (int v = 1; v <= n - 1; ++v) psi -= 1.0 / (x + (double)v);
+        psi -= 1.0 / x;
+        x += (double)n;
+    }
+    double t = 1.0 / x;
+    psi += std::log(x) - 0.5 * t;
+    t *= t;
+    static const double c[8] = {0.08333333333333333, -0.008333333333333333, 0.003968253968253968, -0.004166666666666667,
+                                0.007575757575757576, -0.021092796092796094, 0.08333333333333333, -0.4432598039215686};
+    double p = c[7];
+    for (int i = 6; i >= 0; --i) p = std::fma(p, t, c[i]);
+    psi -= t * p;
+    return psi;
+}
+static double host_lgamma(double x) { int sg; return lgamma_r(x, &sg); }
+// returns -objective and -gradient (NLopt minimises the negated max_objective)
+static double neg_alpha_objective(double a, double *g, double sumE, int K, int V) {
+    *g = -(K * V * (host_digamma(V * a) - host_digamma(a)) + sumE);
+    return -(K * (host_lgamma(V * a) - V * host_lgamma(a)) + a * sumE);
+}
+static double mma_alpha(double x, double sumE, int K, int V, int stop_rule) {
+    const double lb = 1e-7, xtol = 1e-5;
+    double sigma = 1.0, rho = 1.0, g, gcur, fcur;
+    double fmin = neg_alpha_objective(x, &g, sumE, K, V);
+    double xcur = x, xprev = x, xprevprev = x;
+    int k = 0, nev = 1;
+    while (true) {
+        if (++k > 1) xprevprev = xprev;
+        xprev = xcur;
+        while (true) {
+            double u = g;
+            const double v = std::fabs(g) * sigma + 0.5 * rho, sigma2 = sigma * sigma;
+            u *= sigma2;
+            const double r = u / (v * sigma);
+            double dx = (u / v) / (-1 - std::sqrt(std::fabs(1 - r * r)));
+            double xc = x + dx;
+            if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
+            else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
+            if (xc < lb) xc = lb;
+            dx = xc - x;
+            const double dx2 = dx * dx, denominv = 1.0 / (sigma2 - dx2), cc = sigma2 * dx;
+            double gval = fmin, wval = 0.0;
+            gval += (g * cc + (std::fabs(g) * sigma + 0.5 * rho) * dx2) * denominv;
+            wval += 0.5 * dx2 * denominv;
+            xcur = xc;
+            fcur = neg_alpha_objective(xcur, &gcur, sumE, K, V);
+            ++nev;
+            const bool inner_done = gval >= fcur;
+            if (fcur < fmin) { fmin = fcur; x = xcur; g = gcur; }
+            if (nev >= 10000) return x;
+            if (inner_done) break;
+            if (fcur > gval) rho = std::min(10 * rho, 1.1 * (rho + (fcur - gval) / wval));
+        }
+        const double ad = std::fabs(xcur - xprev);
+        bool stop;
+        if (stop_rule == 1) stop = ad < xtol || ad < xtol * (std::fabs(xcur) + std::fabs(xprev)) * 0.5 || xcur == xprev;
+        else stop = (ad <= xtol * std::fabs(xcur)) || !(ad > xtol);
+        if (stop) break;
+        rho = 0.1 * rho > 1e-5 ? 0.1 * rho : 1e-5;
+        if (k > 1) {
+            const double s2 = (xcur - xprev) * (xprev - xprevprev);
+            sigma *= s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
+        }
+    }
+    return x;
+}
+static int mmctm_update_alpha(mmsig_handle *h) {
+    MmctmHost &mm = h->mm;
+    MmctmDev &p = mm.p;
+    std::vector<double> E(mm.G);
+    CU(cudaMemcpyAsync(E.data(), p.Elnphi, mm.G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    for (int m = 0; m < p.M; ++m) {
+        double s = 0.0;
+        for (int t = p.goff[m]; t < p.goff[m + 1]; ++t) s += E[t];
+        mm.alpha_host[m] = mma_alpha(mm.alpha_host[m], s, p.K[m], p.V[m], h->stop_rule);
+    }
+    CU(cudaMemcpyAsync(p.alpha, mm.alpha_host.data(), p.M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_get_alpha(mmsig_handle *h, double *alpha_out) {
+    NEED(h && alpha_out, "null argument");
+    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    memcpy(alpha_out, h->mm.alpha_host.data(), h->mm.p.M * sizeof(double));
+    return 0;
+}
+
 static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
@@ -687,6 +784,8 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
         LaunchScope ls(h, "k_mstep1");
         k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu);
     }
+    if ((flags & MMSIG_FLAG_AUTO_ALPHA) && !freeze_topics)       // src/MMCTM.jl:472-474, after update_γ!
+        if ((rc = mmctm_update_alpha(h))) return rc;
     if (do_sigma) {
         LaunchScope ls(h, "k_moments");
         MK_DISPATCH(p.MK, (k_post<MKP, true, false><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom, nullptr)));

@@ -143,13 +143,11 @@ class MMCTM:
 
     def fit(self, maxiter=100, tol=1e-4, verbose=True, autoalpha=False, updateSigma=True):
         """fit!(model; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true), src/MMCTM.jl:457-494."""
-        if autoalpha:
-            raise NotImplementedError("autoα=true (update_α!, src/MMCTM.jl:252-269) is outside the hot path built here")
-        flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        flags = (capi.FLAG_UPDATE_SIGMA if updateSigma else 0) | (capi.FLAG_AUTO_ALPHA if autoalpha else 0)
         if verbose:
             hist = []
             for it in range(1, maxiter + 1):
-                ll = self.iterate(updateSigma)
+                ll = self.iterate(flags=flags)
                 hist.append(ll)
                 print("%d\tLog-likelihoods: %s" % (it, ", ".join(repr(float(x)) for x in ll)))   # :482
                 if len(hist) > 10 and _converged(hist[-2], hist[-1], tol):
@@ -163,6 +161,10 @@ class MMCTM:
                                                     C.byref(n), C.byref(conv)))
             hist = buf[:n.value].copy()
             self.converged = bool(conv.value)
+        if autoalpha:
+            a = np.zeros(self.M)
+            self.h.check(self.h.lib.mmsig_mmctm_get_alpha(self.h.h, capi.dp(a)))
+            self.alpha = a
         self.elbo = self.calculate_elbo()[0]          # :490
         self.ll = hist[-1].copy()                     # :491
         return hist

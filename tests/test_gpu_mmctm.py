@@ -197,3 +197,19 @@ def test_restarts_config5_shape():
     assert np.array_equal(ll[best], states[best][2]) and np.array_equal(g.ll, states[best][2])
     assert abs(g.calculate_elbo()[0] - eo[best]) <= TOL_ITER * abs(eo[best])
     g.close()
+
+
+def test_auto_alpha(brca):
+    """fit!(autoα=true): update_α! (src/MMCTM.jl:252-269) after update_γ!, 1-D LD_MMA on the host."""
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    o, g = _pair(K, alpha, V, brca, g0)
+    ho = o.fit(maxiter=4, tol=1e-5, autoalpha=True)
+    hg = g.fit(maxiter=4, tol=1e-5, verbose=False, autoalpha=True)
+    assert np.array_equal(g.alpha, o.alpha) and not np.allclose(g.alpha, alpha)     # test/mmctm.jl:291
+    assert np.array_equal(hg, ho)
+    _check_iteration(o, g, ho[-1], hg[-1])
+    eo, to = o.elbo()
+    eg, tg = g.calculate_elbo()
+    assert abs(eg - eo) <= TOL_ITER * abs(eo), (tg, to)
+    g.close()
