@@ -84,9 +84,11 @@ def cpu_baseline(counts_fn, D_total, sample_D, nthreads, steps=1, warmup=0):
     dt = (time.perf_counter() - t) / steps
     its = (1.0 / dt) * (sample_D / float(D_total))
     return {"value": its, "unit": UNIT, "cores": nthreads, "kind": "port",
-            "sample": "oracle (C restatement of src/MMCTM.jl + NLopt LD_MMA; the Julia reference cannot run here), "
-                      "OpenMP over samples on %d threads, %d of the %d samples, %.2f s per iteration of the sample, "
-                      "scaled linearly in D" % (nthreads, sample_D, D_total, dt),
+            "sample": "oracle (C restatement of src/MMCTM.jl + NLopt LD_MMA, literal arithmetic; the Julia reference "
+                      "cannot run here: no julia / libnlopt in the image), OpenMP over samples on %d threads, first %d of "
+                      "the %d samples, %d warm-up + %d timed iterations, %.3f s per iteration of the sample, scaled "
+                      "linearly in D (the loop is O(D)); the reference itself is single-threaded"
+                      % (nthreads, sample_D, D_total, warmup, steps, dt),
             "seconds_per_sample_iteration": dt, "sample_D": sample_D}
 
 
@@ -99,7 +101,7 @@ def run_reference(args):
     nthreads = os.cpu_count() or 1
     sample_D = min(D, args.cpu_samples)
     cb = cpu_baseline(lambda lo, hi: mmsig.synth.generate(D, K_CFG, V_CFG, lo=lo, hi=hi), D, sample_D, nthreads,
-                      steps=max(args.steps, 1), warmup=min(args.warmup, 1))
+                      steps=max(args.steps, 1), warmup=args.warmup)
     line = {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / cb["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -123,7 +125,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--samples", type=int, default=1_000_000)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--cpu-samples", type=int, default=20_000)
+    ap.add_argument("--cpu-samples", type=int, default=100_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
@@ -202,6 +204,9 @@ def main():
         ms = e0.elapsed_time(e1)
         launches = model.h.launch_count() - l0
     ktimes = model.h.kernel_times(reset=True)
+    nev_nu, nev_lam = model.evals()
+    evals = {"nu_mean": float(nev_nu.mean()), "nu_max": int(nev_nu.max()), "lambda_mean": float(nev_lam.mean()),
+             "lambda_max": int(nev_lam.max())}
     if dist is not None:
         t = torch.tensor([ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -281,6 +286,7 @@ def main():
             "samples_iterations_per_sec": value * D,
             "nnz_per_sample": nnz_total / D,
             "ll": [float(x) for x in ll],
+            "mma_evaluations_per_sample_last_iteration": evals,
             "clocks": sampler.summary(),
             "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "ms_per_step": e2e_ms, "what": "set_data + set_state (pinned host -> device), iterate, get_state (device -> pinned host)"},
@@ -290,7 +296,8 @@ def main():
     if not args.no_cpu and world >= 1:
         nthreads = os.cpu_count() or 1
         sample_D = min(D, args.cpu_samples)
-        line["cpu_baseline"] = cpu_baseline(lambda a, b: mmsig.synth.generate(D, K_CFG, V_CFG, lo=a, hi=b), D, sample_D, nthreads)
+        line["cpu_baseline"] = cpu_baseline(lambda a, b: mmsig.synth.generate(D, K_CFG, V_CFG, lo=a, hi=b), D, sample_D,
+                                            nthreads, steps=min(max(args.steps, 1), 3), warmup=args.warmup)
     print(json.dumps(line), flush=True)
     model.close()
     if dist is not None:

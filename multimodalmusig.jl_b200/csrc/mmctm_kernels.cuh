@@ -21,6 +21,7 @@ constexpr int MMA_MAXEVAL = 10000;
 #define MATVEC_UNROLL 4
 #endif
 constexpr int kMatvecUnroll = MATVEC_UNROLL;
+constexpr int SROW_STRIDE = 34;   // doubles per padded row of invΣ in shared memory (>= 32, 16-byte multiple, odd multiple of 16 B / 8)
 #ifndef SOLVE_MIN_BLOCKS
 #define SOLVE_MIN_BLOCKS 4
 #endif
@@ -57,10 +58,12 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     double *thi = smem + KV + (size_t)warp * 2 * KV;
     double *tlo = thi + KV;
-    // smoothed (update_θ!, :183-198): table = Elnϕ, e = exp(λ + Elnϕ);
+    // smoothed (update_θ!, :183-198): θ ∝ exp(λ + Elnϕ), evaluated in the product form
+    //   e = exp(λ_k) · exp(Elnϕ_kv) (DET; the form the reference itself uses in
+    //   unsmoothed_update_θ!): K exps per sample + a K x V table instead of K·nnz exps;
     // unsmoothed (unsmoothed_update_θ!, :496-509): table = ϕ, e = exp(λ) ϕ
     const double *Eg = (unsmoothed ? p.phi : p.Elnphi) + p.goff[m];
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = Eg[i];
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = unsmoothed ? Eg[i] : det_exp(Eg[i]);
     for (int i = lane; i < 2 * KV; i += 32) thi[i] = 0.0;
     __syncthreads();
 
@@ -71,7 +74,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
         double lamk[KP];
         {
             double mine = (lane < K) ? p.lam_prev[d * p.MK + off + lane] : 0.0;
-            if (unsmoothed) mine = det_exp(mine);
+            mine = det_exp(mine);
 #pragma unroll
             for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
         }
@@ -88,7 +91,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
 #pragma unroll
             for (int k = 0; k < KP; ++k)
                 if (k < K) {
-                    e[k] = unsmoothed ? lamk[k] * Eln[k * V + v] : det_exp(lamk[k] + Eln[k * V + v]);
+                    e[k] = lamk[k] * Eln[k * V + v];
                     Z += e[k];
                 }
             const double rz = 1.0 / Z;                 // DET: θ_k = e_k * (1/Z), one division per nonzero
@@ -154,11 +157,15 @@ __device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, cons
         if (lane < MKP) dsh[lane] = c.active ? diff : 0.0;
         __syncwarp();
         double q = 0.0;
+        // row `lane` of invΣ, padded to SROW_STRIDE doubles (208 B): 128-bit loads of neighbouring
+        // lanes fall into distinct bank groups, so both operands come in as LDS.128
+        const double2 *srow = reinterpret_cast<const double2 *>(ST + lane * SROW_STRIDE);
+        const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
 #pragma unroll kMatvecUnroll
-        for (int i = 0; i < MKP; i += 2) {
-            const double2 dv = *reinterpret_cast<const double2 *>(dsh + i);
-            q = fma(ST[i * 32 + lane], dv.x, q);          // ST[i][j] = invΣ[j][i]: conflict-free
-            q = fma(ST[(i + 1) * 32 + lane], dv.y, q);
+        for (int i = 0; i < MKP / 2; ++i) {
+            const double2 sv = srow[i], dv = dv2[i];
+            q = fma(sv.x, dv.x, q);
+            q = fma(sv.y, dv.y, q);
         }
         __syncwarp();
         const double ce = c.c * e;
@@ -263,9 +270,9 @@ __device__ __forceinline__ double block_sum_seq(double e, int lo, int hi, int MK
 // ------------------------------------------------------------------------------------------
 template <int MKP>
 __global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, double2 *partial) {
-    __shared__ double dsh_all[8][MKP];
+    __shared__ __align__(16) double dsh_all[8][MKP];
     __shared__ double2 red[8][2][32];
-    __shared__ double ST[MKP * 32];          // invΣ transposed, zero padded: ST[i*32+j] = invΣ[j][i]
+    __shared__ __align__(16) double ST[32 * SROW_STRIDE];    // invΣ rows, zero padded: ST[j*SROW_STRIDE+i] = invΣ[j][i]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MK = p.MK, M = p.M;
     double *dsh = dsh_all[warp];
@@ -276,8 +283,8 @@ __global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, dou
         if (lane >= p.koff[m]) mod = m;
     const int blo = p.koff[mod], bhi = p.koff[mod + 1];
 
-    for (int t = threadIdx.x; t < MKP * 32; t += blockDim.x) {
-        const int i = t >> 5, j = t & 31;
+    for (int t = threadIdx.x; t < 32 * SROW_STRIDE; t += blockDim.x) {
+        const int j = t / SROW_STRIDE, i = t % SROW_STRIDE;
         ST[t] = (i < MK && j < MK) ? p.invSigma[j * MK + i] : 0.0;
     }
     __syncthreads();
@@ -671,7 +678,7 @@ __global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *ou
     const int K = p.K[m], V = p.V[m], KV = K * V, off = p.koff[m];
     double *Eln = smem;
     const double *Eg = (unsmoothed ? p.phi : p.Elnphi_prev) + p.goff[m];
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = Eg[i];
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = unsmoothed ? Eg[i] : det_exp(Eg[i]);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * 8;
@@ -682,7 +689,7 @@ __global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *ou
             double Z = 0.0;
             for (int k = 0; k < K; ++k) {
                 const double lk = p.lam_prev[d * p.MK + off + k];
-                const double e = unsmoothed ? det_exp(lk) * Eln[k * V + v] : det_exp(lk + Eln[k * V + v]);
+                const double e = det_exp(lk) * Eln[k * V + v];
                 out[w * K + k] = e;
                 Z += e;
             }

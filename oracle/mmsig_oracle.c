@@ -49,7 +49,9 @@
  *         the covariance moments, the LL totals): the EXACTLY ROUNDED sum
  *         of the addends -- order independent by definition, so independent
  *         of how samples are sharded over warps, blocks or GPUs;
- *     (4) theta_k = e_k * (1/Z) (one division per nonzero) instead of e_k / Z.
+ *     (4) theta_k = e_k * (1/Z) (one division per nonzero) instead of e_k / Z,
+ *         with e_k = exp(lambda_k) * exp(Elnphi_kv) (the product form of the
+ *         reference's own unsmoothed_update_theta!, src/MMCTM.jl:503).
  *   Nothing else changes.  tests/ check LITERAL against the reference's
  *   known-answer tests, DET against LITERAL (agreement to ~1e-13 wherever no
  *   MMA branch flips), and the CUDA path against DET.
@@ -690,7 +692,9 @@ void orc_mmctm_update_theta(orc_mmctm *m, int64_t d)
             double *th = m->theta[i] + (size_t)w * K;
             double s = 0.0;
             for (int k = 0; k < K; ++k) {
-                th[k] = xexp(m->arith, lam[off + k] + Eln[(size_t)k * V + v]);
+                /* DET: product form exp(lambda_k) * exp(Elnphi_kv), as unsmoothed_update_theta! (:503) */
+                th[k] = m->arith ? det_exp(lam[off + k]) * det_exp(Eln[(size_t)k * V + v])
+                                 : exp(lam[off + k] + Eln[(size_t)k * V + v]);
                 s += th[k];
             }
             if (m->arith) {     /* DET: theta_k = e_k * (1/Z), one division per nonzero */
