@@ -213,3 +213,29 @@ def test_auto_alpha(brca):
     eg, tg = g.calculate_elbo()
     assert abs(eg - eo) <= TOL_ITER * abs(eo), (tg, to)
     g.close()
+
+
+def test_two_stage_restart_orchestration():
+    """scripts/run_mmctm.jl:163-182 on resident counts, against the same procedure on the oracle."""
+    K, V, D, R = [4, 3], [30, 12], 300, 3
+    counts = small_synth(D, K, V, seed=31)
+    rng = np.random.default_rng(9)
+    G = sum(k * v for k, v in zip(K, V))
+    g0s = rng.integers(1, 101, size=(R, G)).astype(float)
+    g = mmsig.MMCTM(K, [0.1, 0.1], counts, V=V, gamma0=g0s[0])
+    out = mmsig.restarts.fit_model(g, g0s, maxiter=15)
+    ll1, gam = [], []
+    for r in range(R):
+        o = oracle_mmctm(K, [0.1, 0.1], V, counts, g0s[r])
+        h = o.fit(maxiter=15, tol=1e-4)
+        ll1.append(h[-1].copy()); gam.append(o.gamma.copy())
+    ll1 = np.asarray(ll1)
+    assert np.array_equal(out["stage1_ll"], ll1)
+    win = np.argmax(ll1, axis=0)
+    assert out["winners"].tolist() == win.tolist()
+    g2 = np.concatenate([gam[win[0]][:120], gam[win[1]][120:]])
+    o2 = oracle_mmctm(K, [0.1, 0.1], V, counts, g2)
+    h2 = o2.fit(maxiter=15, tol=1e-5)
+    assert np.array_equal(out["stage2_ll"], h2[-1])
+    assert np.array_equal(g.state()["lam"], o2.lam)
+    g.close()
