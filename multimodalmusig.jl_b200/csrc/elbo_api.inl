@@ -33,11 +33,15 @@ static int mmctm_elbo_impl(mmsig_handle *h, double *elbo, double *terms) {
     CU(cudaMemsetAsync(parts, 0, (size_t)p.M * nb * 4 * sizeof(double2), h->stream));
     {
         LaunchScope ls(h, "k_elbo_tables");
-        k_elbo_tables<<<1, 256, 0, h->stream>>>(p, d_tab);
+        const size_t lus = (size_t)2 * p.MK * p.MK * sizeof(double) + p.MK * sizeof(int);
+        CU(allow_max_smem(h, k_elbo_tables));
+        k_elbo_tables<<<1, 256, lus, h->stream>>>(p, d_tab);
     }
     {
         LaunchScope ls(h, "k_elbo_samples");
-        k_elbo_samples<<<nb, 256, 0, h->stream>>>(p, parts);
+        const size_t ess = (size_t)(p.MK * p.MK + 8 * p.MK) * sizeof(double);
+        CU(allow_max_smem(h, k_elbo_samples));
+        k_elbo_samples<<<nb, 256, ess, h->stream>>>(p, parts);
     }
     for (int m = 0; m < p.M; ++m) {
         const size_t smem = (size_t)p.K[m] * p.V[m] * sizeof(double);

@@ -28,10 +28,11 @@ __device__ __forceinline__ void block_reduce_dd_write(double (&hi)[NV], double (
 // Table-only terms (single block): out[0] = ElnPϕ (:271-284), out[1] = ElnQϕ (:338-350),
 // out[2] = ElnPX (:318-336) = Σ_kv (Σ n θ)_kv Elnϕ_kv, out[3] = logdet(invΣ) (:292).
 __global__ void __launch_bounds__(256) k_elbo_tables(MmctmDev p, double *out) {
-    __shared__ double A[MAXMK * MAXMK], B[MAXMK * MAXMK];
-    __shared__ int piv[MAXMK];
+    extern __shared__ double lu_smem[];                  // A, B: MK x MK each; piv: MK ints
     __shared__ double2 red[8 * 3];
     const int G = p.goff[p.M], MK = p.MK;
+    double *A = lu_smem, *B = lu_smem + MK * MK;
+    int *piv = reinterpret_cast<int *>(B + MK * MK);
     double hi[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
     // per (m,k) row pieces handled by one thread each; element-wise pieces strided
     if ((int)threadIdx.x < MK) {
@@ -75,39 +76,35 @@ __global__ void __launch_bounds__(256) k_elbo_tables(MmctmDev p, double *out) {
 //  [1] Σ_d ElnPZ_d (:302-316), stale sumθ, ζ
 //  [2] Σ_d Σ_j log ν_j                        -> ElnQη (:352-358)
 __global__ void __launch_bounds__(256) k_elbo_samples(MmctmDev p, double2 *partial) {
-    __shared__ double S[MAXMK * MAXMK];
+    extern __shared__ double es_smem[];                 // S: MK x MK ; per warp: diff[MK]
     __shared__ double2 red[8 * 3];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MK = p.MK, M = p.M;
+    double *S = es_smem, *dsh = es_smem + MK * MK + warp * MK;
     for (int i = threadIdx.x; i < MK * MK; i += blockDim.x) S[i] = p.invSigma[i];
     __syncthreads();
-    const bool active = lane < MK;
-    int mod = 0;
-    for (int m = 0; m < M; ++m)
-        if (lane >= p.koff[m]) mod = m;
-    const double muj = active ? p.mu[lane] : 0.0;
     double hi[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
     const long long nw = (long long)gridDim.x * 8;
     for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
-        const double lam = active ? p.lam[d * MK + lane] : 0.0;
-        const double nu = active ? p.nu[d * MK + lane] : 1.0;
-        const double diff = lam - muj;
-        double q = 0.0;
-        for (int i = 0; i < MK; ++i) {
-            const double di = shfl_d(diff, i);
-            if (active) q += S[i * MK + lane] * di;          // (Δᵀ S)_j as in diff' * invΣ * diff
-        }
-        if (active) {
-            dd_add(hi[0], lo[0], nu * S[lane * MK + lane]);
+        __syncwarp();
+        for (int j = lane; j < MK; j += 32) dsh[j] = p.lam[d * MK + j] - p.mu[j];
+        __syncwarp();
+        for (int j = lane; j < MK; j += 32) {
+            int mod = 0;
+            for (int m = 0; m < M; ++m)
+                if (j >= p.koff[m]) mod = m;
+            const double lam = p.lam[d * MK + j], nu = p.nu[d * MK + j], diff = dsh[j];
+            double q = 0.0;
+            for (int i = 0; i < MK; ++i) q += S[i * MK + j] * dsh[i];      // (Δᵀ S)_j as in diff' * invΣ * diff
+            dd_add(hi[0], lo[0], nu * S[j * MK + j]);
             dd_add(hi[0], lo[0], q * diff);
             const double zeta = p.zeta[d * M + mod], Ndm = p.N[d * M + mod];
             const double c = Ndm / zeta;
-            dd_add(hi[1], lo[1], lam * p.sumtheta[d * MK + lane]);
+            dd_add(hi[1], lo[1], lam * p.sumtheta[d * MK + j]);
             dd_add(hi[1], lo[1], -(c * det_exp(lam + 0.5 * nu)));
-            if (lane == p.koff[mod]) {
+            if (j == p.koff[mod]) {
                 dd_add(hi[1], lo[1], Ndm);
-                if (Ndm > 0) dd_add(hi[1], lo[1], -(Ndm * det_log(zeta)));
-                else dd_add(hi[1], lo[1], -(Ndm * det_log(zeta)));   // 0 * log ζ, as the reference evaluates it
+                dd_add(hi[1], lo[1], -(Ndm * det_log(zeta)));   // 0 * log ζ for an empty row, as the reference evaluates it
             }
             dd_add(hi[2], lo[2], det_log(nu));
         }

@@ -15,7 +15,7 @@
 namespace mmsig {
 
 constexpr int MAXM = 8;          // modalities
-constexpr int MAXMK = 32;        // ΣK_m: one coordinate per lane
+constexpr int MAXMK = 64;        // ΣK_m: one coordinate per lane up to 32, two per lane up to 64 (mmctm_wide.cuh)
 constexpr int MMA_MAXEVAL = 10000;
 #ifndef MATVEC_UNROLL
 #define MATVEC_UNROLL 4
@@ -547,9 +547,14 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, doub
 __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, double *out, double *logabsdet) {
     const int lane = threadIdx.x & 31;
     for (int k = 0; k < n; ++k) {
-        // first index of the maximum |A[i][k]|, i >= k
-        double best = (lane >= k && lane < n) ? fabs(A[lane * n + k]) : -1.0;
+        // first index of the maximum |A[i][k]|, i >= k (each lane scans rows lane, lane+32)
+        double best = -1.0;
         int bi = lane;
+        for (int i = lane; i < n; i += 32)
+            if (i >= k) {
+                const double a = fabs(A[i * n + k]);
+                if (a > best) { best = a; bi = i; }
+            }
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) {
             const double ob = shfl_xor_d(best, off);
@@ -559,18 +564,21 @@ __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, do
         if (lane == 0) piv[k] = bi;
         if (best == 0.0) return false;
         __syncwarp();
-        if (bi != k && lane < n) {
-            const double t = A[k * n + lane];
-            A[k * n + lane] = A[bi * n + lane];
-            A[bi * n + lane] = t;
-        }
+        if (bi != k)
+            for (int j = lane; j < n; j += 32) {
+                const double t = A[k * n + j];
+                A[k * n + j] = A[bi * n + j];
+                A[bi * n + j] = t;
+            }
         __syncwarp();
         const double inv = 1.0 / A[k * n + k];
         __syncwarp();
-        if (lane > k && lane < n) A[lane * n + k] = A[lane * n + k] * inv;
+        for (int i = lane; i < n; i += 32)
+            if (i > k) A[i * n + k] = A[i * n + k] * inv;
         __syncwarp();
-        if (lane > k && lane < n)
-            for (int i = k + 1; i < n; ++i) A[i * n + lane] -= A[i * n + k] * A[k * n + lane];
+        for (int j = lane; j < n; j += 32)
+            if (j > k)
+                for (int i = k + 1; i < n; ++i) A[i * n + j] -= A[i * n + k] * A[k * n + j];
         __syncwarp();
     }
     if (logabsdet) {
@@ -578,27 +586,27 @@ __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, do
         for (int i = 0; i < n; ++i) r += det_log(fabs(A[i * n + i]));
         *logabsdet = r;
     }
-    if (out && lane < n) {
-        const int c = lane;
-        for (int i = 0; i < n; ++i) B[i * n + c] = (i == c) ? 1.0 : 0.0;
-        for (int k = 0; k < n; ++k)
-            if (piv[k] != k) {
-                const double t = B[k * n + c];
-                B[k * n + c] = B[piv[k] * n + c];
-                B[piv[k] * n + c] = t;
+    if (out)
+        for (int c = lane; c < n; c += 32) {
+            for (int i = 0; i < n; ++i) B[i * n + c] = (i == c) ? 1.0 : 0.0;
+            for (int k = 0; k < n; ++k)
+                if (piv[k] != k) {
+                    const double t = B[k * n + c];
+                    B[k * n + c] = B[piv[k] * n + c];
+                    B[piv[k] * n + c] = t;
+                }
+            for (int i = 0; i < n; ++i) {
+                double s = B[i * n + c];
+                for (int j = 0; j < i; ++j) s -= A[i * n + j] * B[j * n + c];
+                B[i * n + c] = s;
             }
-        for (int i = 0; i < n; ++i) {
-            double s = B[i * n + c];
-            for (int j = 0; j < i; ++j) s -= A[i * n + j] * B[j * n + c];
-            B[i * n + c] = s;
+            for (int i = n - 1; i >= 0; --i) {
+                double s = B[i * n + c];
+                for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * B[j * n + c];
+                B[i * n + c] = s / A[i * n + i];
+            }
+            for (int i = 0; i < n; ++i) out[i * n + c] = B[i * n + c];
         }
-        for (int i = n - 1; i >= 0; --i) {
-            double s = B[i * n + c];
-            for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * B[j * n + c];
-            B[i * n + c] = s / A[i * n + i];
-        }
-        for (int i = 0; i < n; ++i) out[i * n + c] = B[i * n + c];
-    }
     __syncwarp();
     return true;
 }
@@ -607,9 +615,10 @@ __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, do
 // Σ = exact_round(diag Σ_d ν + Σ_d ΔΔᵀ) / D, invΣ = inv(Σ) (src/MMCTM.jl:204-212); ll_m (:417).
 __global__ void __launch_bounds__(32) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
                                                double *ll_out, int *status) {
-    __shared__ double A[MAXMK * MAXMK], B[MAXMK * MAXMK];
-    __shared__ int piv[MAXMK];
+    extern __shared__ double lu_smem[];                  // A, B: MK x MK each; piv: MK ints
     const int MK = p.MK, M = p.M, P2 = MK * MK + M, lane = threadIdx.x;
+    double *A = lu_smem, *B = lu_smem + MK * MK;
+    int *piv = reinterpret_cast<int *>(B + MK * MK);
     for (int i = lane; i < P2; i += 32) {
         double hi = 0.0, lo = 0.0;
         for (int r = 0; r < nranks; ++r) {

@@ -13,6 +13,7 @@
 #include "../../include/mmsig.h"
 #include "det_math.cuh"
 #include "mmctm_kernels.cuh"
+#include "mmctm_wide.cuh"
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
 
@@ -81,6 +82,8 @@ struct MmctmHost {
     int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0};
     size_t smem_theta[MAXM] = {0};
     int grid_solve = 0, grid_post = 0, grid_mom = 0;
+    bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
+    size_t smem_solve = 0;
     double2 *part_mom = nullptr;
     size_t smem_post = 0;
     double2 *part_theta[MAXM] = {nullptr};
@@ -475,7 +478,7 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
         NEED(rowptr[m], "null rowptr");
         MKsum += K[m];
     }
-    if (MKsum > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 32 supported (one coordinate per lane)");
+    if (MKsum > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 64 supported");
     // same shape as what is already resident (a repeated fit! on the same corpus): keep every
     // allocation and launch plan, only refresh the counts
     bool same = h->mm.has_data && h->mm.p.M == M && h->mm.p.D == D && h->mm.p.D_total == D_total;
@@ -560,18 +563,36 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
         if (rc) return rc;
         if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
     }
-    {
+    mm.wide = p.MK > 32;
+    CU(allow_max_smem(h, k_mstep2));
+    auto grid_for = [&](int nb) {
+        return (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+    };
+    if (!mm.wide) {
         int nb = 0;
         MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
-        mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+        mm.grid_solve = grid_for(nb);
         mm.smem_post = (size_t)(512 + mm.G + 256) * sizeof(double);
         if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
         MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, true, false>)));
         MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, false, true>)));
         MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP, false, true>, 256, mm.smem_post)));
-        mm.grid_post = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+        mm.grid_post = grid_for(nb);
         MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP, true, false>, 256, mm.smem_post)));
-        mm.grid_mom = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
+        mm.grid_mom = grid_for(nb);
+    } else {
+        int nb = 0;
+        mm.smem_solve = (size_t)(WMK * WSTRIDE + 8 * WMK) * sizeof(double) + (size_t)8 * 4 * 32 * sizeof(double2);
+        CU(allow_max_smem(h, k_solve_wide));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_wide, 256, mm.smem_solve));
+        mm.grid_solve = grid_for(nb);
+        mm.smem_post = (size_t)(16 + mm.G + 16 * WMK) * sizeof(double);
+        if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
+        CU(allow_max_smem(h, k_loglik_wide));
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loglik_wide, 256, mm.smem_post));
+        mm.grid_post = grid_for(nb);
+        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_moments_wide, 256, 0));
+        mm.grid_mom = grid_for(nb);
     }
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + M;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_solve, (size_t)mm.grid_solve * 2 * p.MK))) return rc;
@@ -627,7 +648,8 @@ extern "C" int32_t mmsig_mmctm_set_state(mmsig_handle *h, const double *alpha, c
     }
     {
         LaunchScope ls(h, "k_zeta");
-        k_zeta<<<mm.grid_solve, 256, 0, h->stream>>>(p);
+        if (mm.wide) k_zeta_props_wide<<<mm.grid_solve, 256, 0, h->stream>>>(p, nullptr, 1);
+        else k_zeta<<<mm.grid_solve, 256, 0, h->stream>>>(p);
     }
     CU(cudaMemsetAsync(p.stats, 0, mm.G * sizeof(double), h->stream));
     CU(cudaStreamSynchronize(h->stream));      // eye / caller buffers may go away
@@ -758,7 +780,8 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
     }
     {
         LaunchScope ls(h, "k_solve");
-        MK_DISPATCH(p.MK, (k_solve<MKP><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve)));
+        if (mm.wide) k_solve_wide<<<mm.grid_solve, 256, mm.smem_solve, h->stream>>>(p, mm.part_solve);
+        else MK_DISPATCH(p.MK, (k_solve<MKP><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve)));
     }
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + p.M;
     {
@@ -787,12 +810,20 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
     if ((flags & MMSIG_FLAG_AUTO_ALPHA) && !freeze_topics)       // src/MMCTM.jl:472-474, after update_γ!
         if ((rc = mmctm_update_alpha(h))) return rc;
     if (do_sigma) {
-        LaunchScope ls(h, "k_moments");
-        MK_DISPATCH(p.MK, (k_post<MKP, true, false><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom, nullptr)));
+        if (mm.wide) {
+            for (int r0 = 0; r0 < p.MK; r0 += 16) {
+                LaunchScope ls(h, "k_moments");
+                k_moments_wide<<<mm.grid_mom, 256, 0, h->stream>>>(p, mm.part_mom, r0);
+            }
+        } else {
+            LaunchScope ls(h, "k_moments");
+            MK_DISPATCH(p.MK, (k_post<MKP, true, false><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom, nullptr)));
+        }
     }
     {
         LaunchScope ls(h, "k_loglik");
-        MK_DISPATCH(p.MK, (k_post<MKP, false, true><<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post, nullptr)));
+        if (mm.wide) k_loglik_wide<<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post);
+        else MK_DISPATCH(p.MK, (k_post<MKP, false, true><<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post, nullptr)));
     }
     {
         // moments (first MK*MK entries) from the moments pass, LL (last M) from the LL pass
@@ -815,7 +846,8 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
     if ((rc = gather(h, mm.rank_p2, mm.gath_p2, P2, &g2))) return rc;
     {
         LaunchScope ls(h, "k_mstep2");
-        k_mstep2<<<1, 32, 0, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
+        const size_t lus = (size_t)2 * p.MK * p.MK * sizeof(double) + p.MK * sizeof(int);
+        k_mstep2<<<1, 32, lus, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
     }
     mm.estep_done = true;
     return 0;
@@ -895,7 +927,8 @@ extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double
         }
         {
             LaunchScope ls(h, "k_props");
-            k_props<<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.props_scratch);
+            if (mm.wide) k_zeta_props_wide<<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.props_scratch, 0);
+            else k_props<<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.props_scratch);
         }
         CU(cudaMemcpyAsync(props, mm.props_scratch, DMK * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     }

@@ -99,7 +99,10 @@ def test_brca_fit_config1(brca):
                                          ([10], [96], 1200, 0.0),                    # config 3: CTM
                                          ([7, 7], [96, 32], 800, 0.1),               # config 5 shape
                                          ([1, 2], [5, 3], 64, 0.3),                  # degenerate sizes
-                                         ([16, 16], [40, 7], 300, 0.0)])             # MK = 32
+                                         ([16, 16], [40, 7], 300, 0.0),              # MK = 32
+                                         ([12, 12, 10], [96, 32, 83], 300, 0.05),    # MK = 34: two coordinates per lane
+                                         ([20, 20], [30, 10], 200, 0.0),             # MK = 40
+                                         ([32, 32], [40, 33], 150, 0.0)])            # MK = 64
 def test_synthetic_three_iterations(K, V, D, empty):
     counts = small_synth(D, K, V, empty_frac=empty)
     alpha = [0.1] * len(K)
@@ -169,8 +172,8 @@ def test_bad_input_is_rejected():
         mmsig.MMCTM([2], [0.1], [(rp, np.array([3, 1, 1], np.int32), np.array([1, 1, 1], np.int32))], V=[4])
     with pytest.raises(mmsig.capi.MmsigError):          # zero count
         mmsig.MMCTM([2], [0.1], [(rp, np.array([0, 1, 1], np.int32), np.array([1, 0, 1], np.int32))], V=[4])
-    with pytest.raises(mmsig.capi.MmsigError):          # sum(K) > 32
-        mmsig.MMCTM([20, 20], [0.1, 0.1], [(rp, np.array([0, 1, 1], np.int32), np.array([1, 1, 1], np.int32))] * 2, V=[4, 4])
+    with pytest.raises(mmsig.capi.MmsigError):          # sum(K) > 64
+        mmsig.MMCTM([32, 32, 1], [0.1] * 3, [(rp, np.array([0, 1, 1], np.int32), np.array([1, 1, 1], np.int32))] * 3, V=[4, 4, 4])
 
 
 def test_restarts_config5_shape():
