@@ -1,7 +1,8 @@
 // lda_api.inl -- host side of the LDA entry points (included by mmsig_api.cu)
 
 template <typename F>
-static int pick_lda_plan(mmsig_handle *h, F kernel, int KV, long long D, int *W_out, int *grid_out, size_t *smem_out) {
+static int pick_lda_plan(mmsig_handle *h, F kernel, int KV /* V * (KP + 2) */, long long D, int *W_out, int *grid_out,
+                         size_t *smem_out) {
     cudaFuncAttributes fa;
     CU(cudaFuncGetAttributes(&fa, kernel));
     CU(allow_max_smem(h, kernel));
@@ -57,7 +58,7 @@ extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_tota
     if ((rc = dev_alloc(h, h->allocs_lda, &L.gamB, DK))) return rc;
     p.gamma = L.gamA;
     p.gamma_next = L.gamB;
-    THETA_DISPATCH(K, rc = pick_lda_plan(h, k_lda_estep<KP, NP>, (int)KV, D, &L.W, &L.grid, &L.smem));
+    THETA_DISPATCH(K, rc = pick_lda_plan(h, k_lda_estep<KP, NP>, V * (KP + 2), D, &L.W, &L.grid, &L.smem));
     if (rc) return rc;
     {
         int nb = 0;

@@ -49,16 +49,24 @@ __global__ void __launch_bounds__(256) k_lda_gamma_init(LdaDev p) {
 }
 
 // One E pass.  partial: [gridDim.x][K*V] (as double2 {sum, 0} so that k_combine can be shared).
+// Shared-memory tables are term-major, [v][KP + 2] (topics of one term contiguous, padded so that
+// the 128-bit accesses of neighbouring lanes -- neighbouring terms -- fall into distinct bank
+// groups): per nonzero the lane streams its term's row with LDS.128 / STS.128 and immediate
+// offsets.  Topics k >= K are zero padding (e^{Elnθ} = 0), so the unrolled loops need no guards.
 template <int KP, int NP>
 __global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, int nwarps_blk, const double *Etab,
                                                    int want_stats) {
     extern __shared__ double smem[];
-    const int K = p.K, V = p.V, KV = K * V;
-    double *E = smem;                                  // e^{Elnβ}, KV
+    constexpr int KPAD = KP + 2;
+    const int K = p.K, V = p.V, TS = V * KPAD;
+    double *E = smem;                                  // e^{Elnβ} (or β), [v][KPAD]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *tab = smem + KV + (size_t)warp * KV;       // this warp's statistics
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) E[i] = Etab[i];     // e^{Elnβ}, or β (unsmoothed)
-    for (int i = lane; i < KV; i += 32) tab[i] = 0.0;
+    double *tab = smem + TS + (size_t)warp * TS;       // this warp's statistics, [v][KPAD]
+    for (int i = threadIdx.x; i < TS; i += blockDim.x) {
+        const int v = i / KPAD, k = i % KPAD;
+        E[i] = k < K ? Etab[k * V + v] : 0.0;
+    }
+    for (int i = lane; i < TS; i += 32) tab[i] = 0.0;
     __syncthreads();
     const long long nw = (long long)gridDim.x * nwarps_blk;
     for (long long d = (long long)blockIdx.x * nwarps_blk + warp; d < p.D; d += nw) {
@@ -73,23 +81,31 @@ __global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, i
         for (int k = 0; k < NP; ++k) g[k] = 0.0;
         for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) {
             const int2 r = p.rec[w];
-            const int v = r.x;
+            const double2 *Ev = reinterpret_cast<const double2 *>(E + r.x * KPAD);
+            double2 *Tv = reinterpret_cast<double2 *>(tab + r.x * KPAD);
             double pk[KP];
             double Z = 0.0;
 #pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (k < K) {
-                    pk[k] = et[k] * E[k * V + v];
-                    Z += pk[k];
-                }
+            for (int k = 0; k < KP; k += 2) {
+                const double2 e2 = Ev[k / 2];
+                pk[k] = et[k] * e2.x;
+                Z += pk[k];
+                pk[k + 1] = et[k + 1] * e2.y;
+                Z += pk[k + 1];
+            }
             const double scale = (double)r.y / Z;
 #pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (k < K) {
-                    const double a = pk[k] * scale;
-                    if (want_stats) tab[k * V + v] += a;
-                    g[k] += a;
+            for (int k = 0; k < KP; k += 2) {
+                const double a0 = pk[k] * scale, a1 = pk[k + 1] * scale;
+                if (want_stats) {
+                    double2 t2 = Tv[k / 2];
+                    t2.x += a0;
+                    t2.y += a1;
+                    Tv[k / 2] = t2;
                 }
+                g[k] += a0;
+                g[k + 1] += a1;
+            }
         }
         __syncwarp();
         warp_multi_reduce<NP>(g, lane);
@@ -98,10 +114,11 @@ __global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, i
         if (idx < K && (lane & (GROUP - 1)) == 0) p.gamma_next[d * K + idx] = p.alpha + g[0];
     }
     __syncthreads();
-    double2 *out = partial + (size_t)blockIdx.x * KV;
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+    double2 *out = partial + (size_t)blockIdx.x * K * V;
+    for (int i = threadIdx.x; i < K * V; i += blockDim.x) {
+        const int k = i / V, v = i % V;
         double s = 0.0;
-        for (int wv = 0; wv < nwarps_blk; ++wv) s += smem[KV + (size_t)wv * KV + i];
+        for (int wv = 0; wv < nwarps_blk; ++wv) s += smem[TS + (size_t)wv * TS + v * KPAD + k];
         out[i] = make_double2(s, 0.0);
     }
 }
