@@ -67,10 +67,24 @@ EXPORTS = sorted(_SIGS)
 _LIB = None
 
 
+def build_if_stale():
+    """(Re)build libmmsig.so with nvcc when it is missing or older than its sources.  Building is
+    not computing: the library still refuses to run without a CUDA device."""
+    import shutil
+    import subprocess
+    src_dir = os.path.join(_HERE, "csrc")
+    srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".inl"))]
+    srcs.append(os.path.join(os.path.dirname(_HERE), "include", "mmsig.h"))
+    stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
+    if stale and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        subprocess.check_call(["make", "-s", "-C", src_dir])
+
+
 def load():
     """dlopen libmmsig.so and declare every entry point of include/mmsig.h."""
     global _LIB
     if _LIB is None:
+        build_if_stale()
         if not os.path.exists(LIB_PATH):
             raise ImportError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                               "(make -C multimodalmusig.jl_b200/csrc); there is no CPU fallback" % LIB_PATH)
