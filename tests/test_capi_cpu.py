@@ -35,10 +35,16 @@ def test_no_cpu_fallback():
 
 
 def test_product_never_imports_the_oracle():
+    """The product path may mention the oracle in comments, never import, include, link or call it."""
     pkg = os.path.join(ROOT, "multimodalmusig.jl_b200")
+    banned = ("import orc", "from orc", "liboracle", "mmsig_oracle", "orc_mmctm", "orc_lda", "orc_mma", "../oracle",
+              "oracle/")
     for dirpath, _, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")):
+            if f.endswith((".py", ".cu", ".cuh", ".inl", ".h")) or f == "Makefile":
                 txt = open(os.path.join(dirpath, f)).read()
-                assert "oracle" not in txt.lower() or f in ("det_math.cuh", "mmctm_kernels.cuh", "lda_kernels.cuh"), f
-                assert "import orc" not in txt and "liboracle" not in txt, f
+                for b in banned:
+                    assert b not in txt, (f, b)
+    for f in ("mmsig.py",):
+        txt = open(os.path.join(ROOT, f)).read()
+        assert "orc" not in txt
