@@ -125,7 +125,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
 
 // ------------------------------------------------------------------------------------------
 // NLopt LD_MMA with zero constraints, one warp per problem, lane j = coordinate j.
-// Restates the recurrence of the oracle's orc_mma_minimize (ORC_ARITH_DET) op for op.
+// Follows the pinned-arithmetic (DET) specification of the recurrence op for op.
 // ------------------------------------------------------------------------------------------
 struct SolveCtx {
     double Sjj;        // invΣ[j][j]
