@@ -14,6 +14,7 @@
 #include "det_math.cuh"
 #include "mmctm_kernels.cuh"
 #include "mmctm_wide.cuh"
+#include "mmctm_pack.cuh"
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
 
@@ -81,7 +82,7 @@ struct MmctmHost {
     std::vector<long long> nnz;
     int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0};
     size_t smem_theta[MAXM] = {0};
-    int grid_solve = 0, grid_post = 0, grid_mom = 0;
+    int grid_solve = 0, grid_post = 0, grid_mom = 0, grid_zeta = 0;
     bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
     size_t smem_solve = 0;
     double2 *part_mom = nullptr;
@@ -570,8 +571,15 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     };
     if (!mm.wide) {
         int nb = 0;
-        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
-        mm.grid_solve = grid_for(nb);
+        if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
+        else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
+        else MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
+        {
+            const int spw = p.MK <= 8 ? 4 : (p.MK <= 16 ? 2 : 1);          // samples per warp
+            mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1),
+                                                                            (D + 8 * spw - 1) / (8 * spw)));
+        }
+        mm.grid_zeta = grid_for(nb);
         mm.smem_post = (size_t)(512 + mm.G + 256) * sizeof(double);
         if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
         MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, true, false>)));
@@ -781,6 +789,8 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
     {
         LaunchScope ls(h, "k_solve");
         if (mm.wide) k_solve_wide<<<mm.grid_solve, 256, mm.smem_solve, h->stream>>>(p, mm.part_solve);
+        else if (p.MK <= 8) k_solve_pack<8><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve);
+        else if (p.MK <= 16) k_solve_pack<16><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve);
         else MK_DISPATCH(p.MK, (k_solve<MKP><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve)));
     }
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + p.M;
