@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
 #include <string>
@@ -83,6 +84,7 @@ struct MmctmHost {
     int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0};
     size_t smem_theta[MAXM] = {0};
     int grid_solve = 0, grid_post = 0, grid_mom = 0, grid_zeta = 0;
+    bool solve_multi = false;          // 16 < sum(K) <= 32: k_solve_multi (4 samples per warp) instead of k_solve
     bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
     size_t smem_solve = 0;
     double2 *part_mom = nullptr;
@@ -565,6 +567,14 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
         if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
     }
     mm.wide = p.MK > 32;
+    {
+        // MMSIG_SOLVE=multi selects k_solve_multi (4 samples per warp, 3-4 coordinates per lane) for
+        // 16 < sum(K) <= 32.  It is bit-identical but measured SLOWER than one sample per warp on
+        // B200 (26.1 vs 21.9 ms at D = 5e5, sum(K) = 24: 168 registers, phase divergence), so it
+        // is off by default and kept for A/B measurements.
+        const char *e = getenv("MMSIG_SOLVE");
+        mm.solve_multi = e && !strcmp(e, "multi");
+    }
     CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
         return (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
@@ -573,11 +583,14 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
         int nb = 0;
         if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
         else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
+        else if (mm.solve_multi && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<3>, 128, 0));
+        else if (mm.solve_multi) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<4>, 128, 0));
         else MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
         {
-            const int spw = p.MK <= 8 ? 4 : (p.MK <= 16 ? 2 : 1);          // samples per warp
+            // samples per block: 8 warps x 1, 2 or 4 (packed), or 4 warps x 4 (multi)
+            const int spb = p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : (mm.solve_multi ? 16 : 8));
             mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1),
-                                                                            (D + 8 * spw - 1) / (8 * spw)));
+                                                                            (D + spb - 1) / spb));
         }
         mm.grid_zeta = grid_for(nb);
         mm.smem_post = (size_t)(512 + mm.G + 256) * sizeof(double);
@@ -791,6 +804,8 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
         if (mm.wide) k_solve_wide<<<mm.grid_solve, 256, mm.smem_solve, h->stream>>>(p, mm.part_solve);
         else if (p.MK <= 8) k_solve_pack<8><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve);
         else if (p.MK <= 16) k_solve_pack<16><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve);
+        else if (mm.solve_multi && p.MK <= 24) k_solve_multi<3><<<mm.grid_solve, 128, 0, h->stream>>>(p, mm.part_solve);
+        else if (mm.solve_multi) k_solve_multi<4><<<mm.grid_solve, 128, 0, h->stream>>>(p, mm.part_solve);
         else MK_DISPATCH(p.MK, (k_solve<MKP><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve)));
     }
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + p.M;

@@ -242,3 +242,17 @@ def test_two_stage_restart_orchestration():
     assert np.array_equal(out["stage2_ll"], h2[-1])
     assert np.array_equal(g.state()["lam"], o2.lam)
     g.close()
+
+
+def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
+    """MMSIG_SOLVE=multi: the alternative k_solve for 16 < sum(K) <= 32 (4 samples per warp); off by
+    default because it measured slower, kept bit-identical."""
+    monkeypatch.setenv("MMSIG_SOLVE", "multi")
+    for K, V in (([10, 8, 6], [96, 32, 83]), ([16, 16], [40, 7])):
+        counts = small_synth(400, K, V, empty_frac=0.05)
+        g0 = mmsig.synth.init_gamma(K, V)
+        o, g = _pair(K, [0.1] * len(K), V, counts, g0)
+        for _ in range(2):
+            ll_o, ll_g = o.iterate(), g.iterate()
+            _check_iteration(o, g, ll_o, ll_g)
+        g.close()
