@@ -70,20 +70,40 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
     const long long *rowptr = p.rowptr[m];
     const int2 *rec = p.rec[m];
     const long long nw = (long long)gridDim.x * nwarps_blk;
-    for (long long d = (long long)blockIdx.x * nwarps_blk + warp; d < p.D; d += nw) {
-        double lamk[KP];
-        {
-            double mine = (lane < K) ? p.lam_prev[d * p.MK + off + lane] : 0.0;
-            mine = det_exp(mine);
-#pragma unroll
-            for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
+    // software pipeline: the row pointers, the first 32 records and λ of the NEXT sample are
+    // requested before the current one is computed (12-20 resident warps per SM cannot hide DRAM
+    // latency on their own: long-scoreboard stalls were the top reason in profiles/r01f)
+    long long d = (long long)blockIdx.x * nwarps_blk + warp;
+    long long beg_n = 0, end_n = 0;
+    int2 r_n = make_int2(0, 1);
+    double lam_n = 0.0;
+    if (d < p.D) {
+        beg_n = rowptr[d];
+        end_n = rowptr[d + 1];
+        if (beg_n + lane < end_n) r_n = rec[beg_n + lane];
+        lam_n = (lane < K) ? p.lam_prev[d * p.MK + off + lane] : 0.0;
+    }
+    for (; d < p.D; d += nw) {
+        const long long beg = beg_n, end = end_n;
+        int2 r = r_n;
+        double mine = lam_n;
+        if (d + nw < p.D) {
+            const long long dn = d + nw;
+            beg_n = rowptr[dn];
+            end_n = rowptr[dn + 1];
+            if (beg_n + lane < end_n) r_n = rec[beg_n + lane];
+            lam_n = (lane < K) ? p.lam_prev[dn * p.MK + off + lane] : 0.0;
         }
+        double lamk[KP];
+        mine = det_exp(mine);
+#pragma unroll
+        for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
         double sth[NP];                     // Σ_w a_kw of this lane's nonzeros (w ≡ lane mod 32)
 #pragma unroll
         for (int k = 0; k < NP; ++k) sth[k] = 0.0;
-        const long long beg = rowptr[d], end = rowptr[d + 1];
         for (long long w = beg + lane; w < end; w += 32) {
-            const int2 r = rec[w];
+            int2 r_next = r;
+            if (w + 32 < end) r_next = rec[w + 32];
             const int v = r.x;
             const double n = (double)r.y;
             double e[KP];
@@ -102,6 +122,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
                     if (want_stats) dd_add(thi[k * V + v], tlo[k * V + v], a);
                     sth[k] += a;
                 }
+            r = r_next;
         }
         __syncwarp();
         // the butterfly tree over lanes (recursive halving computes exactly its partial sums)
@@ -498,11 +519,15 @@ __global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, doub
                     const double *ph = phi + p.goff[m];
                     const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
                     double rs = 0.0;
+                    int2 r = make_int2(0, 1);
+                    if (beg + lane < end) r = p.rec[m][beg + lane];
                     for (long long w = beg + lane; w < end; w += 32) {
-                        const int2 r = p.rec[m][w];
+                        int2 r_next = r;
+                        if (w + 32 < end) r_next = p.rec[m][w + 32];
                         double pw = 0.0;
                         for (int k = 0; k < K; ++k) pw += psh[ko + k] * ph[k * V + r.x];
                         rs += (double)r.y * det_log(pw);
+                        r = r_next;
                     }
                     __syncwarp();
                     double dl = warp_tree_sum(rs);             // row sum: leaf = w mod 32, butterfly
