@@ -270,12 +270,22 @@ def main():
                   for k, v in ktimes.items() if v[1] > 0}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"]) if per_kernel else None
     alg_local = algorithmic_bytes(nnz_local, Dl, MK, M)
+    traffic = None
+    try:        # DRAM bytes of the dominant kernel from the committed ncu capture, per sample x local samples
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+        for name, v in tj["kernels"].items():
+            if dom and name.startswith(dom):
+                traffic = v["dram_bytes_per_sample"][0] * Dl
+                traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at D=%d (%s), scaled by the local sample count" % (tj["D"], "profiles/traffic.json")
+    except Exception:
+        pass
     roof = None
+    traffic_src = locals().get("traffic_src")
     if dom:
         dms = per_kernel[dom]["ms_per_step"] / max(per_kernel[dom]["launches_per_step"], 1)
         ach = alg_local / (dms * 1e-3) / 1e9
         roof = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak,
-                "traffic": None, "peak_source": peak_src,
+                "traffic": traffic, "traffic_source": traffic_src if traffic else None, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_local, "kernel_ms_per_launch": dms,
                 "iteration_gbs_all_kernels": algorithmic_bytes(nnz_total, D, MK, M) / (ms_step * 1e-3) / 1e9,
                 "note": "exact-LD_MMA FP64 mode is FP64-pipe bound, not HBM bound (DESIGN.md); see profiles/"}
