@@ -59,8 +59,11 @@ class ClockSampler(threading.Thread):
         if not self.rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         rows, window = [r for r in self.rows if self.t0 is not None and self.t0 <= r[0] <= self.t1], "timed region"
-        if not rows:                        # region shorter than one nvidia-smi call: use the loaded warm-up too
-            rows, window = self.rows, "warm-up + timed region (timed region shorter than one sample)"
+        if not rows:                        # region shorter than one nvidia-smi call
+            rows = [r for r in self.rows if self.t0 is not None and r[0] >= self.t0]
+            window = "timed region + identical untimed iterations run right after it (timed region shorter than one sample)"
+        if not rows:
+            rows, window = self.rows, "warm-up + timed region"
         sm = sorted(float(r[1]) for r in rows)
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in rows)]
@@ -200,6 +203,12 @@ def main():
         e1.record(stream)
         barrier()
         sampler.t1 = time.perf_counter()
+        # a timed region shorter than one nvidia-smi call leaves no clock sample: keep the same load
+        # running (untimed) until the sampler has seen it at least twice
+        extra_t0 = time.perf_counter()
+        while len([r for r in sampler.rows if r[0] >= sampler.t0]) < 2 and time.perf_counter() - extra_t0 < 5.0:
+            model.iterate()
+        sampler.t_extra = time.perf_counter()
         sampler.stop_flag.set()
         ms = e0.elapsed_time(e1)
         launches = model.h.launch_count() - l0
