@@ -203,13 +203,6 @@ def main():
         e1.record(stream)
         barrier()
         sampler.t1 = time.perf_counter()
-        # a timed region shorter than one nvidia-smi call leaves no clock sample: keep the same load
-        # running (untimed) until the sampler has seen it at least twice
-        extra_t0 = time.perf_counter()
-        while len([r for r in sampler.rows if r[0] >= sampler.t0]) < 2 and time.perf_counter() - extra_t0 < 5.0:
-            model.iterate()
-        sampler.t_extra = time.perf_counter()
-        sampler.stop_flag.set()
         ms = e0.elapsed_time(e1)
         launches = model.h.launch_count() - l0
     ktimes = model.h.kernel_times(reset=True)
@@ -227,6 +220,13 @@ def main():
         nnz_total = float(nnz_local)
     ms_step = ms / args.steps
     value = 1000.0 / ms_step
+    # a timed region shorter than ~1.5 s can fall between two nvidia-smi samples: keep the identical
+    # load running, untimed, on every rank (same count everywhere: the iterations are collective)
+    n_extra = min(500, int(np.ceil(max(0.0, 1500.0 - ms) / ms_step)))
+    for _ in range(n_extra):
+        model.iterate()
+    sampler.stop_flag.set()
+    model.h.kernel_times(reset=True)
 
     # ---- e2e: public API with host buffers; H2D of counts + state, one iteration, D2H of state ----
     lam_h, t1 = pin(np.zeros((Dl, MK)))
