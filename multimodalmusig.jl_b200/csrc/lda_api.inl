@@ -60,6 +60,28 @@ extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_tota
     p.gamma_next = L.gamB;
     THETA_DISPATCH(K, rc = pick_lda_plan(h, k_lda_estep<KP, NP>, V * (KP + 2), D, &L.W, &L.grid, &L.smem));
     if (rc) return rc;
+    L.grid_row = L.grid;
+    // tiled (skinny-product) E pass when the tile fits: NW = ceil(V/32) warps, 32 NW samples per tile
+    {
+        const char *e = getenv("MMSIG_LDA");                 // "row": force the per-nonzero kernel (A/B)
+        L.NW = (V + 31) / 32;
+        L.tile = L.NW <= 8 && !(e && !strcmp(e, "row"));
+        if (L.tile) {
+            int KPv = 0;
+            THETA_DISPATCH(K, KPv = KP);
+            const int TS = 32 * L.NW, VP = V | 1;
+            L.smem_tile = (size_t)(V * (KPv + 2) + TS * VP + TS * KPv) * sizeof(double);
+            if (L.smem_tile > h->smem_optin) L.tile = false;
+        }
+        if (L.tile) {
+            int nb = 0;
+            THETA_DISPATCH(K, CU(allow_max_smem(h, k_lda_estep_tile<KP>)));
+            THETA_DISPATCH(K, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_estep_tile<KP>, L.NW * 32, L.smem_tile)));
+            const long long ntiles = (D + 32 * L.NW - 1) / (32 * L.NW);
+            L.grid_tile = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), ntiles));
+            L.grid = std::max(L.grid, L.grid_tile);          // the partial buffer serves both kernels
+        }
+    }
     {
         int nb = 0;
         L.smem_ll = (KV + 256) * sizeof(double);
@@ -118,10 +140,16 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     L.last_unsmoothed = unsm;
     L.last_frozen = freeze;
     std::swap(p.gamma, p.gamma_next);               // γ_t <- what the previous pass (or init) produced
-    {
+    int nparts = L.grid_row;
+    if (L.tile) {
+        LaunchScope ls(h, "k_lda_estep_tile");
+        THETA_DISPATCH(p.K, (k_lda_estep_tile<KP><<<L.grid_tile, L.NW * 32, L.smem_tile, h->stream>>>(
+                                p, L.part, unsm ? p.beta : p.expElnbeta, !freeze, L.NW)));
+        nparts = L.grid_tile;
+    } else {
         LaunchScope ls(h, "k_lda_estep");
-        THETA_DISPATCH(p.K, (k_lda_estep<KP, NP><<<L.grid, L.W * 32, L.smem, h->stream>>>(p, L.part, L.W,
-                                                                                         unsm ? p.beta : p.expElnbeta, !freeze)));
+        THETA_DISPATCH(p.K, (k_lda_estep<KP, NP><<<L.grid_row, L.W * 32, L.smem, h->stream>>>(p, L.part, L.W,
+                                                                                             unsm ? p.beta : p.expElnbeta, !freeze)));
     }
     const double2 *g = nullptr;
     int rc;
@@ -130,7 +158,7 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
             CombineSegs s{};
             s.nseg = 1;
             s.src[0] = L.part;
-            s.nparts[0] = L.grid;
+            s.nparts[0] = nparts;
             s.n[0] = KV;
             s.dst_off[0] = 0;
             LaunchScope ls(h, "k_combine");

@@ -123,6 +123,137 @@ __global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, i
     }
 }
 
+// ------------------------------------------------------------------------------------------
+// The same E pass as three skinny products over a tile of TS = 32·NW samples (NW = ⌈V/32⌉ warps):
+//   Z[d][v]   = Σ_k e^{Elnθ}[d][k] · E[k][v]                   (lane <-> term, E column in registers)
+//   R[d][v]   = n[d][v] / Z[d][v]                               (dense tile in shared memory)
+//   S[k][v]   = E[k][v] · Σ_d e^{Elnθ}[d][k] · R[d][v]          (lane <-> term: no reduction until the end)
+//   γ'[d][k]  = α + e^{Elnθ}[d][k] · Σ_v E[k][v] · R[d][v]      (lane <-> sample: no reduction at all)
+// i.e. the (D x V)ᵀ(D x K) form of the statistics: every multiply-add is a DFMA on operands that
+// sit in registers or are broadcast from shared memory, and neither output needs a cross-lane
+// reduction per sample (the per-nonzero kernel above spends most of its instructions on those
+// and on shared-memory read-modify-writes).  Results differ from it by reassociation only.
+// ------------------------------------------------------------------------------------------
+template <int KP>
+__global__ void __launch_bounds__(256) k_lda_estep_tile(LdaDev p, double2 *partial, const double *Etab, int want_stats,
+                                                        int NW) {
+    extern __shared__ double smem[];
+    constexpr int KPAD = KP + 2;
+    const int K = p.K, V = p.V, TS = 32 * NW, VP = V | 1;
+    double *Esm = smem;                         // [v][KPAD]
+    double *rt = Esm + V * KPAD;                // [t][VP]   n, then R
+    double *et = rt + TS * VP;                  // [t][KP]   e^{Elnθ}
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int v = warp * 32 + lane;
+    const bool vok = v < V;
+    for (int i = tid; i < V * KPAD; i += blockDim.x) {
+        const int vv = i / KPAD, k = i % KPAD;
+        Esm[i] = k < K ? Etab[k * V + vv] : 0.0;
+    }
+    double Ereg[KP], acc[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+        Ereg[k] = (vok && k < K) ? Etab[k * V + v] : 0.0;
+        acc[k] = 0.0;
+    }
+    __syncthreads();
+    const long long ntiles = (p.D + TS - 1) / TS;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long d0 = tile * TS;
+        // ---- per-sample preparation, thread <-> sample: dense count row of the tile (every lane
+        // walks its own CSR row, so 32 rows are in flight per load instruction), Elnθ (:78-80), e^{Elnθ}
+        {
+            const long long d = d0 + tid;
+            double *row = rt + tid * VP;
+            for (int i = 0; i < V; ++i) row[i] = 0.0;
+            double *er = et + tid * KP;
+            if (d < p.D) {
+                const long long beg = p.rowptr[d], end = p.rowptr[d + 1];
+#pragma unroll 8
+                for (long long w = beg; w < end; ++w) {
+                    const int2 r = p.rec[w];
+                    row[r.x] = (double)r.y;
+                }
+                double gk[KP];
+                double s = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; ++k) {
+                    gk[k] = k < K ? p.gamma[d * K + k] : 1.0;
+                    if (k < K) s += gk[k];
+                }
+                const double ds = det_digamma(s);
+                // independent digamma / exp chains, interleaved four at a time by the unroll
+#pragma unroll 4
+                for (int k = 0; k < KP; ++k) {
+                    const double e = det_exp(det_digamma(gk[k]) - ds);
+                    er[k] = k < K ? e : 0.0;
+                }
+            } else
+                for (int k = 0; k < KP; ++k) er[k] = 0.0;
+        }
+        __syncthreads();
+        // ---- Z, R and the statistics, lane <-> term
+        if (vok) {
+            for (int t = 0; t < TS; ++t) {
+                const double2 *e2 = reinterpret_cast<const double2 *>(et + t * KP);
+                double ek[KP];
+                double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0;       // four partial chains for ILP
+#pragma unroll
+                for (int k = 0; k < KP; k += 4) {
+                    const double2 x2 = e2[k / 2], y2 = e2[k / 2 + 1];
+                    ek[k] = x2.x;
+                    ek[k + 1] = x2.y;
+                    ek[k + 2] = y2.x;
+                    ek[k + 3] = y2.y;
+                    z0 = fma(x2.x, Ereg[k], z0);
+                    z1 = fma(x2.y, Ereg[k + 1], z1);
+                    z2 = fma(y2.x, Ereg[k + 2], z2);
+                    z3 = fma(y2.y, Ereg[k + 3], z3);
+                }
+                const double Z = (z0 + z1) + (z2 + z3);
+                const double n = rt[t * VP + v];
+                const double r = (Z > 0.0) ? n * (1.0 / Z) : 0.0;      // padded samples have Z = 0
+                rt[t * VP + v] = r;
+                if (want_stats)
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) acc[k] = fma(ek[k], r, acc[k]);
+            }
+        }
+        __syncthreads();
+        // ---- γ_{t+1}, thread <-> sample
+        {
+            const long long d = d0 + tid;
+            if (d < p.D) {
+                double g[KP];
+#pragma unroll
+                for (int k = 0; k < KP; ++k) g[k] = 0.0;
+                const double *row = rt + tid * VP;
+                for (int i = 0; i < V; ++i) {
+                    const double r = row[i];
+                    const double2 *E2 = reinterpret_cast<const double2 *>(Esm + i * KPAD);
+#pragma unroll
+                    for (int k = 0; k < KP; k += 2) {
+                        const double2 x2 = E2[k / 2];
+                        g[k] = fma(x2.x, r, g[k]);
+                        g[k + 1] = fma(x2.y, r, g[k + 1]);
+                    }
+                }
+                const double *er = et + tid * KP;
+#pragma unroll
+                for (int k = 0; k < KP; ++k)
+                    if (k < K) p.gamma_next[d * K + k] = p.alpha + er[k] * g[k];
+            }
+        }
+        __syncthreads();
+    }
+    double2 *out = partial + (size_t)blockIdx.x * K * V;
+    if (vok) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) out[k * V + v] = make_double2(Ereg[k] * acc[k], 0.0);    // S = E ∘ (e^{Elnθ})ᵀ R
+    }
+}
+
 // M-step (single block): λ = η + Σ n ϕ (:100-105), Elnβ (:96-98), β (:110-112), e^{Elnβ}.
 __global__ void __launch_bounds__(1024) k_lda_mstep(LdaDev p, const double2 *gathered, int nranks) {
     __shared__ double rowsum[32], rowdig[32];
