@@ -143,7 +143,8 @@ int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, do
 /* model.ϕ[d] for all d, nnz x K row-major ([w][k]), recomputed lazily */
 int32_t mmsig_lda_get_phi(mmsig_handle *h, double *phi_out);
 
-/* ---- test hook: the pinned device math on arrays (fn 0 = exp, 1 = log, 2 = digamma) ---------- */
+/* ---- test hook: the pinned device math on arrays (fn 0 = exp, 1 = log, 2 = digamma; the branch-free
+ * IEEE sequences of det_math.cuh: 3 = x[i] / x[n+i] (x holds 2n values), 4 = 1 / x, 5 = sqrt) ---- */
 int32_t mmsig_debug_math(mmsig_handle *h, int32_t fn, int64_t n, const double *x, double *y);
 
 /* ---- instrumentation ---------------------------------------------------------------------- */

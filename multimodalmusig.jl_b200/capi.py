@@ -6,7 +6,8 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmmsig.so")
+# MMSIG_LIB: developer override used for A/B timing of build variants (profiles/ab_variants.sh)
+LIB_PATH = os.environ.get("MMSIG_LIB") or os.path.join(_HERE, "libmmsig.so")
 
 c_dp = C.POINTER(C.c_double)
 c_i32p = C.POINTER(C.c_int32)
@@ -75,6 +76,8 @@ def build_if_stale():
     src_dir = os.path.join(_HERE, "csrc")
     srcs = [os.path.join(src_dir, f) for f in os.listdir(src_dir) if f.endswith((".cu", ".cuh", ".inl"))]
     srcs.append(os.path.join(os.path.dirname(_HERE), "include", "mmsig.h"))
+    if os.environ.get("MMSIG_LIB"):
+        return
     stale = not os.path.exists(LIB_PATH) or any(os.path.getmtime(f) > os.path.getmtime(LIB_PATH) for f in srcs)
     if stale and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
         subprocess.check_call(["make", "-s", "-C", src_dir])

@@ -169,7 +169,7 @@ __device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, cons
     if (IS_NU) {
         // src/common.jl:25-36, maximised; fused per-coordinate term (DET)
         const double e = det_exp(c.other + 0.5 * x);
-        grad = (-0.5 * c.Sjj - (c.c / 2) * e) + (1.0 / (2 * x));
+        grad = (-0.5 * c.Sjj - (c.c / 2) * e) + fast_rcp(2 * x);
         t = (-0.5 * (x * c.Sjj) - c.c * e) + det_log(x) / 2;
     } else {
         // src/common.jl:11-23
@@ -222,8 +222,10 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             const double v = fabs(g) * sigma + 0.5 * rho;
             const double sigma2 = sigma * sigma;
             u *= sigma2;
-            const double r = u / (v * sigma);
-            double dx = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
+            const double r = fast_div(u, v * sigma);
+            const double om = fabs(1 - r * r);
+            const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+            double dx = fast_div(fast_div(u, v), -1 - sq);
             double xc = x + dx;
             if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
             else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
@@ -231,7 +233,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             if (!c.active) xc = x;                   // dummy lanes stay put
             dx = xc - x;
             const double dx2 = dx * dx;
-            const double denominv = 1.0 / (sigma2 - dx2);
+            const double denominv = fast_rcp(sigma2 - dx2);       // |dx| <= 0.9 sigma
             const double cc = sigma2 * dx;
             double gterm = (g * cc + (fabs(g) * sigma + 0.5 * rho) * dx2) * denominv;
             double wterm = 0.5 * dx2 * denominv;
@@ -260,7 +262,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             stop = __all_sync(FULLMASK, ok || !c.active);
         } else {                    // NLopt >= 2.7: L1 norms, else all |dx| <= xtol_abs
             double dn = ad, xn = c.active ? fabs(xcur) : 0.0;
-            warp_tree_sum2(dn, xn);
+            warp_tree_sum2h(dn, xn, lane);
             stop = __all_sync(FULLMASK, dn <= xtol_rel * xn) || __all_sync(FULLMASK, !(ad > xtol_abs));
         }
         if (stop) break;

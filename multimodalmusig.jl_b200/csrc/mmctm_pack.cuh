@@ -126,8 +126,10 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             const double v = fabs(g) * sigma + 0.5 * rho;
             const double sigma2 = sigma * sigma;
             u *= sigma2;
-            const double r = u / (v * sigma);
-            double dx = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
+            const double r = fast_div(u, v * sigma);
+            const double om = fabs(1 - r * r);
+            const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+            double dx = fast_div(fast_div(u, v), -1 - sq);
             double xc = x + dx;
             if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
             else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
@@ -135,7 +137,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             if (!active) xc = x;
             dx = xc - x;
             const double dx2 = dx * dx;
-            const double denominv = 1.0 / (sigma2 - dx2);
+            const double denominv = fast_rcp(sigma2 - dx2);       // |dx| <= 0.9 sigma
             const double cc = sigma2 * dx;
             gterm = (g * cc + (fabs(g) * sigma + 0.5 * rho) * dx2) * denominv;
             wterm = 0.5 * dx2 * denominv;
@@ -145,7 +147,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
         double t = 0.0, gcur = 1.0;
         if (phase == PH_NU) {
             const double e = det_exp(other + 0.5 * xe);
-            const double grad = (-0.5 * Sjj - (cN / 2) * e) + (1.0 / (2 * xe));
+            const double grad = (-0.5 * Sjj - (cN / 2) * e) + fast_rcp(2 * xe);
             t = (-0.5 * (xe * Sjj) - cN * e) + det_log(xe) / 2;
             gcur = -grad;
         } else if (phase == PH_LAM) {
@@ -357,8 +359,10 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                 const double v = fabs(g[s]) * sigma[s] + 0.5 * rho;
                 const double sigma2 = sigma[s] * sigma[s];
                 u *= sigma2;
-                const double r = u / (v * sigma[s]);
-                double dx = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
+                const double r = fast_div(u, v * sigma[s]);
+                const double om = fabs(1 - r * r);
+                const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+                double dx = fast_div(fast_div(u, v), -1 - sq);
                 double xc = x[s] + dx;
                 if (xc > x[s] + 0.9 * sigma[s]) xc = x[s] + 0.9 * sigma[s];
                 else if (xc < x[s] - 0.9 * sigma[s]) xc = x[s] - 0.9 * sigma[s];
@@ -366,7 +370,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                 if (!active[s]) xc = x[s];
                 dx = xc - x[s];
                 const double dx2 = dx * dx;
-                const double denominv = 1.0 / (sigma2 - dx2);
+                const double denominv = fast_rcp(sigma2 - dx2);       // |dx| <= 0.9 sigma
                 const double cc = sigma2 * dx;
                 gl_[s] = (g[s] * cc + (fabs(g[s]) * sigma[s] + 0.5 * rho) * dx2) * denominv;
                 wl_[s] = 0.5 * dx2 * denominv;
@@ -380,7 +384,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
                 const double e = det_exp(other[s] + 0.5 * xe[s]);
-                const double grad = (-0.5 * Sjj[s] - (cN[s] / 2) * e) + (1.0 / (2 * xe[s]));
+                const double grad = (-0.5 * Sjj[s] - (cN[s] / 2) * e) + fast_rcp(2 * xe[s]);
                 tl[s] = (-0.5 * (xe[s] * Sjj[s]) - cN[s] * e) + det_log(xe[s]) / 2;
                 gcur[s] = -grad;
             }

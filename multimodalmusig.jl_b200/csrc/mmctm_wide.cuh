@@ -25,7 +25,7 @@ __device__ __forceinline__ void wide_eval_local(const double (&x)[WCPL], const W
 #pragma unroll
         for (int s = 0; s < WCPL; ++s) {
             const double e = det_exp(c.other[s] + 0.5 * x[s]);
-            const double grad = (-0.5 * c.Sjj[s] - (c.c[s] / 2) * e) + (1.0 / (2 * x[s]));
+            const double grad = (-0.5 * c.Sjj[s] - (c.c[s] / 2) * e) + fast_rcp(2 * x[s]);
             t[s] = (-0.5 * (x[s] * c.Sjj[s]) - c.c[s] * e) + det_log(x[s]) / 2;
             g[s] = -grad;
         }
@@ -93,8 +93,10 @@ __device__ __forceinline__ int wide_mma_solve(double (&x)[WCPL], const WideCtx &
                 const double v = fabs(g[s]) * sigma[s] + 0.5 * rho;
                 const double sigma2 = sigma[s] * sigma[s];
                 u *= sigma2;
-                const double r = u / (v * sigma[s]);
-                double dx = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
+                const double r = fast_div(u, v * sigma[s]);
+                const double om = fabs(1 - r * r);
+                const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+                double dx = fast_div(fast_div(u, v), -1 - sq);
                 double xn = x[s] + dx;
                 if (xn > x[s] + 0.9 * sigma[s]) xn = x[s] + 0.9 * sigma[s];
                 else if (xn < x[s] - 0.9 * sigma[s]) xn = x[s] - 0.9 * sigma[s];
@@ -102,7 +104,7 @@ __device__ __forceinline__ int wide_mma_solve(double (&x)[WCPL], const WideCtx &
                 if (!c.active[s]) xn = x[s];
                 dx = xn - x[s];
                 const double dx2 = dx * dx;
-                const double denominv = 1.0 / (sigma2 - dx2);
+                const double denominv = fast_rcp(sigma2 - dx2);       // |dx| <= 0.9 sigma
                 const double cc = sigma2 * dx;
                 gl[s] = (g[s] * cc + (fabs(g[s]) * sigma[s] + 0.5 * rho) * dx2) * denominv;
                 wl[s] = 0.5 * dx2 * denominv;
@@ -143,7 +145,7 @@ __device__ __forceinline__ int wide_mma_solve(double (&x)[WCPL], const WideCtx &
         } else {
             double dn = ad[0] + ad[1];
             double xn = (c.active[0] ? fabs(xcur[0]) : 0.0) + (c.active[1] ? fabs(xcur[1]) : 0.0);
-            warp_tree_sum2(dn, xn);
+            warp_tree_sum2h(dn, xn, lane);
             stop = __all_sync(FULLMASK, dn <= xtol_rel * xn) ||
                    __all_sync(FULLMASK, !(ad[0] > xtol_abs) && !(ad[1] > xtol_abs));
         }

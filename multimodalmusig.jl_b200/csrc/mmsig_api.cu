@@ -1010,15 +1010,17 @@ extern "C" int32_t mmsig_mmctm_elbo(mmsig_handle *h, double *elbo, double *terms
 // ---- test hook -----------------------------------------------------------------------------------
 __global__ void k_debug_math(int fn, long long n, const double *x, double *y) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-        y[i] = fn == 0 ? det_exp(x[i]) : fn == 1 ? det_log(x[i]) : det_digamma(x[i]);
+        y[i] = fn == 0 ? det_exp(x[i]) : fn == 1 ? det_log(x[i]) : fn == 2 ? det_digamma(x[i])
+             : fn == 3 ? fast_div(x[i], x[n + i]) : fn == 4 ? fast_rcp(x[i]) : fast_sqrt(x[i]);
 }
 extern "C" int32_t mmsig_debug_math(mmsig_handle *h, int32_t fn, int64_t n, const double *x, double *y) {
-    NEED(h && x && y && n >= 0 && fn >= 0 && fn <= 2, "bad argument");
+    NEED(h && x && y && n >= 0 && fn >= 0 && fn <= 5, "bad argument");
     CU(cudaSetDevice(h->device));
     double *dx = nullptr, *dy = nullptr;
-    CU(cudaMalloc(&dx, std::max<int64_t>(n, 1) * sizeof(double)));
+    const int64_t nin = fn == 3 ? 2 * n : n;             // fn 3 reads numerators x[0..n) and denominators x[n..2n)
+    CU(cudaMalloc(&dx, std::max<int64_t>(nin, 1) * sizeof(double)));
     CU(cudaMalloc(&dy, std::max<int64_t>(n, 1) * sizeof(double)));
-    CU(cudaMemcpyAsync(dx, x, n * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(dx, x, nin * sizeof(double), cudaMemcpyHostToDevice, h->stream));
     {
         LaunchScope ls(h, "k_debug_math");
         k_debug_math<<<h->numSM, 256, 0, h->stream>>>(fn, n, dx, dy);

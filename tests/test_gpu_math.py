@@ -37,3 +37,38 @@ def test_exp_log_digamma_bit_exact():
     yd = _dev(2, xd)
     ref = np.array([L.orc_digamma_det(float(v)) for v in xd])
     assert np.array_equal(yd, ref)
+
+
+def test_branch_free_div_rcp_sqrt_are_ieee():
+    """fast_div / fast_rcp / fast_sqrt (det_math.cuh) are the compiler's correctly rounded
+    sequences minus the exceptional-operand branch: on their stated domain they must equal IEEE
+    division / square root (numpy on the host) bit for bit."""
+    rng = np.random.default_rng(1)
+    n = 1 << 20
+    sign = lambda k: rng.choice([-1.0, 1.0], k)
+    num = np.concatenate([sign(n) * np.exp(rng.uniform(-600, 600, n)), sign(n) * rng.uniform(0, 2, n), np.zeros(64), -np.zeros(64),
+                          sign(n) * np.exp(rng.uniform(-40, 40, n))])
+    den = np.concatenate([sign(n) * np.exp(rng.uniform(-60, 60, n)), -1.0 - rng.uniform(0, 1, n), sign(128) * rng.uniform(1e-6, 3, 128),
+                          sign(n) * np.exp(rng.uniform(-40, 40, n))])
+    # mantissa patterns near 1 and 2 (the hard cases of Newton division)
+    eps = 2.0 ** -52
+    hard = np.concatenate([1.0 + eps * np.arange(0, 4096), 2.0 - eps * np.arange(1, 4097), 1.5 + eps * np.arange(-2048, 2048)])
+    num = np.concatenate([num, rng.permutation(hard), hard])
+    den = np.concatenate([den, hard, rng.permutation(hard)])
+    h = mmsig.capi.Handle()
+    q = np.empty_like(num)
+    x = np.ascontiguousarray(np.concatenate([num, den]))
+    h.check(h.lib.mmsig_debug_math(h.h, 3, num.size, mmsig.capi.dp(x), mmsig.capi.dp(q)))
+    h.close()
+    ref = num / den
+    # a zero numerator yields a zero whose sign may differ from IEEE's (-0 / d -> +0): harmless on
+    # this path (the quotient is only ever added to a non-zero value or squared)
+    bad = ~((q == ref) & ((np.signbit(q) == np.signbit(ref)) | (num == 0)))
+    assert not bad.any(), (num[bad][:5], den[bad][:5], q[bad][:5], ref[bad][:5])
+    d = np.concatenate([sign(n) * np.exp(rng.uniform(-600, 600, n)), rng.uniform(1e-7, 4, n), hard, -hard])
+    r = _dev(4, d)
+    assert np.array_equal(r, 1.0 / d), d[r != 1.0 / d][:5]
+    xs = np.concatenate([np.exp(rng.uniform(-600, 600, n)), rng.uniform(0, 1, n), 2.0 ** -53 * np.arange(1, 4097), hard, hard * 2, hard * 0.5,
+                         1.0 - 2.0 ** -53 * np.arange(1, 4097)])
+    s = _dev(5, xs)
+    assert np.array_equal(s, np.sqrt(xs)), xs[s != np.sqrt(xs)][:5]
