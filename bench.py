@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--cpu-samples", type=int, default=100_000)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--e2e-unpipelined", action="store_true", help="e2e through set_data/set_state/iterate/get_state")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -243,11 +244,16 @@ def main():
     order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
 
     def e2e_step():
-        model._set_data(counts_p, D)                                          # counts H2D (+ row packing)
-        model.set_state(gam_h, lam=lam_h, nu=nu_h, mu=mu_h, Sigma=Sg_h, invSigma=iS_h)   # state H2D
-        ll_ = model.iterate()                                                 # one E+M iteration, LL D2H
-        model.h.check(model.h.lib.mmsig_mmctm_get_state(model.h.h, *[mmsig.capi.dp(out[k]) for k in order]))
-        return ll_
+        if args.e2e_unpipelined:            # the four separate calls, every copy serialised with the kernels
+            model._set_data(counts_p, D)                                          # counts H2D (+ row packing)
+            model.set_state(gam_h, lam=lam_h, nu=nu_h, mu=mu_h, Sigma=Sg_h, invSigma=iS_h)   # state H2D
+            ll_ = model.iterate()                                                 # one E+M iteration, LL D2H
+            model.h.check(model.h.lib.mmsig_mmctm_get_state(model.h.h, *[mmsig.capi.dp(out[k]) for k in order]))
+            return ll_
+        # what fit!(model; maxiter=1) does through the Julia shim: ONE call, host buffers in and out
+        hist, _ = model.fit_host(counts_p, gam_h, lam=lam_h, nu=nu_h, mu=mu_h, Sigma=Sg_h, invSigma=iS_h, maxiter=1,
+                                 out=out, D_total=D)
+        return hist[-1]
     e2e_step()
     barrier()
     t0 = time.perf_counter()
@@ -308,7 +314,9 @@ def main():
             "mma_evaluations_per_sample_last_iteration": evals,
             "clocks": sampler.summary(),
             "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "what": "set_data + set_state (pinned host -> device), iterate, get_state (device -> pinned host)"},
+                    "ms_per_step": e2e_ms, "what": ("set_data + set_state (pinned host -> device), iterate, get_state (device -> pinned host)" if args.e2e_unpipelined else
+                             "mmsig_mmctm_fit_host(maxiter=1): counts + state from pinned host buffers, one E+M iteration, state back to "
+                             "pinned host buffers; copies pipelined behind the E-step chunk by chunk")},
             "gpu_launches": int(launches),
             "kernels": per_kernel,
             "roofline": roof}

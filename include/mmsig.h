@@ -100,6 +100,22 @@ int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *ll_out);
  * ll_hist is maxiter x M.  The ELBO of :490 is mmsig_mmctm_elbo. */
 int32_t mmsig_mmctm_fit(mmsig_handle *h, int32_t maxiter, double tol, uint32_t flags,
                         double *ll_hist, int32_t *n_iter, int32_t *converged);
+/* fit! from and to HOST buffers in one call: exactly mmsig_mmctm_set_data + _set_state + _fit +
+ * _get_state (same arguments, same results bit for bit), with the transfers hidden behind the
+ * E-step: the samples are cut into chunks, chunk c's counts / λ / ν are copied while chunk c-1
+ * runs, and when the loop ends by maxiter the chunk's λ, ν, ζ, props are copied back while the next
+ * chunk runs.  This is what julia/MMSigB200.jl's fit! calls.  Page-locked host buffers overlap
+ * fully; pageable ones still pipeline chunk by chunk.  The counts and the final state stay
+ * resident (mmsig_mmctm_elbo, _get_theta, further _iterate calls work afterwards). */
+int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                             const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
+                             const int32_t *const *count, const double *alpha, const double *gamma,
+                             const double *lambda, const double *nu, const double *mu, const double *Sigma,
+                             const double *invSigma, int32_t maxiter, double tol, uint32_t flags,
+                             double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
+                             double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
+                             double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
+                             double *props_out);
 /* calculate_elbo (src/MMCTM.jl:271-382) with the staleness of :490: θ, ζ, sumθ from the last
  * E-step, everything else current.  terms[7] = ElnPϕ, ElnPη, ElnPZ, ElnPX, ElnQϕ, ElnQη, ElnQZ. */
 int32_t mmsig_mmctm_elbo(mmsig_handle *h, double *elbo, double *terms);

@@ -45,6 +45,9 @@ _SIGS = {
     "mmsig_mmctm_set_phi": (C.c_int32, [C.c_void_p, c_dp]),
     "mmsig_mmctm_iterate": (C.c_int32, [C.c_void_p, C.c_uint32, c_dp]),
     "mmsig_mmctm_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p]),
+    "mmsig_mmctm_fit_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
+                                         C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)] + [c_dp] * 7 +
+                             [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
     "mmsig_mmctm_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_mmctm_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 10),
     "mmsig_mmctm_get_theta": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),

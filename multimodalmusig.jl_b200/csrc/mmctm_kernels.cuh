@@ -40,7 +40,18 @@ struct MmctmDev {
     double2 *nusum;               // MK, rank-summed Σ_d ν (dd) from mstep1 for mstep2
     int *nev_nu, *nev_lam;
     int stop_rule;
+    int accum;                    // != 0: E-step kernels add their block partials to what the slot holds (chunked launches)
 };
+
+// block partial -> its slot; chunked E-steps (mmsig_mmctm_fit_host) launch the same grid once per
+// chunk of samples on one stream and accumulate
+__device__ __forceinline__ void put_partial(double2 *slot, double hi, double lo, int accum) {
+    if (accum) {
+        const double2 o = *slot;
+        dd_merge(hi, lo, o.x, o.y);
+    }
+    *slot = make_double2(hi, lo);
+}
 
 // ------------------------------------------------------------------------------------------
 // θ pass of one modality (src/MMCTM.jl:183-198, :110-117, :224-240).  One warp per sample,
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 
             const double *t = smem + KV + (size_t)wv * 2 * KV;
             dd_merge(hi, lo, t[i], t[KV + i]);
         }
-        out[i] = make_double2(hi, lo);
+        put_partial(out + i, hi, lo, p.accum);
     }
 }
 
@@ -250,7 +261,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             if (nev >= MMA_MAXEVAL) return nev;           // nev is lane-invariant
             if (inner_done) break;
             if (__all_sync(FULLMASK, fcur > gval)) {
-                const double r1 = 10 * rho, r2 = 1.1 * (rho + (fcur - gval) / wval);
+                const double r1 = 10 * rho, r2 = 1.1 * (rho + guarded_div(fcur - gval, wval));
                 rho = r1 < r2 ? r1 : r2;
             }
         }
@@ -350,7 +361,7 @@ __global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, dou
         const int which = threadIdx.x >> 5;
         double hi = 0.0, lo = 0.0;
         for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv][which][lane].x, red[wv][which][lane].y);
-        if (lane < MK) partial[(size_t)blockIdx.x * 2 * MK + which * MK + lane] = make_double2(hi, lo);
+        if (lane < MK) put_partial(partial + (size_t)blockIdx.x * 2 * MK + which * MK + lane, hi, lo, p.accum);
     }
 }
 

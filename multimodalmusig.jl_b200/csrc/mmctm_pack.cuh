@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
                         xprev = xcur;
                     }
                 } else if (f > gval) {
-                    const double r1 = 10 * rho, r2 = 1.1 * (rho + (f - gval) / wterm);
+                    const double r1 = 10 * rho, r2 = 1.1 * (rho + guarded_div(f - gval, wterm));
                     rho = r1 < r2 ? r1 : r2;
                 }
             }
@@ -249,7 +249,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             double hi = 0.0, lo = 0.0;
             for (int wv = 0; wv < 8; ++wv)
                 for (int gg = 0; gg < NG; ++gg) dd_merge(hi, lo, red[wv][which][gg * G + lane].x, red[wv][which][gg * G + lane].y);
-            partial[(size_t)blockIdx.x * 2 * MK + which * MK + lane] = make_double2(hi, lo);
+            put_partial(partial + (size_t)blockIdx.x * 2 * MK + which * MK + lane, hi, lo, p.accum);
         }
     }
 }
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                         ++k;
                     }
                 } else if (f > gval) {
-                    const double r1 = 10 * rho, r2 = 1.1 * (rho + (f - gval) / wterm);
+                    const double r1 = 10 * rho, r2 = 1.1 * (rho + guarded_div(f - gval, wterm));
                     rho = r1 < r2 ? r1 : r2;
                 }
             }
@@ -527,7 +527,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                 const double2 v = red[wv][which * CPL + s][gg * G + l];
                 dd_merge(hi, lo, v.x, v.y);
             }
-        partial[(size_t)blockIdx.x * 2 * MK + which * MK + j] = make_double2(hi, lo);
+        put_partial(partial + (size_t)blockIdx.x * 2 * MK + which * MK + j, hi, lo, p.accum);
     }
 }
 

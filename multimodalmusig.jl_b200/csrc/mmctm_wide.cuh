@@ -127,7 +127,7 @@ __device__ __forceinline__ int wide_mma_solve(double (&x)[WCPL], const WideCtx &
             if (nev >= MMA_MAXEVAL) return nev;
             if (inner_done) break;
             if (__all_sync(FULLMASK, fcur > gval)) {
-                const double r1 = 10 * rho, r2 = 1.1 * (rho + (fcur - gval) / wval);
+                const double r1 = 10 * rho, r2 = 1.1 * (rho + guarded_div(fcur - gval, wval));
                 rho = r1 < r2 ? r1 : r2;
             }
         }
@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(256) k_solve_wide(MmctmDev p, double2 *partial
         const int s = q >> 1, which = q & 1, j = lane + 32 * s;
         double hi = 0.0, lo = 0.0;
         for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[(wv * 4 + q) * 32 + lane].x, red[(wv * 4 + q) * 32 + lane].y);
-        if (j < MK) partial[(size_t)blockIdx.x * 2 * MK + which * MK + j] = make_double2(hi, lo);
+        if (j < MK) put_partial(partial + (size_t)blockIdx.x * 2 * MK + which * MK + j, hi, lo, p.accum);
     }
 }
 

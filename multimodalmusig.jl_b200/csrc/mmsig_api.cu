@@ -114,6 +114,7 @@ struct LdaHost {
 struct mmsig_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
+    cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of mmsig_mmctm_fit_host
     bool own_stream = false;
     std::string err;
     int stop_rule = 0;
@@ -263,6 +264,8 @@ extern "C" int32_t mmsig_destroy(mmsig_handle *h) {
     free_pool(h->allocs_lda);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->own_stream) cudaStreamDestroy(h->stream);
+    if (h->s_in) cudaStreamDestroy(h->s_in);
+    if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
     return 0;
 }
@@ -378,40 +381,34 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
     if (lane == 0 && tot) atomicAdd(ntot, tot);
 }
 
-static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, int V, int M, int m,
-                         const int64_t *rowptr, const int32_t *term, const int32_t *count, double *d_N,
-                         long long *ntot_out) {
+static int check_rowptr(mmsig_handle *h, const int64_t *rowptr, long long D) {
     NEED(rowptr && rowptr[0] == 0, "rowptr[0] must be 0");
     for (long long d = 0; d < D; ++d)
         if (rowptr[d + 1] < rowptr[d]) return fail(h, MMSIG_EINVAL, "rowptr not monotone");
-    const long long nnz = rowptr[D];
-    NEED(nnz == 0 || (term && count), "null term / count");
+    return 0;
+}
+// (re)allocate the device side of one modality's counts when its shape changed
+static int ensure_countbuf(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, long long nnz) {
+    if (cb.D == D && cb.nnz == nnz) return 0;
     int rc;
-    if (cb.D != D || cb.nnz != nnz) {
-        if ((rc = dev_alloc(h, pool, &cb.rowptr, D + 1))) return rc;
-        if ((rc = dev_alloc(h, pool, &cb.rec, nnz))) return rc;
-        if ((rc = dev_alloc(h, pool, &cb.term, nnz))) return rc;
-        if ((rc = dev_alloc(h, pool, &cb.count, nnz))) return rc;
-        if ((rc = dev_alloc(h, pool, &cb.flags, (size_t)4))) return rc;
-        cb.D = D;
-        cb.nnz = nnz;
-    }
-    CU(cudaMemsetAsync(cb.flags, 0, 4 * sizeof(int), h->stream));
-    CU(cudaMemcpyAsync(cb.rowptr, rowptr, (D + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
-    if (nnz) {
-        CU(cudaMemcpyAsync(cb.term, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-        CU(cudaMemcpyAsync(cb.count, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
-    }
-    {
-        LaunchScope ls(h, "k_pack_rows");
-        int grid = (int)std::min<long long>((D + 7) / 8, (long long)h->numSM * 8);
-        k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr, cb.term, cb.count, D, V, cb.rec, d_N, M, m,
-                                                               cb.flags, (unsigned long long *)(cb.flags + 2));
-    }
-    int hf[4] = {0, 0, 0, 0};
-    CU(cudaMemcpyAsync(hf, cb.flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
-    CU(cudaStreamSynchronize(h->stream));
-    CU(cudaGetLastError());
+    if ((rc = dev_alloc(h, pool, &cb.rowptr, D + 1))) return rc;
+    if ((rc = dev_alloc(h, pool, &cb.rec, nnz))) return rc;
+    if ((rc = dev_alloc(h, pool, &cb.term, nnz))) return rc;
+    if ((rc = dev_alloc(h, pool, &cb.count, nnz))) return rc;
+    if ((rc = dev_alloc(h, pool, &cb.flags, (size_t)4))) return rc;
+    cb.D = D;
+    cb.nnz = nnz;
+    return 0;
+}
+// rows [d0, d1) of one modality: validation, (term, count) -> records, row totals
+static void pack_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d1, int V, int M, int m, double *d_N) {
+    LaunchScope ls(h, "k_pack_rows");
+    const long long Dc = d1 - d0;
+    int grid = (int)std::min<long long>((Dc + 7) / 8, (long long)h->numSM * 8);
+    k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr + d0, cb.term, cb.count, Dc, V, cb.rec, d_N + d0 * M, M, m,
+                                                           cb.flags, (unsigned long long *)(cb.flags + 2));
+}
+static int flags_verdict(mmsig_handle *h, const int *hf, long long *ntot_out) {
     if (hf[0] & 1) return fail(h, MMSIG_EINVAL, "term index out of range [0, V)");
     if (hf[0] & 2) return fail(h, MMSIG_EINVAL, "count must be > 0 (zeros are dropped by format_counts_*)");
     if (hf[0] & 4) return fail(h, MMSIG_EINVAL, "terms of a row must be strictly ascending (as format_counts_* produces)");
@@ -419,6 +416,28 @@ static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &c
     memcpy(&nt, hf + 2, 8);
     *ntot_out = (long long)nt;
     return 0;
+}
+
+static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, int V, int M, int m,
+                         const int64_t *rowptr, const int32_t *term, const int32_t *count, double *d_N,
+                         long long *ntot_out) {
+    int rc;
+    if ((rc = check_rowptr(h, rowptr, D))) return rc;
+    const long long nnz = rowptr[D];
+    NEED(nnz == 0 || (term && count), "null term / count");
+    if ((rc = ensure_countbuf(h, pool, cb, D, nnz))) return rc;
+    CU(cudaMemsetAsync(cb.flags, 0, 4 * sizeof(int), h->stream));
+    CU(cudaMemcpyAsync(cb.rowptr, rowptr, (D + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
+    if (nnz) {
+        CU(cudaMemcpyAsync(cb.term, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaMemcpyAsync(cb.count, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+    }
+    pack_launch(h, cb, 0, D, V, M, m, d_N);
+    int hf[4] = {0, 0, 0, 0};
+    CU(cudaMemcpyAsync(hf, cb.flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    return flags_verdict(h, hf, ntot_out);
 }
 
 // ===========================================================================================
@@ -466,15 +485,14 @@ static int pick_theta_plan(mmsig_handle *h, F kernel, int KV, int D, int *W_out,
         else { constexpr int MKP = 32; EXPR; }                    \
     } while (0)
 
-extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
-                                        const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
-                                        const int32_t *const *count) {
-    NEED(h, "null handle");
-    NEED(K && V && rowptr && term && count, "null argument");
+// Shape-dependent part of set_data: allocations and launch plans for (D, D_total, M, K, V, nnz_m).
+// *same_out: the resident shape matched and everything was kept.  Counts are not touched.
+static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K, const int32_t *V,
+                         const int64_t *const *rowptr, bool *same_out) {
+    NEED(K && V && rowptr, "null argument");
     NEED(D >= 1 && D_total >= D, "need 1 <= D <= D_total");
     NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
     if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
-    CU(cudaSetDevice(h->device));
     int MKsum = 0;
     for (int m = 0; m < M; ++m) {
         NEED(K[m] >= 1 && V[m] >= 1, "K[m], V[m] must be >= 1");
@@ -483,24 +501,17 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
         MKsum += K[m];
     }
     if (MKsum > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 64 supported");
+    int rc;
+    for (int m = 0; m < M; ++m)
+        if ((rc = check_rowptr(h, rowptr[m], D))) return rc;
     // same shape as what is already resident (a repeated fit! on the same corpus): keep every
-    // allocation and launch plan, only refresh the counts
+    // allocation and launch plan
     bool same = h->mm.has_data && h->mm.p.M == M && h->mm.p.D == D && h->mm.p.D_total == D_total;
     for (int m = 0; same && m < M; ++m)
         same = h->mm.p.K[m] == K[m] && h->mm.p.V[m] == V[m] && h->mm.cb[m].nnz == rowptr[m][D];
-    int rc;
-    long long ntot[MAXM];
+    *same_out = same;
     if (same) {
-        MmctmHost &mm = h->mm;
-        mm.has_state = false;
-        for (int m = 0; m < M; ++m)
-            if ((rc = upload_counts(h, h->allocs_mm, mm.cb[m], D, V[m], M, m, rowptr[m], term[m], count[m],
-                                    const_cast<double *>(mm.p.N), &ntot[m]))) {
-                mm.has_data = false;
-                return rc;
-            }
-        if ((rc = allsum_ll(h, ntot, M))) return rc;
-        for (int m = 0; m < M; ++m) mm.p.Ntot[m] = (double)ntot[m];
+        h->mm.has_state = false;
         return 0;
     }
     free_pool(h->allocs_mm);
@@ -526,15 +537,11 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     p.N = dN;
     mm.nnz.resize(M);
     for (int m = 0; m < M; ++m) {
-        if ((rc = upload_counts(h, h->allocs_mm, mm.cb[m], D, V[m], M, m, rowptr[m], term[m], count[m], dN, &ntot[m])))
-            return rc;
+        if ((rc = ensure_countbuf(h, h->allocs_mm, mm.cb[m], D, rowptr[m][D]))) return rc;
         p.rowptr[m] = mm.cb[m].rowptr;
         p.rec[m] = mm.cb[m].rec;
         mm.nnz[m] = mm.cb[m].nnz;
     }
-    if ((rc = allsum_ll(h, ntot, M))) return rc;
-    for (int m = 0; m < M; ++m) p.Ntot[m] = (double)ntot[m];
-
     const size_t DMK = (size_t)D * p.MK;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.lamA, DMK))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.lamB, DMK))) return rc;
@@ -627,6 +634,27 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.gath_p1, (size_t)P1 * h->nranks))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.rank_p2, (size_t)P2 + 16))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.gath_p2, (size_t)(P2 + 16) * h->nranks))) return rc;
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                        const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
+                                        const int32_t *const *count) {
+    NEED(h, "null handle");
+    NEED(K && V && rowptr && term && count, "null argument");
+    CU(cudaSetDevice(h->device));
+    bool same = false;
+    int rc = mmctm_prepare(h, D, D_total, M, K, V, rowptr, &same);
+    if (rc) return rc;
+    MmctmHost &mm = h->mm;
+    mm.has_data = false;
+    long long ntot[MAXM];
+    for (int m = 0; m < M; ++m)
+        if ((rc = upload_counts(h, h->allocs_mm, mm.cb[m], D, V[m], M, m, rowptr[m], term[m], count[m],
+                                const_cast<double *>(mm.p.N), &ntot[m])))
+            return rc;
+    if ((rc = allsum_ll(h, ntot, M))) return rc;
+    for (int m = 0; m < M; ++m) mm.p.Ntot[m] = (double)ntot[m];
     mm.has_data = true;
     return 0;
 }
@@ -787,28 +815,61 @@ extern "C" int32_t mmsig_mmctm_get_alpha(mmsig_handle *h, double *alpha_out) {
     return 0;
 }
 
+// view of samples [d0, d1) of the resident shard (rowptr entries are absolute offsets into rec)
+static MmctmDev chunk_view(const MmctmDev &p, long long d0, long long d1, int accum) {
+    MmctmDev q = p;
+    q.D = d1 - d0;
+    for (int m = 0; m < p.M; ++m) q.rowptr[m] = p.rowptr[m] + d0;
+    q.N = p.N + d0 * p.M;
+    q.lam = p.lam + d0 * p.MK;
+    q.lam_prev = p.lam_prev + d0 * p.MK;
+    q.nu = p.nu + d0 * p.MK;
+    q.sumtheta = p.sumtheta + d0 * p.MK;
+    q.zeta = p.zeta + d0 * p.M;
+    q.nev_nu = p.nev_nu + d0;
+    q.nev_lam = p.nev_lam + d0;
+    q.accum = accum;
+    return q;
+}
+
+// E-step kernels (θ pass per modality, then ζ / ν / λ) over the samples of view q
+static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flags) {
+    MmctmHost &mm = h->mm;
+    const int freeze_topics = (flags & MMSIG_FLAG_FREEZE_TOPICS) ? 1 : 0, unsm = (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0;
+    auto cap = [&](int grid, int per_block) { return (int)std::max<long long>(1, std::min<long long>(grid, (q.D + per_block - 1) / per_block)); };
+    for (int m = 0; m < q.M; ++m) {
+        LaunchScope ls(h, "k_theta_stats");
+        THETA_DISPATCH(q.K[m], (k_theta_stats<KP, NP><<<cap(mm.grid_theta[m], mm.W_theta[m]), mm.W_theta[m] * 32, mm.smem_theta[m], h->stream>>>(
+                                   q, m, mm.part_theta[m], mm.W_theta[m], unsm, !freeze_topics)));
+    }
+    {
+        LaunchScope ls(h, "k_solve");
+        if (mm.wide) k_solve_wide<<<cap(mm.grid_solve, 8), 256, mm.smem_solve, h->stream>>>(q, mm.part_solve);
+        else if (q.MK <= 8) k_solve_pack<8><<<cap(mm.grid_solve, 32), 256, 0, h->stream>>>(q, mm.part_solve);
+        else if (q.MK <= 16) k_solve_pack<16><<<cap(mm.grid_solve, 16), 256, 0, h->stream>>>(q, mm.part_solve);
+        else if (mm.solve_multi && q.MK <= 24) k_solve_multi<3><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
+        else if (mm.solve_multi) k_solve_multi<4><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
+        else MK_DISPATCH(q.MK, (k_solve<MKP><<<cap(mm.grid_solve, 8), 256, 0, h->stream>>>(q, mm.part_solve)));
+    }
+}
+
+static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags);
+
 static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
+    MmctmHost &mm = h->mm;
+    MmctmDev &p = mm.p;
+    mm.last_unsmoothed = (flags & MMSIG_FLAG_UNSMOOTHED) != 0;
+    std::swap(p.lam, p.lam_prev);              // lam_prev = λ of the previous iteration (what θ uses)
+    mmctm_estep_launch(h, p, flags);
+    return mmctm_mstep_launch(h, flags);
+}
+
+// everything after the per-sample E-step: combine, exchange, μ, γ, Elnϕ, ϕ, [α], [Σ, invΣ], props / LL
+static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     const int do_sigma = (flags & MMSIG_FLAG_UPDATE_SIGMA) ? 1 : 0;
     const int freeze_topics = (flags & MMSIG_FLAG_FREEZE_TOPICS) ? 1 : 0, freeze_mu = (flags & MMSIG_FLAG_FREEZE_MU) ? 1 : 0;
-    const int unsm = (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0;
-    mm.last_unsmoothed = unsm != 0;
-    std::swap(p.lam, p.lam_prev);              // lam_prev = λ of the previous iteration (what θ uses)
-    for (int m = 0; m < p.M; ++m) {
-        LaunchScope ls(h, "k_theta_stats");
-        THETA_DISPATCH(p.K[m], (k_theta_stats<KP, NP><<<mm.grid_theta[m], mm.W_theta[m] * 32, mm.smem_theta[m], h->stream>>>(
-                                   p, m, mm.part_theta[m], mm.W_theta[m], unsm, !freeze_topics)));
-    }
-    {
-        LaunchScope ls(h, "k_solve");
-        if (mm.wide) k_solve_wide<<<mm.grid_solve, 256, mm.smem_solve, h->stream>>>(p, mm.part_solve);
-        else if (p.MK <= 8) k_solve_pack<8><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve);
-        else if (p.MK <= 16) k_solve_pack<16><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve);
-        else if (mm.solve_multi && p.MK <= 24) k_solve_multi<3><<<mm.grid_solve, 128, 0, h->stream>>>(p, mm.part_solve);
-        else if (mm.solve_multi) k_solve_multi<4><<<mm.grid_solve, 128, 0, h->stream>>>(p, mm.part_solve);
-        else MK_DISPATCH(p.MK, (k_solve<MKP><<<mm.grid_solve, 256, 0, h->stream>>>(p, mm.part_solve)));
-    }
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + p.M;
     {
         CombineSegs s{};
@@ -961,6 +1022,215 @@ extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double
     CU(cudaStreamSynchronize(h->stream));
     CU(cudaGetLastError());
     return 0;
+}
+
+// ---- fit! from / to host buffers in one call, transfers overlapped with the E-step -----------
+// = set_data + set_state + fit + get_state, bit for bit.  The samples are cut into chunks; chunk
+// c's counts, λ, ν travel on a copy stream while chunk c-1 runs k_pack_rows / k_theta_stats /
+// k_solve (block partials accumulate over the chunks), and when the loop is known to end with
+// this iteration (iter == maxiter) the chunk's λ, ν, ζ, props leave on a second copy stream while
+// the next chunk computes.  MMSIG_PIPE_CHUNKS overrides the chunk count (default ~100k samples).
+static int pipe_chunks(long long D) {
+    const char *e = getenv("MMSIG_PIPE_CHUNKS");
+    long long c = e ? atoll(e) : (D + 50000) / 100000;
+    return (int)std::max<long long>(1, std::min<long long>({c, 64LL, D}));
+}
+
+extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                        const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
+                                        const int32_t *const *count, const double *alpha, const double *gamma,
+                                        const double *lambda, const double *nu, const double *mu, const double *Sigma,
+                                        const double *invSigma, int32_t maxiter, double tol, uint32_t flags,
+                                        double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
+                                        double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
+                                        double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
+                                        double *props_out) {
+    NEED(h, "null handle");
+    NEED(K && V && rowptr && term && count, "null argument");
+    NEED(alpha && gamma, "alpha and gamma are required");
+    NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
+    CU(cudaSetDevice(h->device));
+    bool same = false;
+    int rc = mmctm_prepare(h, D, D_total, M, K, V, rowptr, &same);
+    if (rc) return rc;
+    MmctmHost &mm = h->mm;
+    MmctmDev &p = mm.p;
+    mm.has_data = false;
+    mm.has_state = false;
+    for (int m = 0; m < M; ++m) {
+        NEED(alpha[m] > 0, "alpha must be > 0");
+        NEED(rowptr[m][D] == 0 || (term[m] && count[m]), "null term / count");
+    }
+    if (!h->s_in) CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
+    if (!h->s_out) CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
+    const size_t DMK = (size_t)D * p.MK, MK2 = (size_t)p.MK * p.MK;
+    const int MK = p.MK;
+    if (props_out && !mm.props_scratch)
+        if ((rc = dev_alloc(h, h->allocs_mm, &mm.props_scratch, DMK))) return rc;
+
+    // small state, as mmsig_mmctm_set_state
+    mm.alpha_host.assign(alpha, alpha + M);
+    CU(cudaMemcpyAsync(p.alpha, alpha, M * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(p.gamma, gamma, mm.G * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    if (mu) CU(cudaMemcpyAsync(p.mu, mu, MK * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    else CU(cudaMemsetAsync(p.mu, 0, MK * sizeof(double), h->stream));
+    std::vector<double> eye(MK2, 0.0);
+    for (int j = 0; j < MK; ++j) eye[(size_t)j * MK + j] = 1.0;
+    CU(cudaMemcpyAsync(p.Sigma, Sigma ? Sigma : eye.data(), MK2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(p.invSigma, invSigma ? invSigma : eye.data(), MK2 * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, "k_elnphi");
+        k_elnphi<<<1, 1024, 0, h->stream>>>(p);
+    }
+    CU(cudaMemsetAsync(p.stats, 0, mm.G * sizeof(double), h->stream));
+    for (int m = 0; m < M; ++m) CU(cudaMemsetAsync(mm.cb[m].flags, 0, 4 * sizeof(int), h->stream));
+    // the first E-step reads the caller's λ as lam_prev and writes lam
+    p.lam = mm.lamA;
+    p.lam_prev = mm.lamB;
+    if (!lambda) CU(cudaMemsetAsync(p.lam_prev, 0, DMK * sizeof(double), h->stream));
+    if (!nu) fill(h, p.nu, DMK, 1.0);
+
+    const int C = pipe_chunks(D);
+    std::vector<long long> cut(C + 1);
+    for (int c = 0; c <= C; ++c) cut[c] = (long long)((__int128)D * c / C);
+    std::vector<cudaEvent_t> ev_in(C, nullptr), ev_out(C, nullptr);
+    auto free_events = [&]() {
+        cudaStreamSynchronize(h->s_in);        // no copy may outlive the caller's buffers, whatever the exit path
+        cudaStreamSynchronize(h->s_out);
+        for (auto e : ev_in) if (e) cudaEventDestroy(e);
+        for (auto e : ev_out) if (e) cudaEventDestroy(e);
+    };
+    struct EvGuard { decltype(free_events) &f; ~EvGuard() { f(); } } evguard{free_events};
+    for (int c = 0; c < C; ++c) {
+        CU(cudaEventCreateWithFlags(&ev_in[c], cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&ev_out[c], cudaEventDisableTiming));
+    }
+    // the copy stream must not run ahead of the memsets / fills above
+    {
+        cudaEvent_t ev0;
+        CU(cudaEventCreateWithFlags(&ev0, cudaEventDisableTiming));
+        CU(cudaEventRecord(ev0, h->stream));
+        CU(cudaStreamWaitEvent(h->s_in, ev0, 0));
+        cudaEventDestroy(ev0);
+    }
+    auto zero_partials = [&]() -> cudaError_t {
+        for (int m = 0; m < M; ++m) {
+            cudaError_t e = cudaMemsetAsync(mm.part_theta[m], 0, (size_t)mm.grid_theta[m] * p.K[m] * p.V[m] * sizeof(double2), h->stream);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaMemsetAsync(mm.part_solve, 0, (size_t)mm.grid_solve * 2 * MK * sizeof(double2), h->stream);
+    };
+    // E-step of chunk c done -> its outputs leave on s_out (enqueued after all compute, so that a
+    // pageable destination, whose copy blocks the host, cannot hold back the launches)
+    auto after_chunk = [&](int c) -> cudaError_t {
+        const long long d0 = cut[c], d1 = cut[c + 1];
+        if (props_out) {
+            MmctmDev q = chunk_view(p, d0, d1, 0);
+            LaunchScope ls(h, "k_props");
+            const int grid = (int)std::max<long long>(1, std::min<long long>(mm.grid_solve, (q.D + 7) / 8));
+            if (mm.wide) k_zeta_props_wide<<<grid, 256, 0, h->stream>>>(q, mm.props_scratch + d0 * MK, 0);
+            else k_props<<<grid, 256, 0, h->stream>>>(q, mm.props_scratch + d0 * MK);
+        }
+        return cudaEventRecord(ev_out[c], h->stream);
+    };
+    auto drain_chunk = [&](int c) -> cudaError_t {
+        const long long d0 = cut[c], d1 = cut[c + 1];
+        const size_t n = (size_t)(d1 - d0) * MK * sizeof(double);
+        cudaError_t e = cudaStreamWaitEvent(h->s_out, ev_out[c], 0);
+        if (e == cudaSuccess && lambda_out) e = cudaMemcpyAsync(lambda_out + d0 * MK, p.lam + d0 * MK, n, cudaMemcpyDeviceToHost, h->s_out);
+        if (e == cudaSuccess && nu_out) e = cudaMemcpyAsync(nu_out + d0 * MK, p.nu + d0 * MK, n, cudaMemcpyDeviceToHost, h->s_out);
+        if (e == cudaSuccess && zeta_out)
+            e = cudaMemcpyAsync(zeta_out + d0 * M, p.zeta + d0 * M, (size_t)(d1 - d0) * M * sizeof(double), cudaMemcpyDeviceToHost, h->s_out);
+        if (e == cudaSuccess && props_out)
+            e = cudaMemcpyAsync(props_out + d0 * MK, mm.props_scratch + d0 * MK, n, cudaMemcpyDeviceToHost, h->s_out);
+        return e;
+    };
+
+    // ---- iteration 1: upload chunk c while chunk c-1 computes
+    mm.last_unsmoothed = (flags & MMSIG_FLAG_UNSMOOTHED) != 0;
+    bool streamed_out = false;
+    if (C > 1) CU(zero_partials());
+    for (int c = 0; c < C; ++c) {
+        const long long d0 = cut[c], d1 = cut[c + 1];
+        for (int m = 0; m < M; ++m) {
+            CountBuf &cb = mm.cb[m];
+            const long long r0 = c == 0 ? 0 : d0 + 1;          // entry d0 came with the previous chunk
+            CU(cudaMemcpyAsync(cb.rowptr + r0, rowptr[m] + r0, (size_t)(d1 + 1 - r0) * sizeof(long long), cudaMemcpyHostToDevice, h->s_in));
+            const long long w0 = rowptr[m][d0], w1 = rowptr[m][d1];
+            if (w1 > w0) {
+                CU(cudaMemcpyAsync(cb.term + w0, term[m] + w0, (size_t)(w1 - w0) * sizeof(int), cudaMemcpyHostToDevice, h->s_in));
+                CU(cudaMemcpyAsync(cb.count + w0, count[m] + w0, (size_t)(w1 - w0) * sizeof(int), cudaMemcpyHostToDevice, h->s_in));
+            }
+        }
+        const size_t n = (size_t)(d1 - d0) * MK * sizeof(double);
+        if (lambda) CU(cudaMemcpyAsync(p.lam_prev + d0 * MK, lambda + d0 * MK, n, cudaMemcpyHostToDevice, h->s_in));
+        if (nu) CU(cudaMemcpyAsync(p.nu + d0 * MK, nu + d0 * MK, n, cudaMemcpyHostToDevice, h->s_in));
+        CU(cudaEventRecord(ev_in[c], h->s_in));
+        CU(cudaStreamWaitEvent(h->stream, ev_in[c], 0));
+        for (int m = 0; m < M; ++m) pack_launch(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N));
+        mmctm_estep_launch(h, chunk_view(p, d0, d1, C > 1), flags);
+        if (maxiter == 1) CU(after_chunk(c));
+    }
+    if (maxiter == 1) {
+        for (int c = 0; c < C; ++c) CU(drain_chunk(c));
+        streamed_out = true;
+    }
+    // validation verdict and Σ_d N_dm (the LL denominators) before the M-step
+    {
+        int hf[MAXM][4];
+        long long ntot[MAXM];
+        for (int m = 0; m < M; ++m) CU(cudaMemcpyAsync(hf[m], mm.cb[m].flags, sizeof(hf[m]), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+        for (int m = 0; m < M; ++m)
+            if ((rc = flags_verdict(h, hf[m], &ntot[m]))) {
+                cudaStreamSynchronize(h->s_out);
+                return rc;
+            }
+        if ((rc = allsum_ll(h, ntot, M))) return rc;
+        for (int m = 0; m < M; ++m) p.Ntot[m] = (double)ntot[m];
+    }
+    mm.has_data = true;
+    auto finish_iteration = [&](double *ll) -> int {
+        int r = mmctm_mstep_launch(h, flags);
+        if (r) return r;
+        int status = 0;
+        CU(cudaMemcpyAsync(ll, mm.d_ll, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(&status, mm.d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+        if (status) return fail(h, MMSIG_EINVAL, "Sigma is singular (inv failed)");
+        return 0;
+    };
+    if ((rc = finish_iteration(ll_hist))) { cudaStreamSynchronize(h->s_out); return rc; }
+    mm.has_state = true;
+
+    // ---- iterations 2 .. maxiter (src/MMCTM.jl:462-487)
+    int it = 1, conv = 0;
+    for (int iter = 2; iter <= maxiter; ++iter) {
+        double *ll = ll_hist + (size_t)(iter - 1) * M;
+        if (iter == maxiter && C > 1) {
+            // the loop ends here whatever the LL says: let the outputs leave chunk by chunk
+            std::swap(p.lam, p.lam_prev);
+            CU(zero_partials());
+            for (int c = 0; c < C; ++c) {
+                mmctm_estep_launch(h, chunk_view(p, cut[c], cut[c + 1], 1), flags);
+                CU(after_chunk(c));
+            }
+            for (int c = 0; c < C; ++c) CU(drain_chunk(c));
+            streamed_out = true;
+            if ((rc = finish_iteration(ll))) { cudaStreamSynchronize(h->s_out); return rc; }
+        } else if ((rc = mmsig_mmctm_iterate(h, flags, ll))) return rc;
+        it = iter;
+        if (iter > 10 && converged_vec(ll - M, ll, M, tol)) { conv = 1; break; }   // src/MMCTM.jl:485
+    }
+    if (n_iter) *n_iter = it;
+    if (converged) *converged = conv;
+    CU(cudaStreamSynchronize(h->s_out));
+    if (streamed_out)
+        return mmsig_mmctm_get_state(h, nullptr, nullptr, nullptr, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out, phi_out, nullptr);
+    return mmsig_mmctm_get_state(h, lambda_out, nu_out, zeta_out, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out,
+                                 phi_out, props_out);
 }
 
 extern "C" int32_t mmsig_mmctm_get_theta(mmsig_handle *h, int32_t m, double *theta_out) {

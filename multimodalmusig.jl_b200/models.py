@@ -169,6 +169,44 @@ class MMCTM:
         self.ll = hist[-1].copy()                     # :491
         return hist
 
+    def fit_host(self, counts, gamma, lam=None, nu=None, mu=None, Sigma=None, invSigma=None, maxiter=100, tol=1e-4,
+                 updateSigma=True, flags=None, out=None, D_total=None):
+        """fit! in ONE library call from / to host arrays (mmsig_mmctm_fit_host): the same results as
+        _set_data + set_state + fit + state(), with the host<->device copies pipelined behind the
+        E-step chunk by chunk.  counts / gamma / lam ...: what _set_data and set_state take.
+        out: optional dict of preallocated (e.g. page-locked) result arrays keyed as state().
+        Returns (ll_history, out)."""
+        keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32),
+                 np.ascontiguousarray(c, np.int32)) for r, t, c in counts]
+        M = self.M
+        D = len(keep[0][0]) - 1
+        rp = (capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep])
+        tp = (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep])
+        cp = (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep])
+        K = np.asarray(self.K, np.int32)
+        V = np.asarray(self.V, np.int32)
+        MK, G = self.MK, self.G
+        a = [capi.f64(self.alpha, M), capi.f64(gamma, G), capi.f64(lam, D * MK), capi.f64(nu, D * MK),
+             capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
+        if out is None:
+            out = dict(lam=np.empty((D, MK)), nu=np.empty((D, MK)), zeta=np.empty((D, M)), mu=np.empty(MK),
+                       Sigma=np.empty((MK, MK)), invSigma=np.empty((MK, MK)), gamma=np.empty(G), Elnphi=np.empty(G),
+                       phi=np.empty(G), props=np.empty((D, MK)))
+        order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
+        if flags is None:
+            flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        hist = np.zeros((maxiter, M))
+        n, conv = C.c_int32(), C.c_int32()
+        self.h.check(self.h.lib.mmsig_mmctm_fit_host(
+            self.h.h, D, D if D_total is None else D_total, M, K.ctypes.data_as(capi.c_i32p),
+            V.ctypes.data_as(capi.c_i32p), rp, tp, cp, *[capi.dp(x) for x in a], maxiter, tol, flags, capi.dp(hist),
+            C.byref(n), C.byref(conv), *[capi.dp(out.get(k)) for k in order]))
+        self.D = D
+        self.nnz = [int(k[0][-1]) for k in keep]
+        self.converged = bool(conv.value)
+        self.ll = hist[n.value - 1].copy()
+        return hist[:n.value].copy(), out
+
     def fit_restarts(self, gamma0s, maxiter=100, tol=1e-4, updateSigma=True):
         """R independent restarts from the constructor state with gamma0s[r] on the resident counts;
         keeps the best-ELBO fit in the model (README.md:42; scripts/run_mmctm.jl:77-111).

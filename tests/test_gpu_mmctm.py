@@ -256,3 +256,54 @@ def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
             ll_o, ll_g = o.iterate(), g.iterate()
             _check_iteration(o, g, ll_o, ll_g)
         g.close()
+
+
+@pytest.mark.parametrize("maxiter,chunks", [(1, 1), (1, 3), (4, 3), (14, 5)])
+def test_fit_host_equals_the_four_calls(monkeypatch, maxiter, chunks):
+    """mmsig_mmctm_fit_host (transfers pipelined behind the E-step, chunked launches accumulating
+    their block partials) == set_data + set_state + fit + get_state, bit for bit, whether the loop
+    ends by maxiter (outputs streamed out chunk by chunk) or by convergence."""
+    K, V, D = [5, 4, 3], [96, 32, 83], 1500
+    counts = small_synth(D, K, V, seed=3, empty_frac=0.05)
+    g0 = mmsig.synth.init_gamma(K, V)
+    a = mmsig.MMCTM(K, [0.1, 0.2, 0.3], counts, V=V, gamma0=g0)
+    for _ in range(2):                       # a non-trivial starting state
+        a.iterate()
+    s0 = a.state()
+    a.set_state(s0["gamma"], lam=s0["lam"], nu=s0["nu"], mu=s0["mu"], Sigma=s0["Sigma"], invSigma=s0["invSigma"])
+    tol = 1e-3
+    hist_a = a.fit(maxiter=maxiter, tol=tol, verbose=False)
+    sa = a.state()
+    monkeypatch.setenv("MMSIG_PIPE_CHUNKS", str(chunks))
+    # a handle that held a different corpus before: fit_host must re-plan
+    other = small_synth(700, K, V, seed=9)
+    b = mmsig.MMCTM(K, [0.1, 0.2, 0.3], other, V=V, gamma0=g0)
+    hist_b, sb = b.fit_host(counts, s0["gamma"], lam=s0["lam"], nu=s0["nu"], mu=s0["mu"], Sigma=s0["Sigma"],
+                            invSigma=s0["invSigma"], maxiter=maxiter, tol=tol)
+    assert np.array_equal(hist_a, hist_b) and a.converged == b.converged
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    assert b.calculate_elbo()[0] == a.elbo
+    # and again on the now-matching shape (allocation reuse), from the constructor state
+    c = mmsig.MMCTM(K, [0.1, 0.2, 0.3], counts, V=V, gamma0=g0)
+    hist_c = c.fit(maxiter=maxiter, tol=tol, verbose=False)
+    hist_d, sd = b.fit_host(counts, g0, maxiter=maxiter, tol=tol)
+    sc = c.state()
+    assert np.array_equal(hist_c, hist_d)
+    for k in sc:
+        assert np.array_equal(sc[k], sd[k]), k
+    a.close(); b.close(); c.close()
+
+
+def test_fit_host_rejects_bad_counts():
+    K, V, D = [3, 2], [10, 6], 64
+    counts = small_synth(D, K, V, seed=5)
+    g0 = mmsig.synth.init_gamma(K, V)
+    m = mmsig.MMCTM(K, [0.1, 0.1], counts, V=V, gamma0=g0)
+    bad = [(r.copy(), t.copy(), c.copy()) for r, t, c in counts]
+    bad[1][1][0] = 99                                  # term out of range
+    with pytest.raises(mmsig.capi.MmsigError):
+        m.fit_host(bad, g0, maxiter=1)
+    hist, _ = m.fit_host(counts, g0, maxiter=2)        # the handle recovers
+    assert np.isfinite(hist).all()
+    m.close()
