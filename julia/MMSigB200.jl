@@ -71,33 +71,49 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
     h = create(device=device, stop_rule=stop_rule)
     ll = Vector{Float64}[]
     try
+        flags = UInt32((updateΣ ? 1 : 0) | (autoα ? 16 : 0))
+        ζ = zeros(D * M); μ = zeros(MK); Elnϕ = similar(γ); ϕ = similar(γ); props = zeros(D * MK)
+        elbo = Ref(0.0)
         GC.@preserve rowptr term count begin
             rp = [pointer(r) for r in rowptr]; tp = [pointer(t) for t in term]; cp = [pointer(c) for c in count]
-            check(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
-                (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
-                h, D, D, M, K32, V32, rp, tp, cp))
-        end
-        check(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
-            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
-        flags = UInt32((updateΣ ? 1 : 0) | (autoα ? 16 : 0))
-        llbuf = zeros(M)
-        for iter in 1:maxiter                                   # src/MMCTM.jl:462-489
-            check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
-            push!(ll, copy(llbuf))
-            verbose && println("$iter\tLog-likelihoods: ", join(ll[end], ", "))
-            if length(ll) > 10 && check_convergence(ll, tol=tol)
-                model.converged = true
-                break
+            if !verbose
+                # one call: counts + state in, the whole loop of src/MMCTM.jl:462-489, state out, with
+                # the host<->device copies pipelined behind the E-step (mmsig_mmctm_fit_host)
+                hist = zeros(M, maxiter); nit = Ref{Int32}(0); conv = Ref{Int32}(0)
+                check(h, ccall((:mmsig_mmctm_fit_host, LIB), Int32,
+                    (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Int32, Float64, UInt32, Ptr{Float64}, Ref{Int32}, Ref{Int32},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h, D, D, M, K32, V32, rp, tp, cp, model.α, γ, λ, ν, model.μ, Σ, invΣ,
+                    maxiter, tol, flags, hist, nit, conv, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+                ll = [hist[:, i] for i in 1:nit[]]
+                model.converged = conv[] != 0
+            else
+                check(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
+                    (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                    h, D, D, M, K32, V32, rp, tp, cp))
+                check(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
+                llbuf = zeros(M)
+                for iter in 1:maxiter                                   # src/MMCTM.jl:462-489
+                    check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+                    push!(ll, copy(llbuf))
+                    println("$iter\tLog-likelihoods: ", join(ll[end], ", "))      # src/MMCTM.jl:482
+                    if length(ll) > 10 && check_convergence(ll, tol=tol)
+                        model.converged = true
+                        break
+                    end
+                end
+                check(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
             end
         end
-        elbo = Ref(0.0)
         check(h, ccall((:mmsig_mmctm_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
-        ζ = zeros(D * M); μ = zeros(MK); Elnϕ = similar(γ); ϕ = similar(γ); props = zeros(D * MK)
-        check(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
-            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-            h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
         # scatter back into the nested vectors (shapes preserved)
         for d in 1:D
             model.λ[d] .= @view λ[(d - 1) * MK + 1:d * MK]
