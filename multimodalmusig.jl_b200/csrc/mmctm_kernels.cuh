@@ -186,9 +186,9 @@ __device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, cons
         // src/common.jl:11-23
         const double diff = x - c.muj;
         const double e = det_exp(x + c.other);
-        if (lane < MKP) dsh[lane] = c.active ? diff : 0.0;
+        dsh[lane] = c.active ? diff : 0.0;          // all 32 lanes store: no divergent branch around the STS
         __syncwarp();
-        double q = 0.0;
+        double q0 = 0.0, q1 = 0.0;                  // DET: even / odd index fma chains, then one add
         // row `lane` of invΣ, padded to SROW_STRIDE doubles (208 B): 128-bit loads of neighbouring
         // lanes fall into distinct bank groups, so both operands come in as LDS.128
         const double2 *srow = reinterpret_cast<const double2 *>(ST + lane * SROW_STRIDE);
@@ -196,9 +196,10 @@ __device__ __forceinline__ void mma_eval_local(double x, const SolveCtx &c, cons
 #pragma unroll kMatvecUnroll
         for (int i = 0; i < MKP / 2; ++i) {
             const double2 sv = srow[i], dv = dv2[i];
-            q = fma(sv.x, dv.x, q);
-            q = fma(sv.y, dv.y, q);
+            q0 = fma(sv.x, dv.x, q0);
+            q1 = fma(sv.y, dv.y, q1);
         }
+        const double q = q0 + q1;
         __syncwarp();
         const double ce = c.c * e;
         grad = (-q + c.s) - ce;
@@ -235,11 +236,11 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             u *= sigma2;
             const double r = fast_div(u, v * sigma);
             const double om = fabs(1 - r * r);
-            const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+            const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
             double dx = fast_div(fast_div(u, v), -1 - sq);
             double xc = x + dx;
-            if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
-            else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
+            const double mv = 0.9 * sigma, xhi = x + mv, xlo = x - mv;          // move limits: selects, no branches
+            xc = xc > xhi ? xhi : (xc < xlo ? xlo : xc);
             if (xc < lb) xc = lb;
             if (!c.active) xc = x;                   // dummy lanes stay put
             dx = xc - x;
@@ -304,13 +305,13 @@ __device__ __forceinline__ double block_sum_seq(double e, int lo, int hi, int MK
 // ------------------------------------------------------------------------------------------
 template <int MKP>
 __global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, double2 *partial) {
-    __shared__ __align__(16) double dsh_all[8][MKP];
+    __shared__ __align__(16) double dsh_all[8][32];
     __shared__ double2 red[8][2][32];
     __shared__ __align__(16) double ST[32 * SROW_STRIDE];    // invΣ rows, zero padded: ST[j*SROW_STRIDE+i] = invΣ[j][i]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int MK = p.MK, M = p.M;
     double *dsh = dsh_all[warp];
-    if (lane < MKP) dsh[lane] = 0.0;
+    dsh[lane] = 0.0;
     const bool active = lane < MK;
     int mod = 0;
     for (int m = 0; m < M; ++m)

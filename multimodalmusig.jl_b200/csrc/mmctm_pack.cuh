@@ -128,11 +128,11 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             u *= sigma2;
             const double r = fast_div(u, v * sigma);
             const double om = fabs(1 - r * r);
-            const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+            const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
             double dx = fast_div(fast_div(u, v), -1 - sq);
             double xc = x + dx;
-            if (xc > x + 0.9 * sigma) xc = x + 0.9 * sigma;
-            else if (xc < x - 0.9 * sigma) xc = x - 0.9 * sigma;
+            const double mv = 0.9 * sigma, xhi = x + mv, xlo = x - mv;          // move limits: selects, no branches
+            xc = xc > xhi ? xhi : (xc < xlo ? xlo : xc);
             if (xc < lb) xc = lb;
             if (!active) xc = x;
             dx = xc - x;
@@ -155,14 +155,15 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             const double e = det_exp(xe + other);
             dsh[gl] = active ? diff : 0.0;
             __syncwarp(gmask);
-            double q = 0.0;
+            double q = 0.0, qo = 0.0;
             const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
 #pragma unroll
             for (int i = 0; i < G / 2; ++i) {
                 const double2 sv = srow[i], dv = dv2[i];
-                q = fma(sv.x, dv.x, q);
-                q = fma(sv.y, dv.y, q);
+                q = fma(sv.x, dv.x, q);                 // DET: even / odd index chains, then one add
+                qo = fma(sv.y, dv.y, qo);
             }
+            q = q + qo;
             __syncwarp(gmask);
             const double ce = cN * e;
             const double grad = (-q + sth) - ce;
@@ -361,7 +362,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                 u *= sigma2;
                 const double r = fast_div(u, v * sigma[s]);
                 const double om = fabs(1 - r * r);
-                const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+                const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
                 double dx = fast_div(fast_div(u, v), -1 - sq);
                 double xc = x[s] + dx;
                 if (xc > x[s] + 0.9 * sigma[s]) xc = x[s] + 0.9 * sigma[s];
@@ -397,9 +398,9 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
             }
             __syncwarp(gmask);
             const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
-            double q[CPL];
+            double q[CPL], qo[CPL];                     // DET: even / odd index chains, then one add
 #pragma unroll
-            for (int s = 0; s < CPL; ++s) q[s] = 0.0;
+            for (int s = 0; s < CPL; ++s) { q[s] = 0.0; qo[s] = 0.0; }
 #pragma unroll 4
             for (int i = 0; i < MKP / 2; ++i) {
                 const double2 dv = dv2[i];
@@ -407,9 +408,11 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                 for (int s = 0; s < CPL; ++s) {
                     const double2 sv = reinterpret_cast<const double2 *>(ST + (gl + 8 * s) * STRIDE)[i];
                     q[s] = fma(sv.x, dv.x, q[s]);
-                    q[s] = fma(sv.y, dv.y, q[s]);
+                    qo[s] = fma(sv.y, dv.y, qo[s]);
                 }
             }
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) q[s] = q[s] + qo[s];
             __syncwarp(gmask);
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {

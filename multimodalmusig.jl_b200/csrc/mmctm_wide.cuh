@@ -40,15 +40,16 @@ __device__ __forceinline__ void wide_eval_local(const double (&x)[WCPL], const W
 #pragma unroll
         for (int s = 0; s < WCPL; ++s) {
             const double e = det_exp(x[s] + c.other[s]);
-            double q = 0.0;
+            double q = 0.0, qo = 0.0;
             const double2 *srow = reinterpret_cast<const double2 *>(ST + (lane + 32 * s) * WSTRIDE);
             const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
 #pragma unroll 4
             for (int i = 0; i < WMK / 2; ++i) {
                 const double2 sv = srow[i], dv = dv2[i];
-                q = fma(sv.x, dv.x, q);
-                q = fma(sv.y, dv.y, q);
+                q = fma(sv.x, dv.x, q);                 // DET: even / odd index chains, then one add
+                qo = fma(sv.y, dv.y, qo);
             }
+            q = q + qo;
             const double ce = c.c[s] * e;
             const double grad = (-q + c.s[s]) - ce;
             const double a = q * diff[s], b = x[s] * c.s[s];
@@ -95,7 +96,7 @@ __device__ __forceinline__ int wide_mma_solve(double (&x)[WCPL], const WideCtx &
                 u *= sigma2;
                 const double r = fast_div(u, v * sigma[s]);
                 const double om = fabs(1 - r * r);
-                const double sq = om == 0.0 ? 0.0 : fast_sqrt(om);      // om is 0 or >= 2^-53
+                const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
                 double dx = fast_div(fast_div(u, v), -1 - sq);
                 double xn = x[s] + dx;
                 if (xn > x[s] + 0.9 * sigma[s]) xn = x[s] + 0.9 * sigma[s];

@@ -42,7 +42,7 @@
  *         only + * fma / sqrt and bit moves, all IEEE-754 exact-rounded);
  *     (2) sums over the MK coordinates of one sample (objective values, MMA's
  *         gval / wval, the x-tolerance norms): a fixed 32-leaf binary tree
- *         (tree_sum32); mat-vec rows: one fma chain in index order;
+ *         (tree_sum32); mat-vec rows: an even-index and an odd-index fma chain, added;
  *     (3) sums over the nonzeros w of ONE row (sum-theta, the row's
  *         log-likelihood): the same tree, leaf = w mod 32;
  *         sums over SAMPLES d (topic-term statistics, sum lambda, sum nu,
@@ -405,14 +405,17 @@ double orc_lambda_objective(int MK, const double *lam, double *grad,
     for (int j = 0; j < MK; ++j) diff[j] = lam[j] - mu[j];
     for (int j = 0; j < MK; ++j) Eeeta[j] = xexp(arith, lam[j] + 0.5 * nu[j]);
     if (arith) {
-        /* DET: row_j(invSigma).diff as one fma chain in index order; the
-           quadratic form reuses it (q.diff); per-coordinate terms are fused
-           and reduced by the fixed tree. */
+        /* DET: row_j(invSigma).diff as two fma chains in index order, one
+           over the even and one over the odd indices, then one add (two
+           independent dependency chains on the device); the quadratic form
+           reuses it (q.diff); per-coordinate terms are fused and reduced by
+           the fixed tree. */
         double t[MK];
         for (int j = 0; j < MK; ++j) {
-            double s = 0.0;
-            for (int i = 0; i < MK; ++i) s = fma(invSigma[(size_t)j * MK + i], diff[i], s);
-            q[j] = s;
+            double s0 = 0.0, s1 = 0.0;
+            for (int i = 0; i < MK; i += 2) s0 = fma(invSigma[(size_t)j * MK + i], diff[i], s0);
+            for (int i = 1; i < MK; i += 2) s1 = fma(invSigma[(size_t)j * MK + i], diff[i], s1);
+            q[j] = s0 + s1;
         }
         for (int j = 0; j < MK; ++j) {
             double ce = Ndivzeta[j] * Eeeta[j];
