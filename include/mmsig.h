@@ -75,6 +75,27 @@ int32_t     mmsig_synchronize(mmsig_handle *h);
 int32_t mmsig_comm_unique_id(uint8_t id_out[128]);
 int32_t mmsig_comm_init(mmsig_handle *h, const uint8_t id[128], int32_t rank, int32_t nranks);
 
+/* ---- count ingest: format_counts_mmctm / _ctm / _lda (reference src/utils.jl:1-36) on the device ----
+ * make_count_matrix (src/utils.jl:1-7) for every sample of one modality's dense count matrix:
+ * entries > 0 become (term, count) rows in ascending term order, entries <= 0 are dropped.
+ * dense: HOST pointer to D*V integers of elem_bytes (4: int32, 8: int64 = Julia Int) in layout
+ *   MMSIG_DENSE_TERM_MAJOR   dense[v*D + d]  one row per term: the TSV files (data/brca-eu_snv_counts.tsv), a C-order (V, D) array
+ *   MMSIG_DENSE_SAMPLE_MAJOR dense[d*V + v]  Julia's column-major V x D Matrix / one DataFrame column per sample
+ * A count above 2^31-1 is refused (MMSIG_ELIMIT). */
+#define MMSIG_DENSE_TERM_MAJOR   0
+#define MMSIG_DENSE_SAMPLE_MAJOR 1
+/* -> rowptr_out[D+1], *nnz_out; the records stay on the device until _fetch copies them out
+ * (term 0-BASED, count), which also releases them */
+int32_t mmsig_format_counts(mmsig_handle *h, int64_t D, int32_t V, const void *dense, int32_t elem_bytes,
+                            int32_t layout, int64_t *rowptr_out, int64_t *nnz_out);
+int32_t mmsig_format_counts_fetch(mmsig_handle *h, int32_t *term_out, int32_t *count_out);
+/* mmsig_mmctm_set_data / mmsig_lda_set_data from dense matrices: the CSR is built on the device and
+ * never visits the host (dense[m] as above, V[m] terms each) */
+int32_t mmsig_mmctm_set_data_dense(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                   const int32_t *V, const void *const *dense, int32_t elem_bytes, int32_t layout);
+int32_t mmsig_lda_set_data_dense(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
+                                 const void *dense, int32_t elem_bytes, int32_t layout);
+
 /* ---- MMCTM / CTM  (reference src/MMCTM.jl) -------------------------------------------- */
 /* model.X, K, V (src/MMCTM.jl:29-40); with mmsig_comm_init, D and the CSR are this rank's shard
  * and D_total is the global sample count (else pass D_total = D). */

@@ -16,6 +16,7 @@ c_u8p = C.POINTER(C.c_uint8)
 
 FLAG_UPDATE_SIGMA, FLAG_FREEZE_TOPICS, FLAG_FREEZE_MU, FLAG_UNSMOOTHED, FLAG_AUTO_ALPHA = 1, 2, 4, 8, 16
 STOP_NLOPT27, STOP_NLOPT26 = 0, 1
+DENSE_TERM_MAJOR, DENSE_SAMPLE_MAJOR = 0, 1
 
 
 class Config(C.Structure):
@@ -38,6 +39,12 @@ _SIGS = {
     "mmsig_synchronize": (C.c_int32, [C.c_void_p]),
     "mmsig_comm_unique_id": (C.c_int32, [c_u8p]),
     "mmsig_comm_init": (C.c_int32, [C.c_void_p, c_u8p, C.c_int32, C.c_int32]),
+    "mmsig_format_counts": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, c_i64p, c_i64p]),
+    "mmsig_format_counts_fetch": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
+    "mmsig_mmctm_set_data_dense": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
+                                               C.POINTER(C.c_void_p), C.c_int32, C.c_int32]),
+    "mmsig_lda_set_data_dense": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, C.c_void_p,
+                                             C.c_int32, C.c_int32]),
     "mmsig_mmctm_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
                                          C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)]),
     "mmsig_mmctm_set_state": (C.c_int32, [C.c_void_p] + [c_dp] * 7),

@@ -23,6 +23,30 @@ def make_count_csr(dense):
     return rowptr, term, count
 
 
+def format_counts_device(dense, layout=0, handle=None, device=0):
+    """format_counts_lda / one modality of format_counts_mmctm (src/utils.jl:1-36) ON THE GPU
+    (mmsig_format_counts): dense is (V, D) for layout 0 (term-major, the TSV layout) or (D, V) for
+    layout 1 (sample-major, Julia's column-major V x D); int32 or int64.  Returns (rowptr, term0, count)."""
+    import ctypes as C
+    from . import capi
+    a = np.ascontiguousarray(dense)
+    if a.dtype not in (np.int32, np.int64):
+        a = a.astype(np.int64)
+    V, D = (a.shape if layout == 0 else a.shape[::-1])
+    h = handle or capi.Handle(device=device)
+    try:
+        rowptr = np.zeros(D + 1, dtype=np.int64)
+        nnz = C.c_int64()
+        h.check(h.lib.mmsig_format_counts(h.h, D, V, a.ctypes.data_as(C.c_void_p), a.dtype.itemsize, layout,
+                                          rowptr.ctypes.data_as(capi.c_i64p), C.byref(nnz)))
+        term, count = np.zeros(nnz.value, dtype=np.int32), np.zeros(nnz.value, dtype=np.int32)
+        h.check(h.lib.mmsig_format_counts_fetch(h.h, term.ctypes.data_as(capi.c_i32p), count.ctypes.data_as(capi.c_i32p)))
+    finally:
+        if handle is None:
+            h.close()
+    return rowptr, term, count
+
+
 def format_counts_mmctm(dense_list):
     """src/utils.jl:24-36: one CSR triple per modality."""
     return [make_count_csr(x) for x in dense_list]

@@ -23,10 +23,13 @@ static int pick_lda_plan(mmsig_handle *h, F kernel, int KV /* V * (KP + 2) */, l
     return 0;
 }
 
-extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
-                                      const int64_t *rowptr, const int32_t *term, const int32_t *count) {
+// job != nullptr: the counts are already on the device as a counted and scanned dense matrix
+// (mmsig_lda_set_data_dense); else CSR from the host
+static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V, const int64_t *rowptr,
+                             const int32_t *term, const int32_t *count, const DenseJob *job, const double *job_N,
+                             int elem_bytes, int layout) {
     NEED(h, "null handle");
-    NEED(rowptr, "null rowptr");
+    NEED(rowptr || job, "null rowptr");
     NEED(D >= 1 && D_total >= D, "need 1 <= D <= D_total");
     NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
     NEED(K >= 1 && V >= 1, "K, V must be >= 1");
@@ -45,7 +48,15 @@ extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_tota
     if ((rc = dev_alloc(h, h->allocs_lda, &dN, (size_t)D))) return rc;
     p.N = dN;
     long long ntot = 0;
-    if ((rc = upload_counts(h, h->allocs_lda, L.cb, D, V, 1, 0, rowptr, term, count, dN, &ntot))) return rc;
+    if (job) {
+        if ((rc = ensure_countbuf(h, h->allocs_lda, L.cb, D, job->nnz))) return rc;
+        CU(cudaMemcpyAsync(dN, job_N, (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        CU(cudaMemcpyAsync(L.cb.rowptr, job->rowptr, (D + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+        dense_fill(h, *job, D, V, elem_bytes, layout, L.cb.rowptr, L.cb.rec);
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaGetLastError());
+        ntot = job->total;
+    } else if ((rc = upload_counts(h, h->allocs_lda, L.cb, D, V, 1, 0, rowptr, term, count, dN, &ntot))) return rc;
     p.rowptr = L.cb.rowptr;
     p.rec = L.cb.rec;
     L.nnz = L.cb.nnz;
@@ -100,6 +111,27 @@ extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_tota
     if ((rc = dev_alloc(h, h->allocs_lda, &L.d_ll, (size_t)8))) return rc;
     L.has_data = true;
     return 0;
+}
+
+extern "C" int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
+                                      const int64_t *rowptr, const int32_t *term, const int32_t *count) {
+    return lda_set_data_impl(h, D, D_total, K, V, rowptr, term, count, nullptr, nullptr, 0, 0);
+}
+
+// LDA(K, α, η, format_counts_lda(df, cols)) without the host-side CSR (src/utils.jl:9-18)
+extern "C" int32_t mmsig_lda_set_data_dense(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
+                                            const void *dense, int32_t elem_bytes, int32_t layout) {
+    NEED(h, "null handle");
+    NEED(D >= 1 && V >= 1, "D, V must be >= 1");
+    CU(cudaSetDevice(h->device));
+    DenseJob j;
+    double *tmpN = nullptr;
+    if (cudaMalloc(&tmpN, (size_t)D * sizeof(double)) != cudaSuccess) return fail(h, MMSIG_ENOMEM, "cudaMalloc (N)");
+    int rc = dense_count_scan(h, j, D, V, dense, elem_bytes, layout, tmpN, 1, 0);
+    if (!rc) rc = lda_set_data_impl(h, D, D_total, K, V, nullptr, nullptr, nullptr, &j, tmpN, elem_bytes, layout);
+    free_job(j);
+    cudaFree(tmpN);
+    return rc;
 }
 
 extern "C" int32_t mmsig_lda_set_state(mmsig_handle *h, double alpha, double eta, const double *lambda,

@@ -18,6 +18,7 @@
 #include "mmctm_pack.cuh"
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
+#include "ingest_kernels.cuh"
 
 using namespace mmsig;
 
@@ -115,6 +116,8 @@ struct mmsig_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of mmsig_mmctm_fit_host
+    int2 *fmt_rec = nullptr;                           // records of the last mmsig_format_counts
+    long long fmt_nnz = -1;
     bool own_stream = false;
     std::string err;
     int stop_rule = 0;
@@ -264,6 +267,7 @@ extern "C" int32_t mmsig_destroy(mmsig_handle *h) {
     free_pool(h->allocs_lda);
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->own_stream) cudaStreamDestroy(h->stream);
+    cudaFree(h->fmt_rec);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
@@ -488,8 +492,8 @@ static int pick_theta_plan(mmsig_handle *h, F kernel, int KV, int D, int *W_out,
 // Shape-dependent part of set_data: allocations and launch plans for (D, D_total, M, K, V, nnz_m).
 // *same_out: the resident shape matched and everything was kept.  Counts are not touched.
 static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K, const int32_t *V,
-                         const int64_t *const *rowptr, bool *same_out) {
-    NEED(K && V && rowptr, "null argument");
+                         const long long *nnz, bool *same_out) {
+    NEED(K && V && nnz, "null argument");
     NEED(D >= 1 && D_total >= D, "need 1 <= D <= D_total");
     NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
     if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
@@ -497,18 +501,15 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     for (int m = 0; m < M; ++m) {
         NEED(K[m] >= 1 && V[m] >= 1, "K[m], V[m] must be >= 1");
         if (K[m] > 32) return fail(h, MMSIG_ELIMIT, "K[m] <= 32 supported");
-        NEED(rowptr[m], "null rowptr");
         MKsum += K[m];
     }
     if (MKsum > MAXMK) return fail(h, MMSIG_ELIMIT, "sum(K) <= 64 supported");
     int rc;
-    for (int m = 0; m < M; ++m)
-        if ((rc = check_rowptr(h, rowptr[m], D))) return rc;
     // same shape as what is already resident (a repeated fit! on the same corpus): keep every
     // allocation and launch plan
     bool same = h->mm.has_data && h->mm.p.M == M && h->mm.p.D == D && h->mm.p.D_total == D_total;
     for (int m = 0; same && m < M; ++m)
-        same = h->mm.p.K[m] == K[m] && h->mm.p.V[m] == V[m] && h->mm.cb[m].nnz == rowptr[m][D];
+        same = h->mm.p.K[m] == K[m] && h->mm.p.V[m] == V[m] && h->mm.cb[m].nnz == nnz[m];
     *same_out = same;
     if (same) {
         h->mm.has_state = false;
@@ -537,7 +538,7 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     p.N = dN;
     mm.nnz.resize(M);
     for (int m = 0; m < M; ++m) {
-        if ((rc = ensure_countbuf(h, h->allocs_mm, mm.cb[m], D, rowptr[m][D]))) return rc;
+        if ((rc = ensure_countbuf(h, h->allocs_mm, mm.cb[m], D, nnz[m]))) return rc;
         p.rowptr[m] = mm.cb[m].rowptr;
         p.rec[m] = mm.cb[m].rec;
         mm.nnz[m] = mm.cb[m].nnz;
@@ -643,9 +644,16 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     NEED(h, "null handle");
     NEED(K && V && rowptr && term && count, "null argument");
     CU(cudaSetDevice(h->device));
+    if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
+    NEED(D >= 1, "need 1 <= D <= D_total");
     bool same = false;
-    int rc = mmctm_prepare(h, D, D_total, M, K, V, rowptr, &same);
-    if (rc) return rc;
+    int rc;
+    long long nnz[MAXM];
+    for (int m = 0; m < M; ++m) {
+        if ((rc = check_rowptr(h, rowptr[m], D))) return rc;
+        nnz[m] = rowptr[m][D];
+    }
+    if ((rc = mmctm_prepare(h, D, D_total, M, K, V, nnz, &same))) return rc;
     MmctmHost &mm = h->mm;
     mm.has_data = false;
     long long ntot[MAXM];
@@ -1050,9 +1058,16 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
     NEED(alpha && gamma, "alpha and gamma are required");
     NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
     CU(cudaSetDevice(h->device));
+    if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
+    NEED(D >= 1, "need 1 <= D <= D_total");
     bool same = false;
-    int rc = mmctm_prepare(h, D, D_total, M, K, V, rowptr, &same);
-    if (rc) return rc;
+    int rc;
+    long long nnz_m[MAXM];
+    for (int m = 0; m < M; ++m) {
+        if ((rc = check_rowptr(h, rowptr[m], D))) return rc;
+        nnz_m[m] = rowptr[m][D];
+    }
+    if ((rc = mmctm_prepare(h, D, D_total, M, K, V, nnz_m, &same))) return rc;
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     mm.has_data = false;
@@ -1362,6 +1377,8 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
     if (best) *best = best_r;
     return 0;
 }
+
+#include "ingest_api.inl"
 
 extern "C" int32_t mmsig_lda_iterate_flags(mmsig_handle *h, uint32_t flags, double *ll_out);
 #include "lda_api.inl"

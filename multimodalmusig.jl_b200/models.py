@@ -23,14 +23,29 @@ class MMCTM:
     """src/MMCTM.jl:1-108.  counts: list over modalities of (rowptr, term0, count)."""
 
     def __init__(self, K, alpha, counts, V=None, gamma0=None, rng=None, device=0,
-                 stop_rule=capi.STOP_NLOPT27, profile=False, comm=None, D_total=None):
+                 stop_rule=capi.STOP_NLOPT27, profile=False, comm=None, D_total=None, dense=None,
+                 dense_layout=capi.DENSE_TERM_MAJOR):
+        """counts: CSR triples per modality (format_counts_mmctm); or counts=None and dense = list of
+        dense integer matrices ((V_m, D) term-major as the TSV files, or (D, V_m) with
+        dense_layout=DENSE_SAMPLE_MAJOR), turned into CSR on the GPU (mmsig_mmctm_set_data_dense)."""
         self.K = [int(k) for k in K]
         self.M = len(self.K)
         self.alpha = np.asarray(alpha, dtype=np.float64).copy()
-        if len(counts) != self.M or self.alpha.size != self.M:
+        if len(dense if dense is not None else counts) != self.M or self.alpha.size != self.M:
             raise ValueError("K, alpha and counts must have one entry per modality")
-        self.V = infer_V(counts) if V is None else [int(v) for v in V]      # src/MMCTM.jl:94-108
-        self.D = len(counts[0][0]) - 1
+        if dense is not None:
+            lay = dense_layout
+            dense = [np.ascontiguousarray(x if x.dtype in (np.int32, np.int64) else np.asarray(x, np.int64)) for x in map(np.asarray, dense)]
+            if len({x.dtype for x in dense}) != 1:
+                dense = [x.astype(np.int64) for x in dense]
+            if V is None:
+                raise ValueError("V is required with dense counts (scripts/run_mmctm.jl:262 passes it explicitly)")
+            self.V = [int(v) for v in V]
+            self.D = int(dense[0].shape[1] if lay == capi.DENSE_TERM_MAJOR else dense[0].shape[0])
+            counts = [None] * len(dense)
+        else:
+            self.V = infer_V(counts) if V is None else [int(v) for v in V]      # src/MMCTM.jl:94-108
+            self.D = len(counts[0][0]) - 1
         self.MK = sum(self.K)
         self.G = sum(k * v for k, v in zip(self.K, self.V))
         if gamma0 is None:                                                  # init=:random, :59-63
@@ -40,11 +55,23 @@ class MMCTM:
         if comm is not None:
             uid, rank, nranks = comm
             self.h.comm_init(uid, rank, nranks)
-        self._set_data(counts, self.D if D_total is None else D_total)
+        if dense is not None:
+            self._set_data_dense(dense, dense_layout, self.D if D_total is None else D_total)
+        else:
+            self._set_data(counts, self.D if D_total is None else D_total)
         self.set_state(gamma=gamma0)
         self.converged = False
         self.elbo = float("nan")
         self.ll = None
+
+    def _set_data_dense(self, dense, layout, D_total):
+        M = self.M
+        ptrs = (C.c_void_p * M)(*[x.ctypes.data_as(C.c_void_p) for x in dense])
+        K = np.asarray(self.K, np.int32)
+        V = np.asarray(self.V, np.int32)
+        self.h.check(self.h.lib.mmsig_mmctm_set_data_dense(self.h.h, self.D, D_total, M, K.ctypes.data_as(capi.c_i32p),
+                                                           V.ctypes.data_as(capi.c_i32p), ptrs, dense[0].dtype.itemsize, layout))
+        self.nnz = None
 
     def _set_data(self, counts, D_total):
         lib = self.h.lib
@@ -295,13 +322,22 @@ class LDA:
     """src/LDA.jl:1-67.  counts: (rowptr, term0, count)."""
 
     def __init__(self, K, alpha, eta, counts, V=None, lambda0=None, rng=None, device=0, profile=False,
-                 comm=None, D_total=None):
+                 comm=None, D_total=None, dense=None, dense_layout=capi.DENSE_TERM_MAJOR):
+        """counts: CSR triple (format_counts_lda); or counts=None and dense = the (V, D) term-major
+        (or (D, V) sample-major) integer matrix, turned into CSR on the GPU (mmsig_lda_set_data_dense)."""
         self.K = int(K)
         self.alpha, self.eta = float(alpha), float(eta)
-        r, t, c = counts
-        self.V = (int(np.max(t)) + 1 if len(t) else 0) if V is None else int(V)   # src/LDA.jl:57-67
-        self.D = len(r) - 1
-        self.nnz = int(r[-1])
+        if dense is not None:
+            dense = np.asarray(dense)
+            dense = np.ascontiguousarray(dense if dense.dtype in (np.int32, np.int64) else dense.astype(np.int64))
+            Vd, Dd = dense.shape if dense_layout == capi.DENSE_TERM_MAJOR else dense.shape[::-1]
+            self.V = int(Vd) if V is None else int(V)
+            self.D, self.nnz = int(Dd), None
+        else:
+            r, t, c = counts
+            self.V = (int(np.max(t)) + 1 if len(t) else 0) if V is None else int(V)   # src/LDA.jl:57-67
+            self.D = len(r) - 1
+            self.nnz = int(r[-1])
         if lambda0 is None:                                                       # src/LDA.jl:36
             rng = np.random.default_rng() if rng is None else rng
             lambda0 = rng.integers(1, 101, size=self.K * self.V).astype(np.float64)
@@ -309,10 +345,15 @@ class LDA:
         if comm is not None:
             uid, rank, nranks = comm
             self.h.comm_init(uid, rank, nranks)
-        keep = (np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32), np.ascontiguousarray(c, np.int32))
-        self.h.check(self.h.lib.mmsig_lda_set_data(self.h.h, self.D, self.D if D_total is None else D_total,
-                                                   self.K, self.V, keep[0].ctypes.data_as(capi.c_i64p),
-                                                   keep[1].ctypes.data_as(capi.c_i32p), keep[2].ctypes.data_as(capi.c_i32p)))
+        if dense is not None:
+            self.h.check(self.h.lib.mmsig_lda_set_data_dense(self.h.h, self.D, self.D if D_total is None else D_total,
+                                                             self.K, self.V, dense.ctypes.data_as(C.c_void_p),
+                                                             dense.dtype.itemsize, dense_layout))
+        else:
+            keep = (np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32), np.ascontiguousarray(c, np.int32))
+            self.h.check(self.h.lib.mmsig_lda_set_data(self.h.h, self.D, self.D if D_total is None else D_total,
+                                                       self.K, self.V, keep[0].ctypes.data_as(capi.c_i64p),
+                                                       keep[1].ctypes.data_as(capi.c_i32p), keep[2].ctypes.data_as(capi.c_i32p)))
         self.set_state(lambda0)
         self.converged = False
         self.elbo = float("nan")

@@ -1453,3 +1453,32 @@ int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist)
     if (it > 0) m->ll = ll_hist[it - 1];
     return it;
 }
+
+
+/* =====================================================================
+ * Count ingest, src/utils.jl
+ * ===================================================================== */
+
+/* make_count_matrix (src/utils.jl:1-7) applied to every sample of one modality, as
+ * format_counts_lda (:9-18) / format_counts_mmctm (:24-36) do column by column:
+ * idx = findall(counts .> 0); rows [idx, counts[idx]] in ascending idx.  Flat result: CSR with
+ * 0-BASED terms.  dense: D*V int64; layout 0: dense[v*D + d] (term-major, the TSV), 1: dense[d*V + v].
+ * Pass term == NULL to only fill rowptr (sizing pass).  Returns nnz, or -1 if a count exceeds int32. */
+int64_t orc_make_count_csr(int64_t D, int V, const int64_t *dense, int layout,
+                           int64_t *rowptr, int32_t *term, int32_t *cnt)
+{
+    int64_t w = 0;
+    rowptr[0] = 0;
+    for (int64_t d = 0; d < D; ++d) {
+        for (int v = 0; v < V; ++v) {
+            int64_t x = layout == 0 ? dense[(size_t)v * D + d] : dense[(size_t)d * V + v];
+            if (x > 0) {                         /* counts .> 0 */
+                if (x > 2147483647LL) return -1;
+                if (term) { term[w] = (int32_t)v; cnt[w] = (int32_t)x; }
+                ++w;
+            }
+        }
+        rowptr[d + 1] = w;
+    }
+    return w;
+}

@@ -181,6 +181,10 @@ void orc_lda_unsmoothed_update_phi(orc_lda *m);               /* :226-231 */
 double orc_lda_iterate_flags(orc_lda *m, unsigned flags);     /* fit_heldout :275-280, transform :242-246 */
 int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist); /* :198-224 */
 
+/* format_counts_* (src/utils.jl:1-36): dense count matrix -> CSR; see mmsig_oracle.c */
+int64_t orc_make_count_csr(int64_t D, int V, const int64_t *dense, int layout,
+                           int64_t *rowptr, int32_t *term, int32_t *cnt);
+
 #ifdef __cplusplus
 }
 #endif

@@ -70,6 +70,7 @@ def lib():
         f.restype = res
         f.argtypes = list(args)
 
+    sig("orc_make_count_csr", i64, i64, i, c_i64p, i, c_i64p, c_i32p, c_i32p)
     sig("orc_digamma", d, d)
     sig("orc_digamma_det", d, d)
     sig("orc_lgamma", d, d)
@@ -278,3 +279,19 @@ class OracleLDA:
         return v, t
 
     converged = property(lambda s: bool(s.p.contents.converged))
+
+
+def make_count_csr(dense, layout=0):
+    """format_counts_* (src/utils.jl:1-36) by the oracle.  dense: (V, D) array for layout 0
+    (term-major), (D, V) for layout 1 (sample-major).  Returns (rowptr, term0, count)."""
+    a = np.ascontiguousarray(dense, dtype=np.int64)
+    V, D = (a.shape if layout == 0 else a.shape[::-1])
+    L = lib()
+    rowptr = np.zeros(D + 1, dtype=np.int64)
+    nnz = L.orc_make_count_csr(D, V, a.ctypes.data_as(c_i64p), layout, rowptr.ctypes.data_as(c_i64p), None, None)
+    if nnz < 0:
+        raise OverflowError("a count exceeds int32")
+    term, cnt = np.zeros(nnz, dtype=np.int32), np.zeros(nnz, dtype=np.int32)
+    L.orc_make_count_csr(D, V, a.ctypes.data_as(c_i64p), layout, rowptr.ctypes.data_as(c_i64p),
+                         term.ctypes.data_as(c_i32p), cnt.ctypes.data_as(c_i32p))
+    return rowptr, term, cnt
