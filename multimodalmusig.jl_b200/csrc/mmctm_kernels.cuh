@@ -1,8 +1,8 @@
 // mmctm_kernels.cuh -- sm_100a kernels for one MMCTM / CTM variational-EM iteration
 // (reference src/MMCTM.jl:450-479; dataflow in DESIGN.md).  FP64, pinned arithmetic.
 //
-//   k_theta_stats   responsibilities θ over the sparse [term,count] rows of one modality:
-//                   exact Σ_w n θ (sumθ, per sample) and exact Σ_d n θ (K x V statistics)
+//   k_theta_tile    (theta_tile.cuh) the θ pass of one modality as skinny products over sample
+//                   tiles: sumθ per sample and the K x V statistics Σ_d exp(λ) n / Z
 //   k_solve         per-sample ζ, then LD_MMA for ν and for λ (one warp per sample,
 //                   lane j = coordinate j), Σλ / Σν partials
 //   k_combine       block partials -> one double-double vector
@@ -51,108 +51,6 @@ __device__ __forceinline__ void put_partial(double2 *slot, double hi, double lo,
         dd_merge(hi, lo, o.x, o.y);
     }
     *slot = make_double2(hi, lo);
-}
-
-// ------------------------------------------------------------------------------------------
-// θ pass of one modality (src/MMCTM.jl:183-198, :110-117, :224-240).  One warp per sample,
-// lane <-> nonzero w.  Per nonzero: e_k = exp(λ_k + Elnϕ[k][v]), Z = Σ_k e_k (index order),
-// θ_k = e_k (1/Z), addend a = θ_k n.  Σ_w a -> sumθ[d][k]; Σ_d a -> this warp's private
-// double-double K x V table in shared memory (a row's terms are distinct, so lanes never
-// collide).  Nothing of size K x nnz is ever stored.
-// ------------------------------------------------------------------------------------------
-template <int KP, int NP>
-__global__ void __launch_bounds__(256) k_theta_stats(MmctmDev p, int m, double2 *partial, int nwarps_blk, int unsmoothed,
-                                                     int want_stats) {
-    extern __shared__ double smem[];
-    const int K = p.K[m], V = p.V[m], KV = K * V, off = p.koff[m];
-    double *Eln = smem;                       // KV
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *thi = smem + KV + (size_t)warp * 2 * KV;
-    double *tlo = thi + KV;
-    // smoothed (update_θ!, :183-198): θ ∝ exp(λ + Elnϕ), evaluated in the product form
-    //   e = exp(λ_k) · exp(Elnϕ_kv) (DET; the form the reference itself uses in
-    //   unsmoothed_update_θ!): K exps per sample + a K x V table instead of K·nnz exps;
-    // unsmoothed (unsmoothed_update_θ!, :496-509): table = ϕ, e = exp(λ) ϕ
-    const double *Eg = (unsmoothed ? p.phi : p.Elnphi) + p.goff[m];
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) Eln[i] = unsmoothed ? Eg[i] : det_exp(Eg[i]);
-    for (int i = lane; i < 2 * KV; i += 32) thi[i] = 0.0;
-    __syncthreads();
-
-    const long long *rowptr = p.rowptr[m];
-    const int2 *rec = p.rec[m];
-    const long long nw = (long long)gridDim.x * nwarps_blk;
-    // software pipeline: the row pointers, the first 32 records and λ of the NEXT sample are
-    // requested before the current one is computed (12-20 resident warps per SM cannot hide DRAM
-    // latency on their own: long-scoreboard stalls were the top reason in profiles/r01f)
-    long long d = (long long)blockIdx.x * nwarps_blk + warp;
-    long long beg_n = 0, end_n = 0;
-    int2 r_n = make_int2(0, 1);
-    double lam_n = 0.0;
-    if (d < p.D) {
-        beg_n = rowptr[d];
-        end_n = rowptr[d + 1];
-        if (beg_n + lane < end_n) r_n = rec[beg_n + lane];
-        lam_n = (lane < K) ? p.lam_prev[d * p.MK + off + lane] : 0.0;
-    }
-    for (; d < p.D; d += nw) {
-        const long long beg = beg_n, end = end_n;
-        int2 r = r_n;
-        double mine = lam_n;
-        if (d + nw < p.D) {
-            const long long dn = d + nw;
-            beg_n = rowptr[dn];
-            end_n = rowptr[dn + 1];
-            if (beg_n + lane < end_n) r_n = rec[beg_n + lane];
-            lam_n = (lane < K) ? p.lam_prev[dn * p.MK + off + lane] : 0.0;
-        }
-        double lamk[KP];
-        mine = det_exp(mine);
-#pragma unroll
-        for (int k = 0; k < KP; ++k) lamk[k] = shfl_d(mine, k);
-        double sth[NP];                     // Σ_w a_kw of this lane's nonzeros (w ≡ lane mod 32)
-#pragma unroll
-        for (int k = 0; k < NP; ++k) sth[k] = 0.0;
-        for (long long w = beg + lane; w < end; w += 32) {
-            int2 r_next = r;
-            if (w + 32 < end) r_next = rec[w + 32];
-            const int v = r.x;
-            const double n = (double)r.y;
-            double e[KP];
-            double Z = 0.0;
-#pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (k < K) {
-                    e[k] = lamk[k] * Eln[k * V + v];
-                    Z += e[k];
-                }
-            const double rz = 1.0 / Z;                 // DET: θ_k = e_k * (1/Z), one division per nonzero
-#pragma unroll
-            for (int k = 0; k < KP; ++k)
-                if (k < K) {
-                    const double a = (e[k] * rz) * n;
-                    if (want_stats) dd_add(thi[k * V + v], tlo[k * V + v], a);
-                    sth[k] += a;
-                }
-            r = r_next;
-        }
-        __syncwarp();
-        // the butterfly tree over lanes (recursive halving computes exactly its partial sums)
-        warp_multi_reduce<NP>(sth, lane);
-        const int idx = warp_multi_index<NP>(lane);
-        constexpr int GROUP = 32 / NP;            // lanes sharing one index
-        if (idx < K && (lane & (GROUP - 1)) == 0) p.sumtheta[d * p.MK + off + idx] = sth[0];
-    }
-    __syncthreads();
-    // block partial: warps' tables merged in warp order
-    double2 *out = partial + (size_t)blockIdx.x * KV;
-    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
-        double hi = 0.0, lo = 0.0;
-        for (int wv = 0; wv < nwarps_blk; ++wv) {
-            const double *t = smem + KV + (size_t)wv * 2 * KV;
-            dd_merge(hi, lo, t[i], t[KV + i]);
-        }
-        put_partial(out + i, hi, lo, p.accum);
-    }
 }
 
 // ------------------------------------------------------------------------------------------
@@ -402,7 +300,7 @@ __global__ void __launch_bounds__(256) k_combine(CombineSegs s, double2 *dst) {
 // ϕ = γ / Σ_v γ (:244-250), μ = exact_round(Σ_d λ) / D (:200-202).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gathered, int nranks, int freeze_topics,
-                                                 int freeze_mu) {
+                                                 int freeze_mu, int unsmoothed) {
     __shared__ double rowsum[MAXMK], rowdig[MAXMK];
     const int G = p.goff[p.M], MK = p.MK, P1 = G + 2 * MK;
     for (int i = threadIdx.x; i < P1; i += blockDim.x) {
@@ -415,9 +313,12 @@ __global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gath
             if (freeze_topics) continue;
             int m = 0;
             while (i >= p.goff[m + 1]) ++m;
-            p.stats[i] = dd_round(hi, lo);
-            dd_add(hi, lo, p.alpha[m]);
-            p.gamma[i] = dd_round(hi, lo);
+            // gathered: S_kv = Σ_d exp(λ_dk) n_dv / Z_dv (k_theta_tile); Σ n θ_kv = E_kv S_kv with the
+            // table the E-step used, which is still in place here
+            const double S = dd_round(hi, lo);
+            const double E = unsmoothed ? p.phi[i] : det_exp(p.Elnphi[i]);
+            p.stats[i] = E * S;
+            p.gamma[i] = fma(E, S, p.alpha[m]);
             p.Elnphi_prev[i] = p.Elnphi[i];
         } else if (i < G + MK) {
             if (!freeze_mu) p.mu[i - G] = dd_round(hi, lo) / (double)p.D_total;

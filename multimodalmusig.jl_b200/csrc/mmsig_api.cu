@@ -14,6 +14,7 @@
 #include "../../include/mmsig.h"
 #include "det_math.cuh"
 #include "mmctm_kernels.cuh"
+#include "theta_tile.cuh"
 #include "mmctm_wide.cuh"
 #include "mmctm_pack.cuh"
 #include "elbo_kernels.cuh"
@@ -447,28 +448,19 @@ static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &c
 // ===========================================================================================
 // MMCTM
 // ===========================================================================================
+// launch plan of k_theta_tile for one modality: one thread per term, tiles of TILE_S samples
 template <typename F>
-static int pick_theta_plan(mmsig_handle *h, F kernel, int KV, int D, int *W_out, int *grid_out, size_t *smem_out) {
-    cudaFuncAttributes fa;
-    CU(cudaFuncGetAttributes(&fa, kernel));
-    // one template instance can serve several modalities: always opt in to the device maximum
+static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, int V, long long D, int *grid_out, size_t *smem_out) {
+    const int VP = V | 1, NW = (V + 31) / 32;
+    const size_t smem = ((size_t)V * KP + (ereg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP) * sizeof(double);
+    if (smem > h->smem_optin) return fail(h, MMSIG_ELIMIT, "V too large for the theta tile (shared memory)");
     CU(allow_max_smem(h, kernel));
-    int bestW = 0, best_warps = 0, best_blocks = 0;
-    size_t best_smem = 0;
-    for (int W : {8, 4, 2, 1}) {
-        size_t smem = (size_t)(1 + 2 * W) * KV * sizeof(double);
-        if (smem > h->smem_optin) continue;
-        if (W * 32 * fa.numRegs > 65536) continue;
-        int nb = 0;
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, W * 32, smem));
-        if (nb * W > best_warps) { best_warps = nb * W; bestW = W; best_blocks = nb; best_smem = smem; }
-    }
-    if (!bestW) return fail(h, MMSIG_ELIMIT, "K*V topic-term table does not fit in shared memory");
-    *W_out = bestW;
-    *smem_out = best_smem;
-    long long want = (long long)h->numSM * best_blocks;
-    long long cap = ((long long)D + bestW - 1) / bestW;
-    *grid_out = (int)std::max<long long>(1, std::min(want, cap));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NW * 32, smem));
+    if (nb < 1) return fail(h, MMSIG_ELIMIT, "theta tile kernel does not fit on an SM for this K, V");
+    *smem_out = smem;
+    const long long ntiles = (D + TILE_S - 1) / TILE_S;
+    *grid_out = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * nb, ntiles));
     return 0;
 }
 
@@ -480,6 +472,22 @@ static int pick_theta_plan(mmsig_handle *h, F kernel, int KV, int D, int *W_out,
         else if ((K) <= 20) { constexpr int KP = 20, NP = 32; EXPR; } \
         else if ((K) <= 24) { constexpr int KP = 24, NP = 32; EXPR; } \
         else { constexpr int KP = 32, NP = 32; EXPR; }            \
+    } while (0)
+// k_theta_tile instance for (K, V): KP, EREG, NWT
+#define TILE_DISPATCH_NW(V, EXPR)                                          \
+    do {                                                                   \
+        if ((V) <= 128) { constexpr int NWT = 4; EXPR; }                   \
+        else if ((V) <= 256) { constexpr int NWT = 8; EXPR; }              \
+        else if ((V) <= 512) { constexpr int NWT = 16; EXPR; }             \
+        else { constexpr int NWT = 32; EXPR; }                             \
+    } while (0)
+#define TILE_DISPATCH(K, V, EXPR)                                          \
+    do {                                                                   \
+        if ((K) <= 8) { constexpr int KP = 8; constexpr bool EREG = true; TILE_DISPATCH_NW(V, EXPR); }         \
+        else if ((K) <= 12) { constexpr int KP = 12; constexpr bool EREG = true; TILE_DISPATCH_NW(V, EXPR); }  \
+        else if ((K) <= 16) { constexpr int KP = 16; constexpr bool EREG = true; TILE_DISPATCH_NW(V, EXPR); }  \
+        else if ((K) <= 24) { constexpr int KP = 24; constexpr bool EREG = false; TILE_DISPATCH_NW(V, EXPR); } \
+        else { constexpr int KP = 32; constexpr bool EREG = false; TILE_DISPATCH_NW(V, EXPR); }                \
     } while (0)
 #define MK_DISPATCH(MK, EXPR)                                     \
     do {                                                          \
@@ -570,10 +578,13 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     // launch plans
     for (int m = 0; m < M; ++m) {
         const int KV = K[m] * V[m];
-        THETA_DISPATCH(K[m], rc = pick_theta_plan(h, k_theta_stats<KP, NP>, KV, (int)std::min<int64_t>(D, 1 << 30),
-                                                   &mm.W_theta[m], &mm.grid_theta[m], &mm.smem_theta[m]));
+        if (V[m] > 1024) return fail(h, MMSIG_ELIMIT, "V[m] <= 1024 supported");
+        TILE_DISPATCH(K[m], V[m], rc = pick_tile_plan(h, k_theta_tile<KP, EREG, NWT>, KP, EREG, V[m], D, &mm.grid_theta[m],
+                                                      &mm.smem_theta[m]));
         if (rc) return rc;
+        mm.W_theta[m] = TILE_S;
         if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
+        CU(cudaMemsetAsync(mm.part_theta[m], 0, (size_t)mm.grid_theta[m] * KV * sizeof(double2), h->stream));
     }
     mm.wide = p.MK > 32;
     {
@@ -846,9 +857,10 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
     const int freeze_topics = (flags & MMSIG_FLAG_FREEZE_TOPICS) ? 1 : 0, unsm = (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0;
     auto cap = [&](int grid, int per_block) { return (int)std::max<long long>(1, std::min<long long>(grid, (q.D + per_block - 1) / per_block)); };
     for (int m = 0; m < q.M; ++m) {
-        LaunchScope ls(h, "k_theta_stats");
-        THETA_DISPATCH(q.K[m], (k_theta_stats<KP, NP><<<cap(mm.grid_theta[m], mm.W_theta[m]), mm.W_theta[m] * 32, mm.smem_theta[m], h->stream>>>(
-                                   q, m, mm.part_theta[m], mm.W_theta[m], unsm, !freeze_topics)));
+        LaunchScope ls(h, "k_theta_tile");
+        const int nthr = 32 * ((q.V[m] + 31) / 32);
+        TILE_DISPATCH(q.K[m], q.V[m], (k_theta_tile<KP, EREG, NWT><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
+                                          q, m, mm.part_theta[m], unsm, !freeze_topics)));
     }
     {
         LaunchScope ls(h, "k_solve");
@@ -900,7 +912,7 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     if ((rc = gather(h, mm.rank_p1, mm.gath_p1, P1, &g1))) return rc;
     {
         LaunchScope ls(h, "k_mstep1");
-        k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu);
+        k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu, (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0);
     }
     if ((flags & MMSIG_FLAG_AUTO_ALPHA) && !freeze_topics)       // src/MMCTM.jl:472-474, after update_γ!
         if ((rc = mmctm_update_alpha(h))) return rc;
@@ -1034,7 +1046,7 @@ extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double
 
 // ---- fit! from / to host buffers in one call, transfers overlapped with the E-step -----------
 // = set_data + set_state + fit + get_state, bit for bit.  The samples are cut into chunks; chunk
-// c's counts, λ, ν travel on a copy stream while chunk c-1 runs k_pack_rows / k_theta_stats /
+// c's counts, λ, ν travel on a copy stream while chunk c-1 runs k_pack_rows / k_theta_tile /
 // k_solve (block partials accumulate over the chunks), and when the loop is known to end with
 // this iteration (iter == maxiter) the chunk's λ, ν, ζ, props leave on a second copy stream while
 // the next chunk computes.  MMSIG_PIPE_CHUNKS overrides the chunk count (default ~100k samples).

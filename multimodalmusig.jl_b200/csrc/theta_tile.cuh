@@ -1,0 +1,140 @@
+// theta_tile.cuh -- the θ pass of one modality (reference src/MMCTM.jl:183-198 update_θ!, :110-117
+// calculate_sumθ, :224-240 the Σ n θ part of update_γ!) as three skinny products over tiles of 32
+// samples, the (D x K)ᵀ(D x V) form of the statistics:
+//   L[d][k]  = exp(λ_dk)                              E[k][v] = exp(Elnϕ_kv)   (ϕ_kv when unsmoothed, :496-509)
+//   Z[d][v]  = Σ_k L[d][k] E[k][v]                    (index order, two roundings per term)
+//   R[d][v]  = n[d][v] · (1 / Z[d][v])                (dense tile in shared memory, 0 where n = 0)
+//   S[k][v]  = Σ_d L[d][k] · R[d][v]                  (exactly rounded: double-double per thread, lane <-> term)
+//   sumθ[d][k] = L[d][k] · Σ_v E[k][v] R[d][v]        (one fma chain in term order, thread <-> sample)
+// and Σ_d n θ_kv = E[k][v] · S[k][v] (applied in k_mstep1).  θ itself, (L E)(1/Z), is never formed.
+// Against the per-nonzero kernel this replaces (warp per sample, lane <-> nonzero, a private
+// double-double K x V table per warp in shared memory): the accumulators live in registers (no
+// shared-memory read-modify-write per addend, no 15 KB of table per warp capping occupancy at
+// 12-20 warps / SM), and neither output needs a cross-lane reduction.  The results differ from it
+// by roundings only; DESIGN.md section 2 (pinned arithmetic) states this form.
+#pragma once
+#include "mmctm_kernels.cuh"
+
+namespace mmsig {
+
+constexpr int TILE_S = 32;        // samples per tile
+
+// EREG: the thread's column of E in registers (K <= 16); else read from shared memory [k][v].
+// NWT: upper bound of the block's warp count (one thread per term: blockDim = 32 ceil(V / 32)).
+template <int KP, bool EREG, int NWT>
+__global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, double2 *partial, int unsmoothed, int want_stats) {
+    extern __shared__ double smem[];
+    const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    double *Evk = smem;                        // [v][KP]  phase 3 (a sample's thread walks v, reads a row of k)
+    double *Ekv = Evk + V * KP;                // [k][VP]  phase 2 when !EREG
+    double *rt = Ekv + (EREG ? 0 : KP * VP);   // [t][VP]  n, then R
+    double *et = rt + TILE_S * VP;             // [t][KP]  L
+    const int v = tid;
+    const bool vok = v < V;
+    const double *Eg = (unsmoothed ? p.phi : p.Elnphi) + p.goff[m];
+    for (int i = tid; i < V * KP; i += blockDim.x) {
+        const int vv = i / KP, k = i % KP;
+        const double e = k < K ? (unsmoothed ? Eg[k * V + vv] : det_exp(Eg[k * V + vv])) : 0.0;
+        Evk[i] = e;
+        if (!EREG) Ekv[k * VP + vv] = e;
+    }
+    __syncthreads();
+    double Ereg[EREG ? KP : 1];
+    if (EREG) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) Ereg[k] = vok ? Evk[v * KP + k] : 0.0;
+    }
+    double ahi[KP], alo[KP];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) { ahi[k] = 0.0; alo[k] = 0.0; }
+
+    const long long *rowptr = p.rowptr[m];
+    const int2 *rec = p.rec[m];
+    const long long ntiles = (p.D + TILE_S - 1) / TILE_S;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long d0 = tile * TILE_S;
+        // ---- phase 1: clear the count tile, L = exp(λ) (thread <-> (sample, k)), scatter the rows (warp <-> sample)
+        for (int i = tid; i < TILE_S * VP; i += blockDim.x) rt[i] = 0.0;
+        for (int i = tid; i < TILE_S * KP; i += blockDim.x) {
+            const int t = i / KP, k = i % KP;
+            const long long d = d0 + t;
+            et[i] = (k < K && d < p.D) ? det_exp(p.lam_prev[d * p.MK + off + k]) : 0.0;
+        }
+        __syncthreads();
+        for (int t = warp; t < TILE_S; t += NW) {
+            const long long d = d0 + t;
+            if (d < p.D) {
+                const long long beg = rowptr[d], end = rowptr[d + 1];
+                for (long long w = beg + lane; w < end; w += 32) {
+                    const int2 r = rec[w];
+                    rt[t * VP + r.x] = (double)r.y;
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 2: Z, R and the statistics, lane <-> term
+        if (vok) {
+            for (int t = 0; t < TILE_S; ++t) {
+                const double n = rt[t * VP + v];
+                if (n > 0.0) {
+                    const double2 *e2 = reinterpret_cast<const double2 *>(et + t * KP);
+                    double ek[KP];
+#pragma unroll
+                    for (int k = 0; k < KP; k += 2) {
+                        const double2 x = e2[k / 2];
+                        ek[k] = x.x;
+                        ek[k + 1] = x.y;
+                    }
+                    double Z = 0.0;
+#pragma unroll
+                    for (int k = 0; k < KP; ++k) {
+                        const double e = ek[k] * (EREG ? Ereg[k] : Ekv[k * VP + v]);   // padded k: 0 * 0
+                        Z += e;
+                    }
+                    const double R = n * (1.0 / Z);
+                    rt[t * VP + v] = R;
+                    if (want_stats) {
+#pragma unroll
+                        for (int k = 0; k < KP; ++k) dd_add(ahi[k], alo[k], ek[k] * R);
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        // ---- phase 3: sumθ, thread <-> (sample t, k = kg, kg + G, ...), G groups of 32 threads
+        {
+            const int t = lane, kg = warp;
+            const long long d = d0 + t;
+            double g[KP];
+#pragma unroll
+            for (int j = 0; j < KP; ++j) g[j] = 0.0;
+            const double *row = rt + t * VP;
+            for (int vv = 0; vv < V; ++vv) {
+                const double R = row[vv];
+                const double *Er = Evk + vv * KP;
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    const int k = kg + j * NW;
+                    if (k < KP) g[j] = fma(Er[k], R, g[j]);
+                }
+            }
+            if (d < p.D) {
+#pragma unroll
+                for (int j = 0; j < KP; ++j) {
+                    const int k = kg + j * NW;
+                    if (k < K) p.sumtheta[d * p.MK + off + k] = et[t * KP + k] * g[j];
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (vok && want_stats) {
+        double2 *out = partial + (size_t)blockIdx.x * K * V;
+#pragma unroll
+        for (int k = 0; k < KP; ++k)
+            if (k < K) put_partial(out + k * V + v, ahi[k], alo[k], p.accum);
+    }
+}
+
+}  // namespace mmsig

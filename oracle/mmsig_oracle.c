@@ -43,10 +43,12 @@
  *     (2) sums over the MK coordinates of one sample (objective values, MMA's
  *         gval / wval, the x-tolerance norms): a fixed 32-leaf binary tree
  *         (tree_sum32); mat-vec rows: an even-index and an odd-index fma chain, added;
- *     (3) sums over the nonzeros w of ONE row (sum-theta, the row's
- *         log-likelihood): the same tree, leaf = w mod 32;
- *         sums over SAMPLES d (topic-term statistics, sum lambda, sum nu,
- *         the covariance moments, the LL totals): the EXACTLY ROUNDED sum
+ *     (3) the row's log-likelihood (a sum over the nonzeros w of ONE row): the
+ *         same tree, leaf = w mod 32;  sum-theta_k = exp(lambda_k) * (fma chain
+ *         over the row's nonzeros, in term order, of E_kv * R_w), R_w = n_w (1/Z_w);
+ *         sums over SAMPLES d (sum lambda, sum nu, the covariance moments, the
+ *         LL totals, and the topic-term statistics in their product form
+ *         sum n theta_kv = E_kv * sum_d fl(exp(lambda_dk) R_dv)): the EXACTLY ROUNDED sum
  *         of the addends -- order independent by definition, so independent
  *         of how samples are sharded over warps, blocks or GPUs;
  *     (4) theta_k = e_k * (1/Z) (one division per nonzero) instead of e_k / Z,
@@ -612,6 +614,7 @@ orc_mmctm *orc_mmctm_new(int M, const int *K, const int *V, int64_t D,
     m->term = (int32_t **)malloc(sizeof(void *) * M);
     m->cnt = (int32_t **)malloc(sizeof(void *) * M);
     m->theta = (double **)malloc(sizeof(void *) * M);
+    m->rz = (double **)malloc(sizeof(void *) * M);
     m->N = (int64_t *)calloc((size_t)D * M, sizeof(int64_t));
     for (int i = 0; i < M; ++i) {
         int64_t nnz = rowptr[i][D];
@@ -624,6 +627,7 @@ orc_mmctm *orc_mmctm_new(int M, const int *K, const int *V, int64_t D,
         /* theta = fill(1/K) (:52-57) */
         m->theta[i] = (double *)malloc(sizeof(double) * (nnz ? nnz : 1) * K[i]);
         for (int64_t t = 0; t < nnz * K[i]; ++t) m->theta[i][t] = 1.0 / K[i];
+        m->rz[i] = (double *)calloc((size_t)(nnz ? nnz : 1), sizeof(double));
         for (int64_t d = 0; d < D; ++d) {         /* N (:38) */
             int64_t s = 0;
             for (int64_t w = rowptr[i][d]; w < rowptr[i][d + 1]; ++w) s += cnt[i][w];
@@ -650,6 +654,9 @@ orc_mmctm *orc_mmctm_new(int M, const int *K, const int *V, int64_t D,
     m->ll = (double *)calloc(M, sizeof(double));
     m->nev_nu = (int32_t *)calloc(D ? D : 1, sizeof(int32_t));
     m->nev_lambda = (int32_t *)calloc(D ? D : 1, sizeof(int32_t));
+    m->expl = (double *)calloc((size_t)(D ? D : 1) * MK, sizeof(double));
+    m->sumtheta_e = (double *)calloc((size_t)(D ? D : 1) * MK, sizeof(double));
+    m->theta_unsm = 0;
     m->stop_rule = ORC_STOP_NLOPT27;
     m->nthreads = 1;
     m->converged = 0;                                                /* :88 */
@@ -660,9 +667,10 @@ void orc_mmctm_free(orc_mmctm *m)
 {
     if (!m) return;
     for (int i = 0; i < m->M; ++i) {
-        free(m->rowptr[i]); free(m->term[i]); free(m->cnt[i]); free(m->theta[i]);
+        free(m->rowptr[i]); free(m->term[i]); free(m->cnt[i]); free(m->theta[i]); free(m->rz[i]);
     }
-    free(m->rowptr); free(m->term); free(m->cnt); free(m->theta);
+    free(m->rowptr); free(m->term); free(m->cnt); free(m->theta); free(m->rz);
+    free(m->expl); free(m->sumtheta_e);
     free(m->K); free(m->V); free(m->koff); free(m->goff); free(m->alpha);
     free(m->N); free(m->mu); free(m->Sigma); free(m->invSigma);
     free(m->lambda); free(m->nu); free(m->zeta); free(m->props);
@@ -702,10 +710,13 @@ void orc_mmctm_update_theta(orc_mmctm *m, int64_t d)
             }
             if (m->arith) {     /* DET: theta_k = e_k * (1/Z), one division per nonzero */
                 double rz = 1.0 / s;
+                m->rz[i][w] = rz;
                 for (int k = 0; k < K; ++k) th[k] = th[k] * rz;
             } else
                 for (int k = 0; k < K; ++k) th[k] /= s;
         }
+        if (m->arith)
+            for (int k = 0; k < K; ++k) m->expl[(size_t)d * m->MK + off + k] = det_exp(lam[off + k]);
     }
 }
 
@@ -726,10 +737,13 @@ void orc_mmctm_unsmoothed_update_theta(orc_mmctm *m, int64_t d)
             }
             if (m->arith) {
                 double rz = 1.0 / s;
+                m->rz[i][w] = rz;
                 for (int k = 0; k < K; ++k) th[k] = th[k] * rz;
             } else
                 for (int k = 0; k < K; ++k) th[k] /= s;
         }
+        if (m->arith)
+            for (int k = 0; k < K; ++k) m->expl[(size_t)d * m->MK + off + k] = det_exp(lam[off + k]);
     }
 }
 
@@ -739,12 +753,20 @@ void orc_mmctm_calc_sumtheta(const orc_mmctm *m, int64_t d, double *out)
     for (int i = 0; i < m->M; ++i) {
         int K = m->K[i], off = m->koff[i];
         for (int k = 0; k < K; ++k) {
-            if (m->arith) {     /* DET: the row's addends through the fixed tree (leaf = w mod 32) */
-                int64_t b = m->rowptr[i][d], n = m->rowptr[i][d + 1] - b;
-                double t[n ? n : 1];
-                for (int64_t w = 0; w < n; ++w)
-                    t[w] = m->theta[i][(size_t)(b + w) * K + k] * (double)m->cnt[i][b + w];
-                out[off + k] = tree_sum32(t, (int)n);
+            if (m->arith) {
+                /* DET: sum-theta_k = exp(lambda_k) * sum_w E_kv R_w with R_w = n_w * (1/Z_w), the
+                   sum as one fma chain over the row's nonzeros in term order (on the device: a
+                   thread per sample walking the dense R row; absent terms add exactly 0).  Valid
+                   right after update_theta(d): uses the table that call used. */
+                int V = m->V[i];
+                double s = 0.0;
+                for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w) {
+                    int v = m->term[i][w];
+                    double E = m->theta_unsm ? m->phi[m->goff[i] + (size_t)k * V + v]
+                                             : det_exp(m->Elnphi[m->goff[i] + (size_t)k * V + v]);
+                    s = fma(E, (double)m->cnt[i][w] * m->rz[i][w], s);
+                }
+                out[off + k] = m->expl[(size_t)d * m->MK + off + k] * s;
                 continue;
             }
             double s = 0.0;
@@ -811,6 +833,7 @@ void orc_mmctm_update_lambda(orc_mmctm *m, int64_t d)
     double Ndz[MK], st[MK], lb[MK], ub[MK], x[MK], minf;
     orc_mmctm_calc_Ndivzeta(m, d, Ndz);
     orc_mmctm_calc_sumtheta(m, d, st);
+    memcpy(m->sumtheta_e + (size_t)d * MK, st, sizeof(double) * MK);     /* the ELBO reuses it (stale theta, :490) */
     for (int j = 0; j < MK; ++j) { lb[j] = -HUGE_VAL; ub[j] = HUGE_VAL; }
     memcpy(x, m->lambda + (size_t)d * MK, sizeof(double) * MK);
     obj_data o = { MK, m->nu + (size_t)d * MK, Ndz, st, m->mu, m->invSigma, m->arith };
@@ -896,24 +919,29 @@ void orc_mmctm_update_Elnphi(orc_mmctm *m)
 /* src/MMCTM.jl:224-242 */
 void orc_mmctm_update_gamma(orc_mmctm *m)
 {
-    if (m->arith) {     /* DET: gamma_kv = exact_round(alpha + sum of the same addends) */
+    if (m->arith) {
+        /* DET: S_kv = exactly rounded sum over samples of fl(exp(lambda_dk) * R_dv), R = n * (1/Z)
+           (the (D x K)^T (D x V) product form of the statistics); sum n theta = E_kv * S_kv and
+           gamma_kv = fma(E_kv, S_kv, alpha), E the table of the E-step (still current here). */
         int64_t G = m->goff[m->M];
         dd_t *acc = (dd_t *)calloc((size_t)G, sizeof(dd_t));
-        for (int i = 0; i < m->M; ++i)
-            for (int64_t t = 0; t < (int64_t)m->K[i] * m->V[i]; ++t)
-                acc[m->goff[i] + t].hi = m->alpha[i];
         for (int64_t d = 0; d < m->D; ++d)
             for (int i = 0; i < m->M; ++i) {
                 int K = m->K[i], V = m->V[i];
                 dd_t *g = acc + m->goff[i];
+                const double *L = m->expl + (size_t)d * m->MK + m->koff[i];
                 for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w) {
                     int v = m->term[i][w];
-                    double n = (double)m->cnt[i][w];
-                    for (int k = 0; k < K; ++k)
-                        dd_add(&g[(size_t)k * V + v], m->theta[i][(size_t)w * K + k] * n);
+                    double R = (double)m->cnt[i][w] * m->rz[i][w];
+                    for (int k = 0; k < K; ++k) dd_add(&g[(size_t)k * V + v], L[k] * R);
                 }
             }
-        for (int64_t t = 0; t < G; ++t) m->gamma[t] = dd_round(acc[t]);
+        for (int i = 0; i < m->M; ++i)
+            for (int64_t t = 0; t < (int64_t)m->K[i] * m->V[i]; ++t) {
+                int64_t x = m->goff[i] + t;
+                double E = m->theta_unsm ? m->phi[x] : det_exp(m->Elnphi[x]);
+                m->gamma[x] = fma(E, dd_round(acc[x]), m->alpha[i]);
+            }
         free(acc);
         orc_mmctm_update_Elnphi(m);
         return;
@@ -1057,7 +1085,8 @@ double orc_mmctm_elbo(const orc_mmctm *m, double *terms)
         double st[MK], Ndz[MK];
         for (int64_t d = 0; d < m->D; ++d) {
             const double *lam = m->lambda + (size_t)d * MK, *nu = m->nu + (size_t)d * MK;
-            orc_mmctm_calc_sumtheta(m, d, st);
+            if (m->arith) memcpy(st, m->sumtheta_e + (size_t)d * MK, sizeof(double) * MK);   /* tables have moved on */
+            else orc_mmctm_calc_sumtheta(m, d, st);
             orc_mmctm_calc_Ndivzeta(m, d, Ndz);
             double a = 0.0, b = 0.0, sN = 0.0, c = 0.0;
             for (int j = 0; j < MK; ++j) a += lam[j] * st[j];
@@ -1114,6 +1143,7 @@ double orc_mmctm_elbo(const orc_mmctm *m, double *terms)
 /* body of the fit! loop, src/MMCTM.jl:463-479 */
 void orc_mmctm_iterate(orc_mmctm *m, int updateSigma, int autoalpha, double *ll)
 {
+    m->theta_unsm = 0;
 #ifdef _OPENMP
     #pragma omp parallel for schedule(dynamic, 16) num_threads(m->nthreads > 0 ? m->nthreads : 1)
 #endif
@@ -1134,6 +1164,7 @@ void orc_mmctm_iterate(orc_mmctm *m, int updateSigma, int autoalpha, double *ll)
 void orc_mmctm_iterate_flags(orc_mmctm *m, unsigned flags, double *ll)
 {
     const int unsm = (flags & ORC_FLAG_UNSMOOTHED) != 0;
+    m->theta_unsm = unsm;
 #ifdef _OPENMP
     #pragma omp parallel for schedule(dynamic, 16) num_threads(m->nthreads > 0 ? m->nthreads : 1)
 #endif

@@ -114,6 +114,11 @@ typedef struct {
     double *ll;                   /* M */
     /* diagnostics: objective evaluations of the last E-step, per sample      */
     int32_t *nev_nu, *nev_lambda; /* D each */
+    /* DET bookkeeping of the last E-step (what the device keeps in registers / HBM):  */
+    double **rz;                  /* [M] nnz_m : 1 / Z_w                                   */
+    double *expl;                 /* D x MK   : exp(lambda) as update_theta saw it         */
+    double *sumtheta_e;           /* D x MK   : sum-theta of the last E-step (:110-117)    */
+    int theta_unsm;               /* table of the last E-step: 0 exp(Elnphi), 1 phi        */
 } orc_mmctm;
 
 orc_mmctm *orc_mmctm_new(int M, const int *K, const int *V, int64_t D,

@@ -39,6 +39,7 @@ class MMCTM(C.Structure):
         ("stop_rule", C.c_int), ("arith", C.c_int), ("nthreads", C.c_int), ("converged", C.c_int),
         ("elbo", C.c_double), ("ll", c_dp),
         ("nev_nu", c_i32p), ("nev_lambda", c_i32p),
+        ("rz", C.POINTER(c_dp)), ("expl", c_dp), ("sumtheta_e", c_dp), ("theta_unsm", C.c_int),
     ]
 
 

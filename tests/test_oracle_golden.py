@@ -48,14 +48,32 @@ def _set_theta(m, mod, d, th):
     m.theta(mod)[rp[d]:rp[d + 1], :] = np.asarray(th, float).T
 
 
-@pytest.mark.parametrize("arith", ARITHS)
-def test_sumtheta(golden, arith):
-    m = _toy(golden, arith)
+def test_sumtheta(golden):
+    m = _toy(golden, orc.ARITH_LITERAL)
     th = golden["sumtheta"]["theta_d1"]
     _set_theta(m, 0, 0, th[0]); _set_theta(m, 1, 0, th[1])
     out = np.zeros(5)
     m.L.orc_mmctm_calc_sumtheta(m.p, 0, orc._dp(out))
     np.testing.assert_allclose(out, golden["sumtheta"]["expected_d1"], rtol=RTOL)
+
+
+def test_sumtheta_det_product_form_equals_definition(golden):
+    """The pinned specification evaluates calculate_sumθ (src/MMCTM.jl:110-117) in the product form
+    exp(λ_k) Σ_w E_kv n_w / Z_w on the E-step's own intermediates instead of on the stored θ; it must
+    equal Σ_w n_w θ_kw of the θ the same E-step stored, to rounding."""
+    m = _toy(golden, orc.ARITH_DET)
+    for d in range(m.D):
+        m.L.orc_mmctm_update_theta(m.p, d)
+        out = np.zeros(m.MK)
+        m.L.orc_mmctm_calc_sumtheta(m.p, d, orc._dp(out))
+        ref, off = np.zeros(m.MK), 0
+        for mod in range(m.M):
+            rp, _, cnt = m._keep[mod]
+            th = m.theta(mod)[rp[d]:rp[d + 1], :]
+            K = th.shape[1]
+            ref[off:off + K] = (th * np.asarray(cnt[rp[d]:rp[d + 1]], float)[:, None]).sum(axis=0)
+            off += K
+        np.testing.assert_allclose(out, ref, rtol=1e-13)
 
 
 @pytest.mark.parametrize("arith", ARITHS)
@@ -125,10 +143,28 @@ def test_update_mu_Sigma(golden, arith):
     np.testing.assert_allclose(m.invSigma, g["expected_invSigma"], rtol=1e-12, atol=1e-14)
 
 
-@pytest.mark.parametrize("arith", ARITHS)
-def test_update_gamma_Elnphi(golden, arith):
+def test_update_gamma_det_product_form_equals_definition(golden):
+    """Pinned specification: γ_kv = fma(E_kv, Σ_d exp(λ_dk) n_dv / Z_dv, α) (the (D x K)ᵀ(D x V) form, on
+    the E-step's intermediates) must equal update_γ! (src/MMCTM.jl:224-240) on the θ that E-step stored."""
+    m = _toy(golden, orc.ARITH_DET)
+    for d in range(m.D):
+        m.L.orc_mmctm_update_theta(m.p, d)
+    ref = []
+    for mod in range(m.M):
+        rp, term, cnt = m._keep[mod]
+        th = m.theta(mod)
+        K, V = th.shape[1], m.V[mod]
+        g = np.full((K, V), m.alpha[mod])
+        for w in range(th.shape[0]):
+            g[:, term[w]] += th[w] * cnt[w]
+        ref.append(g.ravel())
+    m.L.orc_mmctm_update_gamma(m.p)
+    np.testing.assert_allclose(m.gamma, np.concatenate(ref), rtol=1e-13)
+
+
+def test_update_gamma_Elnphi(golden):
     g = golden["update_gamma"]
-    m = _toy(golden, arith)
+    m = _toy(golden, orc.ARITH_LITERAL)
     _set_theta(m, 0, 0, g["theta"]["d1m1"]); _set_theta(m, 0, 1, g["theta"]["d2m1"])
     _set_theta(m, 1, 0, g["theta"]["d1m2"]); _set_theta(m, 1, 1, g["theta"]["d2m2"])
     m.L.orc_mmctm_update_gamma(m.p)
