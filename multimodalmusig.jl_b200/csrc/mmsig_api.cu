@@ -452,7 +452,7 @@ static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &c
 template <typename F>
 static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, int V, long long D, int *grid_out, size_t *smem_out) {
     const int VP = V | 1, NW = (V + 31) / 32;
-    const size_t smem = ((size_t)V * KP + (ereg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP) * sizeof(double);
+    const size_t smem = ((size_t)V * KP + (ereg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP + TILE_S + 2) * sizeof(double);
     if (smem > h->smem_optin) return fail(h, MMSIG_ELIMIT, "V too large for the theta tile (shared memory)");
     CU(allow_max_smem(h, kernel));
     int nb = 0;

@@ -30,6 +30,7 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
     double *Ekv = Evk + V * KP;                // [k][VP]  phase 2 when !EREG
     double *rt = Ekv + (EREG ? 0 : KP * VP);   // [t][VP]  n, then R
     double *et = rt + TILE_S * VP;             // [t][KP]  L
+    long long *rp = reinterpret_cast<long long *>(et + TILE_S * KP);   // [TILE_S + 1] row pointers of the tile
     const int v = tid;
     const bool vok = v < V;
     const double *Eg = (unsmoothed ? p.phi : p.Elnphi) + p.goff[m];
@@ -54,23 +55,24 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
     const long long ntiles = (p.D + TILE_S - 1) / TILE_S;
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long d0 = tile * TILE_S;
-        // ---- phase 1: clear the count tile, L = exp(λ) (thread <-> (sample, k)), scatter the rows (warp <-> sample)
+        // ---- phase 1: clear the count tile, L = exp(λ) (thread <-> (sample, k)), the tile's row pointers
         for (int i = tid; i < TILE_S * VP; i += blockDim.x) rt[i] = 0.0;
         for (int i = tid; i < TILE_S * KP; i += blockDim.x) {
             const int t = i / KP, k = i % KP;
             const long long d = d0 + t;
             et[i] = (k < K && d < p.D) ? det_exp(p.lam_prev[d * p.MK + off + k]) : 0.0;
         }
+        for (int i = tid; i <= TILE_S; i += blockDim.x) rp[i] = rowptr[min(d0 + i, p.D)];
         __syncthreads();
-        for (int t = warp; t < TILE_S; t += NW) {
-            const long long d = d0 + t;
-            if (d < p.D) {
-                const long long beg = rowptr[d], end = rowptr[d + 1];
-                for (long long w = beg + lane; w < end; w += 32) {
-                    const int2 r = rec[w];
-                    rt[t * VP + r.x] = (double)r.y;
-                }
-            }
+        // scatter: the tile's records are one contiguous range of rec, streamed by all threads (every
+        // thread has its loads in flight at once); the sample of a record by bisection of the 33 pointers
+        for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
+            const int2 r = rec[w];
+            int t = 0;
+#pragma unroll
+            for (int step = TILE_S / 2; step >= 1; step >>= 1)
+                if (rp[t + step] <= w) t += step;
+            rt[t * VP + r.x] = (double)r.y;
         }
         __syncthreads();
         // ---- phase 2: Z, R and the statistics, lane <-> term
@@ -102,28 +104,31 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
             }
         }
         __syncthreads();
-        // ---- phase 3: sumθ, thread <-> (sample t, k = kg, kg + G, ...), G groups of 32 threads
+        // ---- phase 3: sumθ, thread <-> (sample t, four consecutive k): per term one load of R, two 128-bit
+        // loads of E, four DFMAs.  Warp kq takes the k-quads kq, kq + NW, ...
         {
-            const int t = lane, kg = warp;
+            const int t = lane;
             const long long d = d0 + t;
-            double g[KP];
-#pragma unroll
-            for (int j = 0; j < KP; ++j) g[j] = 0.0;
             const double *row = rt + t * VP;
-            for (int vv = 0; vv < V; ++vv) {
-                const double R = row[vv];
-                const double *Er = Evk + vv * KP;
-#pragma unroll
-                for (int j = 0; j < KP; ++j) {
-                    const int k = kg + j * NW;
-                    if (k < KP) g[j] = fma(Er[k], R, g[j]);
+            for (int kb = 4 * warp; kb < KP; kb += 4 * NW) {
+                double g0 = 0.0, g1 = 0.0, g2 = 0.0, g3 = 0.0;
+#pragma unroll 4
+                for (int vv = 0; vv < V; ++vv) {
+                    const double R = row[vv];
+                    const double2 *E2 = reinterpret_cast<const double2 *>(Evk + vv * KP + kb);
+                    const double2 a = E2[0], b = E2[1];
+                    g0 = fma(a.x, R, g0);
+                    g1 = fma(a.y, R, g1);
+                    g2 = fma(b.x, R, g2);
+                    g3 = fma(b.y, R, g3);
                 }
-            }
-            if (d < p.D) {
-#pragma unroll
-                for (int j = 0; j < KP; ++j) {
-                    const int k = kg + j * NW;
-                    if (k < K) p.sumtheta[d * p.MK + off + k] = et[t * KP + k] * g[j];
+                if (d < p.D) {
+                    const double *L = et + t * KP + kb;
+                    double *st = p.sumtheta + d * p.MK + off + kb;
+                    if (kb + 0 < K) st[0] = L[0] * g0;
+                    if (kb + 1 < K) st[1] = L[1] * g1;
+                    if (kb + 2 < K) st[2] = L[2] * g2;
+                    if (kb + 3 < K) st[3] = L[3] * g3;
                 }
             }
         }
