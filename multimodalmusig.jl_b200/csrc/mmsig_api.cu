@@ -1049,10 +1049,10 @@ extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double
 // c's counts, λ, ν travel on a copy stream while chunk c-1 runs k_pack_rows / k_theta_tile /
 // k_solve (block partials accumulate over the chunks), and when the loop is known to end with
 // this iteration (iter == maxiter) the chunk's λ, ν, ζ, props leave on a second copy stream while
-// the next chunk computes.  MMSIG_PIPE_CHUNKS overrides the chunk count (default ~100k samples).
+// the next chunk computes.  MMSIG_PIPE_CHUNKS overrides the chunk count (default ~150k samples).
 static int pipe_chunks(long long D) {
     const char *e = getenv("MMSIG_PIPE_CHUNKS");
-    long long c = e ? atoll(e) : (D + 50000) / 100000;
+    long long c = e ? atoll(e) : (D + 75000) / 150000;
     return (int)std::max<long long>(1, std::min<long long>({c, 64LL, D}));
 }
 
@@ -1119,7 +1119,22 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
 
     const int C = pipe_chunks(D);
     std::vector<long long> cut(C + 1);
-    for (int c = 0; c <= C; ++c) cut[c] = (long long)((__int128)D * c / C);
+    {
+        // equal chunks by default; MMSIG_PIPE_RATIO > 1 makes them grow geometrically (a smaller first
+        // upload).  Measured at D = 1e6 (profiles/chunks_sweep.sh): 6-10 chunks of ratio 1.0-1.3 all
+        // give 51.6-52.5 ms per call against 45.0 ms resident; 16 / 24 chunks 54.2 / 58.6 ms.
+        const char *e = getenv("MMSIG_PIPE_RATIO");
+        const double ratio = e ? std::max(1.0, atof(e)) : 1.0;
+        std::vector<double> w(C);
+        double tot = 0.0, x = 1.0;
+        for (int c = 0; c < C; ++c) { w[c] = x; tot += x; x *= ratio; }
+        double acc = 0.0;
+        cut[0] = 0;
+        for (int c = 0; c < C; ++c) {
+            acc += w[c];
+            cut[c + 1] = c + 1 == C ? D : std::min<long long>(D, std::max<long long>(cut[c] + 1, (long long)(D * (acc / tot))));
+        }
+    }
     std::vector<cudaEvent_t> ev_in(C, nullptr), ev_out(C, nullptr);
     auto free_events = [&]() {
         cudaStreamSynchronize(h->s_in);        // no copy may outlive the caller's buffers, whatever the exit path
