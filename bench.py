@@ -111,7 +111,7 @@ def run_reference(args):
             "config": workload_config(D, args.gpus), "cpu_baseline": cb,
             "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def workload_config(D, n):
@@ -119,6 +119,16 @@ def workload_config(D, n):
                         "(SNV96/SV32/ID83), FP64, exact LD_MMA E-step; BASELINE.json configs[3]" % D,
             "samples": D, "K": K_CFG, "V": V_CFG, "parallelism": "samples sharded over %d rank(s)" % n,
             "l2": "inputs per iteration (>= 2.6 GB at D=1e6) exceed the 126 MB L2; no flush needed"}
+
+
+def emit(line):
+    """The ONE JSON line goes to the process's original stdout; everything else a library prints to
+    fd 1 meanwhile (NCCL's version banner, for one) has been routed to stderr."""
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
+
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
 
 
 def main():
@@ -325,7 +335,7 @@ def main():
         sample_D = min(D, args.cpu_samples)
         line["cpu_baseline"] = cpu_baseline(lambda a, b: mmsig.synth.generate(D, K_CFG, V_CFG, lo=a, hi=b), D, sample_D,
                                             nthreads, steps=min(max(args.steps, 1), 3), warmup=args.warmup)
-    print(json.dumps(line), flush=True)
+    emit(line)
     model.close()
     if dist is not None:
         dist.destroy_process_group()

@@ -23,7 +23,7 @@ constexpr int MMA_MAXEVAL = 10000;
 constexpr int kMatvecUnroll = MATVEC_UNROLL;
 constexpr int SROW_STRIDE = 34;   // doubles per padded row of invΣ in shared memory (>= 32, 16-byte multiple, odd multiple of 16 B / 8)
 #ifndef SOLVE_MIN_BLOCKS
-#define SOLVE_MIN_BLOCKS 4
+#define SOLVE_MIN_BLOCKS 3
 #endif
 
 struct MmctmDev {
