@@ -24,7 +24,34 @@ def main():
     uid = [mmsig.capi.comm_unique_id() if rank == 0 else None]
     dist.broadcast_object_list(uid, 0)
     comm = (uid[0], rank, world)
-    if mode == "mmctm":
+    if mode == "mmctm_host":
+        # the one-call fit from host buffers (chunked, transfers pipelined), every rank on its shard
+        os.environ["MMSIG_PIPE_CHUNKS"] = "3"
+        K, V = [10, 8, 6], [96, 32, 83]
+        full = mmsig.synth.generate(D, K, V, key=6)
+        b = mmsig.counts.shard_rows([c[0] for c in full], world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        shard = [mmsig.counts.slice_csr(c, lo, hi) for c in full]
+        g0 = mmsig.synth.init_gamma(K, V)
+        m = mmsig.MMCTM(K, [0.1] * 3, shard, V=V, gamma0=g0, device=local, comm=comm, D_total=D)
+        hist, s = m.fit_host(shard, g0, maxiter=3, D_total=D)
+        elbo = m.calculate_elbo()[0]
+        parts = [None] * world
+        dist.gather_object((lo, hi, s["lam"], s["nu"], s["props"], s["zeta"]), parts if rank == 0 else None, 0)
+        if rank == 0:
+            import orc
+            o = orc.OracleMMCTM(K, [0.1] * 3, V, full, g0, arith=orc.ARITH_DET, nthreads=os.cpu_count() or 1)
+            llo = o.fit(maxiter=3, tol=1e-4)
+            for i, k in enumerate(("lam", "nu", "props", "zeta")):
+                assert np.array_equal(np.concatenate([p[2 + i] for p in parts]), getattr(o, k)), k
+            for k in ("gamma", "mu", "Sigma", "invSigma", "phi"):
+                assert np.array_equal(s[k], getattr(o, k)), k
+            assert np.array_equal(hist, np.asarray(llo))
+            eo = o.elbo()[0]
+            assert abs(elbo - eo) <= 1e-12 * abs(eo), (elbo, eo)
+            print("MULTI-RANK PARITY OK mmctm_host world=%d D=%d" % (world, D), flush=True)
+        m.close()
+    elif mode == "mmctm":
         K, V = [10, 8, 6], [96, 32, 83]
         full = mmsig.synth.generate(D, K, V, key=5)
         b = mmsig.counts.shard_rows([c[0] for c in full], world)
