@@ -7,7 +7,7 @@
 //                   lane j = coordinate j), Σλ / Σν partials
 //   k_combine       block partials -> one double-double vector
 //   k_mstep1        γ, Elnϕ, ϕ, μ
-//   k_post          ΣΔΔᵀ partials, softmax props and the per-modality log-likelihood pass
+//   k_moments       ΣΔΔᵀ partials (k_loglik_tile, theta_tile.cuh: props and the log-likelihood pass)
 //   k_mstep2        Σ, invΣ (LU with partial pivoting, one warp), LL
 #pragma once
 #include "det_math.cuh"
@@ -374,105 +374,41 @@ __global__ void __launch_bounds__(1024) k_elnphi(MmctmDev p) {
 }
 
 // ------------------------------------------------------------------------------------------
-// Post pass: ΣΔΔᵀ partials with the new μ (src/MMCTM.jl:204-210), props = softmax(λ block)
-// (:145-154) and the per-modality log-likelihood (:384-448), lane <-> nonzero.
-// partial: [gridDim.x][MK*MK + M] dd.
+// Moments pass: ΣΔΔᵀ partials with the new μ (src/MMCTM.jl:204-210); lane j owns row j.
+// partial: [gridDim.x][MK*MK + M] dd (the last M entries belong to the log-likelihood tiles).
 // ------------------------------------------------------------------------------------------
-template <int MKP, bool DO_MOMENTS, bool DO_LL>
-__global__ void __launch_bounds__(256) k_post(MmctmDev p, double2 *partial, double *props_out) {
+template <int MKP>
+__global__ void __launch_bounds__(256) k_moments(MmctmDev p, double2 *partial) {
     extern __shared__ double smem[];
-    const int G = p.goff[p.M], MK = p.MK, M = p.M;
+    const int MK = p.MK, M = p.M;
     double2 *red = reinterpret_cast<double2 *>(smem);      // 256 double2 = 512 doubles
-    double *phi = smem + 512;                             // G
-    double *psh_all = phi + G;                            // 8 x 32
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *psh = psh_all + warp * 32;
-    if (DO_LL)
-        for (int i = threadIdx.x; i < G; i += blockDim.x) phi[i] = p.phi[i];
-    __syncthreads();
     const bool active = lane < MK;
-    int mod = 0;
-    for (int m = 0; m < M; ++m)
-        if (lane >= p.koff[m]) mod = m;
-    const int blo = p.koff[mod], bhi = p.koff[mod + 1];
     const double muj = active ? p.mu[lane] : 0.0;
-
-    constexpr int NM = DO_MOMENTS ? MKP : 1;
-    double mhi[NM], mlo[NM];
+    double mhi[MKP], mlo[MKP];
 #pragma unroll
-    for (int i = 0; i < NM; ++i) { mhi[i] = 0.0; mlo[i] = 0.0; }
-    double llh[MAXM], lll[MAXM];
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) { llh[m] = 0.0; lll[m] = 0.0; }
-
+    for (int i = 0; i < MKP; ++i) { mhi[i] = 0.0; mlo[i] = 0.0; }
     const long long nw = (long long)gridDim.x * 8;
     for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
         const double lam = active ? p.lam[d * MK + lane] : 0.0;
-        if (DO_MOMENTS) {
-            const double diff = lam - muj;
+        const double diff = lam - muj;
 #pragma unroll
-            for (int i = 0; i < NM; ++i) {
-                const double di = shfl_d(diff, i);
-                if (i < MK) dd_add(mhi[i], mlo[i], diff * di);
-            }
-        }
-        if (!DO_LL) continue;
-        // props
-        const double e = active ? det_exp(lam) : 0.0;
-        const double s = block_sum_seq(e, blo, bhi, MK);
-        const double pr = active ? e / s : 0.0;
-        if (props_out && active) props_out[d * MK + lane] = pr;
-        __syncwarp();
-        psh[lane] = pr;
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m) {
-            if (m < M) {
-                const double docN = p.N[d * M + m];
-                if (docN > 0) {
-                    const int K = p.K[m], V = p.V[m], ko = p.koff[m];
-                    const double *ph = phi + p.goff[m];
-                    const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
-                    double rs = 0.0;
-                    int2 r = make_int2(0, 1);
-                    if (beg + lane < end) r = p.rec[m][beg + lane];
-                    for (long long w = beg + lane; w < end; w += 32) {
-                        int2 r_next = r;
-                        if (w + 32 < end) r_next = p.rec[m][w + 32];
-                        double pw = 0.0;
-                        for (int k = 0; k < K; ++k) pw += psh[ko + k] * ph[k * V + r.x];
-                        rs += (double)r.y * det_log(pw);
-                        r = r_next;
-                    }
-                    __syncwarp();
-                    double dl = warp_tree_sum(rs);             // row sum: leaf = w mod 32, butterfly
-                    dl = dl / docN;
-                    dd_add(llh[m], lll[m], dl * docN);     // identical in every lane
-                }
-            }
+        for (int i = 0; i < MKP; ++i) {
+            const double di = shfl_d(diff, i);
+            if (i < MK) dd_add(mhi[i], mlo[i], diff * di);
         }
     }
     // block combine through shared memory, one moment column at a time
     __syncthreads();
     double2 *out = partial + (size_t)blockIdx.x * (MK * MK + M);
 #pragma unroll
-    for (int i = 0; i < (DO_MOMENTS ? MKP : 0); ++i) {
+    for (int i = 0; i < MKP; ++i) {
         red[warp * 32 + lane] = make_double2(mhi[i], mlo[i]);
         __syncthreads();
         if (warp == 0 && active && i < MK) {
             double hi = 0.0, lo = 0.0;
             for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv * 32 + lane].x, red[wv * 32 + lane].y);
             out[lane * MK + i] = make_double2(hi, lo);          // Σ_d diff_lane * diff_i
-        }
-        __syncthreads();
-    }
-    for (int m = 0; m < (DO_LL ? M : 0); ++m) {
-        if (lane == 0) red[warp] = make_double2(llh[m], lll[m]);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double hi = 0.0, lo = 0.0;
-            for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv].x, red[wv].y);
-            out[MK * MK + m] = make_double2(hi, lo);
         }
         __syncthreads();
     }

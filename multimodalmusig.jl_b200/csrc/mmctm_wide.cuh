@@ -328,67 +328,4 @@ __global__ void __launch_bounds__(256) k_moments_wide(MmctmDev p, double2 *parti
         }
 }
 
-// log-likelihood pass for the wide layout (same arithmetic as k_post<.,0,1>)
-__global__ void __launch_bounds__(256) k_loglik_wide(MmctmDev p, double2 *partial) {
-    extern __shared__ double smem[];
-    const int G = p.goff[p.M], MK = p.MK, M = p.M;
-    double2 *red = reinterpret_cast<double2 *>(smem);      // 8 double2
-    double *phi = smem + 16;
-    double *psh_all = phi + G;                              // 8 x WMK props, then 8 x WMK exps
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *psh = psh_all + warp * WMK, *esh = psh_all + 8 * WMK + warp * WMK;
-    for (int i = threadIdx.x; i < G; i += blockDim.x) phi[i] = p.phi[i];
-    __syncthreads();
-    double llh[MAXM], lll[MAXM];
-#pragma unroll
-    for (int m = 0; m < MAXM; ++m) { llh[m] = 0.0; lll[m] = 0.0; }
-    const long long nw = (long long)gridDim.x * 8;
-    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
-        __syncwarp();
-        for (int j = lane; j < MK; j += 32) esh[j] = det_exp(p.lam[d * MK + j]);
-        __syncwarp();
-        for (int j = lane; j < MK; j += 32) {
-            int mod = 0;
-            for (int m = 0; m < M; ++m)
-                if (j >= p.koff[m]) mod = m;
-            psh[j] = esh[j] / smem_block_sum(esh, p.koff[mod], p.koff[mod + 1]);
-        }
-        __syncwarp();
-#pragma unroll
-        for (int m = 0; m < MAXM; ++m) {
-            if (m < M) {
-                const double docN = p.N[d * M + m];
-                if (docN > 0) {
-                    const int K = p.K[m], V = p.V[m], ko = p.koff[m];
-                    const double *ph = phi + p.goff[m];
-                    const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
-                    double rs = 0.0;
-                    for (long long w = beg + lane; w < end; w += 32) {
-                        const int2 r = p.rec[m][w];
-                        double pw = 0.0;
-                        for (int k = 0; k < K; ++k) pw += psh[ko + k] * ph[k * V + r.x];
-                        rs += (double)r.y * det_log(pw);
-                    }
-                    __syncwarp();
-                    double dl = warp_tree_sum(rs);
-                    dl = dl / docN;
-                    dd_add(llh[m], lll[m], dl * docN);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    double2 *out = partial + (size_t)blockIdx.x * (MK * MK + M);
-    for (int m = 0; m < M; ++m) {
-        if (lane == 0) red[warp] = make_double2(llh[m], lll[m]);
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            double hi = 0.0, lo = 0.0;
-            for (int wv = 0; wv < 8; ++wv) dd_merge(hi, lo, red[wv].x, red[wv].y);
-            out[MK * MK + m] = make_double2(hi, lo);
-        }
-        __syncthreads();
-    }
-}
-
 }  // namespace mmsig

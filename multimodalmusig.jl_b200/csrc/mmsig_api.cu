@@ -83,8 +83,8 @@ struct MmctmHost {
     MmctmDev p{};
     int G = 0;
     std::vector<long long> nnz;
-    int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0};
-    size_t smem_theta[MAXM] = {0};
+    int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0}, grid_ll[MAXM] = {0};
+    size_t smem_theta[MAXM] = {0}, smem_ll[MAXM] = {0};
     int grid_solve = 0, grid_post = 0, grid_mom = 0, grid_zeta = 0;
     bool solve_multi = false;          // 16 < sum(K) <= 32: k_solve_multi (4 samples per warp) instead of k_solve
     bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
@@ -473,6 +473,21 @@ static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, int V, l
         else if ((K) <= 24) { constexpr int KP = 24, NP = 32; EXPR; } \
         else { constexpr int KP = 32, NP = 32; EXPR; }            \
     } while (0)
+template <typename F>
+static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, int V, long long D, int *grid_out, size_t *smem_out) {
+    const int VP = V | 1, NW = (V + 31) / 32;
+    const size_t smem = ((preg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP + TILE_S + (size_t)NW * 32 + TILE_S + 2) * sizeof(double);
+    if (smem > h->smem_optin) return fail(h, MMSIG_ELIMIT, "V too large for the log-likelihood tile (shared memory)");
+    CU(allow_max_smem(h, kernel));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NW * 32, smem));
+    if (nb < 1) return fail(h, MMSIG_ELIMIT, "log-likelihood tile kernel does not fit on an SM for this K, V");
+    *smem_out = smem;
+    const long long ntiles = (D + TILE_S - 1) / TILE_S;
+    *grid_out = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * nb, ntiles));
+    return 0;
+}
+
 // k_theta_tile instance for (K, V): KP, EREG, NWT
 #define TILE_DISPATCH_NW(V, EXPR)                                          \
     do {                                                                   \
@@ -583,6 +598,8 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
                                                       &mm.smem_theta[m]));
         if (rc) return rc;
         mm.W_theta[m] = TILE_S;
+        TILE_DISPATCH(K[m], V[m], rc = pick_ll_plan(h, k_loglik_tile<KP, EREG, NWT>, KP, EREG, V[m], D, &mm.grid_ll[m], &mm.smem_ll[m]));
+        if (rc) return rc;
         if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
         CU(cudaMemsetAsync(mm.part_theta[m], 0, (size_t)mm.grid_theta[m] * KV * sizeof(double2), h->stream));
     }
@@ -613,13 +630,9 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
                                                                             (D + spb - 1) / spb));
         }
         mm.grid_zeta = grid_for(nb);
-        mm.smem_post = (size_t)(512 + mm.G + 256) * sizeof(double);
-        if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
-        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, true, false>)));
-        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_post<MKP, false, true>)));
-        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP, false, true>, 256, mm.smem_post)));
-        mm.grid_post = grid_for(nb);
-        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_post<MKP, true, false>, 256, mm.smem_post)));
+        mm.smem_post = (size_t)512 * sizeof(double);
+        MK_DISPATCH(p.MK, CU(allow_max_smem(h, k_moments<MKP>)));
+        MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_moments<MKP>, 256, mm.smem_post)));
         mm.grid_mom = grid_for(nb);
     } else {
         int nb = 0;
@@ -627,14 +640,12 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         CU(allow_max_smem(h, k_solve_wide));
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_wide, 256, mm.smem_solve));
         mm.grid_solve = grid_for(nb);
-        mm.smem_post = (size_t)(16 + mm.G + 16 * WMK) * sizeof(double);
-        if (mm.smem_post > h->smem_optin) return fail(h, MMSIG_ELIMIT, "topic-term table does not fit in shared memory");
-        CU(allow_max_smem(h, k_loglik_wide));
-        CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_loglik_wide, 256, mm.smem_post));
-        mm.grid_post = grid_for(nb);
         CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_moments_wide, 256, 0));
         mm.grid_mom = grid_for(nb);
     }
+    // partial buffer of the log-likelihood tiles (one dd per block and modality) and grid of the ELBO kernels
+    mm.grid_post = grid_for(4);
+    for (int m = 0; m < M; ++m) mm.grid_post = std::max(mm.grid_post, mm.grid_ll[m]);
     const int P1 = mm.G + 2 * p.MK, P2 = p.MK * p.MK + M;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_solve, (size_t)mm.grid_solve * 2 * p.MK))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_post, (size_t)mm.grid_post * P2))) return rc;
@@ -924,28 +935,31 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
             }
         } else {
             LaunchScope ls(h, "k_moments");
-            MK_DISPATCH(p.MK, (k_post<MKP, true, false><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom, nullptr)));
+            MK_DISPATCH(p.MK, (k_moments<MKP><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom)));
         }
     }
-    {
-        LaunchScope ls(h, "k_loglik");
-        if (mm.wide) k_loglik_wide<<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post);
-        else MK_DISPATCH(p.MK, (k_post<MKP, false, true><<<mm.grid_post, 256, mm.smem_post, h->stream>>>(p, mm.part_post, nullptr)));
+    for (int m = 0; m < p.M; ++m) {
+        LaunchScope ls(h, "k_loglik_tile");
+        const int nthr = 32 * ((p.V[m] + 31) / 32);
+        TILE_DISPATCH(p.K[m], p.V[m], (k_loglik_tile<KP, EREG, NWT><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
+                                          p, m, mm.part_post + p.MK * p.MK + m, P2)));
     }
     {
         // moments (first MK*MK entries) from the moments pass, LL (last M) from the LL pass
         CombineSegs s{};
-        s.nseg = 2;
+        s.nseg = 1 + p.M;
         s.src[0] = mm.part_mom;
         s.nparts[0] = do_sigma ? mm.grid_mom : 0;
         s.n[0] = p.MK * p.MK;
         s.dst_off[0] = 0;
         s.stride[0] = P2;
-        s.src[1] = mm.part_post + p.MK * p.MK;
-        s.nparts[1] = mm.grid_post;
-        s.n[1] = p.M;
-        s.dst_off[1] = p.MK * p.MK;
-        s.stride[1] = P2;
+        for (int m = 0; m < p.M; ++m) {
+            s.src[1 + m] = mm.part_post + p.MK * p.MK + m;
+            s.nparts[1 + m] = mm.grid_ll[m];
+            s.n[1 + m] = 1;
+            s.dst_off[1 + m] = p.MK * p.MK + m;
+            s.stride[1 + m] = P2;
+        }
         LaunchScope ls(h, "k_combine");
         k_combine<<<(P2 + 7) / 8, 256, 0, h->stream>>>(s, mm.rank_p2);
     }

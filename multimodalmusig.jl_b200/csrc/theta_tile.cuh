@@ -143,3 +143,123 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
 }
 
 }  // namespace mmsig
+
+namespace mmsig {
+
+// ------------------------------------------------------------------------------------------
+// The log-likelihood pass of one modality (reference src/MMCTM.jl:384-448 with update_props!
+// :145-154 folded in) over the same 32-sample tiles:
+//   P[d][k]  = exp(λ_dk) / Σ_k' exp(λ_dk')            (softmax of the block, no max-subtraction)
+//   pw[d][v] = Σ_k P[d][k] ϕ[k][v]                    (index order, two roundings per term)
+//   x[d][v]  = n[d][v] · log pw[d][v]                 (dense tile in shared memory, 0 where n = 0)
+//   row sum  = blocks of 32 terms summed in term order, the blocks added in order  (DET)
+//   ll_m     = Σ_d (row/N_dm)·N_dm, exactly rounded over samples, / Σ_d N_dm   (k_mstep2)
+// lane <-> term for pw and the logarithm (ϕ column in registers), thread <-> (sample, block) for
+// the sums.  One double-double per sample slot, reduced once per block at the end.
+// partial[blockIdx.x * pstride] receives the block's sum.
+// ------------------------------------------------------------------------------------------
+template <int KP, bool PREG, int NWT>
+__global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, double2 *partial, int pstride) {
+    extern __shared__ double smem[];
+    const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1, M = p.M;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
+    double *Pkv = smem;                              // [k][VP] when !PREG
+    double *xt = Pkv + (PREG ? 0 : KP * VP);         // [t][VP]  n, then n log pw
+    double *pt = xt + TILE_S * VP;                   // [t][KP]  exp(λ), then props
+    double *ssum = pt + TILE_S * KP;                 // [t]
+    double *bsum = ssum + TILE_S;                    // [NW][32]
+    long long *rp = reinterpret_cast<long long *>(bsum + NW * 32);
+    const int v = tid;
+    const bool vok = v < V;
+    const double *ph = p.phi + p.goff[m];
+    if (!PREG) {
+        for (int i = tid; i < KP * V; i += blockDim.x) {
+            const int k = i / V, vv = i % V;
+            Pkv[k * VP + vv] = k < K ? ph[k * V + vv] : 0.0;
+        }
+        __syncthreads();
+    }
+    double Preg[PREG ? KP : 1];
+    if (PREG) {
+#pragma unroll
+        for (int k = 0; k < KP; ++k) Preg[k] = (vok && k < K) ? ph[k * V + v] : 0.0;
+    }
+    double ahi = 0.0, alo = 0.0;                      // threads 0..31: Σ over this block's tiles of sample slot t
+    const long long *rowptr = p.rowptr[m];
+    const int2 *rec = p.rec[m];
+    const long long ntiles = (p.D + TILE_S - 1) / TILE_S;
+    for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long long d0 = tile * TILE_S;
+        for (int i = tid; i < TILE_S * VP; i += blockDim.x) xt[i] = 0.0;
+        for (int i = tid; i < TILE_S * KP; i += blockDim.x) {
+            const int t = i / KP, k = i % KP;
+            const long long d = d0 + t;
+            pt[i] = (k < K && d < p.D) ? det_exp(p.lam[d * p.MK + off + k]) : 0.0;
+        }
+        for (int i = tid; i <= TILE_S; i += blockDim.x) rp[i] = rowptr[min(d0 + i, p.D)];
+        __syncthreads();
+        for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
+            const int2 r = rec[w];
+            int t = 0;
+#pragma unroll
+            for (int step = TILE_S / 2; step >= 1; step >>= 1)
+                if (rp[t + step] <= w) t += step;
+            xt[t * VP + r.x] = (double)r.y;
+        }
+        if (tid < TILE_S) {
+            double s = 0.0;
+            for (int k = 0; k < K; ++k) s += pt[tid * KP + k];      // index order (src/MMCTM.jl:150)
+            ssum[tid] = s;
+        }
+        __syncthreads();
+        for (int i = tid; i < TILE_S * KP; i += blockDim.x) {
+            const int t = i / KP, k = i % KP;
+            if (k < K && d0 + t < p.D) pt[i] = pt[i] / ssum[t];
+        }
+        __syncthreads();
+        if (vok) {
+            for (int t = 0; t < TILE_S; ++t) {
+                const double n = xt[t * VP + v];
+                if (n > 0.0) {
+                    const double2 *p2 = reinterpret_cast<const double2 *>(pt + t * KP);
+                    double pw = 0.0;
+#pragma unroll
+                    for (int k = 0; k < KP; k += 2) {
+                        const double2 x = p2[k / 2];
+                        pw += x.x * (PREG ? Preg[k] : Pkv[k * VP + v]);          // padded k: 0 * 0
+                        pw += x.y * (PREG ? Preg[k + 1] : Pkv[(k + 1) * VP + v]);
+                    }
+                    xt[t * VP + v] = n * det_log(pw);
+                }
+            }
+        }
+        __syncthreads();
+        {
+            const double *row = xt + lane * VP;
+            const int vb = 32 * warp, ve = min(V, vb + 32);
+            double b = 0.0;
+            for (int vv = vb; vv < ve; ++vv) b += row[vv];
+            bsum[warp * 32 + lane] = b;
+        }
+        __syncthreads();
+        if (tid < TILE_S) {
+            const long long d = d0 + tid;
+            if (d < p.D) {
+                const double docN = p.N[d * M + m];
+                if (docN > 0) {
+                    double rs = bsum[tid];
+                    for (int j = 1; j < NW; ++j) rs += bsum[j * 32 + tid];
+                    const double dl = rs / docN;                     // src/MMCTM.jl:399
+                    dd_add(ahi, alo, dl * docN);                     // :412
+                }
+            }
+        }
+        __syncthreads();
+    }
+    if (warp == 0) {
+        warp_dd_allreduce(ahi, alo);
+        if (lane == 0) partial[(size_t)blockIdx.x * pstride] = make_double2(ahi, alo);
+    }
+}
+
+}  // namespace mmsig

@@ -43,8 +43,8 @@
  *     (2) sums over the MK coordinates of one sample (objective values, MMA's
  *         gval / wval, the x-tolerance norms): a fixed 32-leaf binary tree
  *         (tree_sum32); mat-vec rows: an even-index and an odd-index fma chain, added;
- *     (3) the row's log-likelihood (a sum over the nonzeros w of ONE row): the
- *         same tree, leaf = w mod 32;  sum-theta_k = exp(lambda_k) * (fma chain
+ *     (3) the row's log-likelihood (a sum over the nonzeros w of ONE row): blocks
+ *         of 32 terms summed in term order, the blocks added in order;  sum-theta_k = exp(lambda_k) * (fma chain
  *         over the row's nonzeros, in term order, of E_kv * R_w), R_w = n_w (1/Z_w);
  *         sums over SAMPLES d (sum lambda, sum nu, the covariance moments, the
  *         LL totals, and the topic-term statistics in their product form
@@ -1036,7 +1036,16 @@ void orc_mmctm_loglikelihoods(const orc_mmctm *m, double *ll)
                     if (m->arith) tl[w - rb] = (double)m->cnt[i][w] * det_log(pw);
                     else dl += (double)m->cnt[i][w] * log(pw);
                 }
-                if (m->arith) dl = tree_sum32(tl, (int)rn);   /* DET: row sum through the fixed tree */
+                if (m->arith) {
+                    /* DET: blocks of 32 TERMS summed in term order, the blocks added in order
+                       (on the device: a thread per (sample, block) over the dense tile row) */
+                    int nb = (V + 31) / 32;
+                    double bs[nb];
+                    for (int j = 0; j < nb; ++j) bs[j] = 0.0;
+                    for (int64_t w = 0; w < rn; ++w) bs[m->term[i][rb + w] / 32] += tl[w];
+                    dl = bs[0];
+                    for (int j = 1; j < nb; ++j) dl += bs[j];
+                }
                 dl = dl / (double)docN;                       /* :399 */
                 if (m->arith) dd_add(&tot_dd, dl * (double)docN);
                 else tot += dl * (double)docN;                /* :412 */
