@@ -130,11 +130,11 @@ __global__ void __launch_bounds__(256) k_elbo_qz(MmctmDev p, int m, double2 *par
         for (long long w = beg + lane; w < end; w += 32) {
             const int2 r = p.rec[m][w];
             double Z = 0.0;
-            for (int k = 0; k < K; ++k) Z += det_exp(p.lam_prev[d * p.MK + off + k]) * Eln[k * V + r.x];
+            for (int k = 0; k < K; ++k) Z += det_exp(p.lam_prev[d * p.MK + off + k]) * Eln[k * V + (r.x & 0xffff)];
             double s = 0.0;
             const double rz = 1.0 / Z;
             for (int k = 0; k < K; ++k) {
-                const double th = (det_exp(p.lam_prev[d * p.MK + off + k]) * Eln[k * V + r.x]) * rz;
+                const double th = (det_exp(p.lam_prev[d * p.MK + off + k]) * Eln[k * V + (r.x & 0xffff)]) * rz;
                 if (th > 0.0) s += th * det_log(th);
             }
             dd_add(hi[0], lo[0], (double)r.y * s);

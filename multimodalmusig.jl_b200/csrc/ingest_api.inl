@@ -32,7 +32,7 @@ static int panel_samples(int V, int layout, int elem_bytes, size_t *smem_out) {
 }
 template <typename T, bool FILL>
 static void launch_panel(mmsig_handle *h, const T *dense, long long D, int V, int layout, int PS, size_t smem, long long *rowptr,
-                         double *N, int n_stride, int n_off, int *flags, int2 *rec) {
+                         double *N, int n_stride, int n_off, int *flags, int2 *rec, int tag = 0) {
     auto kernel = k_dense_panel<T, FILL>;
     cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     int nb = 0;
@@ -40,7 +40,7 @@ static void launch_panel(mmsig_handle *h, const T *dense, long long D, int V, in
     const long long npanels = (D + PS - 1) / PS;
     const int grid = (int)std::max<long long>(1, std::min<long long>(npanels, (long long)h->numSM * std::max(nb, 1)));
     kernel<<<grid, 256, smem, h->stream>>>(dense, D, V, layout, PS, rowptr, N, n_stride, n_off, flags,
-                                           flags ? (unsigned long long *)(flags + 2) : nullptr, rec);
+                                           flags ? (unsigned long long *)(flags + 2) : nullptr, rec, tag);
 }
 
 static int launch_scan(mmsig_handle *h, long long *x, long long n) {
@@ -104,22 +104,23 @@ static int dense_count_scan(mmsig_handle *h, DenseJob &j, long long D, int V, co
     return 0;
 }
 template <typename T>
-static void dense_fill_t(mmsig_handle *h, const T *dense, long long D, int V, int layout, const long long *rowptr, int2 *rec) {
+static void dense_fill_t(mmsig_handle *h, const T *dense, long long D, int V, int layout, const long long *rowptr, int2 *rec, int tag) {
     size_t smem = 0;
     const int PS = panel_samples(V, layout, (int)sizeof(T), &smem);
     if (PS) {
-        launch_panel<T, true>(h, dense, D, V, layout, PS, smem, const_cast<long long *>(rowptr), nullptr, 0, 0, nullptr, rec);
+        launch_panel<T, true>(h, dense, D, V, layout, PS, smem, const_cast<long long *>(rowptr), nullptr, 0, 0, nullptr, rec, tag);
         return;
     }
     const long long units = layout == 0 ? (D + 255) / 256 : (D + 7) / 8;
     const int grid = (int)std::max<long long>(1, std::min<long long>(units, (long long)h->numSM * 8));
-    k_dense_fill<T><<<grid, 256, 0, h->stream>>>(dense, D, V, layout, rowptr, rec);
+    k_dense_fill<T><<<grid, 256, 0, h->stream>>>(dense, D, V, layout, rowptr, rec, tag);
 }
+// tag != 0: records carry the sample's slot in its 32-sample tile (MMCTM's tile kernels)
 static void dense_fill(mmsig_handle *h, const DenseJob &j, long long D, int V, int elem_bytes, int layout,
-                       const long long *rowptr, int2 *rec) {
+                       const long long *rowptr, int2 *rec, int tag = 0) {
     LaunchScope ls(h, "k_dense_fill");
-    if (elem_bytes == 4) dense_fill_t<int32_t>(h, (const int32_t *)j.dense, D, V, layout, rowptr, rec);
-    else dense_fill_t<long long>(h, (const long long *)j.dense, D, V, layout, rowptr, rec);
+    if (elem_bytes == 4) dense_fill_t<int32_t>(h, (const int32_t *)j.dense, D, V, layout, rowptr, rec, tag);
+    else dense_fill_t<long long>(h, (const long long *)j.dense, D, V, layout, rowptr, rec, tag);
 }
 
 // ---- format_counts_lda / one modality of format_counts_mmctm -> CSR on the host ----------------
@@ -212,7 +213,7 @@ extern "C" int32_t mmsig_mmctm_set_data_dense(mmsig_handle *h, int64_t D, int64_
     cudaError_t e = cudaMemcpyAsync(const_cast<double *>(mm.p.N), tmpN, (size_t)D * M * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
     for (int m = 0; m < M && e == cudaSuccess; ++m) {
         e = cudaMemcpyAsync(mm.cb[m].rowptr, jobs[m].rowptr, (D + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream);
-        dense_fill(h, jobs[m], D, V[m], elem_bytes, layout, mm.cb[m].rowptr, mm.cb[m].rec);
+        dense_fill(h, jobs[m], D, V[m], elem_bytes, layout, mm.cb[m].rowptr, mm.cb[m].rec, 1);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();

@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(256) k_scan_add(long long *x, long long n, con
 
 template <typename T>
 __global__ void __launch_bounds__(256) k_dense_fill(const T *__restrict__ dense, long long D, int V, int layout,
-                                                    const long long *__restrict__ rowptr, int2 *rec) {
+                                                    const long long *__restrict__ rowptr, int2 *rec, int tag) {
     if (layout == 0) {
         const long long nthr = (long long)gridDim.x * blockDim.x;
         for (long long d = (long long)blockIdx.x * blockDim.x + threadIdx.x; d < D; d += nthr) {
@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) k_dense_fill(const T *__restrict__ dense,
 #pragma unroll 8
             for (int v = 0; v < V; ++v) {
                 const long long x = (long long)col[(size_t)v * D];
-                if (x > 0) rec[w++] = make_int2(v, (int)x);
+                if (x > 0) rec[w++] = make_int2(tag ? (v | (int)((d & 31) << 16)) : v, (int)x);
             }
         }
     } else {
@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(256) k_dense_fill(const T *__restrict__ dense,
                 const int v = v0 + lane;
                 const long long x = v < V ? (long long)row[v] : 0;
                 const unsigned m = __ballot_sync(0xffffffffu, x > 0);
-                if (x > 0) rec[w + __popc(m & lt)] = make_int2(v, (int)x);
+                if (x > 0) rec[w + __popc(m & lt)] = make_int2(tag ? (v | (int)((d & 31) << 16)) : v, (int)x);
                 w += __popc(m);
             }
         }
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(256) k_dense_fill(const T *__restrict__ dense,
 template <typename T, bool FILL>
 __global__ void __launch_bounds__(256) k_dense_panel(const T *__restrict__ dense, long long D, int V, int layout, int PS,
                                                      long long *rowptr, double *N, int n_stride, int n_off, int *flags,
-                                                     unsigned long long *total, int2 *rec) {
+                                                     unsigned long long *total, int2 *rec, int tag) {
     extern __shared__ int sm[];                    // PS * VP staged counts, then PS + 1 row pointers (FILL)
     const int VP = V | 1, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     long long *rp = reinterpret_cast<long long *>(sm + ((PS * VP + 1) & ~1));
@@ -226,7 +226,7 @@ __global__ void __launch_bounds__(256) k_dense_panel(const T *__restrict__ dense
                     const int v = v0 + lane;
                     const int x = v < V ? row[v] : 0;
                     const unsigned m = __ballot_sync(0xffffffffu, x > 0);
-                    if (x > 0) rec[w + __popc(m & lt)] = make_int2(v, x);
+                    if (x > 0) rec[w + __popc(m & lt)] = make_int2(tag ? (v | (int)(((d0 + sidx) & 31) << 16)) : v, x);
                     w += __popc(m);
                 }
             } else {
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(256) k_dense_panel(const T *__restrict__ dense
 __global__ void __launch_bounds__(256) k_unpack_rec(const int2 *__restrict__ rec, long long n, int *term, int *count) {
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const int2 r = rec[i];
-        term[i] = r.x;
+        term[i] = r.x & 0xffff;
         count[i] = r.y;
     }
 }

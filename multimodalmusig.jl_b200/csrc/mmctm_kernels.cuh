@@ -570,7 +570,7 @@ __global__ void __launch_bounds__(256) k_theta_out(MmctmDev p, int m, double *ou
     for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
         const long long beg = p.rowptr[m][d], end = p.rowptr[m][d + 1];
         for (long long w = beg + lane; w < end; w += 32) {
-            const int v = p.rec[m][w].x;
+            const int v = p.rec[m][w].x & 0xffff;                 // low half: term (high half: tile slot tag)
             double Z = 0.0;
             for (int k = 0; k < K; ++k) {
                 const double lk = p.lam_prev[d * p.MK + off + k];

@@ -362,8 +362,11 @@ static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
 
 // ---- count ingest: (term, count) -> packed records, row totals, validation ------------------
 // flags: bit0 term out of range, bit1 count <= 0, bit2 terms of a row not strictly ascending
+// tag != 0 (MMCTM): bits 16..20 of rec.x carry (tag_base + d) mod 32, the sample's slot in its
+// 32-sample tile, so that the tile kernels scatter a record without searching the row pointers
 __global__ void k_pack_rows(const long long *rowptr, const int *term, const int *count, long long D, int V,
-                            int2 *rec, double *N, int M, int m, int *flags, unsigned long long *ntot) {
+                            int2 *rec, double *N, int M, int m, int *flags, unsigned long long *ntot, int tag,
+                            long long tag_base) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     int bad = 0;
@@ -376,7 +379,7 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
             if (t < 0 || t >= V) bad |= 1;
             if (c <= 0) bad |= 2;
             if (w > beg && term[w - 1] >= t) bad |= 4;
-            rec[w] = make_int2(t, c);
+            rec[w] = make_int2(tag ? (t | (int)(((tag_base + d) & 31) << 16)) : t, c);
             s += c;
         }
         for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(FULLMASK, s, off);
@@ -406,12 +409,13 @@ static int ensure_countbuf(mmsig_handle *h, std::vector<void *> &pool, CountBuf 
     return 0;
 }
 // rows [d0, d1) of one modality: validation, (term, count) -> records, row totals
-static void pack_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d1, int V, int M, int m, double *d_N) {
+static void pack_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d1, int V, int M, int m, double *d_N,
+                        int tag = 0) {
     LaunchScope ls(h, "k_pack_rows");
     const long long Dc = d1 - d0;
     int grid = (int)std::min<long long>((Dc + 7) / 8, (long long)h->numSM * 8);
     k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr + d0, cb.term, cb.count, Dc, V, cb.rec, d_N + d0 * M, M, m,
-                                                           cb.flags, (unsigned long long *)(cb.flags + 2));
+                                                           cb.flags, (unsigned long long *)(cb.flags + 2), tag, d0);
 }
 static int flags_verdict(mmsig_handle *h, const int *hf, long long *ntot_out) {
     if (hf[0] & 1) return fail(h, MMSIG_EINVAL, "term index out of range [0, V)");
@@ -425,7 +429,7 @@ static int flags_verdict(mmsig_handle *h, const int *hf, long long *ntot_out) {
 
 static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, int V, int M, int m,
                          const int64_t *rowptr, const int32_t *term, const int32_t *count, double *d_N,
-                         long long *ntot_out) {
+                         long long *ntot_out, int tag = 0) {
     int rc;
     if ((rc = check_rowptr(h, rowptr, D))) return rc;
     const long long nnz = rowptr[D];
@@ -437,7 +441,7 @@ static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &c
         CU(cudaMemcpyAsync(cb.term, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(cb.count, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
-    pack_launch(h, cb, 0, D, V, M, m, d_N);
+    pack_launch(h, cb, 0, D, V, M, m, d_N, tag);
     int hf[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(hf, cb.flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -681,7 +685,7 @@ extern "C" int32_t mmsig_mmctm_set_data(mmsig_handle *h, int64_t D, int64_t D_to
     long long ntot[MAXM];
     for (int m = 0; m < M; ++m)
         if ((rc = upload_counts(h, h->allocs_mm, mm.cb[m], D, V[m], M, m, rowptr[m], term[m], count[m],
-                                const_cast<double *>(mm.p.N), &ntot[m])))
+                                const_cast<double *>(mm.p.N), &ntot[m], 1)))
             return rc;
     if ((rc = allsum_ll(h, ntot, M))) return rc;
     for (int m = 0; m < M; ++m) mm.p.Ntot[m] = (double)ntot[m];
@@ -1146,7 +1150,8 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         cut[0] = 0;
         for (int c = 0; c < C; ++c) {
             acc += w[c];
-            cut[c + 1] = c + 1 == C ? D : std::min<long long>(D, std::max<long long>(cut[c] + 1, (long long)(D * (acc / tot))));
+            // multiples of 32: a chunk's tiles coincide with the shard's (the slot tag of a record is d mod 32)
+            cut[c + 1] = c + 1 == C ? D : std::min<long long>(D, std::max<long long>(cut[c] + 32, ((long long)(D * (acc / tot)) + 31) / 32 * 32));
         }
     }
     std::vector<cudaEvent_t> ev_in(C, nullptr), ev_out(C, nullptr);
@@ -1223,7 +1228,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         if (nu) CU(cudaMemcpyAsync(p.nu + d0 * MK, nu + d0 * MK, n, cudaMemcpyHostToDevice, h->s_in));
         CU(cudaEventRecord(ev_in[c], h->s_in));
         CU(cudaStreamWaitEvent(h->stream, ev_in[c], 0));
-        for (int m = 0; m < M; ++m) pack_launch(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N));
+        for (int m = 0; m < M; ++m) pack_launch(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N), 1);
         mmctm_estep_launch(h, chunk_view(p, d0, d1, C > 1), flags);
         if (maxiter == 1) CU(after_chunk(c));
     }

@@ -62,17 +62,14 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
             const long long d = d0 + t;
             et[i] = (k < K && d < p.D) ? det_exp(p.lam_prev[d * p.MK + off + k]) : 0.0;
         }
-        for (int i = tid; i <= TILE_S; i += blockDim.x) rp[i] = rowptr[min(d0 + i, p.D)];
+        if (tid == 0) { rp[0] = rowptr[d0]; rp[TILE_S] = rowptr[min(d0 + TILE_S, p.D)]; }
         __syncthreads();
         // scatter: the tile's records are one contiguous range of rec, streamed by all threads (every
-        // thread has its loads in flight at once); the sample of a record by bisection of the 33 pointers
+        // thread has its loads in flight at once); a record carries its sample's slot in the tile
+#pragma unroll 4
         for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
             const int2 r = rec[w];
-            int t = 0;
-#pragma unroll
-            for (int step = TILE_S / 2; step >= 1; step >>= 1)
-                if (rp[t + step] <= w) t += step;
-            rt[t * VP + r.x] = (double)r.y;
+            rt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;        // slot tag | term (k_pack_rows)
         }
         __syncthreads();
         // ---- phase 2: Z, R and the statistics, lane <-> term
@@ -196,15 +193,12 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
             const long long d = d0 + t;
             pt[i] = (k < K && d < p.D) ? det_exp(p.lam[d * p.MK + off + k]) : 0.0;
         }
-        for (int i = tid; i <= TILE_S; i += blockDim.x) rp[i] = rowptr[min(d0 + i, p.D)];
+        if (tid == 0) { rp[0] = rowptr[d0]; rp[TILE_S] = rowptr[min(d0 + TILE_S, p.D)]; }
         __syncthreads();
+#pragma unroll 4
         for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
             const int2 r = rec[w];
-            int t = 0;
-#pragma unroll
-            for (int step = TILE_S / 2; step >= 1; step >>= 1)
-                if (rp[t + step] <= w) t += step;
-            xt[t * VP + r.x] = (double)r.y;
+            xt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;        // slot tag | term (k_pack_rows)
         }
         if (tid < TILE_S) {
             double s = 0.0;
