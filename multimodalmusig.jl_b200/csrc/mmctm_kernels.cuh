@@ -113,7 +113,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
                                          double *dsh, int lane, int stop_rule) {
     const double lb = IS_NU ? 1e-7 : -__longlong_as_double(0x7ff0000000000000LL);
     const double xtol_rel = 1e-4, xtol_abs = 1e-4;
-    double sigma = 1.0;              // a bound is infinite -> sigma = 1
+    double sigma = 1.0, isig = 1.0;  // a bound is infinite -> sigma = 1; isig = 1 / sigma, refreshed when sigma moves
     double rho = 1.0;
     double g, fmin, fcur, gcur;
     {
@@ -132,10 +132,11 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             const double v = fabs(g) * sigma + 0.5 * rho;
             const double sigma2 = sigma * sigma;
             u *= sigma2;
-            const double r = fast_div(u, v * sigma);
+            const double qv = fast_div(u, v);
+            const double r = qv * isig;               // DET: u / (v sigma) as (u / v)(1 / sigma): one division per evaluation less
             const double om = fabs(1 - r * r);
             const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
-            double dx = fast_div(fast_div(u, v), -1 - sq);
+            double dx = fast_div(qv, -1 - sq);
             double xc = x + dx;
             const double mv = 0.9 * sigma, xhi = x + mv, xlo = x - mv;          // move limits: selects, no branches
             xc = xc > xhi ? xhi : (xc < xlo ? xlo : xc);
@@ -181,6 +182,7 @@ __device__ __forceinline__ int mma_solve(double &x, const SolveCtx &c, const dou
             const double s2 = (xcur - xprev) * (xprev - xprevprev);
             const double gam = s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
             sigma *= gam;
+            isig = fast_rcp(sigma);
         }
     }
     return nev;

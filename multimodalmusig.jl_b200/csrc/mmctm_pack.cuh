@@ -126,10 +126,11 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             const double v = fabs(g) * sigma + 0.5 * rho;
             const double sigma2 = sigma * sigma;
             u *= sigma2;
-            const double r = fast_div(u, v * sigma);
+            const double qv = fast_div(u, v);
+                const double r = qv * fast_rcp(sigma);      // DET: (u / v)(1 / sigma)
             const double om = fabs(1 - r * r);
             const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
-            double dx = fast_div(fast_div(u, v), -1 - sq);
+            double dx = fast_div(qv, -1 - sq);
             double xc = x + dx;
             const double mv = 0.9 * sigma, xhi = x + mv, xlo = x - mv;          // move limits: selects, no branches
             xc = xc > xhi ? xhi : (xc < xlo ? xlo : xc);
@@ -360,10 +361,11 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
                 const double v = fabs(g[s]) * sigma[s] + 0.5 * rho;
                 const double sigma2 = sigma[s] * sigma[s];
                 u *= sigma2;
-                const double r = fast_div(u, v * sigma[s]);
+                const double qv = fast_div(u, v);
+                const double r = qv * fast_rcp(sigma[s]);      // DET: (u / v)(1 / sigma)
                 const double om = fabs(1 - r * r);
                 const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
-                double dx = fast_div(fast_div(u, v), -1 - sq);
+                double dx = fast_div(qv, -1 - sq);
                 double xc = x[s] + dx;
                 if (xc > x[s] + 0.9 * sigma[s]) xc = x[s] + 0.9 * sigma[s];
                 else if (xc < x[s] - 0.9 * sigma[s]) xc = x[s] - 0.9 * sigma[s];

@@ -94,10 +94,11 @@ __device__ __forceinline__ int wide_mma_solve(double (&x)[WCPL], const WideCtx &
                 const double v = fabs(g[s]) * sigma[s] + 0.5 * rho;
                 const double sigma2 = sigma[s] * sigma[s];
                 u *= sigma2;
-                const double r = fast_div(u, v * sigma[s]);
+                const double qv = fast_div(u, v);
+                const double r = qv * fast_rcp(sigma[s]);      // DET: (u / v)(1 / sigma)
                 const double om = fabs(1 - r * r);
                 const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
-                double dx = fast_div(fast_div(u, v), -1 - sq);
+                double dx = fast_div(qv, -1 - sq);
                 double xn = x[s] + dx;
                 if (xn > x[s] + 0.9 * sigma[s]) xn = x[s] + 0.9 * sigma[s];
                 else if (xn < x[s] - 0.9 * sigma[s]) xn = x[s] - 0.9 * sigma[s];

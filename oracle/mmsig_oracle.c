@@ -328,7 +328,10 @@ int orc_mma_minimize(unsigned n, orc_func f, void *fdata,
                 sigma2 = sigma[j] * sigma[j];
                 u *= sigma2;
                 {
-                    double r = u / (v * sigma[j]);
+                    /* DET: u / (v sigma) as (u / v) * (1 / sigma) -- the device keeps 1 / sigma
+                       per coordinate and refreshes it when sigma moves, one division less per
+                       evaluation; differs from the literal by two roundings */
+                    double r = arith ? (u / v) * (1.0 / sigma[j]) : u / (v * sigma[j]);
                     dx = (u / v) / (-1 - sqrt(fabs(1 - r * r)));
                 }
                 xcur[j] = x[j] + dx;
