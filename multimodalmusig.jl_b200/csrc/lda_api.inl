@@ -34,6 +34,7 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
     NEED(h->nranks > 1 || D_total == D, "D_total != D without mmsig_comm_init");
     NEED(K >= 1 && V >= 1, "K, V must be >= 1");
     if (K > 32) return fail(h, MMSIG_ELIMIT, "K <= 32 supported");
+    if (V > 65535) return fail(h, MMSIG_ELIMIT, "V <= 65535 supported");
     CU(cudaSetDevice(h->device));
     free_pool(h->allocs_lda);
     h->lda = LdaHost();
@@ -52,11 +53,11 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
         if ((rc = ensure_countbuf(h, h->allocs_lda, L.cb, D, job->nnz))) return rc;
         CU(cudaMemcpyAsync(dN, job_N, (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CU(cudaMemcpyAsync(L.cb.rowptr, job->rowptr, (D + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
-        dense_fill(h, *job, D, V, elem_bytes, layout, L.cb.rowptr, L.cb.rec);
+        dense_fill(h, *job, D, V, elem_bytes, layout, L.cb.rowptr, L.cb.rec, 1);
         CU(cudaStreamSynchronize(h->stream));
         CU(cudaGetLastError());
         ntot = job->total;
-    } else if ((rc = upload_counts(h, h->allocs_lda, L.cb, D, V, 1, 0, rowptr, term, count, dN, &ntot))) return rc;
+    } else if ((rc = upload_counts(h, h->allocs_lda, L.cb, D, V, 1, 0, rowptr, term, count, dN, &ntot, 1))) return rc;
     p.rowptr = L.cb.rowptr;
     p.rec = L.cb.rec;
     L.nnz = L.cb.nnz;
@@ -93,6 +94,30 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
             L.grid = std::max(L.grid, L.grid_tile);          // the partial buffer serves both kernels
         }
     }
+    // 32-sample tiles, one thread per term (lda_tile.cuh): the default when they fit
+    {
+        const char *e = getenv("MMSIG_LDA");                 // "tile96": the 32·NW-sample tile kernel (A/B)
+        int KPv = 0;
+        THETA_DISPATCH(K, KPv = KP);
+        const int VP = V | 1, NW = (V + 31) / 32;
+        L.smem_t32 = ((size_t)V * KPv + (size_t)LDA_TS * VP + (size_t)LDA_TS * KPv + LDA_TS + 4) * sizeof(double);
+        L.smem_llt = ((size_t)LDA_TS * VP + (size_t)LDA_TS * KPv + LDA_TS + (size_t)NW * 32 + 4) * sizeof(double);
+        L.t32 = V <= 1024 && KPv <= 24 && L.smem_t32 <= h->smem_optin && !(e && (!strcmp(e, "row") || !strcmp(e, "tile96")));
+        if (L.t32) {
+            int nb = 0, nb2 = 0;
+            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(allow_max_smem(h, k_lda_estep_t32<KP, NWT>))));
+            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_estep_t32<KP, NWT>, NW * 32, L.smem_t32))));
+            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(allow_max_smem(h, k_lda_ll_tile<KP, NWT>))));
+            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lda_ll_tile<KP, NWT>, NW * 32, L.smem_llt))));
+            if (nb < 1 || nb2 < 1) L.t32 = false;
+            else {
+                const long long ntiles = (D + LDA_TS - 1) / LDA_TS;
+                L.grid_t32 = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * nb, ntiles));
+                L.grid_llt = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * nb2, ntiles));
+                L.grid = std::max(L.grid, L.grid_t32);
+            }
+        }
+    }
     {
         int nb = 0;
         L.smem_ll = (KV + 256) * sizeof(double);
@@ -103,7 +128,7 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
         L.grid_ll = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
     }
     if ((rc = dev_alloc(h, h->allocs_lda, &L.part, (size_t)L.grid * KV))) return rc;
-    if ((rc = dev_alloc(h, h->allocs_lda, &L.part_ll, (size_t)L.grid_ll * 8))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &L.part_ll, (size_t)std::max(L.grid_ll, L.grid_llt) * 8))) return rc;
     if ((rc = dev_alloc(h, h->allocs_lda, &L.rank_p, KV + 16))) return rc;
     if ((rc = dev_alloc(h, h->allocs_lda, &L.gath_p, (KV + 16) * h->nranks))) return rc;
     if ((rc = dev_alloc(h, h->allocs_lda, &L.rank_ll, (size_t)16))) return rc;
@@ -173,7 +198,13 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     L.last_frozen = freeze;
     std::swap(p.gamma, p.gamma_next);               // γ_t <- what the previous pass (or init) produced
     int nparts = L.grid_row;
-    if (L.tile) {
+    if (L.t32) {
+        LaunchScope ls(h, "k_lda_estep_t32");
+        const int nthr = 32 * ((p.V + 31) / 32);
+        THETA_DISPATCH(p.K, TILE_DISPATCH_NW(p.V, (k_lda_estep_t32<KP, NWT><<<L.grid_t32, nthr, L.smem_t32, h->stream>>>(
+                                                      p, L.part, unsm ? p.beta : p.expElnbeta, !freeze))));
+        nparts = L.grid_t32;
+    } else if (L.tile) {
         LaunchScope ls(h, "k_lda_estep_tile");
         THETA_DISPATCH(p.K, (k_lda_estep_tile<KP><<<L.grid_tile, L.NW * 32, L.smem_tile, h->stream>>>(
                                 p, L.part, unsm ? p.beta : p.expElnbeta, !freeze, L.NW)));
@@ -200,7 +231,11 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
         LaunchScope ls(h, "k_lda_mstep");
         k_lda_mstep<<<1, 1024, 0, h->stream>>>(p, g, h->nranks);
     }
-    {
+    if (L.t32) {
+        LaunchScope ls(h, "k_lda_ll_tile");
+        const int nthr = 32 * ((p.V + 31) / 32);
+        THETA_DISPATCH(p.K, TILE_DISPATCH_NW(p.V, (k_lda_ll_tile<KP, NWT><<<L.grid_llt, nthr, L.smem_llt, h->stream>>>(p, L.part_ll))));
+    } else {
         LaunchScope ls(h, "k_lda_ll");
         k_lda_ll<<<L.grid_ll, 256, L.smem_ll, h->stream>>>(p, L.part_ll);
     }
@@ -208,7 +243,7 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
         CombineSegs s{};
         s.nseg = 1;
         s.src[0] = L.part_ll;
-        s.nparts[0] = L.grid_ll;
+        s.nparts[0] = L.t32 ? L.grid_llt : L.grid_ll;
         s.n[0] = 1;
         s.dst_off[0] = 0;
         LaunchScope ls(h, "k_combine");

@@ -81,8 +81,8 @@ __global__ void __launch_bounds__(256) k_lda_estep(LdaDev p, double2 *partial, i
         for (int k = 0; k < NP; ++k) g[k] = 0.0;
         for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) {
             const int2 r = p.rec[w];
-            const double2 *Ev = reinterpret_cast<const double2 *>(E + r.x * KPAD);
-            double2 *Tv = reinterpret_cast<double2 *>(tab + r.x * KPAD);
+            const double2 *Ev = reinterpret_cast<const double2 *>(E + (r.x & 0xffff) * KPAD);
+            double2 *Tv = reinterpret_cast<double2 *>(tab + (r.x & 0xffff) * KPAD);
             double pk[KP];
             double Z = 0.0;
 #pragma unroll
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_lda_estep_tile(LdaDev p, double2 *parti
 #pragma unroll 8
                 for (long long w = beg; w < end; ++w) {
                     const int2 r = p.rec[w];
-                    row[r.x] = (double)r.y;
+                    row[r.x & 0xffff] = (double)r.y;
                 }
                 double gk[KP];
                 double s = 0.0;
@@ -328,7 +328,7 @@ __global__ void __launch_bounds__(256) k_lda_ll(LdaDev p, double2 *partial) {
         for (long long w = p.rowptr[d] + lane; w < p.rowptr[d + 1]; w += 32) {
             const int2 r = p.rec[w];
             double dot = 0.0;
-            for (int k = 0; k < K; ++k) dot += th[k] * beta[k * V + r.x];
+            for (int k = 0; k < K; ++k) dot += th[k] * beta[k * V + (r.x & 0xffff)];
             dd_add(hi, lo, (double)r.y * det_log(dot));
         }
     }
@@ -403,13 +403,13 @@ __global__ void __launch_bounds__(256) k_lda_elbo(LdaDev p, double2 *partial, do
             const int2 r = p.rec[w];
             const double n = (double)r.y;
             double Z = 0.0;
-            for (int k = 0; k < K; ++k) Z += et[k] * Eprev[k * V + r.x];
+            for (int k = 0; k < K; ++k) Z += et[k] * Eprev[k * V + (r.x & 0xffff)];
             double a = 0.0, b = 0.0, c = 0.0;
             for (int k = 0; k < K; ++k) {
-                const double ph = et[k] * Eprev[k * V + r.x] / Z;
+                const double ph = et[k] * Eprev[k * V + (r.x & 0xffff)] / Z;
                 if (phi_out) phi_out[w * K + k] = ph;
                 a += ph * el[k] * n;
-                b += ph * Eln[k * V + r.x] * n;
+                b += ph * Eln[k * V + (r.x & 0xffff)] * n;
                 if (ph > 0.0) c += ph * det_log(ph);
             }
             dd_add(hi[1], lo[1], a);

@@ -19,6 +19,7 @@
 #include "mmctm_pack.cuh"
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
+#include "lda_tile.cuh"
 #include "ingest_kernels.cuh"
 
 using namespace mmsig;
@@ -105,9 +106,9 @@ struct LdaHost {
     CountBuf cb;
     LdaDev p{};
     long long nnz = 0;
-    int grid = 0, W = 0, grid_ll = 0, grid_row = 0, grid_tile = 0, NW = 0;
-    bool tile = false;
-    size_t smem = 0, smem_ll = 0, smem_elbo = 0, smem_tile = 0;
+    int grid = 0, W = 0, grid_ll = 0, grid_row = 0, grid_tile = 0, NW = 0, grid_t32 = 0, grid_llt = 0;
+    bool tile = false, t32 = false;
+    size_t smem = 0, smem_ll = 0, smem_elbo = 0, smem_tile = 0, smem_t32 = 0, smem_llt = 0;
     double2 *part = nullptr, *part_ll = nullptr, *rank_p = nullptr, *gath_p = nullptr, *rank_ll = nullptr, *gath_ll = nullptr;
     double *d_ll = nullptr;
     double *gamA = nullptr, *gamB = nullptr;
