@@ -266,6 +266,19 @@ def main():
         return hist[-1]
     e2e_step()
     barrier()
+    # the link this leg runs over: one plain pinned-host -> device copy of the largest count array
+    big = max((t for t in keep), key=lambda t: t.numel() * t.element_size())
+    dev_buf = torch.empty_like(big, device="cuda")
+    c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    dev_buf.copy_(big, non_blocking=True)
+    torch.cuda.synchronize()
+    c0.record()
+    dev_buf.copy_(big, non_blocking=True)
+    c1.record()
+    torch.cuda.synchronize()
+    h2d_gbs = big.numel() * big.element_size() / (c0.elapsed_time(c1) * 1e-3) / 1e9
+    del dev_buf
+    barrier()
     t0 = time.perf_counter()
     for _ in range(args.e2e_steps):
         e2e_step()
@@ -324,7 +337,7 @@ def main():
             "mma_evaluations_per_sample_last_iteration": evals,
             "clocks": sampler.summary(),
             "e2e": {"value": 1000.0 / e2e_ms, "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "ms_per_step": e2e_ms, "what": ("set_data + set_state (pinned host -> device), iterate, get_state (device -> pinned host)" if args.e2e_unpipelined else
+                    "ms_per_step": e2e_ms, "h2d_link_gbs_measured": h2d_gbs, "what": ("set_data + set_state (pinned host -> device), iterate, get_state (device -> pinned host)" if args.e2e_unpipelined else
                              "mmsig_mmctm_fit_host(maxiter=1): counts + state from pinned host buffers, one E+M iteration, state back to "
                              "pinned host buffers; copies pipelined behind the E-step chunk by chunk")},
             "gpu_launches": int(launches),

@@ -41,7 +41,20 @@ struct MmctmDev {
     int *nev_nu, *nev_lam;
     int stop_rule;
     int accum;                    // != 0: E-step kernels add their block partials to what the slot holds (chunked launches)
+    unsigned long long *work;     // sample counter of the solve kernels (zeroed before each launch)
 };
+
+// Dynamic distribution of samples over the warps (lane groups) of a solve kernel: the cost of a
+// sample is its number of MMA evaluations (40-90 here), so a static stride leaves the kernel
+// waiting for its unluckiest warp (+5 % at 280 samples per warp, +13 % at 40, i.e. in the chunked
+// launches of mmsig_mmctm_fit_host).  One atomicAdd per sample against ~16 k instructions of work.
+__device__ __forceinline__ long long next_sample(unsigned long long *work, unsigned mask, int leader, bool is_leader) {
+    unsigned long long d = 0;
+    if (is_leader) d = atomicAdd(work, 1ULL);
+    const unsigned hi = (unsigned)__shfl_sync(mask, (int)(d >> 32), leader);
+    const unsigned lo = (unsigned)__shfl_sync(mask, (int)(d & 0xffffffffu), leader);
+    return (long long)(((unsigned long long)hi << 32) | lo);
+}
 
 // block partial -> its slot; chunked E-steps (mmsig_mmctm_fit_host) launch the same grid once per
 // chunk of samples on one stream and accumulate
@@ -229,8 +242,7 @@ __global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, dou
     c.muj = active ? p.mu[lane] : 0.0;
 
     double lsh = 0.0, lsl = 0.0, nsh = 0.0, nsl = 0.0;
-    const long long nw = (long long)gridDim.x * 8;
-    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+    for (long long d = next_sample(p.work, FULLMASK, 0, lane == 0); d < p.D; d = next_sample(p.work, FULLMASK, 0, lane == 0)) {
         const long long base = d * MK + lane;
         double lam = active ? p.lam_prev[base] : 0.0;
         double nu = active ? p.nu[base] : 1.5;

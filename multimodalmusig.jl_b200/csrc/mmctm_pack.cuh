@@ -86,15 +86,16 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
     double fmin = 0.0, rho = 1.0;
     double cN = 0.0, sth = 0.0, other = 0.0, lam0 = 0.0;                                  // per lane context
     double lsh = 0.0, lsl = 0.0, nsh = 0.0, nsl = 0.0;
-    const long long ngroups = (long long)gridDim.x * 8 * NG;
-    long long d = ((long long)blockIdx.x * 8 + warp) * NG + grp;
     long long dcur = -1;
+    bool exhausted = false;
 
     while (true) {
         // ---- groups without work take their next sample (src/MMCTM.jl:450-453: ζ from the old λ, ν)
-        if (phase == PH_IDLE && d < p.D) {
-            dcur = d;
-            d += ngroups;
+        if (phase == PH_IDLE && !exhausted) {
+            dcur = next_sample(p.work, gmask, grp * G, gl == 0);
+            if (dcur >= p.D) exhausted = true;
+        }
+        if (phase == PH_IDLE && !exhausted) {
             const long long base = dcur * MK + gl;
             lam0 = active ? p.lam_prev[base] : 0.0;
             const double nu0 = active ? p.nu[base] : 1.5;
@@ -315,14 +316,15 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev 
         acc[0][s] = acc[1][s] = acc[2][s] = acc[3][s] = 0.0;
     }
     double fmin = 0.0, rho = 1.0;
-    const long long ngroups = (long long)gridDim.x * NW * NG;
-    long long d = ((long long)blockIdx.x * NW + warp) * NG + grp;
     long long dcur = -1;
+    bool exhausted = false;
 
     while (true) {
-        if (phase == PH_IDLE && d < p.D) {
-            dcur = d;
-            d += ngroups;
+        if (phase == PH_IDLE && !exhausted) {
+            dcur = next_sample(p.work, gmask, grp * G, gl == 0);
+            if (dcur >= p.D) exhausted = true;
+        }
+        if (phase == PH_IDLE && !exhausted) {
             double nu0[CPL];
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {

@@ -204,7 +204,7 @@ __global__ void __launch_bounds__(256) k_solve_wide(MmctmDev p, double2 *partial
 #pragma unroll
         for (int s = 0; s < WCPL; ++s) acc[a][s] = 0.0;
     const long long nw = (long long)gridDim.x * 8;
-    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
+    for (long long d = next_sample(p.work, FULLMASK, 0, lane == 0); d < p.D; d = next_sample(p.work, FULLMASK, 0, lane == 0)) {
         double lam[WCPL], nu[WCPL];
         __syncwarp();
 #pragma unroll

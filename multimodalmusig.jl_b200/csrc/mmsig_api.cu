@@ -579,6 +579,7 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     if ((rc = dev_alloc(h, h->allocs_mm, &p.zeta, (size_t)D * M))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_nu, (size_t)D))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_lam, (size_t)D))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.work, (size_t)2))) return rc;
     p.lam = mm.lamA;
     p.lam_prev = mm.lamB;
     for (double **t : {&p.gamma, &p.Elnphi, &p.Elnphi_prev, &p.phi, &p.stats})
@@ -878,6 +879,7 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         TILE_DISPATCH(q.K[m], q.V[m], (k_theta_tile<KP, EREG, NWT><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
                                           q, m, mm.part_theta[m], unsm, !freeze_topics)));
     }
+    cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);      // the solve kernels draw samples from this counter
     {
         LaunchScope ls(h, "k_solve");
         if (mm.wide) k_solve_wide<<<cap(mm.grid_solve, 8), 256, mm.smem_solve, h->stream>>>(q, mm.part_solve);
@@ -1069,6 +1071,24 @@ extern "C" int32_t mmsig_mmctm_get_state(mmsig_handle *h, double *lambda, double
 // k_solve (block partials accumulate over the chunks), and when the loop is known to end with
 // this iteration (iter == maxiter) the chunk's λ, ν, ζ, props leave on a second copy stream while
 // the next chunk computes.  MMSIG_PIPE_CHUNKS overrides the chunk count (default ~150k samples).
+// MMSIG_TRACE=1: host-side wall-clock marks of mmsig_mmctm_fit_host on stderr (where an end-to-end call spends its time)
+struct HostTrace {
+    bool on;
+    double t0, last;
+    static double now() {
+        timespec ts;
+        clock_gettime(CLOCK_MONOTONIC, &ts);
+        return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+    }
+    HostTrace() : on(getenv("MMSIG_TRACE") != nullptr), t0(now()), last(t0) {}
+    void mark(const char *what) {
+        if (!on) return;
+        const double t = now();
+        fprintf(stderr, "[mmsig trace] %-28s +%8.3f ms  (%8.3f ms)\n", what, t - last, t - t0);
+        last = t;
+    }
+};
+
 static int pipe_chunks(long long D) {
     const char *e = getenv("MMSIG_PIPE_CHUNKS");
     long long c = e ? atoll(e) : (D + 75000) / 150000;
@@ -1089,16 +1109,20 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
     NEED(alpha && gamma, "alpha and gamma are required");
     NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
     CU(cudaSetDevice(h->device));
+    HostTrace trace;
     if (M < 1 || M > MAXM) return fail(h, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
     NEED(D >= 1, "need 1 <= D <= D_total");
     bool same = false;
     int rc;
     long long nnz_m[MAXM];
     for (int m = 0; m < M; ++m) {
-        if ((rc = check_rowptr(h, rowptr[m], D))) return rc;
+        // the row pointers are validated chunk by chunk, right before each chunk's copies are sized
+        // from them (2.7 ms of host time at D = 1e6 that would otherwise precede the first copy)
+        NEED(rowptr[m] && rowptr[m][0] == 0 && rowptr[m][D] >= 0, "rowptr[0] must be 0");
         nnz_m[m] = rowptr[m][D];
     }
     if ((rc = mmctm_prepare(h, D, D_total, M, K, V, nnz_m, &same))) return rc;
+    trace.mark(same ? "plan reused" : "plan + allocations");
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     mm.has_data = false;
@@ -1215,6 +1239,8 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
     for (int c = 0; c < C; ++c) {
         const long long d0 = cut[c], d1 = cut[c + 1];
         for (int m = 0; m < M; ++m) {
+            for (long long d = d0; d < d1; ++d)
+                if (rowptr[m][d + 1] < rowptr[m][d] || rowptr[m][d + 1] > nnz_m[m]) return fail(h, MMSIG_EINVAL, "rowptr not monotone");
             CountBuf &cb = mm.cb[m];
             const long long r0 = c == 0 ? 0 : d0 + 1;          // entry d0 came with the previous chunk
             CU(cudaMemcpyAsync(cb.rowptr + r0, rowptr[m] + r0, (size_t)(d1 + 1 - r0) * sizeof(long long), cudaMemcpyHostToDevice, h->s_in));
@@ -1233,6 +1259,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         mmctm_estep_launch(h, chunk_view(p, d0, d1, C > 1), flags);
         if (maxiter == 1) CU(after_chunk(c));
     }
+    trace.mark("chunks enqueued");
     if (maxiter == 1) {
         for (int c = 0; c < C; ++c) CU(drain_chunk(c));
         streamed_out = true;
@@ -1252,6 +1279,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         if ((rc = allsum_ll(h, ntot, M))) return rc;
         for (int m = 0; m < M; ++m) p.Ntot[m] = (double)ntot[m];
     }
+    trace.mark("E-step of iteration 1 done");
     mm.has_data = true;
     auto finish_iteration = [&](double *ll) -> int {
         int r = mmctm_mstep_launch(h, flags);
@@ -1265,6 +1293,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         return 0;
     };
     if ((rc = finish_iteration(ll_hist))) { cudaStreamSynchronize(h->s_out); return rc; }
+    trace.mark("M-step of iteration 1 done");
     mm.has_state = true;
 
     // ---- iterations 2 .. maxiter (src/MMCTM.jl:462-487)
@@ -1289,6 +1318,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
     if (n_iter) *n_iter = it;
     if (converged) *converged = conv;
     CU(cudaStreamSynchronize(h->s_out));
+    trace.mark("loop done, outputs drained");
     if (streamed_out)
         return mmsig_mmctm_get_state(h, nullptr, nullptr, nullptr, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out, phi_out, nullptr);
     return mmsig_mmctm_get_state(h, lambda_out, nu_out, zeta_out, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out,

@@ -304,6 +304,10 @@ def test_fit_host_rejects_bad_counts():
     bad[1][1][0] = 99                                  # term out of range
     with pytest.raises(mmsig.capi.MmsigError):
         m.fit_host(bad, g0, maxiter=1)
+    bad2 = [(r.copy(), t.copy(), c.copy()) for r, t, c in counts]
+    bad2[0][0][40] = bad2[0][0][41] + 1                # row pointers not monotone
+    with pytest.raises(mmsig.capi.MmsigError):
+        m.fit_host(bad2, g0, maxiter=1)
     hist, _ = m.fit_host(counts, g0, maxiter=2)        # the handle recovers
     assert np.isfinite(hist).all()
     m.close()
