@@ -26,10 +26,9 @@ static int mmctm_elbo_impl(mmsig_handle *h, double *elbo, double *terms) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     const int nb = mm.grid_post;
-    double2 *parts = nullptr;      // [M][nb][4]
-    double *d_tab = nullptr;
-    CU(cudaMalloc(&parts, (size_t)p.M * nb * 4 * sizeof(double2)));
-    CU(cudaMalloc(&d_tab, 4 * sizeof(double)));
+    // scratch lives with the plan (no cudaMalloc / cudaFree -- an implicit device synchronisation -- per call)
+    double2 *parts = mm.part_elbo;                                       // [M][nb][4]
+    double *d_tab = reinterpret_cast<double *>(mm.part_elbo + (size_t)p.M * nb * 4);
     CU(cudaMemsetAsync(parts, 0, (size_t)p.M * nb * 4 * sizeof(double2), h->stream));
     {
         LaunchScope ls(h, "k_elbo_tables");
@@ -61,8 +60,6 @@ static int mmctm_elbo_impl(mmsig_handle *h, double *elbo, double *terms) {
     CU(cudaMemcpyAsync(hp.data(), g, hp.size() * sizeof(double2), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaMemcpyAsync(tab, d_tab, sizeof(tab), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
-    cudaFree(parts);
-    cudaFree(d_tab);
     CU(cudaGetLastError());
     long double s[4] = {0, 0, 0, 0};
     for (int r = 0; r < h->nranks; ++r)

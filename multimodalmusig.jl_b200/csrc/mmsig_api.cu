@@ -118,6 +118,7 @@ struct mmsig_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of mmsig_mmctm_fit_host
+    long long *allsum_buf = nullptr;                   // scratch of allsum_ll (multi-rank totals)
     int2 *fmt_rec = nullptr;                           // records of the last mmsig_format_counts
     long long fmt_nnz = -1;
     bool own_stream = false;
@@ -270,6 +271,7 @@ extern "C" int32_t mmsig_destroy(mmsig_handle *h) {
     if (h->comm) g_nccl.CommDestroy(h->comm);
     if (h->own_stream) cudaStreamDestroy(h->stream);
     cudaFree(h->fmt_rec);
+    cudaFree(h->allsum_buf);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
@@ -342,9 +344,9 @@ extern "C" int32_t mmsig_kernel_times(mmsig_handle *h, int32_t n_max, const char
 // sum of per-rank int64 totals (Σ_d N_dm) over ranks, on the host
 static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
     if (h->nranks == 1) return 0;
-    long long *d_in = nullptr, *d_out = nullptr;
-    CU(cudaMalloc(&d_in, n * sizeof(long long)));
-    CU(cudaMalloc(&d_out, (size_t)n * h->nranks * sizeof(long long)));
+    NEED(n <= MAXM, "allsum_ll: too many values");
+    if (!h->allsum_buf) CU(cudaMalloc(&h->allsum_buf, (size_t)MAXM * (h->nranks + 1) * sizeof(long long)));   // kept: no malloc / free per call
+    long long *d_in = h->allsum_buf, *d_out = h->allsum_buf + MAXM;
     CU(cudaMemcpyAsync(d_in, vals, n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     int rc = g_nccl.AllGather(d_in, d_out, (size_t)n * sizeof(long long), kNcclInt8, h->comm, h->stream);
     if (rc != 0) return fail(h, MMSIG_ENCCL, "ncclAllGather (totals) failed");
@@ -356,8 +358,6 @@ static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
         for (int r = 0; r < h->nranks; ++r) s += all[(size_t)r * n + i];
         vals[i] = s;
     }
-    cudaFree(d_in);
-    cudaFree(d_out);
     return 0;
 }
 
@@ -658,7 +658,7 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_mom, (size_t)mm.grid_mom * P2))) return rc;
     CU(cudaMemsetAsync(mm.part_post, 0, (size_t)mm.grid_post * P2 * sizeof(double2), h->stream));
     CU(cudaMemsetAsync(mm.part_mom, 0, (size_t)mm.grid_mom * P2 * sizeof(double2), h->stream));
-    if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_elbo, (size_t)mm.grid_post * 8))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_elbo, (size_t)M * mm.grid_post * 4 + 8))) return rc;   // ELBO partials [M][grid_post][4] + 4 table terms
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.rank_p1, (size_t)P1))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.gath_p1, (size_t)P1 * h->nranks))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.rank_p2, (size_t)P2 + 16))) return rc;
@@ -1091,7 +1091,9 @@ struct HostTrace {
 
 static int pipe_chunks(long long D) {
     const char *e = getenv("MMSIG_PIPE_CHUNKS");
-    long long c = e ? atoll(e) : (D + 75000) / 150000;
+    // ~150k samples per chunk, but at least 4 chunks once a shard is worth pipelining at all (a rank
+    // of an 8-GPU run holds 125k samples of the 1M corpus)
+    long long c = e ? atoll(e) : std::max<long long>((D + 75000) / 150000, std::min<long long>(4, D / 16384));
     return (int)std::max<long long>(1, std::min<long long>({c, 64LL, D}));
 }
 
