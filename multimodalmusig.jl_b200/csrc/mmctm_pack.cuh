@@ -82,7 +82,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
     // per-group state (identical in all lanes of a group unless noted "per lane")
     int phase = PH_IDLE, k = 0, nev = 0, nev_nu = 0;
     bool init = false;
-    double x = 0.0, g = 0.0, xcur = 0.0, xprev = 0.0, xprevprev = 0.0, sigma = 1.0;      // per lane
+    double x = 0.0, g = 0.0, xcur = 0.0, xprev = 0.0, xprevprev = 0.0, sigma = 1.0, isig = 1.0;      // per lane (isig = 1 / sigma)
     double fmin = 0.0, rho = 1.0;
     double cN = 0.0, sth = 0.0, other = 0.0, lam0 = 0.0;                                  // per lane context
     double lsh = 0.0, lsl = 0.0, nsh = 0.0, nsl = 0.0;
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
             const double sigma2 = sigma * sigma;
             u *= sigma2;
             const double qv = fast_div(u, v);
-                const double r = qv * fast_rcp(sigma);      // DET: (u / v)(1 / sigma)
+                const double r = qv * isig;                 // DET: (u / v)(1 / sigma)
             const double om = fabs(1 - r * r);
             const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
             double dx = fast_div(qv, -1 - sq);
@@ -202,6 +202,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
                 k = 1;
                 rho = 1.0;
                 sigma = 1.0;
+                isig = 1.0;
                 init = false;
             } else {
                 xcur = xe;
@@ -216,6 +217,7 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
                         if (k > 1) {
                             const double s2 = (xcur - xprev) * (xprev - xprevprev);
                             sigma *= s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
+                            isig = fast_rcp(sigma);
                         }
                         ++k;
                         xprevprev = xprev;
