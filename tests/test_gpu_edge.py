@@ -123,3 +123,20 @@ def test_lda_edge_cases():
     s = g.state()
     assert rel_err(s["gamma"], o.gamma) <= 1e-12 and rel_err(s["lam"], o.lam) <= 1e-12
     g.close()
+
+
+@pytest.mark.parametrize("K,V,D", [
+    ([1], [1], 5),                       # one topic, one term
+    ([32], [33], 70),                    # K at its per-modality limit, V one past a warp
+    ([3, 17], [64, 65], 97),             # V on and one past a 32-term block boundary; D not a multiple of the tile
+    ([2, 3, 1, 2, 3, 1, 2, 2], [7, 33, 2, 12, 40, 3, 31, 32], 45),   # 8 modalities (the limit)
+    ([5, 4], [300, 17], 31),             # several warps of terms, fewer samples than one tile
+    ([13, 12, 11], [40, 100, 9], 65),    # sum(K) = 36: the two-coordinates-per-lane path with the tile kernels
+])
+def test_awkward_shapes_of_the_tile_kernels(K, V, D):
+    """Term counts around the 32-term blocks, sample counts around the 32-sample tiles, the K and M
+    limits, both solve layouts: θ pass, solve, log-likelihood and ELBO against the oracle."""
+    rng = np.random.default_rng(sum(V) + D)
+    dense = [rng.poisson(1.5, size=(v, D)) for v in V]
+    dense[0][:, D // 2] = 0                                   # an empty row in the first modality
+    _run(K, V, [make_count_csr(x) for x in dense], iters=2, seed=D)
