@@ -6,6 +6,7 @@
 // micro-tiles.  Records carry their sample's slot in the tile (k_pack_rows, tag).
 #pragma once
 #include "lda_kernels.cuh"
+#include "theta_tile.cuh"
 
 namespace mmsig {
 
@@ -44,7 +45,13 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
             const long long d = d0 + t;
             et[i] = (k < K && d < p.D) ? p.gamma[d * K + k] : 0.0;
         }
-        if (tid == 0) { rp[0] = p.rowptr[d0]; rp[1] = p.rowptr[min(d0 + LDA_TS, p.D)]; }
+        if (tid == 0) {
+            rp[0] = p.rowptr[d0];
+            rp[1] = p.rowptr[min(d0 + LDA_TS, p.D)];
+            const long long dn = min(d0 + (long long)gridDim.x * LDA_TS, p.D);      // this block's next tile
+            rp[2] = p.rowptr[dn];
+            rp[3] = p.rowptr[min(dn + LDA_TS, p.D)];
+        }
         __syncthreads();
 #pragma unroll 4
         for (long long w = rp[0] + tid; w < rp[1]; w += blockDim.x) {
@@ -62,6 +69,7 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
             et[i] = (k < K && d0 + t < p.D) ? det_exp(det_digamma(et[i]) - ssum[t]) : 0.0;
         }
         __syncthreads();
+        prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);    // next tile's records towards L2
         // ---- phase 2: Z, R and the statistics, lane <-> term
         if (vok) {
             for (int t = 0; t < LDA_TS; ++t) {
@@ -157,7 +165,13 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
             const long long d = d0 + t;
             pt[i] = (k < K && d < p.D) ? p.gamma[d * K + k] : 0.0;
         }
-        if (tid == 0) { rp[0] = p.rowptr[d0]; rp[1] = p.rowptr[min(d0 + LDA_TS, p.D)]; }
+        if (tid == 0) {
+            rp[0] = p.rowptr[d0];
+            rp[1] = p.rowptr[min(d0 + LDA_TS, p.D)];
+            const long long dn = min(d0 + (long long)gridDim.x * LDA_TS, p.D);      // this block's next tile
+            rp[2] = p.rowptr[dn];
+            rp[3] = p.rowptr[min(dn + LDA_TS, p.D)];
+        }
         __syncthreads();
 #pragma unroll 4
         for (long long w = rp[0] + tid; w < rp[1]; w += blockDim.x) {
@@ -175,6 +189,7 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
             if (k < K && d0 + t < p.D) pt[i] = pt[i] / ssum[t];
         }
         __syncthreads();
+        prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);
         if (vok) {
             for (int t = 0; t < LDA_TS; ++t) {
                 const double n = xt[t * VP + v];
