@@ -61,6 +61,10 @@ typedef struct {
 } mmsig_config;
 
 int32_t     mmsig_version(void);
+/* the sizes beyond which set_data answers MMSIG_ELIMIT: modalities, sum of K_m, K_m, V_m of MMCTM
+ * (V_m additionally has to fit the theta tile in shared memory), V of LDA.  Needs no device. */
+int32_t     mmsig_limits(int32_t *max_modalities, int32_t *max_sum_K, int32_t *max_K, int32_t *max_V_mmctm,
+                         int32_t *max_V_lda);
 int32_t     mmsig_create(const mmsig_config *cfg, mmsig_handle **out);
 int32_t     mmsig_destroy(mmsig_handle *h);
 const char *mmsig_last_error(const mmsig_handle *h);           /* h may be NULL: last create error */

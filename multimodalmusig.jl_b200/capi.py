@@ -32,6 +32,7 @@ class MmsigError(RuntimeError):
 
 _SIGS = {
     "mmsig_version": (C.c_int32, []),
+    "mmsig_limits": (C.c_int32, [c_i32p] * 5),
     "mmsig_create": (C.c_int32, [C.POINTER(Config), C.POINTER(C.c_void_p)]),
     "mmsig_destroy": (C.c_int32, [C.c_void_p]),
     "mmsig_last_error": (C.c_char_p, [C.c_void_p]),

@@ -230,7 +230,17 @@ static cudaError_t allow_max_smem(mmsig_handle *h, F kernel) {
 }
 
 // ---- generic ------------------------------------------------------------------------------
-extern "C" int32_t mmsig_version(void) { return 100; }
+extern "C" int32_t mmsig_version(void) { return 110; }
+
+extern "C" int32_t mmsig_limits(int32_t *max_modalities, int32_t *max_sum_K, int32_t *max_K, int32_t *max_V_mmctm,
+                                int32_t *max_V_lda) {
+    if (max_modalities) *max_modalities = MAXM;
+    if (max_sum_K) *max_sum_K = MAXMK;
+    if (max_K) *max_K = 32;
+    if (max_V_mmctm) *max_V_mmctm = 1024;
+    if (max_V_lda) *max_V_lda = 65535;
+    return 0;
+}
 
 extern "C" const char *mmsig_last_error(const mmsig_handle *h) { return h ? h->err.c_str() : g_last_error.c_str(); }
 

@@ -48,3 +48,13 @@ def test_product_never_imports_the_oracle():
     for f in ("mmsig.py",):
         txt = open(os.path.join(ROOT, f)).read()
         assert "orc" not in txt
+
+
+def test_limits_need_no_device():
+    import ctypes as C
+    import mmsig
+    lib = mmsig.capi.load()
+    v = [C.c_int32() for _ in range(5)]
+    assert lib.mmsig_limits(*[C.byref(x) for x in v]) == 0
+    assert [x.value for x in v] == [8, 64, 32, 1024, 65535]
+    assert lib.mmsig_version() >= 110
