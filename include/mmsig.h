@@ -100,6 +100,13 @@ int32_t mmsig_mmctm_set_data_dense(mmsig_handle *h, int64_t D, int64_t D_total, 
 int32_t mmsig_lda_set_data_dense(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
                                  const void *dense, int32_t elem_bytes, int32_t layout);
 
+/* the count TSV files the reference reads (README.md:14-16, data/brca-eu_snv_counts.tsv: a `term`
+ * column, one column per sample): dimensions, then the integer body as a V x D term-major int32
+ * matrix (what the calls above take with MMSIG_DENSE_TERM_MAJOR).  Host only, no handle; errors
+ * are reported through mmsig_last_error(NULL).  Term and sample names stay with the caller. */
+int32_t mmsig_tsv_dims(const char *path, int64_t *V, int64_t *D);
+int32_t mmsig_tsv_read(const char *path, int64_t V, int64_t D, int32_t *dense_term_major);
+
 /* ---- MMCTM / CTM  (reference src/MMCTM.jl) -------------------------------------------- */
 /* model.X, K, V (src/MMCTM.jl:29-40); with mmsig_comm_init, D and the CSR are this rank's shard
  * and D_total is the global sample count (else pass D_total = D). */

@@ -40,6 +40,8 @@ _SIGS = {
     "mmsig_synchronize": (C.c_int32, [C.c_void_p]),
     "mmsig_comm_unique_id": (C.c_int32, [c_u8p]),
     "mmsig_comm_init": (C.c_int32, [C.c_void_p, c_u8p, C.c_int32, C.c_int32]),
+    "mmsig_tsv_dims": (C.c_int32, [C.c_char_p, c_i64p, c_i64p]),
+    "mmsig_tsv_read": (C.c_int32, [C.c_char_p, C.c_int64, C.c_int64, c_i32p]),
     "mmsig_format_counts": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, c_i64p, c_i64p]),
     "mmsig_format_counts_fetch": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
     "mmsig_mmctm_set_data_dense": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,

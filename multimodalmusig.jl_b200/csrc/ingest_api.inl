@@ -224,3 +224,81 @@ extern "C" int32_t mmsig_mmctm_set_data_dense(mmsig_handle *h, int64_t D, int64_
     mm.has_data = true;
     return 0;
 }
+
+
+// ---- count TSV files (data/*.tsv: header `term<TAB>sample...`, one line per term) ----------------
+// Host-side reader for the numeric body, in the layout the ingest kernels take directly
+// (MMSIG_DENSE_TERM_MAJOR).  The names (first column, header) stay with the caller's language.
+static int tsv_scan(const char *path, long long *V, long long *D, std::vector<int32_t> *out, std::string &err) {
+    FILE *f = fopen(path, "rb");
+    if (!f) { err = std::string("cannot open ") + path; return MMSIG_EINVAL; }
+    std::vector<char> buf;
+    {
+        fseek(f, 0, SEEK_END);
+        const long n = ftell(f);
+        fseek(f, 0, SEEK_SET);
+        buf.resize((size_t)std::max<long>(n, 0) + 1);
+        const size_t got = fread(buf.data(), 1, buf.size() - 1, f);
+        buf[got] = 0;
+        buf.resize(got + 1);
+        fclose(f);
+    }
+    const char *p = buf.data(), *end = buf.data() + buf.size() - 1;
+    // header: count the tabs
+    long long ncol = 0;
+    while (p < end && *p != '\n') { if (*p == '\t') ++ncol; ++p; }
+    if (p < end) ++p;
+    long long rows = 0;
+    while (p < end) {
+        if (*p == '\n' || *p == '\r') { ++p; continue; }                 // blank line
+        while (p < end && *p != '\t' && *p != '\n') ++p;                  // the term name
+        long long c = 0;
+        while (p < end && *p == '\t') {
+            ++p;
+            bool neg = false;
+            if (p < end && (*p == '-' || *p == '+')) { neg = *p == '-'; ++p; }
+            if (p >= end || *p < '0' || *p > '9') { err = "non-integer count in row " + std::to_string(rows + 1); return MMSIG_EINVAL; }
+            long long x = 0;
+            while (p < end && *p >= '0' && *p <= '9') {
+                x = x * 10 + (*p - '0');
+                if (x > 2147483647LL) { err = "a count exceeds 2^31-1 in row " + std::to_string(rows + 1); return MMSIG_ELIMIT; }
+                ++p;
+            }
+            if (out) (*out)[(size_t)rows * ncol + c] = (int32_t)(neg ? -x : x);
+            ++c;
+        }
+        if (p < end && *p == '\r') ++p;
+        if (p < end && *p != '\n') { err = "unexpected character in row " + std::to_string(rows + 1); return MMSIG_EINVAL; }
+        if (c != ncol) { err = "row " + std::to_string(rows + 1) + " has " + std::to_string(c) + " counts, the header names " + std::to_string(ncol); return MMSIG_EINVAL; }
+        ++rows;
+    }
+    *V = rows;
+    *D = ncol;
+    return 0;
+}
+
+extern "C" int32_t mmsig_tsv_dims(const char *path, int64_t *V, int64_t *D) {
+    mmsig_handle *h = nullptr;
+    NEED(path && V && D, "null argument");
+    std::string err;
+    long long v = 0, d = 0;
+    const int rc = tsv_scan(path, &v, &d, nullptr, err);
+    if (rc) return fail(h, rc, err);
+    *V = v;
+    *D = d;
+    return 0;
+}
+
+extern "C" int32_t mmsig_tsv_read(const char *path, int64_t V, int64_t D, int32_t *dense_term_major) {
+    mmsig_handle *h = nullptr;
+    NEED(path && dense_term_major && V >= 0 && D >= 0, "bad argument");
+    std::string err;
+    long long v = 0, d = 0;
+    int rc = tsv_scan(path, &v, &d, nullptr, err);
+    if (rc) return fail(h, rc, err);
+    NEED(v == V && d == D, "dimensions differ from mmsig_tsv_dims");
+    std::vector<int32_t> tmp((size_t)V * D);
+    if ((rc = tsv_scan(path, &v, &d, &tmp, err))) return fail(h, rc, err);
+    memcpy(dense_term_major, tmp.data(), tmp.size() * sizeof(int32_t));
+    return 0;
+}

@@ -8,6 +8,26 @@ import numpy as np
 from .counts import read_tsv  # noqa: F401  (re-exported: the reader lives with the CSR helpers)
 
 
+def read_counts_tsv_native(path):
+    """The integer body of a count TSV through the library's C++ reader (mmsig_tsv_dims / _read):
+    a (V, D) int32 matrix, term-major, ready for MMCTM(..., dense=[...]) / format_counts_device.
+    Names come from the first column / header as in read_tsv."""
+    import ctypes as C
+    from . import capi
+    lib = capi.load()
+    V, D = C.c_int64(), C.c_int64()
+    b = str(path).encode()
+    if lib.mmsig_tsv_dims(b, C.byref(V), C.byref(D)) != 0:
+        raise ValueError((lib.mmsig_last_error(None) or b"").decode())
+    dense = np.empty((V.value, D.value), dtype=np.int32)
+    if lib.mmsig_tsv_read(b, V.value, D.value, dense.ctypes.data_as(capi.c_i32p)) != 0:
+        raise ValueError((lib.mmsig_last_error(None) or b"").decode())
+    with open(path) as f:
+        samples = f.readline().rstrip("\r\n").split("\t")[1:]
+        terms = [line.split("\t", 1)[0] for line in f if line.strip()]
+    return terms, samples, dense
+
+
 def julia_float_str(x):
     """Shortest round-trip decimal in the style Julia's `show(::Float64)` / CSV.write / writedlm
     use (digits as Python's repr; plain notation for 1e-4 <= |x| < 1e6, else d.ddde±x)

@@ -98,3 +98,30 @@ def test_lda_set_data_dense_equals_csr_path():
     for _ in range(3):
         assert a.iterate() == b.iterate()
     a.close(); b.close()
+
+
+def test_tsv_file_to_device_csr(tmp_path):
+    """data/*.tsv-shaped files -> C++ reader -> dense term-major matrices -> CSR built on the GPU ->
+    the same iterations as the host path (read_tsv + format_counts_mmctm + set_data)."""
+    from mmsig import io
+    from mmsig.counts import read_tsv, format_counts_mmctm
+    K, V, D = [3, 2], [12, 7], 300
+    rng = np.random.default_rng(8)
+    paths, dense = [], []
+    for m, v in enumerate(V):
+        x = rng.poisson(1.2, (v, D))
+        p = tmp_path / ("m%d.tsv" % m)
+        io.write_counts_tsv(p, ["t%d" % i for i in range(v)], ["s%d" % i for i in range(D)], x)
+        paths.append(p)
+        dense.append(x)
+    native = [io.read_counts_tsv_native(p)[2] for p in paths]
+    assert all(np.array_equal(a, b) for a, b in zip(native, dense))
+    g0 = mmsig.synth.init_gamma(K, V)
+    a = mmsig.MMCTM(K, [0.1, 0.1], format_counts_mmctm([read_tsv(p)[2] for p in paths]), V=V, gamma0=g0)
+    b = mmsig.MMCTM(K, [0.1, 0.1], None, V=V, gamma0=g0, dense=native)
+    for _ in range(2):
+        assert np.array_equal(a.iterate(), b.iterate())
+    sa, sb = a.state(), b.state()
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    a.close(); b.close()

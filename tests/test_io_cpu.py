@@ -59,3 +59,31 @@ def test_result_tables(tmp_path):
     assert np.array_equal(io.read_dlm(tmp_path / "cov.tsv"), S)
     io.write_dlm(tmp_path / "mean.tsv", np.array([0.5, -1.25]))
     assert (tmp_path / "mean.tsv").read_text() == "0.5\n-1.25\n"
+
+
+def test_native_tsv_reader_equals_python_reader(tmp_path):
+    """mmsig_tsv_dims / mmsig_tsv_read (host-side C++ in libmmsig.so, no GPU needed) against read_tsv."""
+    import pytest
+    rng = np.random.default_rng(3)
+    dense = rng.poisson(40.0, (96, 57))
+    dense[5, 7] = 0
+    dense[0, 0] = 2**31 - 1
+    terms = ["A[C->%s]%d" % ("ATG"[i % 3], i) for i in range(96)]
+    samples = ["DO%d" % i for i in range(57)]
+    p = tmp_path / "c.tsv"
+    io.write_counts_tsv(p, terms, samples, dense)
+    t, s, d = io.read_counts_tsv_native(p)
+    t2, s2, d2 = read_tsv(p)
+    assert t == t2 == terms and s == s2 == samples
+    assert d.dtype == np.int32 and np.array_equal(d, d2)
+    # Windows line ends and a trailing blank line
+    q = tmp_path / "crlf.tsv"
+    q.write_bytes(p.read_bytes().replace(b"\n", b"\r\n") + b"\r\n")
+    assert np.array_equal(io.read_counts_tsv_native(q)[2], d2)
+    # ragged row, non-integer, overflow, missing file
+    (tmp_path / "bad1.tsv").write_text("term\ta\tb\nx\t1\ny\t1\t2\n")
+    (tmp_path / "bad2.tsv").write_text("term\ta\nx\t1.5\n")
+    (tmp_path / "bad3.tsv").write_text("term\ta\nx\t2147483648\n")
+    for name in ("bad1.tsv", "bad2.tsv", "bad3.tsv", "missing.tsv"):
+        with pytest.raises(ValueError):
+            io.read_counts_tsv_native(tmp_path / name)
