@@ -3,7 +3,7 @@
 # The Julia API stays as it is: format_counts_mmctm/ctm/lda, MMCTM(K, α, X), LDA(K, α, η, X),
 # fit!(model; tol), model.ϕ / model.props / model.β / model.θ.  Loading this file after
 # `using MultiModalMuSig` replaces the two `fit!` methods (reference src/MMCTM.jl:457-494,
-# src/LDA.jl:198-224) by thin wrappers that flatten the model state, `ccall` libmmsig.so
+# src/LDA.jl:198-224) and MMCTM's `fit_heldout` / `transform` (:554-586, :511-552) by thin wrappers that flatten the model state, `ccall` libmmsig.so
 # (include/mmsig.h) and scatter the results back into the nested vectors.  Model construction,
 # including the random γ / λ initialisation (src/MMCTM.jl:59-63, src/LDA.jl:36), is untouched.
 #
@@ -12,7 +12,7 @@
 module MMSigB200
 
 using MultiModalMuSig
-import MultiModalMuSig: fit!, MMCTM, LDA, check_convergence
+import MultiModalMuSig: fit!, fit_heldout, transform, MMCTM, LDA, check_convergence
 
 const LIB = get(ENV, "MMSIG_LIB", joinpath(@__DIR__, "..", "multimodalmusig.jl_b200", "libmmsig.so"))
 
@@ -141,6 +141,81 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
         destroy(h)
     end
     return ll
+end
+
+# ---- fit_heldout / transform (src/MMCTM.jl:554-586, :511-552): the same E-step with the topics and
+# (unless fit_gaussian) the Gaussian prior frozen, selected by flags of mmsig_mmctm_iterate:
+#   MMSIG_FLAG_UPDATE_SIGMA = 1, FREEZE_TOPICS = 2, FREEZE_MU = 4, UNSMOOTHED = 8
+function frozen_loop!(newmodel::MMCTM, ϕsrc, flags::UInt32; maxiter, tol, verbose, device=0, stop_rule=0)
+    D, M, MK = newmodel.D, newmodel.M, sum(newmodel.K)
+    rowptr, term, count = flatten_counts(newmodel.X, M)
+    K32, V32 = Int32.(newmodel.K), Int32.(newmodel.V)
+    λ, ν = flat_rows(newmodel.λ), flat_rows(newmodel.ν)
+    γ, ϕ = flat_tables(newmodel.γ), flat_tables(ϕsrc)
+    Σ, invΣ = collect(transpose(newmodel.Σ)), collect(transpose(newmodel.invΣ))
+    h = create(device=device, stop_rule=stop_rule)
+    ll = Vector{Float64}[]
+    try
+        GC.@preserve rowptr term count begin
+            rp = [pointer(r) for r in rowptr]; tp = [pointer(t) for t in term]; cp = [pointer(c) for c in count]
+            check(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                h, D, D, M, K32, V32, rp, tp, cp))
+        end
+        check(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, newmodel.α, γ, λ, ν, newmodel.μ, Σ, invΣ))
+        check(h, ccall((:mmsig_mmctm_set_phi, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, ϕ))   # newmodel.ϕ = deepcopy(model.ϕ)
+        llbuf = zeros(M)
+        for iter in 1:maxiter
+            check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+            push!(ll, copy(llbuf))
+            verbose && println("$iter\tLog-likelihoods: ", join(ll[end], ", "))
+            if length(ll) > 10 && check_convergence(ll, tol=tol)
+                newmodel.converged = true
+                break
+            end
+        end
+        ζ = zeros(D * M); μ = zeros(MK); props = zeros(D * MK)
+        check(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, λ, ν, ζ, μ, Σ, invΣ, C_NULL, C_NULL, C_NULL, props))
+        for d in 1:D
+            newmodel.λ[d] .= @view λ[(d - 1) * MK + 1:d * MK]
+            newmodel.ν[d] .= @view ν[(d - 1) * MK + 1:d * MK]
+            newmodel.ζ[d] .= @view ζ[(d - 1) * M + 1:d * M]
+            off = 0
+            for m in 1:M
+                newmodel.props[d][m] = props[(d - 1) * MK + off + 1:(d - 1) * MK + off + newmodel.K[m]]
+                off += newmodel.K[m]
+            end
+        end
+        newmodel.μ .= μ
+        newmodel.Σ .= transpose(reshape(Σ, MK, MK)); newmodel.invΣ .= transpose(reshape(invΣ, MK, MK))
+        newmodel.ll = ll[end]
+    finally
+        destroy(h)
+    end
+    return newmodel
+end
+
+function fit_heldout(Xheldout::Vector{Vector{Matrix{Int}}}, model::MMCTM; maxiter=100, verbose=false, device=0)
+    heldout_model = MMCTM(model.K, model.α, Xheldout)                       # src/MMCTM.jl:557-563
+    heldout_model.μ .= model.μ; heldout_model.Σ .= model.Σ; heldout_model.invΣ .= model.invΣ
+    heldout_model.γ = deepcopy(model.γ); heldout_model.Elnϕ = deepcopy(model.Elnϕ); heldout_model.ϕ = deepcopy(model.ϕ)
+    return frozen_loop!(heldout_model, model.ϕ, UInt32(2 | 4); maxiter=maxiter, tol=1e-4, verbose=verbose, device=device)
+end
+
+function transform(model::MMCTM, X::Vector{Vector{Matrix{Int}}}; maxiter=1000, tol=1e4, fit_gaussian=false,
+                   verbose=false, device=0)
+    newmodel = MMCTM(model.K, model.α, X)                                   # src/MMCTM.jl:514-520 (invΣ stays I, as there)
+    newmodel.ϕ = deepcopy(model.ϕ)
+    if !fit_gaussian
+        newmodel.μ = deepcopy(model.μ); newmodel.Σ = deepcopy(model.Σ)
+    end
+    flags = UInt32(2 | 8 | (fit_gaussian ? 1 : 4))
+    return frozen_loop!(newmodel, model.ϕ, flags; maxiter=maxiter, tol=tol, verbose=verbose, device=device)
 end
 
 function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
