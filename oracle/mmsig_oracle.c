@@ -660,6 +660,9 @@ orc_mmctm *orc_mmctm_new(int M, const int *K, const int *V, int64_t D,
     m->expl = (double *)calloc((size_t)(D ? D : 1) * MK, sizeof(double));
     m->sumtheta_e = (double *)calloc((size_t)(D ? D : 1) * MK, sizeof(double));
     m->theta_unsm = 0;
+    m->factored = 0;
+    m->nfeat = NULL; m->feat = NULL; m->J = NULL; m->foff = NULL; m->aoff = NULL;
+    m->alphaf = m->gammaf = m->Elnphif = NULL;
     m->stop_rule = ORC_STOP_NLOPT27;
     m->nthreads = 1;
     m->converged = 0;                                                /* :88 */
@@ -674,6 +677,11 @@ void orc_mmctm_free(orc_mmctm *m)
     }
     free(m->rowptr); free(m->term); free(m->cnt); free(m->theta); free(m->rz);
     free(m->expl); free(m->sumtheta_e);
+    if (m->factored) {
+        for (int i = 0; i < m->M; ++i) { free(m->feat[i]); free(m->J[i]); }
+        free(m->nfeat); free(m->feat); free(m->J); free(m->foff); free(m->aoff);
+        free(m->alphaf); free(m->gammaf); free(m->Elnphif);
+    }
     free(m->K); free(m->V); free(m->koff); free(m->goff); free(m->alpha);
     free(m->N); free(m->mu); free(m->Sigma); free(m->invSigma);
     free(m->lambda); free(m->nu); free(m->zeta); free(m->props);
@@ -707,6 +715,15 @@ void orc_mmctm_update_theta(orc_mmctm *m, int64_t d)
             double s = 0.0;
             for (int k = 0; k < K; ++k) {
                 /* DET: product form exp(lambda_k) * exp(Elnphi_kv), as unsmoothed_update_theta! (:503) */
+                if (!m->arith && m->factored) {      /* src/IMMCTM.jl:158-166: exp(lambda) times one exp per feature */
+                    int nf = m->nfeat[i];
+                    int64_t rowlen = (m->foff[i + 1] - m->foff[i]) / K, o = m->foff[i] + (int64_t)k * rowlen;
+                    th[k] = exp(lam[off + k]);
+                    for (int f = 0; f < nf; ++f) {
+                        th[k] *= exp(m->Elnphif[o + m->feat[i][(size_t)v * nf + f]]);
+                        o += m->J[i][f];
+                    }
+                } else
                 th[k] = m->arith ? det_exp(lam[off + k]) * det_exp(Eln[(size_t)k * V + v])
                                  : exp(lam[off + k] + Eln[(size_t)k * V + v]);
                 s += th[k];
@@ -922,6 +939,7 @@ void orc_mmctm_update_Elnphi(orc_mmctm *m)
 /* src/MMCTM.jl:224-242 */
 void orc_mmctm_update_gamma(orc_mmctm *m)
 {
+    if (m->factored) { orc_immctm_update_gamma(m); return; }
     if (m->arith) {
         /* DET: S_kv = exactly rounded sum over samples of fl(exp(lambda_dk) * R_dv), R = n * (1/Z)
            (the (D x K)^T (D x V) product form of the statistics); sum n theta = E_kv * S_kv and
@@ -982,6 +1000,7 @@ void orc_mmctm_update_props(orc_mmctm *m)
 /* src/MMCTM.jl:244-250 */
 void orc_mmctm_update_phi(orc_mmctm *m)
 {
+    if (m->factored) return;      /* the composite phi follows the feature tables (orc_immctm_update_Elnphi) */
     for (int i = 0; i < m->M; ++i)
         for (int k = 0; k < m->K[i]; ++k) {
             const double *g = m->gamma + m->goff[i] + (size_t)k * m->V[i];
@@ -1004,6 +1023,24 @@ static double neg_alpha_obj(unsigned n, const double *x, double *grad, void *p)
 /* src/MMCTM.jl:252-269 : 1-D LD_MMA, lb 1e-7, xtol 1e-5 */
 void orc_mmctm_update_alpha(orc_mmctm *m)
 {
+    if (m->factored) {          /* src/IMMCTM.jl:223-241: one alpha per (modality, feature) */
+        for (int i = 0; i < m->M; ++i) {
+            int K = m->K[i], nf = m->nfeat[i];
+            int64_t rowlen = (m->foff[i + 1] - m->foff[i]) / K, fo = 0;
+            for (int f = 0; f < nf; ++f) {
+                double s = 0.0;
+                for (int k = 0; k < K; ++k)
+                    for (int j = 0; j < m->J[i][f]; ++j) s += m->Elnphif[m->foff[i] + (int64_t)k * rowlen + fo + j];
+                double q[3] = { s, (double)K, (double)m->J[i][f] };
+                double lb = 1e-7, ub = HUGE_VAL, x = m->alphaf[m->aoff[i] + f], minf;
+                orc_mma_minimize(1, neg_alpha_obj, q, &lb, &ub, &x, &minf, 1e-5, 1e-5,
+                                 m->stop_rule, ORC_ARITH_LITERAL, NULL);
+                m->alphaf[m->aoff[i] + f] = x;
+                fo += m->J[i][f];
+            }
+        }
+        return;
+    }
     for (int i = 0; i < m->M; ++i) {
         double s = 0.0;
         for (int64_t t = 0; t < (int64_t)m->K[i] * m->V[i]; ++t)
@@ -1065,8 +1102,27 @@ double orc_mmctm_elbo(const orc_mmctm *m, double *terms)
 {
     int MK = m->MK;
     double t[7] = {0, 0, 0, 0, 0, 0, 0};
+    /* IMMCTM: ElnPphi src/IMMCTM.jl:244-261, ElnQphi :311-325 over the feature tables */
+    if (m->factored)
+        for (int i = 0; i < m->M; ++i)
+            for (int k = 0; k < m->K[i]; ++k) {
+                int64_t o = m->foff[i] + (int64_t)k * ((m->foff[i + 1] - m->foff[i]) / m->K[i]);
+                for (int f = 0; f < m->nfeat[i]; ++f) {
+                    int Jf = m->J[i][f];
+                    double a = m->alphaf[m->aoff[i] + f];
+                    double fillv[Jf];
+                    for (int j = 0; j < Jf; ++j) fillv[j] = a;
+                    t[0] -= orc_logmvbeta(fillv, Jf);
+                    t[4] += -orc_logmvbeta(m->gammaf + o, Jf);
+                    for (int j = 0; j < Jf; ++j) {
+                        t[0] += (a - 1) * m->Elnphif[o + j];
+                        t[4] += (m->gammaf[o + j] - 1) * m->Elnphif[o + j];
+                    }
+                    o += Jf;
+                }
+            }
     /* ElnPphi :271-284 */
-    for (int i = 0; i < m->M; ++i) {
+    for (int i = 0; i < m->M && !m->factored; ++i) {
         double *fillv = (double *)malloc(sizeof(double) * m->V[i]);
         for (int v = 0; v < m->V[i]; ++v) fillv[v] = m->alpha[i];
         for (int k = 0; k < m->K[i]; ++k) {
@@ -1123,7 +1179,7 @@ double orc_mmctm_elbo(const orc_mmctm *m, double *terms)
             }
         }
     /* ElnQphi :338-350 */
-    for (int i = 0; i < m->M; ++i)
+    for (int i = 0; i < m->M && !m->factored; ++i)
         for (int k = 0; k < m->K[i]; ++k) {
             const double *g = m->gamma + m->goff[i] + (size_t)k * m->V[i];
             t[4] += -orc_logmvbeta(g, m->V[i]);
@@ -1497,6 +1553,159 @@ int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist)
     return it;
 }
 
+
+/* =====================================================================
+ * IMMCTM (src/IMMCTM.jl): feature-factorised topics.  Everything per sample (zeta, theta, nu,
+ * lambda: src/IMMCTM.jl:105-172 are the MMCTM functions over the composite table) is shared
+ * with the MMCTM above; what differs is the M-step over the feature tables and the two
+ * table terms of the ELBO.
+ * DET specification: the composite log-table Elnphi_kv = sum_i Elnphi_k,i,f(v,i) (index order,
+ * from 0) so that theta uses exp(lambda) * exp(Elnphi_kv) exactly as the MMCTM does (the
+ * literal reference multiplies one exp per feature: roundings only); phi_kv = prod_i phi_k,i,f(v,i)
+ * (index order, from 1); gamma_k,i,j = alpha_i + (sum over v with f(v,i) = j, ascending v, of
+ * sum-n-theta_kv), with sum-n-theta_kv = E_kv S_kv as in the MMCTM.
+ * ===================================================================== */
+int64_t orc_immctm_table_size(const orc_mmctm *m) { return m->factored ? m->foff[m->M] : 0; }
+
+/* src/IMMCTM.jl:186-195, then the composite K x V tables */
+void orc_immctm_update_Elnphi(orc_mmctm *m)
+{
+    for (int i = 0; i < m->M; ++i) {
+        int K = m->K[i], V = m->V[i], nf = m->nfeat[i];
+        int64_t rowlen = (m->foff[i + 1] - m->foff[i]) / K;
+        for (int k = 0; k < K; ++k) {
+            int64_t o = m->foff[i] + (int64_t)k * rowlen;
+            for (int f = 0; f < nf; ++f) {
+                int Jf = m->J[i][f];
+                double sg = 0.0;
+                for (int j = 0; j < Jf; ++j) sg += m->gammaf[o + j];
+                double ds = digamma_a(m->arith, sg);
+                for (int j = 0; j < Jf; ++j) m->Elnphif[o + j] = digamma_a(m->arith, m->gammaf[o + j]) - ds;
+                o += Jf;
+            }
+            for (int v = 0; v < V; ++v) {
+                double e = 0.0, ph = 1.0;
+                int64_t oo = m->foff[i] + (int64_t)k * rowlen;
+                for (int f = 0; f < nf; ++f) {
+                    int Jf = m->J[i][f], j = m->feat[i][(size_t)v * nf + f];
+                    double sg = 0.0;
+                    for (int jj = 0; jj < Jf; ++jj) sg += m->gammaf[oo + jj];
+                    e += m->Elnphif[oo + j];
+                    ph *= m->gammaf[oo + j] / sg;        /* phi as calculate_loglikelihoods builds it, :423-426 */
+                    oo += Jf;
+                }
+                m->Elnphi[m->goff[i] + (size_t)k * V + v] = e;
+                m->phi[m->goff[i] + (size_t)k * V + v] = ph;
+            }
+        }
+    }
+}
+
+void orc_immctm_enable(orc_mmctm *m, const int *nfeat, const int *const *feat,
+                       const double *alphaf, const double *gammaf0)
+{
+    int M = m->M;
+    m->nfeat = (int *)malloc(sizeof(int) * M);
+    m->feat = (int **)malloc(sizeof(void *) * M);
+    m->J = (int **)malloc(sizeof(void *) * M);
+    m->foff = (int64_t *)malloc(sizeof(int64_t) * (M + 1));
+    m->aoff = (int *)malloc(sizeof(int) * (M + 1));
+    m->foff[0] = 0; m->aoff[0] = 0;
+    for (int i = 0; i < M; ++i) {
+        int nf = nfeat[i], V = m->V[i];
+        m->nfeat[i] = nf;
+        m->feat[i] = (int *)malloc(sizeof(int) * (size_t)V * nf);
+        memcpy(m->feat[i], feat[i], sizeof(int) * (size_t)V * nf);
+        m->J[i] = (int *)calloc(nf, sizeof(int));
+        int64_t rowlen = 0;
+        for (int f = 0; f < nf; ++f) {                 /* J = maximum(features, dims=1), src/IMMCTM.jl:44 */
+            for (int v = 0; v < V; ++v)
+                if (feat[i][(size_t)v * nf + f] + 1 > m->J[i][f]) m->J[i][f] = feat[i][(size_t)v * nf + f] + 1;
+            rowlen += m->J[i][f];
+        }
+        m->foff[i + 1] = m->foff[i] + rowlen * m->K[i];
+        m->aoff[i + 1] = m->aoff[i] + nf;
+    }
+    int64_t T = m->foff[M];
+    m->alphaf = (double *)malloc(sizeof(double) * m->aoff[M]);
+    memcpy(m->alphaf, alphaf, sizeof(double) * m->aoff[M]);
+    m->gammaf = (double *)malloc(sizeof(double) * T);
+    m->Elnphif = (double *)malloc(sizeof(double) * T);
+    memcpy(m->gammaf, gammaf0, sizeof(double) * T);
+    m->factored = 1;
+    orc_immctm_update_Elnphi(m);                         /* :69-70 */
+    for (int64_t t = 0; t < m->goff[M]; ++t) m->gamma[t] = 0.0 / 0.0;   /* no K x V gamma in this model */
+}
+
+/* src/IMMCTM.jl:197-221 */
+void orc_immctm_update_gamma(orc_mmctm *m)
+{
+    int64_t T = m->foff[m->M];
+    for (int i = 0; i < m->M; ++i) {
+        int K = m->K[i], nf = m->nfeat[i];
+        int64_t rowlen = (m->foff[i + 1] - m->foff[i]) / K;
+        for (int k = 0; k < K; ++k) {
+            int64_t o = m->foff[i] + (int64_t)k * rowlen;
+            for (int f = 0; f < nf; ++f) {
+                for (int j = 0; j < m->J[i][f]; ++j) m->gammaf[o + j] = m->alphaf[m->aoff[i] + f];
+                o += m->J[i][f];
+            }
+        }
+    }
+    (void)T;
+    if (m->arith) {
+        /* DET: sum-n-theta_kv = E_kv S_kv exactly as orc_mmctm_update_gamma (S = exactly rounded
+           sum over samples of fl(exp(lambda_dk) R_dv)), then per feature value the plain sum over
+           the terms that carry it, ascending v */
+        int64_t G = m->goff[m->M];
+        dd_t *acc = (dd_t *)calloc((size_t)G, sizeof(dd_t));
+        for (int64_t d = 0; d < m->D; ++d)
+            for (int i = 0; i < m->M; ++i) {
+                int K = m->K[i], V = m->V[i];
+                dd_t *g = acc + m->goff[i];
+                const double *L = m->expl + (size_t)d * m->MK + m->koff[i];
+                for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w) {
+                    int v = m->term[i][w];
+                    double R = (double)m->cnt[i][w] * m->rz[i][w];
+                    for (int k = 0; k < K; ++k) dd_add(&g[(size_t)k * V + v], L[k] * R);
+                }
+            }
+        for (int i = 0; i < m->M; ++i) {
+            int K = m->K[i], V = m->V[i], nf = m->nfeat[i];
+            int64_t rowlen = (m->foff[i + 1] - m->foff[i]) / K;
+            for (int k = 0; k < K; ++k)
+                for (int v = 0; v < V; ++v) {
+                    int64_t x = m->goff[i] + (size_t)k * V + v;
+                    double st = det_exp(m->Elnphi[x]) * dd_round(acc[x]);
+                    int64_t o = m->foff[i] + (int64_t)k * rowlen;
+                    for (int f = 0; f < nf; ++f) {
+                        m->gammaf[o + m->feat[i][(size_t)v * nf + f]] += st;
+                        o += m->J[i][f];
+                    }
+                }
+        }
+        free(acc);
+    } else {
+        for (int64_t d = 0; d < m->D; ++d)
+            for (int i = 0; i < m->M; ++i) {
+                int K = m->K[i], nf = m->nfeat[i];
+                int64_t rowlen = (m->foff[i + 1] - m->foff[i]) / K;
+                for (int64_t w = m->rowptr[i][d]; w < m->rowptr[i][d + 1]; ++w) {
+                    int v = m->term[i][w];
+                    double n = (double)m->cnt[i][w];
+                    for (int k = 0; k < K; ++k) {
+                        double nt = m->theta[i][(size_t)w * K + k] * n;
+                        int64_t o = m->foff[i] + (int64_t)k * rowlen;
+                        for (int f = 0; f < nf; ++f) {
+                            m->gammaf[o + m->feat[i][(size_t)v * nf + f]] += nt;
+                            o += m->J[i][f];
+                        }
+                    }
+                }
+            }
+    }
+    orc_immctm_update_Elnphi(m);
+}
 
 /* =====================================================================
  * Count ingest, src/utils.jl

@@ -119,6 +119,16 @@ typedef struct {
     double *expl;                 /* D x MK   : exp(lambda) as update_theta saw it         */
     double *sumtheta_e;           /* D x MK   : sum-theta of the last E-step (:110-117)    */
     int theta_unsm;               /* table of the last E-step: 0 exp(Elnphi), 1 phi        */
+    /* IMMCTM (src/IMMCTM.jl): the topic-term distribution of modality m factorises over I_m
+       features, phi_kv = prod_i phi_k,i,f(v,i).  factored != 0: gamma/Elnphi/phi (K x V) above are
+       the COMPOSITE tables derived from the feature tables below.                           */
+    int factored;
+    int *nfeat;                   /* [M]   I_m                                              */
+    int **feat;                   /* [M]   V_m x I_m row-major, 0-BASED feature values      */
+    int **J;                      /* [M][I_m] values per feature                            */
+    int64_t *foff;                /* [M+1] offsets of the flat feature tables, layout [m][k][i][j] */
+    int *aoff;                    /* [M+1] offsets into alphaf ([m][i])                     */
+    double *alphaf, *gammaf, *Elnphif;
 } orc_mmctm;
 
 orc_mmctm *orc_mmctm_new(int M, const int *K, const int *V, int64_t D,
@@ -185,6 +195,14 @@ double orc_lda_iterate(orc_lda *m);         /* :202-209 */
 void orc_lda_unsmoothed_update_phi(orc_lda *m);               /* :226-231 */
 double orc_lda_iterate_flags(orc_lda *m, unsigned flags);     /* fit_heldout :275-280, transform :242-246 */
 int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist); /* :198-224 */
+
+/* IMMCTM (src/IMMCTM.jl:1-108): switch a freshly constructed model to feature-factorised topics.
+ * nfeat[M], feat[m] V_m x I_m (0-based values), alphaf [m][i], gammaf0 [m][k][i][j] (ctor: rand 1:100) */
+void orc_immctm_enable(orc_mmctm *m, const int *nfeat, const int *const *feat,
+                       const double *alphaf, const double *gammaf0);
+void orc_immctm_update_Elnphi(orc_mmctm *m);   /* src/IMMCTM.jl:186-195 + composite K x V tables */
+void orc_immctm_update_gamma(orc_mmctm *m);    /* :197-221 */
+int64_t orc_immctm_table_size(const orc_mmctm *m);
 
 /* format_counts_* (src/utils.jl:1-36): dense count matrix -> CSR; see mmsig_oracle.c */
 int64_t orc_make_count_csr(int64_t D, int V, const int64_t *dense, int layout,

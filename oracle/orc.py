@@ -40,6 +40,8 @@ class MMCTM(C.Structure):
         ("elbo", C.c_double), ("ll", c_dp),
         ("nev_nu", c_i32p), ("nev_lambda", c_i32p),
         ("rz", C.POINTER(c_dp)), ("expl", c_dp), ("sumtheta_e", c_dp), ("theta_unsm", C.c_int),
+        ("factored", C.c_int), ("nfeat", c_ip), ("feat", C.POINTER(c_ip)), ("J", C.POINTER(c_ip)),
+        ("foff", c_i64p), ("aoff", c_ip), ("alphaf", c_dp), ("gammaf", c_dp), ("Elnphif", c_dp),
     ]
 
 
@@ -71,6 +73,10 @@ def lib():
         f.restype = res
         f.argtypes = list(args)
 
+    sig("orc_immctm_enable", None, pm, c_ip, C.POINTER(c_ip), c_dp, c_dp)
+    sig("orc_immctm_update_Elnphi", None, pm)
+    sig("orc_immctm_update_gamma", None, pm)
+    sig("orc_immctm_table_size", i64, pm)
     sig("orc_make_count_csr", i64, i64, i, c_i64p, i, c_i64p, c_i32p, c_i32p)
     sig("orc_digamma", d, d)
     sig("orc_digamma_det", d, d)
@@ -222,6 +228,41 @@ class OracleMMCTM:
         return ll
 
     converged = property(lambda s: bool(s.p.contents.converged))
+
+
+class OracleIMMCTM(OracleMMCTM):
+    """IMMCTM (reference src/IMMCTM.jl): MMCTM whose topics factorise over features.
+    features: list over modalities of (V_m, I_m) integer arrays with 0-BASED feature values;
+    alphaf: list over modalities of per-feature alphas (or one float per modality, :93-100);
+    gammaf0: flat [m][k][i][j] table (the constructor's rand(1:100), :60-67)."""
+
+    def __init__(self, K, alphaf, features, counts, gammaf0, arith=ARITH_LITERAL, stop_rule=STOP_NLOPT27, nthreads=1):
+        feats = [np.ascontiguousarray(f, dtype=np.int32) for f in features]
+        V = [f.shape[0] for f in feats]
+        self.I = [f.shape[1] for f in feats]
+        self.J = [[int(f[:, i].max()) + 1 for i in range(f.shape[1])] for f in feats]
+        al = [np.full(n, float(a)) if np.ndim(a) == 0 else np.asarray(a, float) for a, n in zip(alphaf, self.I)]
+        G = sum(k * v for k, v in zip(K, V))
+        super().__init__(K, [a[0] for a in al], V, counts, np.ones(G), arith=arith, stop_rule=stop_rule, nthreads=nthreads)
+        self._feats = feats
+        self.T = sum(k * sum(j) for k, j in zip(K, self.J))
+        g0 = np.ascontiguousarray(gammaf0, dtype=np.float64)
+        assert g0.size == self.T
+        nf = np.asarray(self.I, dtype=np.int32)
+        fp = (c_ip * self.M)(*[f.ctypes.data_as(c_ip) for f in feats])
+        alf = np.ascontiguousarray(np.concatenate(al))
+        self.L.orc_immctm_enable(self.p, nf.ctypes.data_as(c_ip), fp, _dp(alf), _dp(g0))
+        for d in range(self.D):
+            self.L.orc_mmctm_update_zeta(self.p, d)
+
+    gammaf = property(lambda s: s._arr("gammaf", (s.T,)))
+    Elnphif = property(lambda s: s._arr("Elnphif", (s.T,)))
+    alphaf = property(lambda s: s._arr("alphaf", (sum(s.I),)))
+
+    def table(self, flat, m, k, i):
+        """View of feature i of topic k of modality m in a flat [m][k][i][j] table."""
+        o = sum(int(self.K[mm]) * sum(self.J[mm]) for mm in range(m)) + k * sum(self.J[m]) + sum(self.J[m][:i])
+        return flat[o:o + self.J[m][i]]
 
 
 class OracleLDA:
