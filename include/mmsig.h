@@ -169,6 +169,20 @@ int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double *gamma0, i
 /* diagnostics: objective evaluations LD_MMA spent per sample in the last E-step */
 int32_t mmsig_mmctm_get_evals(mmsig_handle *h, int32_t *nev_nu, int32_t *nev_lambda);
 
+/* ---- IMMCTM  (reference src/IMMCTM.jl): topics factorised over features --------------------------
+ * phi_kv = prod_i phi_k,i,f(v,i).  The per-sample E-step (src/IMMCTM.jl:105-172, :518-523) is the
+ * MMCTM's over composite K x V tables; the M-step (:174-221) runs over the feature tables.
+ * Call order: mmsig_mmctm_set_data, mmsig_immctm_set_features, mmsig_immctm_set_state, then
+ * mmsig_mmctm_iterate / _fit / _elbo / _get_state (lambda, nu, zeta, mu, Sigma, invSigma, props; gamma is
+ * a placeholder, Elnphi / phi are the composite tables), mmsig_immctm_get_tables.
+ * features[m]: V_m x I_m row-major, 0-BASED feature values (model.features[m] - 1); tables are flat
+ * [m][k][i][j] (model.γ[m][k][i][j]), alpha [m][i] (model.α[m][i]).  MMSIG_FLAG_AUTO_ALPHA is
+ * update_α! of :223-241; MMSIG_FLAG_UNSMOOTHED is refused (the IMMCTM has no transform). */
+int32_t mmsig_immctm_set_features(mmsig_handle *h, const int32_t *nfeat, const int32_t *const *features);
+int32_t mmsig_immctm_set_state(mmsig_handle *h, const double *alphaf, const double *gammaf, const double *lambda,
+                               const double *nu, const double *mu, const double *Sigma, const double *invSigma);
+int32_t mmsig_immctm_get_tables(mmsig_handle *h, double *gammaf, double *Elnphif, double *alphaf);
+
 /* ---- LDA  (reference src/LDA.jl) -------------------------------------------------------- */
 int32_t mmsig_lda_set_data(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V,
                            const int64_t *rowptr, const int32_t *term, const int32_t *count);

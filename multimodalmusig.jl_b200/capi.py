@@ -64,6 +64,9 @@ _SIGS = {
     "mmsig_mmctm_restarts": (C.c_int32, [C.c_void_p, C.c_int32, c_dp, C.c_int32, C.c_double, C.c_uint32, c_dp, c_dp,
                                          c_i32p, c_i32p]),
     "mmsig_mmctm_get_evals": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
+    "mmsig_immctm_set_features": (C.c_int32, [C.c_void_p, c_i32p, C.POINTER(c_i32p)]),
+    "mmsig_immctm_set_state": (C.c_int32, [C.c_void_p] + [c_dp] * 7),
+    "mmsig_immctm_get_tables": (C.c_int32, [C.c_void_p, c_dp, c_dp, c_dp]),
     "mmsig_lda_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p]),
     "mmsig_lda_set_state": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, c_dp, c_dp]),
     "mmsig_lda_iterate": (C.c_int32, [C.c_void_p, c_dp]),

@@ -34,6 +34,25 @@ __global__ void __launch_bounds__(256) k_elbo_tables(MmctmDev p, double *out) {
     double *A = lu_smem, *B = lu_smem + MK * MK;
     int *piv = reinterpret_cast<int *>(B + MK * MK);
     double hi[3] = {0, 0, 0}, lo[3] = {0, 0, 0};
+    if (p.factored) {
+        // IMMCTM: ElnPϕ (src/IMMCTM.jl:244-261) and ElnQϕ (:311-325) over the feature tables
+        for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
+            const double a = p.alphaf[p.row_alpha[r]];
+            const double *g = p.gammaf + p.row_off[r];
+            double r0 = 0.0, s0 = 0.0, r1 = 0.0, s1 = 0.0;
+            for (int j = 0; j < p.row_len[r]; ++j) { r0 += lgamma(a); s0 += a; r1 += lgamma(g[j]); s1 += g[j]; }
+            r0 -= lgamma(s0);
+            r1 -= lgamma(s1);
+            dd_add(hi[0], lo[0], -r0);
+            dd_add(hi[1], lo[1], -r1);
+        }
+        for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+            const double E = p.Elnphif[t];
+            dd_add(hi[0], lo[0], (p.alphaf[p.row_alpha[p.ent_row[t]]] - 1) * E);
+            dd_add(hi[1], lo[1], (p.gammaf[t] - 1) * E);
+        }
+        for (int i = threadIdx.x; i < G; i += blockDim.x) dd_add(hi[2], lo[2], p.stats[i] * p.Elnphi[i]);
+    } else {
     // per (m,k) row pieces handled by one thread each; element-wise pieces strided
     if ((int)threadIdx.x < MK) {
         int m = 0;
@@ -56,6 +75,7 @@ __global__ void __launch_bounds__(256) k_elbo_tables(MmctmDev p, double *out) {
         dd_add(hi[0], lo[0], (p.alpha[m] - 1) * E);
         dd_add(hi[1], lo[1], (p.gamma[i] - 1) * E);
         dd_add(hi[2], lo[2], p.stats[i] * E);
+    }
     }
     double2 res[3];
     __shared__ double2 outsh[3];

@@ -42,6 +42,14 @@ struct MmctmDev {
     int stop_rule;
     int accum;                    // != 0: E-step kernels add their block partials to what the slot holds (chunked launches)
     unsigned long long *work;     // sample counter of the solve kernels (zeroed before each launch)
+    // IMMCTM (reference src/IMMCTM.jl): topics factorised over features.  factored != 0: Elnphi / phi
+    // (K x V) are COMPOSITE tables derived from the feature tables gammaf / Elnphif ([m][k][i][j] flat)
+    int factored, T, R;           // T entries, R rows (m, k, i) of the feature tables
+    int nfeat[MAXM], foff[MAXM + 1], aoff[MAXM + 1];
+    const int *feat[MAXM];        // V_m x I_m row-major, 0-based feature values
+    const int *ent_row;           // [T] row of an entry
+    const int *row_off, *row_len, *row_alpha;   // [R] first entry, J, index into alphaf
+    double *gammaf, *Elnphif, *alphaf;
 };
 
 // Dynamic distribution of samples over the warps (lane groups) of a solve kernel: the cost of a
@@ -385,6 +393,96 @@ __global__ void __launch_bounds__(1024) k_elnphi(MmctmDev p) {
         p.Elnphi_prev[i] = p.Elnphi[i];
         p.phi[i] = p.gamma[i];                  // model.ϕ = deepcopy(model.γ), src/MMCTM.jl:80
     }
+}
+
+// ------------------------------------------------------------------------------------------
+// IMMCTM M-step, part 1 (single block; reference src/IMMCTM.jl:186-221).  From the feature tables
+// γf: Elnϕf = ψ(γf) - ψ(Σ_j γf), then the composite tables every per-sample kernel reads,
+// Elnϕ_kv = Σ_i Elnϕf_k,i,f(v,i) (index order, from 0) and ϕ_kv = Π_i γf / Σ_j γf (index order,
+// from 1).  rowsum / rowdig: R doubles each in shared memory.
+// ------------------------------------------------------------------------------------------
+__device__ inline void immctm_compose(const MmctmDev &p, double *rowsum, double *rowdig) {
+    for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
+        const double *g = p.gammaf + p.row_off[r];
+        double s = 0.0;
+        for (int j = 0; j < p.row_len[r]; ++j) s += g[j];
+        rowsum[r] = s;
+        rowdig[r] = det_digamma(s);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) p.Elnphif[t] = det_digamma(p.gammaf[t]) - rowdig[p.ent_row[t]];
+    __syncthreads();
+    const int G = p.goff[p.M];
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        int m = 0;
+        while (i >= p.goff[m + 1]) ++m;
+        const int V = p.V[m], nf = p.nfeat[m], k = (i - p.goff[m]) / V, v = (i - p.goff[m]) % V;
+        // rows of (m, k) are consecutive: first row index = aoff-based count
+        int r = 0;
+        for (int mm = 0; mm < m; ++mm) r += p.K[mm] * p.nfeat[mm];
+        r += k * nf;
+        double e = 0.0, ph = 1.0;
+        for (int f = 0; f < nf; ++f, ++r) {
+            const int t = p.row_off[r] + p.feat[m][v * nf + f];
+            e += p.Elnphif[t];
+            ph *= p.gammaf[t] / rowsum[r];
+        }
+        p.Elnphi[i] = e;
+        p.phi[i] = ph;
+    }
+}
+
+// constructor / set_state: composite tables from γf (src/IMMCTM.jl:69-70)
+__global__ void __launch_bounds__(1024) k_icompose(MmctmDev p) {
+    extern __shared__ double ism[];
+    immctm_compose(p, ism, ism + p.R);
+    __syncthreads();
+    const int G = p.goff[p.M];
+    for (int i = threadIdx.x; i < G; i += blockDim.x) { p.Elnphi_prev[i] = p.Elnphi[i]; p.gamma[i] = p.phi[i]; }
+}
+
+// gathered: [nranks][G + 2 MK] dd as for k_mstep1.  Σ n θ_kv = E_kv S_kv, then
+// γf_k,i,j = α_i + Σ_{v: f(v,i) = j} Σ n θ_kv (ascending v), Elnϕf, the composite tables, μ.
+__global__ void __launch_bounds__(1024) k_imstep1(MmctmDev p, const double2 *gathered, int nranks, int freeze_topics,
+                                                  int freeze_mu) {
+    extern __shared__ double ism[];
+    const int G = p.goff[p.M], MK = p.MK, P1 = G + 2 * MK;
+    for (int i = threadIdx.x; i < P1; i += blockDim.x) {
+        double hi = 0.0, lo = 0.0;
+        for (int r = 0; r < nranks; ++r) {
+            const double2 v = gathered[(size_t)r * P1 + i];
+            dd_merge(hi, lo, v.x, v.y);
+        }
+        if (i < G) {
+            if (freeze_topics) continue;
+            const double S = dd_round(hi, lo);
+            p.stats[i] = det_exp(p.Elnphi[i]) * S;
+            p.Elnphi_prev[i] = p.Elnphi[i];
+        } else if (i < G + MK) {
+            if (!freeze_mu) p.mu[i - G] = dd_round(hi, lo) / (double)p.D_total;
+        } else {
+            p.nusum[i - G - MK] = make_double2(hi, lo);
+        }
+    }
+    if (freeze_topics) return;
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+        const int r = p.ent_row[t], j = t - p.row_off[r];
+        // (m, k, f) of row r
+        int m = 0, base = 0;
+        while (r >= base + p.K[m] * p.nfeat[m]) { base += p.K[m] * p.nfeat[m]; ++m; }
+        const int nf = p.nfeat[m], k = (r - base) / nf, f = (r - base) % nf, V = p.V[m];
+        const double *st = p.stats + p.goff[m] + k * V;
+        const int *ft = p.feat[m];
+        double acc = p.alphaf[p.row_alpha[r]];
+        for (int v = 0; v < V; ++v)
+            if (ft[v * nf + f] == j) acc += st[v];
+        p.gammaf[t] = acc;
+    }
+    __syncthreads();
+    immctm_compose(p, ism, ism + p.R);
+    __syncthreads();
+    for (int i = threadIdx.x; i < G; i += blockDim.x) p.gamma[i] = p.phi[i];      // model.γ has no K x V form here
 }
 
 // ------------------------------------------------------------------------------------------

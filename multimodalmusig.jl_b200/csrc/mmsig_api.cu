@@ -99,6 +99,8 @@ struct MmctmHost {
     int *d_status = nullptr;
     double *lamA = nullptr, *lamB = nullptr;
     double *snap[16] = {nullptr};       // best-restart snapshot of mmsig_mmctm_restarts, kept with the plan
+    std::vector<double> alphaf_host;    // IMMCTM: per-(modality, feature) alpha
+    std::vector<int> row_len_host, row_m_host;   // IMMCTM: J and modality of every feature-table row
     std::vector<double> alpha_host;
 };
 
@@ -842,6 +844,29 @@ static double mma_alpha(double x, double sumE, int K, int V, int stop_rule) {
 static int mmctm_update_alpha(mmsig_handle *h) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
+    if (p.factored) {            // src/IMMCTM.jl:223-241: one alpha per (modality, feature), on the feature tables
+        std::vector<double> E(p.T);
+        CU(cudaMemcpyAsync(E.data(), p.Elnphif, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<int> roff(p.R);
+        CU(cudaMemcpyAsync(roff.data(), p.row_off, p.R * sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        int r0 = 0;
+        for (int m = 0; m < p.M; ++m) {
+            const int nf = p.nfeat[m], K = p.K[m];
+            for (int f = 0; f < nf; ++f) {
+                double s = 0.0;
+                const int J = mm.row_len_host[r0 + f];
+                for (int k = 0; k < K; ++k)
+                    for (int j = 0; j < J; ++j) s += E[roff[r0 + k * nf + f] + j];
+                double &a = mm.alphaf_host[p.aoff[m] + f];
+                a = mma_alpha(a, s, K, J, h->stop_rule);
+            }
+            r0 += K * nf;
+        }
+        CU(cudaMemcpyAsync(p.alphaf, mm.alphaf_host.data(), mm.alphaf_host.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return 0;
+    }
     std::vector<double> E(mm.G);
     CU(cudaMemcpyAsync(E.data(), p.Elnphi, mm.G * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -941,7 +966,8 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     if ((rc = gather(h, mm.rank_p1, mm.gath_p1, P1, &g1))) return rc;
     {
         LaunchScope ls(h, "k_mstep1");
-        k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu, (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0);
+        if (p.factored) k_imstep1<<<1, 1024, (size_t)2 * p.R * sizeof(double), h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu);
+        else k_mstep1<<<1, 1024, 0, h->stream>>>(p, g1, h->nranks, freeze_topics, freeze_mu, (flags & MMSIG_FLAG_UNSMOOTHED) ? 1 : 0);
     }
     if ((flags & MMSIG_FLAG_AUTO_ALPHA) && !freeze_topics)       // src/MMCTM.jl:472-474, after update_γ!
         if ((rc = mmctm_update_alpha(h))) return rc;
@@ -995,6 +1021,7 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
 extern "C" int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *ll_out) {
     NEED(h, "null handle");
     NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    NEED(!(h->mm.p.factored && (flags & MMSIG_FLAG_UNSMOOTHED)), "the IMMCTM has no unsmoothed E-step (no transform in src/IMMCTM.jl)");
     CU(cudaSetDevice(h->device));
     int rc = mmctm_iterate_async(h, flags);
     if (rc) return rc;
@@ -1138,6 +1165,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
     trace.mark(same ? "plan reused" : "plan + allocations");
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
+    NEED(!p.factored, "mmsig_mmctm_fit_host takes the MMCTM's K x V state; use set_data / mmsig_immctm_set_state / fit for the IMMCTM");
     mm.has_data = false;
     mm.has_state = false;
     for (int m = 0; m < M; ++m) {
@@ -1408,6 +1436,117 @@ extern "C" int32_t mmsig_debug_math(mmsig_handle *h, int32_t fn, int64_t n, cons
     return 0;
 }
 
+// ---- IMMCTM (reference src/IMMCTM.jl): feature-factorised topics on the MMCTM path -----------------
+// Every per-sample kernel is the MMCTM's over composite K x V tables; only the M-step over the
+// feature tables (k_imstep1) and two table terms of the ELBO differ.
+extern "C" int32_t mmsig_immctm_set_features(mmsig_handle *h, const int32_t *nfeat, const int32_t *const *features) {
+    NEED(h && nfeat && features, "null argument");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_data, "mmsig_mmctm_set_data first");
+    NEED(!mm.p.factored, "features are already set for this corpus");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    std::vector<int> ent_row, row_off, row_len, row_alpha, row_m;
+    p.foff[0] = 0;
+    p.aoff[0] = 0;
+    int rc;
+    for (int m = 0; m < p.M; ++m) {
+        const int nf = nfeat[m], V = p.V[m];
+        NEED(nf >= 1 && nf <= 16 && features[m], "1 <= features per modality <= 16");
+        std::vector<int> J(nf, 0);
+        for (int v = 0; v < V; ++v)
+            for (int f = 0; f < nf; ++f) {
+                const int x = features[m][(size_t)v * nf + f];
+                NEED(x >= 0, "feature values are 0-based and non-negative");
+                J[f] = std::max(J[f], x + 1);               // J = maximum(features, dims=1), src/IMMCTM.jl:44
+            }
+        int *dfeat = nullptr;
+        if ((rc = dev_alloc(h, h->allocs_mm, &dfeat, (size_t)V * nf))) return rc;
+        CU(cudaMemcpyAsync(dfeat, features[m], (size_t)V * nf * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+        p.feat[m] = dfeat;
+        p.nfeat[m] = nf;
+        int t = p.foff[m];
+        for (int k = 0; k < p.K[m]; ++k)
+            for (int f = 0; f < nf; ++f) {
+                row_off.push_back(t);
+                row_len.push_back(J[f]);
+                row_alpha.push_back(p.aoff[m] + f);
+                row_m.push_back(m);
+                for (int j = 0; j < J[f]; ++j) ent_row.push_back((int)row_off.size() - 1);
+                t += J[f];
+            }
+        p.foff[m + 1] = t;
+        p.aoff[m + 1] = p.aoff[m] + nf;
+    }
+    p.T = p.foff[p.M];
+    p.R = (int)row_off.size();
+    if ((size_t)2 * p.R * sizeof(double) > 48 * 1024) return fail(h, MMSIG_ELIMIT, "too many feature-table rows");
+    auto up = [&](const std::vector<int> &v, const int **dst) -> int {
+        int *d = nullptr;
+        int r = dev_alloc(h, h->allocs_mm, &d, v.size());
+        if (r) return r;
+        if (cudaMemcpyAsync(d, v.data(), v.size() * sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+            return fail(h, MMSIG_ECUDA, "cudaMemcpyAsync (feature index tables)");
+        *dst = d;
+        return 0;
+    };
+    if ((rc = up(ent_row, &p.ent_row)) || (rc = up(row_off, &p.row_off)) || (rc = up(row_len, &p.row_len)) ||
+        (rc = up(row_alpha, &p.row_alpha)))
+        return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.gammaf, (size_t)p.T))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.Elnphif, (size_t)p.T))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &p.alphaf, (size_t)p.aoff[p.M]))) return rc;
+    CU(cudaStreamSynchronize(h->stream));            // the index vectors go out of scope
+    mm.row_len_host = row_len;
+    mm.row_m_host = row_m;
+    p.factored = 1;
+    mm.has_state = false;
+    return 0;
+}
+
+// model.α ([m][i]), γ ([m][k][i][j] flat), λ, ν, μ, Σ, invΣ; NULL => the constructor's value (src/IMMCTM.jl:48-77)
+extern "C" int32_t mmsig_immctm_set_state(mmsig_handle *h, const double *alphaf, const double *gammaf, const double *lambda,
+                                          const double *nu, const double *mu, const double *Sigma, const double *invSigma) {
+    NEED(h && alphaf && gammaf, "alpha and gamma are required");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_data && mm.p.factored, "mmsig_mmctm_set_data and mmsig_immctm_set_features first");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    const int nA = p.aoff[p.M];
+    for (int i = 0; i < nA; ++i) NEED(alphaf[i] > 0, "alpha must be > 0");
+    mm.alphaf_host.assign(alphaf, alphaf + nA);
+    // the K x V gamma of the MMCTM state call is a placeholder here: k_icompose overwrites every table it seeds
+    std::vector<double> a0(p.M, 1.0), g0((size_t)mm.G, 1.0);
+    p.factored = 0;                                   // the plain call derives Elnphi from the placeholder ...
+    int rc = mmsig_mmctm_set_state(h, a0.data(), g0.data(), lambda, nu, mu, Sigma, invSigma);
+    p.factored = 1;
+    if (rc) return rc;
+    mm.has_state = false;
+    CU(cudaMemcpyAsync(p.alphaf, alphaf, nA * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(p.gammaf, gammaf, p.T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, "k_icompose");              // ... and this replaces it by the composite tables (:69-70)
+        k_icompose<<<1, 1024, (size_t)2 * p.R * sizeof(double), h->stream>>>(p);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    mm.has_state = true;
+    return 0;
+}
+
+extern "C" int32_t mmsig_immctm_get_tables(mmsig_handle *h, double *gammaf, double *Elnphif, double *alphaf) {
+    NEED(h, "null handle");
+    MmctmHost &mm = h->mm;
+    NEED(mm.has_state && mm.p.factored, "mmsig_immctm_set_state first");
+    CU(cudaSetDevice(h->device));
+    MmctmDev &p = mm.p;
+    if (gammaf) CU(cudaMemcpyAsync(gammaf, p.gammaf, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Elnphif) CU(cudaMemcpyAsync(Elnphif, p.Elnphif, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    if (alphaf) memcpy(alphaf, mm.alphaf_host.data(), mm.alphaf_host.size() * sizeof(double));
+    return 0;
+}
+
 // ---- restarts (config 5) ----------------------------------------------------------------------
 extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double *gamma0, int32_t maxiter, double tol,
                                         uint32_t flags, double *elbo_out, double *ll_out, int32_t *n_iter_out,
@@ -1415,6 +1554,7 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
     NEED(h, "null handle");
     MmctmHost &mm = h->mm;
     NEED(mm.has_state, "mmsig_mmctm_set_state first (it provides alpha)");
+    NEED(!mm.p.factored, "restarts of the IMMCTM are not wired (gamma0 is a K x V table)");
     NEED(R >= 1 && gamma0 && maxiter >= 1, "R >= 1, gamma0 and maxiter >= 1 required");
     CU(cudaSetDevice(h->device));
     MmctmDev &p = mm.p;

@@ -318,6 +318,52 @@ def _converged(prev, cur, tol):
     return bool(r < tol)
 
 
+class IMMCTM(MMCTM):
+    """src/IMMCTM.jl:1-108: an MMCTM whose topics factorise over features.
+    features: list over modalities of (V_m, I_m) integer arrays, 0-BASED feature values
+    (model.features[m] .- 1); alpha: one value per modality (src/IMMCTM.jl:93-100) or per (modality,
+    feature); gammaf0: flat [m][k][i][j] table (the constructor draws rand(1:100), :60-67).
+    fit / iterate / calculate_elbo / state are the MMCTM's; state()['gamma'] is a placeholder."""
+
+    def __init__(self, K, alpha, features, counts, gammaf0=None, rng=None, **kw):
+        self.features = [np.ascontiguousarray(f, dtype=np.int32) for f in features]
+        self.I = [f.shape[1] for f in self.features]
+        self.J = [[int(f[:, i].max()) + 1 for i in range(f.shape[1])] for f in self.features]
+        self.alphaf = np.concatenate([np.full(n, float(a)) if np.ndim(a) == 0 else np.asarray(a, float)
+                                      for a, n in zip(alpha, self.I)])
+        self.T = sum(int(k) * sum(j) for k, j in zip(K, self.J))
+        if gammaf0 is None:
+            rng = np.random.default_rng() if rng is None else rng
+            gammaf0 = rng.integers(1, 101, size=self.T).astype(np.float64)
+        self._gammaf0 = np.ascontiguousarray(gammaf0, dtype=np.float64)
+        V = [f.shape[0] for f in self.features]
+        self._in_ctor = True          # MMCTM.__init__ calls set_state with its K x V placeholder
+        super().__init__(K, [1.0] * len(V), counts, V=V, gamma0=np.ones(sum(int(k) * v for k, v in zip(K, V))), **kw)
+        self._in_ctor = False
+
+    def _set_data(self, counts, D_total):
+        super()._set_data(counts, D_total)
+        M = self.M
+        nf = np.asarray(self.I, np.int32)
+        fp = (capi.c_i32p * M)(*[f.ctypes.data_as(capi.c_i32p) for f in self.features])
+        self.h.check(self.h.lib.mmsig_immctm_set_features(self.h.h, nf.ctypes.data_as(capi.c_i32p), fp))
+
+    def set_state(self, gamma=None, lam=None, nu=None, mu=None, Sigma=None, invSigma=None, alpha=None):
+        """gamma: the flat feature table [m][k][i][j] (None / the constructor's placeholder -> gammaf0)."""
+        g = self._gammaf0 if gamma is None or self._in_ctor else capi.f64(gamma, self.T)
+        if alpha is not None:
+            self.alphaf = np.asarray(alpha, dtype=np.float64).copy()
+        D, MK = self.D, self.MK
+        a = [capi.f64(self.alphaf, sum(self.I)), capi.f64(g, self.T), capi.f64(lam, D * MK), capi.f64(nu, D * MK),
+             capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
+        self.h.check(self.h.lib.mmsig_immctm_set_state(self.h.h, *[capi.dp(x) for x in a]))
+
+    def tables(self):
+        g, e, a = np.empty(self.T), np.empty(self.T), np.empty(sum(self.I))
+        self.h.check(self.h.lib.mmsig_immctm_get_tables(self.h.h, capi.dp(g), capi.dp(e), capi.dp(a)))
+        return dict(gammaf=g, Elnphif=e, alphaf=a)
+
+
 class LDA:
     """src/LDA.jl:1-67.  counts: (rowptr, term0, count)."""
 

@@ -1,0 +1,66 @@
+"""IMMCTM (reference src/IMMCTM.jl) on the MMCTM's kernels with the feature-table M-step
+(k_imstep1): against the oracle's pinned arithmetic, bit-exact like the MMCTM."""
+import numpy as np
+import pytest
+
+import orc
+import mmsig
+from mmsig.counts import make_count_csr
+
+pytestmark = pytest.mark.gpu
+
+
+def _grid_features(*sizes):
+    """All combinations of feature values (e.g. mutation type x context), one term per row."""
+    g = np.stack(np.meshgrid(*[np.arange(s) for s in sizes], indexing="ij"), -1).reshape(-1, len(sizes))
+    return np.ascontiguousarray(g, dtype=np.int32)
+
+
+def _case(seed, D, K, feats, autoalpha=False, iters=3):
+    rng = np.random.default_rng(seed)
+    counts = [make_count_csr(rng.poisson(2.0, size=(f.shape[0], D))) for f in feats]
+    J = [[int(f[:, i].max()) + 1 for i in range(f.shape[1])] for f in feats]
+    T = sum(k * sum(j) for k, j in zip(K, J))
+    g0 = rng.integers(1, 101, T).astype(float)
+    alpha = [0.1 + 0.05 * m for m in range(len(K))]
+    o = orc.OracleIMMCTM(K, alpha, feats, counts, g0, arith=orc.ARITH_DET, nthreads=8)
+    g = mmsig.IMMCTM(K, alpha, feats, counts, gammaf0=g0)
+    for _ in range(iters):
+        ll_o = o.iterate(autoalpha=autoalpha)
+        ll_g = g.iterate(flags=mmsig.capi.FLAG_UPDATE_SIGMA | (mmsig.capi.FLAG_AUTO_ALPHA if autoalpha else 0))
+        s, t = g.state(), g.tables()
+        for k in ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "Elnphi", "phi", "props"):
+            assert np.array_equal(s[k], getattr(o, k)), k
+        assert np.array_equal(t["gammaf"], o.gammaf) and np.array_equal(t["Elnphif"], o.Elnphif)
+        assert np.array_equal(ll_g, ll_o)
+        if autoalpha:
+            np.testing.assert_allclose(t["alphaf"], o.alphaf, rtol=1e-12)
+    eo, eg = o.elbo(), g.calculate_elbo()
+    assert abs(eg[0] - eo[0]) <= 1e-12 * abs(eo[0]), (eg, eo)
+    np.testing.assert_allclose(eg[1], eo[1], rtol=1e-10, atol=1e-6)
+    g.close()
+
+
+def test_immctm_two_modalities():
+    _case(1, 300, [3, 2], [_grid_features(6, 4, 4), _grid_features(5)])       # SNV-like 96 terms as 6 x 4 x 4, plus a flat modality
+
+
+def test_immctm_three_modalities_and_a_one_feature_model():
+    _case(2, 150, [4, 3, 2], [_grid_features(3, 2), _grid_features(2, 2, 2), _grid_features(7)], iters=2)
+    _case(3, 97, [2], [_grid_features(9)], iters=2)
+
+
+def test_immctm_auto_alpha():
+    _case(4, 200, [3, 2], [_grid_features(4, 3), _grid_features(2, 5)], autoalpha=True, iters=2)
+
+
+def test_immctm_refuses_what_it_has_not():
+    feats = [_grid_features(3, 2)]
+    rng = np.random.default_rng(5)
+    counts = [make_count_csr(rng.poisson(2.0, size=(6, 40)))]
+    g = mmsig.IMMCTM([2], [0.1], feats, counts, rng=rng)
+    with pytest.raises(mmsig.capi.MmsigError):
+        g.iterate(flags=mmsig.capi.FLAG_UNSMOOTHED | mmsig.capi.FLAG_FREEZE_TOPICS)
+    with pytest.raises(mmsig.capi.MmsigError):
+        g.fit_restarts(np.ones((2, 2 * 6)), maxiter=2)
+    g.close()
