@@ -358,6 +358,22 @@ class IMMCTM(MMCTM):
              capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
         self.h.check(self.h.lib.mmsig_immctm_set_state(self.h.h, *[capi.dp(x) for x in a]))
 
+    def fit_heldout(self, counts_heldout, maxiter=100, verbose=False, device=0):
+        """fit_heldout(Xheldout, model::IMMCTM; maxiter=100) (src/IMMCTM.jl:547-579): a model on the
+        held-out samples with this one's μ, Σ, invΣ and feature tables; per iteration E-step and LL."""
+        s, t = self.state(props=False), self.tables()
+        new = IMMCTM(self.K, [t["alphaf"][sum(self.I[:m]):sum(self.I[:m + 1])] for m in range(self.M)], self.features,
+                     counts_heldout, gammaf0=t["gammaf"], device=device)
+        new.set_state(t["gammaf"], mu=s["mu"], Sigma=s["Sigma"], invSigma=s["invSigma"])
+        new.ll_history = new._loop(capi.FLAG_FREEZE_TOPICS | capi.FLAG_FREEZE_MU, maxiter, 1e-4, verbose)
+        return new
+
+    def transform(self, *a, **k):
+        raise NotImplementedError("the reference defines no transform for the IMMCTM")
+
+    def predict_modality_eta(self, *a, **k):
+        raise NotImplementedError("predict_modality_η of the IMMCTM (src/IMMCTM.jl:581-627) is not wired yet")
+
     def tables(self):
         g, e, a = np.empty(self.T), np.empty(self.T), np.empty(sum(self.I))
         self.h.check(self.h.lib.mmsig_immctm_get_tables(self.h.h, capi.dp(g), capi.dp(e), capi.dp(a)))

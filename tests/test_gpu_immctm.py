@@ -64,3 +64,28 @@ def test_immctm_refuses_what_it_has_not():
     with pytest.raises(mmsig.capi.MmsigError):
         g.fit_restarts(np.ones((2, 2 * 6)), maxiter=2)
     g.close()
+
+
+def test_immctm_fit_heldout():
+    """fit_heldout (src/IMMCTM.jl:547-579): frozen feature tables and Gaussian prior, E-step + LL only."""
+    rng = np.random.default_rng(6)
+    feats = [_grid_features(4, 3), _grid_features(6)]
+    K, alpha = [3, 2], [0.1, 0.2]
+    tr = [make_count_csr(rng.poisson(2.0, size=(f.shape[0], 200))) for f in feats]
+    ho = [make_count_csr(rng.poisson(2.0, size=(f.shape[0], 77))) for f in feats]
+    T = sum(k * sum(int(f[:, i].max()) + 1 for i in range(f.shape[1])) for k, f in zip(K, feats))
+    g0 = rng.integers(1, 101, T).astype(float)
+    o = orc.OracleIMMCTM(K, alpha, feats, tr, g0, arith=orc.ARITH_DET, nthreads=8)
+    g = mmsig.IMMCTM(K, alpha, feats, tr, gammaf0=g0)
+    for _ in range(3):
+        o.iterate(); g.iterate()
+    oh = orc.OracleIMMCTM(K, alpha, feats, ho, o.gammaf.copy(), arith=orc.ARITH_DET, nthreads=8)
+    oh.mu[:] = o.mu; oh.Sigma[:] = o.Sigma; oh.invSigma[:] = o.invSigma
+    ll_o = [oh.iterate_flags(orc.FLAG_FREEZE_TOPICS | orc.FLAG_FREEZE_MU) for _ in range(4)]
+    gh = g.fit_heldout(ho, maxiter=4)
+    assert np.array_equal(gh.ll_history, np.asarray(ll_o))
+    s = gh.state()
+    for k in ("lam", "nu", "zeta", "props", "phi", "Elnphi"):
+        assert np.array_equal(s[k], getattr(oh, k)), k
+    assert np.array_equal(gh.tables()["gammaf"], o.gammaf)
+    g.close(); gh.close()
