@@ -371,8 +371,32 @@ class IMMCTM(MMCTM):
     def transform(self, *a, **k):
         raise NotImplementedError("the reference defines no transform for the IMMCTM")
 
-    def predict_modality_eta(self, *a, **k):
-        raise NotImplementedError("predict_modality_η of the IMMCTM (src/IMMCTM.jl:581-627) is not wired yet")
+    def _table_slices(self):
+        """(start, stop) of every modality in the flat [m][k][i][j] tables and in alphaf."""
+        t = np.cumsum([0] + [int(k) * sum(j) for k, j in zip(self.K, self.J)])
+        a = np.cumsum([0] + self.I)
+        return t, a
+
+    def predict_modality_eta(self, counts_obs, m, maxiter=100, device=0):
+        """predict_modality_η(Xobs, m, model::IMMCTM; maxiter=100) (src/IMMCTM.jl:581-627): fit λ on the
+        observed modalities with their feature tables and the Gaussian prior frozen, then
+        η_u = μ_u + Σ_uo invΣ[o,o] (λ - μ_o).  Runs exactly `maxiter` E-steps, like the MMCTM's."""
+        s, t = self.state(props=False), self.tables()
+        obsM = [i for i in range(self.M) if i != m]
+        ko = np.cumsum([0] + self.K)
+        ts, asl = self._table_slices()
+        un = np.arange(ko[m], ko[m + 1])
+        ob = np.concatenate([np.arange(ko[i], ko[i + 1]) for i in obsM])
+        g_obs = np.concatenate([t["gammaf"][ts[i]:ts[i + 1]] for i in obsM])
+        om = IMMCTM([self.K[i] for i in obsM], [t["alphaf"][asl[i]:asl[i + 1]] for i in obsM],
+                    [self.features[i] for i in obsM], counts_obs, gammaf0=g_obs, device=device)
+        om.set_state(g_obs, mu=s["mu"][ob], Sigma=s["Sigma"][np.ix_(ob, ob)], invSigma=s["invSigma"][np.ix_(ob, ob)])
+        for _ in range(maxiter):
+            om.iterate(flags=capi.FLAG_FREEZE_TOPICS | capi.FLAG_FREEZE_MU)
+        lam = om.lam
+        om.close()
+        A = s["Sigma"][np.ix_(un, ob)] @ s["invSigma"][np.ix_(ob, ob)]
+        return s["mu"][un] + (lam - s["mu"][ob]) @ A.T
 
     def tables(self):
         g, e, a = np.empty(self.T), np.empty(self.T), np.empty(sum(self.I))

@@ -89,3 +89,31 @@ def test_immctm_fit_heldout():
         assert np.array_equal(s[k], getattr(oh, k)), k
     assert np.array_equal(gh.tables()["gammaf"], o.gammaf)
     g.close(); gh.close()
+
+
+def test_immctm_predict_modality_eta():
+    """predict_modality_η (src/IMMCTM.jl:581-627): the observed modalities' sub-model with frozen tables."""
+    rng = np.random.default_rng(7)
+    feats = [_grid_features(4, 3), _grid_features(2, 2, 2), _grid_features(5)]
+    K, alpha = [3, 2, 2], [0.1, 0.1, 0.1]
+    tr = [make_count_csr(rng.poisson(2.0, size=(f.shape[0], 250))) for f in feats]
+    J = [[int(f[:, i].max()) + 1 for i in range(f.shape[1])] for f in feats]
+    ts = np.cumsum([0] + [k * sum(j) for k, j in zip(K, J)])
+    g0 = rng.integers(1, 101, ts[-1]).astype(float)
+    o = orc.OracleIMMCTM(K, alpha, feats, tr, g0, arith=orc.ARITH_DET, nthreads=8)
+    g = mmsig.IMMCTM(K, alpha, feats, tr, gammaf0=g0)
+    for _ in range(3):
+        o.iterate(); g.iterate()
+    m = 1
+    obs = [make_count_csr(rng.poisson(2.0, size=(feats[i].shape[0], 60))) for i in (0, 2)]
+    eta = g.predict_modality_eta(obs, m, maxiter=5)
+    ob, un = np.r_[0:3, 5:7], np.r_[3:5]
+    g_obs = np.concatenate([o.gammaf[ts[0]:ts[1]], o.gammaf[ts[2]:ts[3]]])
+    oc = orc.OracleIMMCTM([3, 2], [0.1, 0.1], [feats[0], feats[2]], obs, g_obs, arith=orc.ARITH_DET, nthreads=8)
+    oc.mu[:] = o.mu[ob]; oc.Sigma[:] = o.Sigma[np.ix_(ob, ob)]; oc.invSigma[:] = o.invSigma[np.ix_(ob, ob)]
+    for _ in range(5):
+        oc.iterate_flags(orc.FLAG_FREEZE_TOPICS | orc.FLAG_FREEZE_MU)
+    ref = o.mu[un] + (oc.lam - o.mu[ob]) @ (o.Sigma[np.ix_(un, ob)] @ o.invSigma[np.ix_(ob, ob)]).T
+    assert eta.shape == (60, 2)
+    np.testing.assert_array_equal(eta, ref)
+    g.close()
