@@ -177,7 +177,9 @@ int32_t mmsig_mmctm_get_evals(mmsig_handle *h, int32_t *nev_nu, int32_t *nev_lam
  * a placeholder, Elnphi / phi are the composite tables), mmsig_immctm_get_tables.
  * features[m]: V_m x I_m row-major, 0-BASED feature values (model.features[m] - 1); tables are flat
  * [m][k][i][j] (model.γ[m][k][i][j]), alpha [m][i] (model.α[m][i]).  MMSIG_FLAG_AUTO_ALPHA is
- * update_α! of :223-241; MMSIG_FLAG_UNSMOOTHED is refused (the IMMCTM has no transform). */
+ * update_α! of :223-241; MMSIG_FLAG_UNSMOOTHED is refused (the IMMCTM has no transform).
+ * mmsig_mmctm_restarts takes R feature tables ([r][m][k][i][j]) as gamma0 in this mode; mmsig_mmctm_fit_host
+ * is the MMCTM's only. */
 int32_t mmsig_immctm_set_features(mmsig_handle *h, const int32_t *nfeat, const int32_t *const *features);
 int32_t mmsig_immctm_set_state(mmsig_handle *h, const double *alphaf, const double *gammaf, const double *lambda,
                                const double *nu, const double *mu, const double *Sigma, const double *invSigma);

@@ -1554,11 +1554,11 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
     NEED(h, "null handle");
     MmctmHost &mm = h->mm;
     NEED(mm.has_state, "mmsig_mmctm_set_state first (it provides alpha)");
-    NEED(!mm.p.factored, "restarts of the IMMCTM are not wired (gamma0 is a K x V table)");
     NEED(R >= 1 && gamma0 && maxiter >= 1, "R >= 1, gamma0 and maxiter >= 1 required");
     CU(cudaSetDevice(h->device));
     MmctmDev &p = mm.p;
     const size_t DMK = (size_t)p.D * p.MK, G = mm.G, MK2 = (size_t)p.MK * p.MK, DM = (size_t)p.D * p.M;
+    const size_t GT = p.factored ? (size_t)p.T : G;       // a restart's gamma0: K x V tables, or the IMMCTM's [m][k][i][j] tables
     // snapshot buffers for the best restart
     struct Snap { double **live; size_t n; double *copy; };
     std::vector<Snap> snaps = {{&p.lam, DMK, nullptr}, {&p.lam_prev, DMK, nullptr}, {&p.nu, DMK, nullptr},
@@ -1566,6 +1566,10 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
                                {&p.Elnphi, G, nullptr}, {&p.Elnphi_prev, G, nullptr}, {&p.phi, G, nullptr},
                                {&p.stats, G, nullptr}, {&p.mu, (size_t)p.MK, nullptr}, {&p.Sigma, MK2, nullptr},
                                {&p.invSigma, MK2, nullptr}};
+    if (p.factored) {
+        snaps.push_back({&p.gammaf, (size_t)p.T, nullptr});
+        snaps.push_back({&p.Elnphif, (size_t)p.T, nullptr});
+    }
     // the snapshot buffers live with the plan: a cudaMalloc / cudaFree pair per call costs up to
     // 0.9 s of driver time for the frees alone (measured, MMSIG_TRACE) against 0.6 s of fitting
     if (R > 1)
@@ -1577,14 +1581,15 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
             snaps[i].copy = mm.snap[i];
         }
     std::vector<double> hist((size_t)maxiter * p.M);
-    std::vector<double> alpha = mm.alpha_host;
+    std::vector<double> alpha = mm.alpha_host, alphaf = mm.alphaf_host;
     HostTrace trace;
     trace.mark("restarts: snapshot buffers");
     int best_r = -1;
     double best_e = 0.0;
     int rc = 0;
     for (int r = 0; r < R && !rc; ++r) {
-        rc = mmsig_mmctm_set_state(h, alpha.data(), gamma0 + (size_t)r * G, nullptr, nullptr, nullptr, nullptr, nullptr);
+        rc = p.factored ? mmsig_immctm_set_state(h, alphaf.data(), gamma0 + (size_t)r * GT, nullptr, nullptr, nullptr, nullptr, nullptr)
+                        : mmsig_mmctm_set_state(h, alpha.data(), gamma0 + (size_t)r * GT, nullptr, nullptr, nullptr, nullptr, nullptr);
         if (rc) break;
         int nit = 0, conv = 0;
         trace.mark("restart: state set");

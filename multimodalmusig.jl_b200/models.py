@@ -371,6 +371,14 @@ class IMMCTM(MMCTM):
     def transform(self, *a, **k):
         raise NotImplementedError("the reference defines no transform for the IMMCTM")
 
+    def fit_restarts(self, gammaf0s, maxiter=100, tol=1e-4, updateSigma=True):
+        """R independent restarts from the constructor state with the feature tables gammaf0s[r]."""
+        G, self.G = self.G, self.T            # MMCTM.fit_restarts sizes a restart's table by self.G
+        try:
+            return super().fit_restarts(gammaf0s, maxiter=maxiter, tol=tol, updateSigma=updateSigma)
+        finally:
+            self.G = G
+
     def _table_slices(self):
         """(start, stop) of every modality in the flat [m][k][i][j] tables and in alphaf."""
         t = np.cumsum([0] + [int(k) * sum(j) for k, j in zip(self.K, self.J)])

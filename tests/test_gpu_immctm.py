@@ -61,8 +61,28 @@ def test_immctm_refuses_what_it_has_not():
     g = mmsig.IMMCTM([2], [0.1], feats, counts, rng=rng)
     with pytest.raises(mmsig.capi.MmsigError):
         g.iterate(flags=mmsig.capi.FLAG_UNSMOOTHED | mmsig.capi.FLAG_FREEZE_TOPICS)
-    with pytest.raises(mmsig.capi.MmsigError):
-        g.fit_restarts(np.ones((2, 2 * 6)), maxiter=2)
+    g.close()
+
+
+def test_immctm_restarts():
+    """Independent restarts (README.md:42) of the IMMCTM: per-restart ELBO, LL and the best state."""
+    rng = np.random.default_rng(8)
+    feats = [_grid_features(4, 3), _grid_features(6)]
+    K, alpha = [3, 2], [0.1, 0.1]
+    counts = [make_count_csr(rng.poisson(2.0, size=(f.shape[0], 150))) for f in feats]
+    T = 3 * 7 + 2 * 6
+    g0s = rng.integers(1, 101, size=(3, T)).astype(float)
+    g = mmsig.IMMCTM(K, alpha, feats, counts, gammaf0=g0s[0])
+    elbo, ll, nit, best = g.fit_restarts(g0s, maxiter=4)
+    ref = []
+    for r in range(3):
+        o = orc.OracleIMMCTM(K, alpha, feats, counts, g0s[r], arith=orc.ARITH_DET, nthreads=8)
+        h = o.fit(maxiter=4)
+        ref.append((o.elbo()[0], h[-1], o.gammaf.copy(), o.lam.copy()))
+        assert np.array_equal(ll[r], h[-1])
+        assert abs(elbo[r] - ref[r][0]) <= 1e-12 * abs(ref[r][0])
+    assert best == int(np.argmax([x[0] for x in ref])) and list(nit) == [4, 4, 4]
+    assert np.array_equal(g.tables()["gammaf"], ref[best][2]) and np.array_equal(g.state()["lam"], ref[best][3])
     g.close()
 
 
