@@ -12,7 +12,7 @@
 module MMSigB200
 
 using MultiModalMuSig
-import MultiModalMuSig: fit!, fit_heldout, transform, MMCTM, LDA, check_convergence
+import MultiModalMuSig: fit!, fit_heldout, transform, MMCTM, IMMCTM, LDA, check_convergence
 
 const LIB = get(ENV, "MMSIG_LIB", joinpath(@__DIR__, "..", "multimodalmusig.jl_b200", "libmmsig.so"))
 
@@ -216,6 +216,77 @@ function transform(model::MMCTM, X::Vector{Vector{Matrix{Int}}}; maxiter=1000, t
     end
     flags = UInt32(2 | 8 | (fit_gaussian ? 1 : 4))
     return frozen_loop!(newmodel, model.ϕ, flags; maxiter=maxiter, tol=tol, verbose=verbose, device=device)
+end
+
+# ---- fit!(::IMMCTM) (src/IMMCTM.jl:525-545): the MMCTM's device path over composite tables; the
+# feature tables travel flat in the index order model.γ[m][k][i][j], model.α[m][i], and
+# model.features[m] goes over as a V x I row-major block of 0-based values.
+flat_ftables(t) = collect(reduce(vcat, [reduce(vcat, [reduce(vcat, tk) for tk in tm]) for tm in t]))   # [m][k][i][j]
+
+function fit!(model::IMMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, device=0, stop_rule=0)
+    D, M, MK = model.D, model.M, sum(model.K)
+    rowptr, term, count = flatten_counts(model.X, M)
+    K32, V32, I32 = Int32.(model.K), Int32.(model.V), Int32.(model.I)
+    feats = [Int32.(collect(transpose(model.features[m] .- 1))) for m in 1:M]      # I x V column-major = V x I row-major
+    λ, ν = flat_rows(model.λ), flat_rows(model.ν)
+    γ, α = flat_ftables(model.γ), collect(reduce(vcat, model.α))
+    Σ, invΣ = collect(transpose(model.Σ)), collect(transpose(model.invΣ))
+    h = create(device=device, stop_rule=stop_rule)
+    ll = Vector{Float64}[]
+    try
+        GC.@preserve rowptr term count feats begin
+            rp = [pointer(r) for r in rowptr]; tp = [pointer(t) for t in term]; cp = [pointer(c) for c in count]
+            fp = [pointer(f) for f in feats]
+            check(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
+                (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                h, D, D, M, K32, V32, rp, tp, cp))
+            check(h, ccall((:mmsig_immctm_set_features, LIB), Int32, (Ptr{Cvoid}, Ptr{Int32}, Ptr{Ptr{Int32}}), h, I32, fp))
+        end
+        check(h, ccall((:mmsig_immctm_set_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, α, γ, λ, ν, model.μ, Σ, invΣ))
+        flags = UInt32(1 | (autoα ? 16 : 0))                    # the IMMCTM's fit! always updates Σ (:533)
+        llbuf = zeros(M)
+        for iter in 1:maxiter
+            check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+            push!(ll, copy(llbuf))
+            verbose && println("$iter\tLog-likelihoods: ", join(ll[end], ", "))
+            if length(ll) > 10 && check_convergence(ll, tol=tol)
+                model.converged = true
+                break
+            end
+        end
+        elbo = Ref(0.0)
+        check(h, ccall((:mmsig_mmctm_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
+        ζ = zeros(D * M); μ = zeros(MK); Elnϕ = similar(γ)
+        check(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, λ, ν, ζ, μ, Σ, invΣ, C_NULL, C_NULL, C_NULL, C_NULL))
+        check(h, ccall((:mmsig_immctm_get_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}), h, γ, Elnϕ, α))
+        for d in 1:D
+            model.λ[d] .= @view λ[(d - 1) * MK + 1:d * MK]
+            model.ν[d] .= @view ν[(d - 1) * MK + 1:d * MK]
+            model.ζ[d] .= @view ζ[(d - 1) * M + 1:d * M]
+        end
+        model.μ .= μ
+        model.Σ .= transpose(reshape(Σ, MK, MK)); model.invΣ .= transpose(reshape(invΣ, MK, MK))
+        o = 0; a = 0
+        for m in 1:M
+            for k in 1:model.K[m], i in 1:model.I[m]
+                r = (o + 1):(o + model.J[m][i])
+                model.γ[m][k][i] .= @view γ[r]; model.Elnϕ[m][k][i] .= @view Elnϕ[r]
+                o += model.J[m][i]
+            end
+            model.α[m] .= @view α[(a + 1):(a + model.I[m])]
+            a += model.I[m]
+        end
+        model.elbo = elbo[]
+        model.ll = ll[end]
+    finally
+        destroy(h)
+    end
+    return ll
 end
 
 function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
