@@ -1316,12 +1316,15 @@ orc_lda *orc_lda_new(int K, int V, int64_t D, const int64_t *rowptr,
     m->phi = (double *)malloc(sizeof(double) * (nnz ? nnz : 1) * K);
     for (int64_t t = 0; t < nnz * K; ++t) m->phi[t] = 1.0 / K;  /* :46-49 */
     m->nthreads = 1;
+    m->factored = 0; m->nfeat = 0; m->feat = NULL; m->J = NULL; m->T = 0;
+    m->etaf = m->lambdaf = m->Elnbetaf = NULL;
     return m;
 }
 
 void orc_lda_free(orc_lda *m)
 {
     if (!m) return;
+    if (m->factored) { free(m->feat); free(m->J); free(m->etaf); free(m->lambdaf); free(m->Elnbetaf); }
     free(m->rowptr); free(m->term); free(m->cnt); free(m->N);
     free(m->lambda); free(m->Elnbeta); free(m->beta);
     free(m->gamma); free(m->Elntheta); free(m->theta); free(m->phi);
@@ -1408,6 +1411,7 @@ double orc_lda_iterate_flags(orc_lda *m, unsigned flags)
 /* src/LDA.jl:96-98 */
 void orc_lda_update_Elnbeta(orc_lda *m)
 {
+    if (m->factored) { orc_ilda_update_Elnbeta(m); return; }
     for (int k = 0; k < m->K; ++k) {
         double s = 0.0;
         for (int v = 0; v < m->V; ++v) s += m->lambda[(size_t)k * m->V + v];
@@ -1421,6 +1425,31 @@ void orc_lda_update_Elnbeta(orc_lda *m)
 void orc_lda_update_lambda(orc_lda *m)
 {
     int K = m->K, V = m->V;
+    if (m->factored) {          /* src/ILDA.jl:105-125: lambda_i[j, :] = eta_i + sum over the nonzeros whose term carries j */
+        int nf = m->nfeat;
+        int64_t rowlen = m->T / K;
+        for (int k = 0; k < K; ++k) {
+            int64_t o = (int64_t)k * rowlen;
+            for (int f = 0; f < nf; ++f) {
+                for (int j = 0; j < m->J[f]; ++j) m->lambdaf[o + j] = m->etaf[f];
+                o += m->J[f];
+            }
+        }
+        for (int64_t d = 0; d < m->D; ++d)
+            for (int64_t w = m->rowptr[d]; w < m->rowptr[d + 1]; ++w) {
+                int v = m->term[w];
+                for (int k = 0; k < K; ++k) {
+                    double np = m->phi[(size_t)w * K + k] * (double)m->cnt[w];
+                    int64_t o = (int64_t)k * rowlen;
+                    for (int f = 0; f < nf; ++f) {
+                        m->lambdaf[o + m->feat[(size_t)v * nf + f]] += np;
+                        o += m->J[f];
+                    }
+                }
+            }
+        orc_ilda_update_Elnbeta(m);
+        return;
+    }
     for (int t = 0; t < V * K; ++t) m->lambda[t] = m->eta;
     for (int64_t d = 0; d < m->D; ++d)
         for (int64_t w = m->rowptr[d]; w < m->rowptr[d + 1]; ++w) {
@@ -1434,6 +1463,7 @@ void orc_lda_update_lambda(orc_lda *m)
 /* src/LDA.jl:110-112 */
 void orc_lda_update_beta(orc_lda *m)
 {
+    if (m->factored) { orc_ilda_compose(m); return; }      /* src/ILDA.jl:127-129 */
     for (int k = 0; k < m->K; ++k) {
         double s = 0.0;
         for (int v = 0; v < m->V; ++v) s += m->lambda[(size_t)k * m->V + v];
@@ -1480,6 +1510,18 @@ double orc_lda_elbo(const orc_lda *m, double *terms)
     /* ElnPbeta :114-118 */
     s = 0.0; for (int i = 0; i < V * K; ++i) s += m->Elnbeta[i];
     t[0] = K * (orc_lgamma(V * m->eta) - V * orc_lgamma(m->eta)) + (m->eta - 1) * s;
+    if (m->factored) {          /* src/ILDA.jl:131-140, per feature */
+        int64_t rowlen = m->T / K, fo = 0;
+        t[0] = 0.0;
+        for (int f = 0; f < m->nfeat; ++f) {
+            double se = 0.0;
+            for (int k = 0; k < K; ++k)
+                for (int j = 0; j < m->J[f]; ++j) se += m->Elnbetaf[(int64_t)k * rowlen + fo + j];
+            t[0] += K * (orc_lgamma(m->J[f] * m->etaf[f]) - m->J[f] * orc_lgamma(m->etaf[f]));
+            t[0] += (m->etaf[f] - 1) * se;
+            fo += m->J[f];
+        }
+    }
     /* ElnPtheta :120-124 */
     s = 0.0; for (int64_t i = 0; i < (int64_t)K * m->D; ++i) s += m->Elntheta[i];
     t[1] = m->D * (orc_lgamma(K * m->alpha) - K * orc_lgamma(m->alpha)) + (m->alpha - 1) * s;
@@ -1508,6 +1550,26 @@ double orc_lda_elbo(const orc_lda *m, double *terms)
         }
         for (int i = 0; i < V * K; ++i) c += (m->lambda[i] - 1) * m->Elnbeta[i];
         t[4] = a - b - c;
+        if (m->factored) {
+            /* src/ILDA.jl:174-181 as written: `lnq = ...` inside the loop over features, not `+=`, so
+               only the LAST feature contributes.  Reproduced (the ELBO is only reported, never optimised). */
+            int64_t rowlen = m->T / K, fo = 0;
+            for (int f = 0; f < m->nfeat; ++f) {
+                a = b = c = 0.0;
+                for (int k = 0; k < K; ++k) {
+                    double cs = 0.0;
+                    for (int j = 0; j < m->J[f]; ++j) {
+                        double l = m->lambdaf[(int64_t)k * rowlen + fo + j];
+                        a += orc_lgamma(l);
+                        cs += l;
+                        c += (l - 1) * m->Elnbetaf[(int64_t)k * rowlen + fo + j];
+                    }
+                    b += orc_lgamma(cs);
+                }
+                t[4] = a - b - c;
+                fo += m->J[f];
+            }
+        }
     }
     /* ElnQtheta :148-152 */
     {
@@ -1553,6 +1615,76 @@ int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist)
     return it;
 }
 
+
+/* =====================================================================
+ * ILDA (src/ILDA.jl): LDA whose topics factorise over features.  The per-sample updates
+ * (update_phi :64-78, update_gamma :84-92, log-likelihood :203-233) run over the composite
+ * tables Elnbeta_kv = sum_i Elnbeta_i[f(v,i), k] and beta_kv = prod_i beta_i[f(v,i), k] exactly as
+ * the LDA's (the literal reference adds / multiplies per nonzero: roundings only); the M-step
+ * (:105-129) runs over the feature tables, flat [k][i][j].
+ * ===================================================================== */
+void orc_ilda_compose(orc_lda *m)
+{
+    int K = m->K, V = m->V, nf = m->nfeat;
+    int64_t rowlen = m->T / K;
+    for (int k = 0; k < K; ++k)
+        for (int v = 0; v < V; ++v) {
+            double e = 0.0, b = 1.0;
+            int64_t o = (int64_t)k * rowlen;
+            for (int f = 0; f < nf; ++f) {
+                int j = m->feat[(size_t)v * nf + f];
+                double sl = 0.0;
+                for (int jj = 0; jj < m->J[f]; ++jj) sl += m->lambdaf[o + jj];
+                e += m->Elnbetaf[o + j];
+                b *= m->lambdaf[o + j] / sl;              /* update_beta!, :127-129 */
+                o += m->J[f];
+            }
+            m->Elnbeta[(size_t)k * V + v] = e;
+            m->beta[(size_t)k * V + v] = b;
+        }
+}
+
+/* src/ILDA.jl:97-103 */
+void orc_ilda_update_Elnbeta(orc_lda *m)
+{
+    int K = m->K, nf = m->nfeat;
+    int64_t rowlen = m->T / K;
+    for (int k = 0; k < K; ++k) {
+        int64_t o = (int64_t)k * rowlen;
+        for (int f = 0; f < nf; ++f) {
+            double sl = 0.0;
+            for (int j = 0; j < m->J[f]; ++j) sl += m->lambdaf[o + j];
+            double ds = digamma_a(m->arith, sl);
+            for (int j = 0; j < m->J[f]; ++j) m->Elnbetaf[o + j] = digamma_a(m->arith, m->lambdaf[o + j]) - ds;
+            o += m->J[f];
+        }
+    }
+    orc_ilda_compose(m);
+}
+
+void orc_ilda_enable(orc_lda *m, int nfeat, const int *feat, const double *etaf, const double *lambdaf0)
+{
+    int V = m->V;
+    m->nfeat = nfeat;
+    m->feat = (int *)malloc(sizeof(int) * (size_t)V * nfeat);
+    memcpy(m->feat, feat, sizeof(int) * (size_t)V * nfeat);
+    m->J = (int *)calloc(nfeat, sizeof(int));
+    int64_t rowlen = 0;
+    for (int f = 0; f < nfeat; ++f) {                     /* J = maximum(features, dims=1), :35 */
+        for (int v = 0; v < V; ++v)
+            if (feat[(size_t)v * nfeat + f] + 1 > m->J[f]) m->J[f] = feat[(size_t)v * nfeat + f] + 1;
+        rowlen += m->J[f];
+    }
+    m->T = rowlen * m->K;
+    m->etaf = (double *)malloc(sizeof(double) * nfeat);
+    memcpy(m->etaf, etaf, sizeof(double) * nfeat);
+    m->lambdaf = (double *)malloc(sizeof(double) * m->T);
+    m->Elnbetaf = (double *)malloc(sizeof(double) * m->T);
+    memcpy(m->lambdaf, lambdaf0, sizeof(double) * m->T);
+    m->factored = 1;
+    orc_ilda_update_Elnbeta(m);                           /* :42 */
+    for (int i = 0; i < m->K * V; ++i) m->lambda[i] = 0.0 / 0.0;     /* no K x V lambda in this model */
+}
 
 /* =====================================================================
  * IMMCTM (src/IMMCTM.jl): feature-factorised topics.  Everything per sample (zeta, theta, nu,

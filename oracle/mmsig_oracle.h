@@ -176,6 +176,14 @@ typedef struct {
     int nthreads;
     int converged;
     double elbo, ll;
+    /* ILDA (src/ILDA.jl): beta_kv = prod_i beta_i[f(v,i), k].  factored != 0: lambda / Elnbeta / beta
+       (K x V) above are COMPOSITE tables derived from the feature tables below ([k][i][j] flat). */
+    int factored, nfeat;
+    int *feat;                           /* V x I row-major, 0-BASED feature values */
+    int *J;                              /* [I] */
+    int64_t T;                           /* K * sum_i J_i */
+    double *etaf;                        /* [I] */
+    double *lambdaf, *Elnbetaf;
 } orc_lda;
 
 orc_lda *orc_lda_new(int K, int V, int64_t D, const int64_t *rowptr,
@@ -195,6 +203,12 @@ double orc_lda_iterate(orc_lda *m);         /* :202-209 */
 void orc_lda_unsmoothed_update_phi(orc_lda *m);               /* :226-231 */
 double orc_lda_iterate_flags(orc_lda *m, unsigned flags);     /* fit_heldout :275-280, transform :242-246 */
 int orc_lda_fit(orc_lda *m, int maxiter, double tol, double *ll_hist); /* :198-224 */
+
+/* ILDA (src/ILDA.jl:1-62): switch a freshly constructed LDA model to feature-factorised topics.
+ * feat V x I (0-based), etaf [I], lambdaf0 [k][i][j] (ctor: rand 1:100) */
+void orc_ilda_enable(orc_lda *m, int nfeat, const int *feat, const double *etaf, const double *lambdaf0);
+void orc_ilda_compose(orc_lda *m);            /* composite Elnbeta / beta from the feature tables */
+void orc_ilda_update_Elnbeta(orc_lda *m);     /* src/ILDA.jl:97-103 */
 
 /* IMMCTM (src/IMMCTM.jl:1-108): switch a freshly constructed model to feature-factorised topics.
  * nfeat[M], feat[m] V_m x I_m (0-based values), alphaf [m][i], gammaf0 [m][k][i][j] (ctor: rand 1:100) */

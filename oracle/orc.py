@@ -54,6 +54,8 @@ class LDA(C.Structure):
         ("gamma", c_dp), ("Elntheta", c_dp), ("theta", c_dp), ("phi", c_dp),
         ("arith", C.c_int), ("nthreads", C.c_int), ("converged", C.c_int),
         ("elbo", C.c_double), ("ll", C.c_double),
+        ("factored", C.c_int), ("nfeat", C.c_int), ("feat", c_ip), ("J", c_ip), ("T", C.c_int64),
+        ("etaf", c_dp), ("lambdaf", c_dp), ("Elnbetaf", c_dp),
     ]
 
 
@@ -73,6 +75,9 @@ def lib():
         f.restype = res
         f.argtypes = list(args)
 
+    sig("orc_ilda_enable", None, pl, i, c_ip, c_dp, c_dp)
+    sig("orc_ilda_compose", None, pl)
+    sig("orc_ilda_update_Elnbeta", None, pl)
     sig("orc_immctm_enable", None, pm, c_ip, C.POINTER(c_ip), c_dp, c_dp)
     sig("orc_immctm_update_Elnphi", None, pm)
     sig("orc_immctm_update_gamma", None, pm)
@@ -337,3 +342,30 @@ def make_count_csr(dense, layout=0):
     L.orc_make_count_csr(D, V, a.ctypes.data_as(c_i64p), layout, rowptr.ctypes.data_as(c_i64p),
                          term.ctypes.data_as(c_i32p), cnt.ctypes.data_as(c_i32p))
     return rowptr, term, cnt
+
+
+class OracleILDA(OracleLDA):
+    """ILDA (reference src/ILDA.jl): LDA whose topics factorise over features.
+    features: (V, I) integer array with 0-BASED feature values; eta: scalar or one per feature (:54-58);
+    lambdaf0: flat [k][i][j] table (the constructor's rand(1:100), :38)."""
+
+    def __init__(self, K, alpha, eta, features, counts, lambdaf0, arith=ARITH_LITERAL, nthreads=1):
+        f = np.ascontiguousarray(features, dtype=np.int32)
+        V, I = f.shape
+        self.I = I
+        self.J = [int(f[:, i].max()) + 1 for i in range(I)]
+        et = np.full(I, float(eta)) if np.ndim(eta) == 0 else np.asarray(eta, dtype=np.float64)
+        super().__init__(K, alpha, float(et[0]), V, counts, np.ones(int(K) * V), arith=arith, nthreads=nthreads)
+        self._feat = f
+        self.T = int(K) * sum(self.J)
+        l0 = np.ascontiguousarray(lambdaf0, dtype=np.float64)
+        assert l0.size == self.T
+        self.L.orc_ilda_enable(self.p, I, f.ctypes.data_as(c_ip), _dp(np.ascontiguousarray(et)), _dp(l0))
+
+    lambdaf = property(lambda s: s._arr("lambdaf", (s.T,)))
+    Elnbetaf = property(lambda s: s._arr("Elnbetaf", (s.T,)))
+    etaf = property(lambda s: s._arr("etaf", (s.I,)))
+
+    def table(self, flat, k, i):
+        o = k * sum(self.J) + sum(self.J[:i])
+        return flat[o:o + self.J[i]]
