@@ -207,6 +207,20 @@ int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, do
 /* model.ϕ[d] for all d, nnz x K row-major ([w][k]), recomputed lazily */
 int32_t mmsig_lda_get_phi(mmsig_handle *h, double *phi_out);
 
+/* ---- ILDA  (reference src/ILDA.jl): LDA whose topics factorise over features ---------------------
+ * beta_kv = prod_i beta_i[f(v,i), k].  The per-sample passes (update_phi / update_gamma / loglikelihood,
+ * src/ILDA.jl:60-103, :183-199) are the LDA's over composite K x V tables; the M-step (:105-129) runs over
+ * the feature tables.  Call order: mmsig_lda_set_data, mmsig_ilda_set_features, mmsig_ilda_set_state, then
+ * mmsig_lda_iterate / _iterate_flags / _fit / _elbo / _get_state (lambda there = the statistics sum n phi of
+ * the last M-step; Elnbeta / beta are the composite tables), mmsig_ilda_get_tables.
+ * features: V x I row-major, 0-BASED feature values (model.features - 1); tables are flat [k][i][j]
+ * (model.lambda[i][j, k]); eta [i] (model.eta[i], :54-58 fills a scalar).  mmsig_lda_elbo evaluates
+ * calculate_ElnQbeta as written at :174-181 (only the last feature contributes). */
+int32_t mmsig_ilda_set_features(mmsig_handle *h, int32_t nfeat, const int32_t *features);
+int32_t mmsig_ilda_set_state(mmsig_handle *h, double alpha, const double *eta, const double *lambdaf,
+                             const double *gamma_next);
+int32_t mmsig_ilda_get_tables(mmsig_handle *h, double *lambdaf, double *Elnbetaf);
+
 /* ---- test hook: the pinned device math on arrays (fn 0 = exp, 1 = log, 2 = digamma; the branch-free
  * IEEE sequences of det_math.cuh: 3 = x[i] / x[n+i] (x holds 2n values), 4 = 1 / x, 5 = sqrt) ---- */
 int32_t mmsig_debug_math(mmsig_handle *h, int32_t fn, int64_t n, const double *x, double *y);

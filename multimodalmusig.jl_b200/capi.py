@@ -69,6 +69,9 @@ _SIGS = {
     "mmsig_immctm_get_tables": (C.c_int32, [C.c_void_p, c_dp, c_dp, c_dp]),
     "mmsig_lda_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p]),
     "mmsig_lda_set_state": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, c_dp, c_dp]),
+    "mmsig_ilda_set_features": (C.c_int32, [C.c_void_p, C.c_int32, c_i32p]),
+    "mmsig_ilda_set_state": (C.c_int32, [C.c_void_p, C.c_double, c_dp, c_dp, c_dp]),
+    "mmsig_ilda_get_tables": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_lda_iterate": (C.c_int32, [C.c_void_p, c_dp]),
     "mmsig_lda_set_beta": (C.c_int32, [C.c_void_p, c_dp]),
     "mmsig_lda_iterate_flags": (C.c_int32, [C.c_void_p, C.c_uint32, c_dp]),

@@ -229,7 +229,8 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
         }
         if ((rc = gather(h, L.rank_p, L.gath_p, KV, &g))) return rc;
         LaunchScope ls(h, "k_lda_mstep");
-        k_lda_mstep<<<1, 1024, 0, h->stream>>>(p, g, h->nranks);
+        if (p.factored) k_ilda_mstep<<<1, 1024, (size_t)2 * p.R * sizeof(double), h->stream>>>(p, g, h->nranks);
+        else k_lda_mstep<<<1, 1024, 0, h->stream>>>(p, g, h->nranks);
     }
     if (L.t32) {
         LaunchScope ls(h, "k_lda_ll_tile");
@@ -364,10 +365,42 @@ extern "C" int32_t mmsig_lda_elbo(mmsig_handle *h, double *elbo, double *terms) 
     const double K = p.K, V = p.V, Dt = (double)p.D_total;
     double t[7];
     t[0] = K * (std::lgamma(V * p.eta) - V * std::lgamma(p.eta)) + (p.eta - 1) * tab[0];          // :114-118
+    double t4_factored = 0.0;
+    if (p.factored) {
+        // ILDA: the two table terms over the feature tables, on the host (a few hundred numbers).
+        // ElnPβ src/ILDA.jl:131-140; ElnQβ :174-181 AS WRITTEN: `lnq = ...` inside the loop over the
+        // features, so only the last feature contributes (reproduced; the ELBO is only reported).
+        std::vector<double> lf(p.T), ef(p.T);
+        CU(cudaMemcpyAsync(lf.data(), p.lambdaf, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaMemcpyAsync(ef.data(), p.Elnbetaf, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        const int nf = p.nfeat, rowlen = p.T / p.K;
+        int fo = 0;
+        t[0] = 0.0;
+        for (int f = 0; f < nf; ++f) {
+            const int J = L.J_host[f];
+            const double eta = L.etaf_host[f];
+            double se = 0.0, a = 0.0, b = 0.0, c = 0.0;
+            for (int k = 0; k < p.K; ++k) {
+                double cs = 0.0;
+                for (int j = 0; j < J; ++j) {
+                    const double l = lf[(size_t)k * rowlen + fo + j], e = ef[(size_t)k * rowlen + fo + j];
+                    se += e;
+                    a += std::lgamma(l);
+                    cs += l;
+                    c += (l - 1) * e;
+                }
+                b += std::lgamma(cs);
+            }
+            t[0] += K * (std::lgamma(J * eta) - J * std::lgamma(eta)) + (eta - 1) * se;
+            t4_factored = a - b - c;
+            fo += J;
+        }
+    }
     t[1] = Dt * (std::lgamma(K * p.alpha) - K * std::lgamma(p.alpha)) + (p.alpha - 1) * s[0].x;   // :120-124
     t[2] = s[1].x;                                                                               // :126-132
     t[3] = s[2].x;                                                                               // :134-140
-    t[4] = tab[1] - tab[2] - tab[3];                                                             // :142-146
+    t[4] = p.factored ? t4_factored : tab[1] - tab[2] - tab[3];                                  // :142-146
     t[5] = s[4].x - s[5].x - s[6].x;                                                             // :148-152
     t[6] = s[3].x;                                                                               // :154-160
     if (terms) memcpy(terms, t, sizeof(t));
@@ -424,5 +457,102 @@ extern "C" int32_t mmsig_lda_get_phi(mmsig_handle *h, double *phi_out) {
     CU(cudaMemcpyAsync(phi_out, d, n * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     cudaFree(d);
+    return 0;
+}
+
+
+// ---- ILDA (reference src/ILDA.jl) on the LDA path: composite K x V tables for the per-sample kernels, the
+// M-step over the feature tables (k_ilda_mstep).  Call order: mmsig_lda_set_data, mmsig_ilda_set_features,
+// mmsig_ilda_set_state, then mmsig_lda_iterate / _fit / _elbo / _get_state, mmsig_ilda_get_tables.
+extern "C" int32_t mmsig_ilda_set_features(mmsig_handle *h, int32_t nfeat, const int32_t *features) {
+    NEED(h && features, "null argument");
+    LdaHost &L = h->lda;
+    NEED(L.has_data, "mmsig_lda_set_data first");
+    NEED(!L.p.factored, "features are already set for this corpus");
+    NEED(nfeat >= 1 && nfeat <= 16, "1 <= features <= 16");
+    CU(cudaSetDevice(h->device));
+    LdaDev &p = L.p;
+    const int V = p.V, K = p.K;
+    std::vector<int> J(nfeat, 0), ent_row, row_off, row_len, row_eta;
+    for (int v = 0; v < V; ++v)
+        for (int f = 0; f < nfeat; ++f) {
+            const int x = features[(size_t)v * nfeat + f];
+            NEED(x >= 0, "feature values are 0-based and non-negative");
+            J[f] = std::max(J[f], x + 1);                       // J = maximum(features, dims=1), src/ILDA.jl:35
+        }
+    int t = 0;
+    for (int k = 0; k < K; ++k)
+        for (int f = 0; f < nfeat; ++f) {
+            row_off.push_back(t);
+            row_len.push_back(J[f]);
+            row_eta.push_back(f);
+            for (int j = 0; j < J[f]; ++j) ent_row.push_back((int)row_off.size() - 1);
+            t += J[f];
+        }
+    p.T = t;
+    p.R = (int)row_off.size();
+    p.nfeat = nfeat;
+    if ((size_t)2 * p.R * sizeof(double) > 48 * 1024) return fail(h, MMSIG_ELIMIT, "too many feature-table rows");
+    int rc;
+    auto up = [&](const int *src, size_t n, const int **dst) -> int {
+        int *d = nullptr;
+        int r = dev_alloc(h, h->allocs_lda, &d, n);
+        if (r) return r;
+        if (cudaMemcpyAsync(d, src, n * sizeof(int), cudaMemcpyHostToDevice, h->stream) != cudaSuccess)
+            return fail(h, MMSIG_ECUDA, "cudaMemcpyAsync (feature index tables)");
+        *dst = d;
+        return 0;
+    };
+    if ((rc = up(features, (size_t)V * nfeat, &p.feat)) || (rc = up(ent_row.data(), ent_row.size(), &p.ent_row)) ||
+        (rc = up(row_off.data(), row_off.size(), &p.row_off)) || (rc = up(row_len.data(), row_len.size(), &p.row_len)) ||
+        (rc = up(row_eta.data(), row_eta.size(), &p.row_eta)))
+        return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &p.lambdaf, (size_t)p.T))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &p.Elnbetaf, (size_t)p.T))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_lda, &p.etaf, (size_t)nfeat))) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    L.J_host = J;
+    p.factored = 1;
+    L.has_state = false;
+    return 0;
+}
+
+// model.α, η ([i]), λ ([k][i][j] flat: model.λ[i][j, k]); gamma [d][k] or NULL => constructor state (src/ILDA.jl:38-52)
+extern "C" int32_t mmsig_ilda_set_state(mmsig_handle *h, double alpha, const double *etaf, const double *lambdaf,
+                                        const double *gamma_next) {
+    NEED(h && etaf && lambdaf, "eta and lambda are required");
+    LdaHost &L = h->lda;
+    NEED(L.has_data && L.p.factored, "mmsig_lda_set_data and mmsig_ilda_set_features first");
+    CU(cudaSetDevice(h->device));
+    LdaDev &p = L.p;
+    for (int f = 0; f < p.nfeat; ++f) NEED(etaf[f] > 0, "eta must be > 0");
+    L.etaf_host.assign(etaf, etaf + p.nfeat);
+    std::vector<double> l0((size_t)p.K * p.V, 1.0);            // placeholder K x V table: k_ilda_compose replaces what it seeds
+    p.factored = 0;
+    int rc = mmsig_lda_set_state(h, alpha, etaf[0], l0.data(), gamma_next);
+    p.factored = 1;
+    if (rc) return rc;
+    L.has_state = false;
+    CU(cudaMemcpyAsync(p.etaf, etaf, p.nfeat * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(p.lambdaf, lambdaf, p.T * sizeof(double), cudaMemcpyHostToDevice, h->stream));
+    {
+        LaunchScope ls(h, "k_ilda_compose");
+        k_ilda_compose<<<1, 1024, (size_t)2 * p.R * sizeof(double), h->stream>>>(p);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    CU(cudaGetLastError());
+    L.has_state = true;
+    return 0;
+}
+
+extern "C" int32_t mmsig_ilda_get_tables(mmsig_handle *h, double *lambdaf, double *Elnbetaf) {
+    NEED(h, "null handle");
+    LdaHost &L = h->lda;
+    NEED(L.has_state && L.p.factored, "mmsig_ilda_set_state first");
+    CU(cudaSetDevice(h->device));
+    LdaDev &p = L.p;
+    if (lambdaf) CU(cudaMemcpyAsync(lambdaf, p.lambdaf, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    if (Elnbetaf) CU(cudaMemcpyAsync(Elnbetaf, p.Elnbetaf, p.T * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
     return 0;
 }

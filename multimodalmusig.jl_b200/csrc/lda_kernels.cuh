@@ -25,6 +25,14 @@ struct LdaDev {
     double alpha, eta;
     double *lam, *Elnbeta, *Elnbeta_prev, *beta, *expElnbeta, *expElnbeta_prev;   // K x V, [k][v]
     double *gamma, *gamma_next;  // D x K, [d][k]
+    // ILDA (reference src/ILDA.jl): beta_kv = prod_i beta_i[f(v,i), k].  factored != 0: Elnbeta / expElnbeta /
+    // beta (K x V) are COMPOSITE tables derived from the feature tables lambdaf / Elnbetaf ([k][i][j] flat);
+    // lam (K x V) then holds the statistics sum_d n phi of the last M-step
+    int factored, nfeat, T, R;
+    const int *feat;             // V x I row-major, 0-based feature values
+    const int *ent_row;          // [T] row (k, i) of an entry
+    const int *row_off, *row_len, *row_eta;   // [R] first entry, J_i, feature index i
+    double *lambdaf, *Elnbetaf, *etaf;
 };
 
 // Elnθ of one sample on lanes k < K (all lanes get ψ(Σγ) consistently)
@@ -302,6 +310,65 @@ __global__ void __launch_bounds__(1024) k_lda_elnbeta(LdaDev p) {
         p.expElnbeta_prev[i] = p.expElnbeta[i];
         p.beta[i] = 0.0;
     }
+}
+
+// ---- ILDA (src/ILDA.jl:97-129): Elnβ_i = ψ(λ_i) - ψ(Σ_j λ_i), then the composite tables the per-sample
+// kernels read: Elnβ_kv = Σ_i Elnβ_i[f(v,i), k] (index order, from 0), e^{Elnβ_kv}, β_kv = Π_i λ_i / Σ_j λ_i.
+// rowsum / rowdig: R doubles each in shared memory.
+__device__ inline void ilda_compose(const LdaDev &p, double *rowsum, double *rowdig, bool keep_prev) {
+    for (int r = threadIdx.x; r < p.R; r += blockDim.x) {
+        const double *l = p.lambdaf + p.row_off[r];
+        double s = 0.0;
+        for (int j = 0; j < p.row_len[r]; ++j) s += l[j];
+        rowsum[r] = s;
+        rowdig[r] = det_digamma(s);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) p.Elnbetaf[t] = det_digamma(p.lambdaf[t]) - rowdig[p.ent_row[t]];
+    __syncthreads();
+    const int KV = p.K * p.V, nf = p.nfeat;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        const int k = i / p.V, v = i % p.V;
+        int r = k * nf;
+        double e = 0.0, b = 1.0;
+        for (int f = 0; f < nf; ++f, ++r) {
+            const int t = p.row_off[r] + p.feat[v * nf + f];
+            e += p.Elnbetaf[t];
+            b *= p.lambdaf[t] / rowsum[r];
+        }
+        if (keep_prev) { p.Elnbeta_prev[i] = p.Elnbeta[i]; p.expElnbeta_prev[i] = p.expElnbeta[i]; }
+        p.Elnbeta[i] = e;
+        p.expElnbeta[i] = det_exp(e);
+        p.beta[i] = b;
+        if (!keep_prev) { p.Elnbeta_prev[i] = e; p.expElnbeta_prev[i] = p.expElnbeta[i]; }
+    }
+}
+// constructor / set_state (src/ILDA.jl:38-42)
+__global__ void __launch_bounds__(1024) k_ilda_compose(LdaDev p) {
+    extern __shared__ double ism[];
+    ilda_compose(p, ism, ism + p.R, false);
+}
+// M-step (single block): statistics S_kv = Σ_d n ϕ (gathered), λ_i[j, k] = η_i + Σ_{v: f(v,i) = j} S_kv
+// (ascending v, src/ILDA.jl:105-125), then the tables above
+__global__ void __launch_bounds__(1024) k_ilda_mstep(LdaDev p, const double2 *gathered, int nranks) {
+    extern __shared__ double ism[];
+    const int K = p.K, V = p.V, KV = K * V, nf = p.nfeat;
+    for (int i = threadIdx.x; i < KV; i += blockDim.x) {
+        double hi = 0.0, lo = 0.0;
+        for (int r = 0; r < nranks; ++r) dd_merge(hi, lo, gathered[(size_t)r * KV + i].x, gathered[(size_t)r * KV + i].y);
+        p.lam[i] = dd_round(hi, lo);
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < p.T; t += blockDim.x) {
+        const int r = p.ent_row[t], j = t - p.row_off[r], k = r / nf, f = r % nf;
+        const double *st = p.lam + k * V;
+        double acc = p.etaf[p.row_eta[r]];
+        for (int v = 0; v < V; ++v)
+            if (p.feat[v * nf + f] == j) acc += st[v];
+        p.lambdaf[t] = acc;
+    }
+    __syncthreads();
+    ilda_compose(p, ism, ism + p.R, true);
 }
 
 // log-likelihood pass (src/LDA.jl:174-188) with θ_t = γ_t / Σγ_t and the new β.

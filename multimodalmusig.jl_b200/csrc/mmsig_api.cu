@@ -115,6 +115,8 @@ struct LdaHost {
     double2 *part = nullptr, *part_ll = nullptr, *rank_p = nullptr, *gath_p = nullptr, *rank_ll = nullptr, *gath_ll = nullptr;
     double *d_ll = nullptr;
     double *gamA = nullptr, *gamB = nullptr;
+    std::vector<int> J_host;            // ILDA: values per feature
+    std::vector<double> etaf_host;      // ILDA: eta per feature
 };
 
 struct mmsig_handle {

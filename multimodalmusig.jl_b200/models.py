@@ -448,10 +448,13 @@ class LDA:
             self.h.check(self.h.lib.mmsig_lda_set_data(self.h.h, self.D, self.D if D_total is None else D_total,
                                                        self.K, self.V, keep[0].ctypes.data_as(capi.c_i64p),
                                                        keep[1].ctypes.data_as(capi.c_i32p), keep[2].ctypes.data_as(capi.c_i32p)))
-        self.set_state(lambda0)
+        self._init_state(lambda0)
         self.converged = False
         self.elbo = float("nan")
         self.ll = float("nan")
+
+    def _init_state(self, lambda0):
+        self.set_state(lambda0)
 
     def set_state(self, lam, gamma_next=None):
         self.h.check(self.h.lib.mmsig_lda_set_state(self.h.h, self.alpha, self.eta,
@@ -545,3 +548,59 @@ class LDA:
 
     def close(self):
         self.h.close()
+
+
+class ILDA(LDA):
+    """src/ILDA.jl:1-58: LDA whose topics factorise over features, β_kv = Π_i β_i[f(v,i), k].
+    features: (V, I) integer array, 0-BASED values (model.features .- 1); eta: scalar or one per feature;
+    lambdaf0: flat [k][i][j] table (the constructor's rand(1:100, J[i], K), :38)."""
+
+    def __init__(self, K, alpha, eta, features, counts, lambdaf0=None, rng=None, **kw):
+        f = np.ascontiguousarray(features, dtype=np.int32)
+        if f.ndim != 2:
+            raise ValueError("features must be a (V, I) matrix")
+        self._features = f
+        self.I = int(f.shape[1])
+        self.J = [int(f[:, i].max()) + 1 for i in range(self.I)]
+        self.T = int(K) * sum(self.J)
+        self.etaf = np.full(self.I, float(eta)) if np.ndim(eta) == 0 else np.ascontiguousarray(eta, dtype=np.float64)
+        if self.etaf.size != self.I:
+            raise ValueError("one eta per feature")
+        if lambdaf0 is None:
+            rng = np.random.default_rng() if rng is None else rng
+            lambdaf0 = rng.integers(1, 101, size=self.T).astype(np.float64)
+        self._lambdaf0 = lambdaf0
+        super().__init__(K, alpha, float(self.etaf[0]), counts, V=f.shape[0], lambda0=np.ones(int(K) * f.shape[0]), **kw)
+
+    def _init_state(self, lambda0):
+        self.h.check(self.h.lib.mmsig_ilda_set_features(self.h.h, self.I, self._features.ctypes.data_as(capi.c_i32p)))
+        self.set_state(self._lambdaf0)
+
+    def set_state(self, lambdaf, gamma_next=None):
+        self.h.check(self.h.lib.mmsig_ilda_set_state(self.h.h, self.alpha, capi.dp(self.etaf),
+                                                     capi.dp(capi.f64(lambdaf, self.T)),
+                                                     capi.dp(capi.f64(gamma_next, self.D * self.K))))
+
+    def tables(self):
+        """(λ, Elnβ) feature tables, flat [k][i][j]."""
+        lf, ef = np.empty(self.T), np.empty(self.T)
+        self.h.check(self.h.lib.mmsig_ilda_get_tables(self.h.h, capi.dp(lf), capi.dp(ef)))
+        return lf, ef
+
+    def table(self, flat, k, i):
+        o = k * sum(self.J) + sum(self.J[:i])
+        return flat[o:o + self.J[i]]
+
+    def set_beta(self, beta):
+        raise NotImplementedError("the ILDA's β follows its feature tables")
+
+    def transform(self, *a, **k):
+        raise NotImplementedError("the reference's ILDA has no working transform (src/ILDA.jl)")
+
+    def fit_heldout(self, counts_heldout, maxiter=100, verbose=False, device=0):
+        """fit_heldout(Xheldout, model::ILDA; maxiter=100): the feature tables frozen."""
+        lf, _ = self.tables()
+        new = ILDA(self.K, self.alpha, self.etaf, self._features, counts_heldout, lambdaf0=lf, device=device)
+        new.ll_history = new._loop(capi.FLAG_FREEZE_TOPICS, maxiter, 1e-4, verbose)
+        new.elbo = new.calculate_elbo()[0]
+        return new
