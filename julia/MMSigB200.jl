@@ -12,7 +12,7 @@
 module MMSigB200
 
 using MultiModalMuSig
-import MultiModalMuSig: fit!, fit_heldout, transform, MMCTM, IMMCTM, LDA, check_convergence
+import MultiModalMuSig: fit!, fit_heldout, transform, MMCTM, IMMCTM, LDA, ILDA, check_convergence
 
 const LIB = get(ENV, "MMSIG_LIB", joinpath(@__DIR__, "..", "multimodalmusig.jl_b200", "libmmsig.so"))
 
@@ -324,6 +324,64 @@ function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
             h, λ, Elnβ, β, γ, Elnθ, θ))
         model.λ .= reshape(λ, V, K); model.Elnβ .= reshape(Elnβ, V, K); model.β .= reshape(β, V, K)
         model.γ .= reshape(γ, K, D); model.Elnθ .= reshape(Elnθ, K, D); model.θ .= reshape(θ, K, D)
+        model.elbo = elbo[]
+        model.ll = ll[end]
+    finally
+        destroy(h)
+    end
+    return ll
+end
+
+# ---- fit!(::ILDA) (src/ILDA.jl:233-259): the LDA's device path over composite tables; the M-step runs over
+# the feature tables λ_i[j, k] (mmsig_ilda_*).  Tables travel flat as [k][i][j].
+function fit!(model::ILDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
+    D, K, I, J = model.D, model.K, model.I, model.J
+    V = size(model.features, 1)
+    rowptr = zeros(Int64, D + 1)
+    for d in 1:D rowptr[d + 1] = rowptr[d] + size(model.X[d], 1) end
+    term = Vector{Int32}(undef, rowptr[end]); count = Vector{Int32}(undef, rowptr[end])
+    for d in 1:D
+        r = (rowptr[d] + 1):rowptr[d + 1]
+        term[r] .= model.X[d][:, 1] .- 1; count[r] .= model.X[d][:, 2]
+    end
+    feat = Int32.(vec(permutedims(model.features .- 1)))       # V x I row-major, 0-based
+    flat(t) = Float64[t[i][j, k] for k in 1:K for i in 1:I for j in 1:J[i]]
+    function unflat!(t, x)
+        o = 0
+        for k in 1:K, i in 1:I, j in 1:J[i]
+            t[i][j, k] = x[o += 1]
+        end
+    end
+    λ = flat(model.λ)
+    h = create(device=device)
+    ll = Float64[]
+    try
+        check(h, ccall((:mmsig_lda_set_data, LIB), Int32,
+            (Ptr{Cvoid}, Int64, Int64, Int32, Int32, Ptr{Int64}, Ptr{Int32}, Ptr{Int32}), h, D, D, K, V, rowptr, term, count))
+        check(h, ccall((:mmsig_ilda_set_features, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Int32}), h, I, feat))
+        check(h, ccall((:mmsig_ilda_set_state, LIB), Int32, (Ptr{Cvoid}, Float64, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, model.α, model.η, λ, C_NULL))
+        l = Ref(0.0)
+        for iter in 1:maxiter
+            check(h, ccall((:mmsig_lda_iterate, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}), h, l))
+            push!(ll, l[])
+            verbose && println("$iter\tLog-likelihood: ", ll[end])
+            if length(ll) > 10 && check_convergence(ll, tol=tol)
+                model.converged = true
+                break
+            end
+        end
+        elbo = Ref(0.0)
+        check(h, ccall((:mmsig_lda_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
+        Elnβ = similar(λ); γ = zeros(K * D); Elnθ = zeros(K * D); θ = zeros(K * D)
+        check(h, ccall((:mmsig_ilda_get_tables, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}), h, λ, Elnβ))
+        check(h, ccall((:mmsig_lda_get_state, LIB), Int32,
+            (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+            h, C_NULL, C_NULL, C_NULL, γ, Elnθ, θ))
+        unflat!(model.λ, λ); unflat!(model.Elnβ, Elnβ)
+        model.β = [model.λ[i] ./ sum(model.λ[i], dims=1) for i in 1:I]      # update_β!, src/ILDA.jl:127-129
+        model.γ .= reshape(γ, K, D); model.Elnθ .= reshape(Elnθ, K, D)
+        model.θ = reshape(θ, K, D)
         model.elbo = elbo[]
         model.ll = ll[end]
     finally
