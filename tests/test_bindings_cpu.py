@@ -1,0 +1,115 @@
+"""The three statements of the drop-in boundary must agree argument for argument: the prototypes in
+include/mmsig.h, the ctypes signatures in multimodalmusig.jl_b200/capi.py (what the tests and the bench
+call through) and the `ccall`s of julia/MMSigB200.jl (what a MultiModalMuSig.jl maintainer loads; there
+is no Julia in the build image, so this static check is what keeps the shim from drifting)."""
+import ctypes as C
+import os
+import re
+
+import mmsig
+from conftest import ROOT
+
+
+def _ckind(t):
+    t = t.strip()
+    if "*" in t or t.endswith("]"):
+        return "ptr"
+    t = re.sub(r"\bconst\b", "", t).split()
+    base = t[0] if len(t) <= 2 else " ".join(t[:-1])
+    return {"int32_t": "i32", "uint32_t": "u32", "int64_t": "i64", "uint64_t": "u64", "double": "f64",
+            "int": "i32", "size_t": "u64", "void": "void"}[base]
+
+
+def _header():
+    src = open(os.path.join(ROOT, "include", "mmsig.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    out = {}
+    for ret, name, args in re.findall(r"([A-Za-z_][A-Za-z0-9_ \*]*?)\b(mmsig_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", src):
+        args = " ".join(args.split())
+        params = [] if args in ("", "void") else [_ckind(a) for a in args.split(",")]
+        out[name] = (_ckind(ret) if "*" not in ret else "ptr", params)
+    return out
+
+
+_CT = {C.c_int32: "i32", C.c_uint32: "u32", C.c_int64: "i64", C.c_uint64: "u64", C.c_double: "f64",
+       C.c_void_p: "ptr", C.c_char_p: "ptr", C.c_size_t: "u64", None: "void"}
+
+
+def _ctkind(t):
+    if t in _CT:
+        return _CT[t]
+    assert hasattr(t, "_type_") or hasattr(t, "contents"), t      # POINTER(...)
+    return "ptr"
+
+
+def test_ctypes_signatures_match_the_header():
+    H = _header()
+    assert len(H) >= 40
+    for name, (res, args) in mmsig.capi._SIGS.items():
+        hret, hargs = H[name]
+        assert [_ctkind(a) for a in args] == hargs, name
+        assert _ctkind(res) == hret, name
+
+
+_JL = {"Int32": "i32", "UInt32": "u32", "Int64": "i64", "UInt64": "u64", "Float64": "f64", "Cint": "i32",
+       "Cstring": "ptr", "Cvoid": "void"}
+
+
+def _jlkind(t):
+    t = t.strip()
+    if t.startswith(("Ptr{", "Ref{")) or t == "Cstring":
+        return "ptr"
+    return _JL[t]
+
+
+def _split_top(s):
+    out, depth, cur = [], 0, ""
+    for ch in s:
+        if ch in "({[":
+            depth += 1
+        elif ch in ")}]":
+            depth -= 1
+        if ch == "," and depth == 0:
+            out.append(cur)
+            cur = ""
+        else:
+            cur += ch
+    if cur.strip():
+        out.append(cur)
+    return [x.strip() for x in out]
+
+
+def _ccalls():
+    src = open(os.path.join(ROOT, "julia", "MMSigB200.jl")).read()
+    src = re.sub(r"#[^\n]*", "", src)
+    calls = []
+    for m in re.finditer(r"ccall\(\(:(mmsig_[a-z0-9_]+),\s*LIB\)\s*,", src):
+        i, depth = m.end(), 1                       # walk to the matching ')' of ccall(
+        while depth:
+            depth += {"(": 1, ")": -1}.get(src[i], 0)
+            i += 1
+        parts = _split_top(src[m.end():i - 1])
+        ret, types, vals = parts[0], parts[1], parts[2:]
+        assert types.startswith("(") and types.endswith(")"), (m.group(1), types)
+        calls.append((m.group(1), ret, _split_top(types[1:-1]), vals))
+    return calls
+
+
+def test_julia_ccalls_match_the_header():
+    H = _header()
+    calls = _ccalls()
+    assert len(calls) >= 30
+    for name, ret, types, vals in calls:
+        assert name in H, "%s is not declared in include/mmsig.h" % name
+        hret, hargs = H[name]
+        assert [_jlkind(t) for t in types] == hargs, (name, types, hargs)
+        assert len(vals) == len(types), (name, "argument count differs from the type tuple")
+        assert _jlkind(ret) == hret or (hret == "ptr" and ret.startswith("Ptr")), (name, ret)
+
+
+def test_julia_shim_covers_the_model_families():
+    src = open(os.path.join(ROOT, "julia", "MMSigB200.jl")).read()
+    for sig in ("fit!(model::MMCTM", "fit!(model::IMMCTM", "fit!(model::LDA", "fit!(model::ILDA", "function fit_heldout",
+                "function transform"):
+        assert sig in src, sig
