@@ -1134,7 +1134,7 @@ static int pipe_chunks(long long D) {
     // ~150k samples per chunk, but at least 4 chunks once a shard is worth pipelining at all (a rank
     // of an 8-GPU run holds 125k samples of the 1M corpus)
     long long c = e ? atoll(e) : std::max<long long>((D + 75000) / 150000, std::min<long long>(4, D / 16384));
-    return (int)std::max<long long>(1, std::min<long long>({c, 64LL, D}));
+    return (int)std::max<long long>(1, std::min<long long>({c, 64LL, (D + 31) / 32}));     // a chunk holds at least one tile of 32 samples
 }
 
 extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
