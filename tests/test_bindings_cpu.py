@@ -113,3 +113,21 @@ def test_julia_shim_covers_the_model_families():
     for sig in ("fit!(model::MMCTM", "fit!(model::IMMCTM", "fit!(model::LDA", "fit!(model::ILDA", "function fit_heldout",
                 "function transform"):
         assert sig in src, sig
+
+
+def test_julia_shim_blocks_and_brackets_balance():
+    """No Julia in the image: at least every block opener has its `end` and every bracket closes."""
+    src = open(os.path.join(ROOT, "julia", "MMSigB200.jl")).read()
+    src = re.sub(r'"(?:\\.|[^"\\])*"', '""', src)
+    src = re.sub(r"#[^\n]*", "", src)
+    prev = None
+    while prev != src:                      # bracketed content goes first (`end` as an index, comprehensions)
+        prev = src
+        src = re.sub(r"\[[^\[\]()]*\]", "_", src)
+        src = re.sub(r"\([^()\[\]]*\)", "_", src)
+    assert src.count("(") == src.count(")") and src.count("[") == src.count("]")
+    depth = 0
+    for t in re.findall(r"\b(function|for|if|while|try|let|begin|do|struct|module|quote|end)\b", src):
+        depth += -1 if t == "end" else 1
+        assert depth >= 0
+    assert depth == 0
