@@ -131,3 +131,18 @@ def test_julia_shim_blocks_and_brackets_balance():
         depth += -1 if t == "end" else 1
         assert depth >= 0
     assert depth == 0
+
+
+def test_julia_shim_touches_only_fields_the_reference_structs_have():
+    """tests/golden/reference_struct_fields.json: the field names of the reference's model structs
+    (generated by tests/golden/make_struct_fields.py in the build container)."""
+    import json
+    ref = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_struct_fields.json")))
+    shim = open(os.path.join(ROOT, "julia", "MMSigB200.jl")).read()
+    seen = 0
+    for m in re.finditer(r"function (\w+!?)\((?:[^)]*?)(model|newmodel)::(\w+)(.*?)\nend\n", shim, re.S):
+        typ, body = m.group(3), m.group(4)
+        used = set(re.findall(r"\b(?:model|newmodel|heldout_model)\.([^\s\.\[\]\(\),;=+\-*/:]+)", body))
+        assert used and used <= set(ref[typ]), (m.group(1), typ, used - set(ref[typ]))
+        seen += 1
+    assert seen >= 7
