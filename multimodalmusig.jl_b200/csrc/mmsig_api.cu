@@ -234,7 +234,7 @@ static cudaError_t allow_max_smem(mmsig_handle *h, F kernel) {
 }
 
 // ---- generic ------------------------------------------------------------------------------
-extern "C" int32_t mmsig_version(void) { return 110; }
+extern "C" int32_t mmsig_version(void) { return 111; }     // 111: mmsig_ilda_*
 
 extern "C" int32_t mmsig_limits(int32_t *max_modalities, int32_t *max_sum_K, int32_t *max_K, int32_t *max_V_mmctm,
                                 int32_t *max_V_lda) {

@@ -57,4 +57,4 @@ def test_limits_need_no_device():
     v = [C.c_int32() for _ in range(5)]
     assert lib.mmsig_limits(*[C.byref(x) for x in v]) == 0
     assert [x.value for x in v] == [8, 64, 32, 1024, 65535]
-    assert lib.mmsig_version() >= 110
+    assert lib.mmsig_version() >= 111
