@@ -4,6 +4,8 @@ Tolerances (north_star): one E+M iteration from an identical state within 1e-12 
 ϕ, λ, ν, μ, Σ, ELBO; a fixed-iteration fit within 1e-8 relative ELBO.  Against the oracle's
 pinned arithmetic (ORC_ARITH_DET) the per-sample results are required to be BIT-EXACT, because
 anything looser lets MMA's branch decisions diverge."""
+import os
+
 import numpy as np
 import pytest
 
@@ -253,6 +255,22 @@ def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
         g0 = mmsig.synth.init_gamma(K, V)
         o, g = _pair(K, [0.1] * len(K), V, counts, g0)
         for _ in range(2):
+            ll_o, ll_g = o.iterate(), g.iterate()
+            _check_iteration(o, g, ll_o, ll_g)
+        g.close()
+
+
+@pytest.mark.skipif(os.environ.get("MMSIG_EXPERIMENTAL") != "1",
+                    reason="experimental kernels (not yet measured on a GPU): run with MMSIG_EXPERIMENTAL=1")
+def test_split_phase_solver_is_bit_identical(monkeypatch):
+    """MMSIG_SOLVE=split (csrc/mmctm_split.cuh): update_ν! for every sample, then update_λ!, as two kernels with
+    the packing of k_solve_multi; same arithmetic, so bit-identical, including the per-sample evaluation counts."""
+    monkeypatch.setenv("MMSIG_SOLVE", "split")
+    for K, V in (([10, 8, 6], [96, 32, 83]), ([16, 16], [40, 7]), ([9, 8], [30, 20])):
+        counts = small_synth(400, K, V, empty_frac=0.05)
+        g0 = mmsig.synth.init_gamma(K, V)
+        o, g = _pair(K, [0.1] * len(K), V, counts, g0)
+        for _ in range(3):
             ll_o, ll_g = o.iterate(), g.iterate()
             _check_iteration(o, g, ll_o, ll_g)
         g.close()
