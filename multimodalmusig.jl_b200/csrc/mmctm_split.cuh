@@ -16,16 +16,27 @@
 
 namespace mmsig {
 
-template <int CPL, int PH>
-__global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev p, double2 *partial) {
+// slots of one lane: coordinates gl, gl + G, gl + 2G, ...; their sum in the order of the 32-leaf tree's top levels
+template <int CPL>
+__device__ __forceinline__ double slot_sum_g(const double (&v)[CPL]) {
+    if (CPL == 2) return v[0] + v[1];                    // G = 16: level 16
+    if (CPL == 3) return (v[0] + v[2]) + v[1];           // G = 8: levels 16, 8 (slot 3 is absent: + 0 exactly)
+    return (v[0] + v[2]) + (v[1] + v[CPL - 1]);          // CPL == 4
+}
+
+// G lanes per sample (32 / G samples per warp), CPL coordinates per lane (coordinate j on lane j % G, slot j / G);
+// (G, CPL) = (8, 3), (8, 4): four samples per warp; (16, 2): two samples per warp, fewer registers.
+template <int G, int CPL, int PH>
+__global__ void __launch_bounds__(128, (G == 16 ? 4 : MULTI_MIN_BLOCKS)) k_solve_phase(MmctmDev p, double2 *partial) {
     constexpr bool NU = PH == PH_NU;
-    constexpr int G = 8, NG = 4, MKP = 8 * CPL, STRIDE = 34, NW = 4;     // NW warps per block
+    constexpr int NG = 32 / G, MKP = G * CPL, STRIDE = 34, NW = 4;       // NW warps per block
+    static_assert(MKP <= 32 && (G == 8 || G == 16), "one 32-leaf tree per sample");
     __shared__ __align__(16) double ST[NU ? 2 : 32 * STRIDE];            // invΣ rows: λ phase only
     __shared__ __align__(16) double dsh_all[NW][NG][STRIDE];
     __shared__ double2 red[NW][CPL][32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, gl = lane % G;
-    const unsigned gmask = 0xffu << (grp * G);
+    const unsigned gmask = ((1u << G) - 1u) << (grp * G);
     const int MK = p.MK, M = p.M;
     double *dsh = dsh_all[warp][grp];
     if (!NU)
@@ -40,7 +51,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
     double Sjj[CPL], muj[CPL];
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
-        const int j = gl + 8 * s;
+        const int j = gl + G * s;
         active[s] = j < MK;
         mod[s] = 0;
         for (int m = 0; m < M; ++m)
@@ -79,10 +90,10 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
                 double nu0[CPL], lam0[CPL];
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
-                    const long long base = dcur * MK + gl + 8 * s;
+                    const long long base = dcur * MK + gl + G * s;
                     lam0[s] = active[s] ? p.lam_prev[base] : 0.0;
                     nu0[s] = active[s] ? p.nu[base] : 1.5;
-                    dsh[gl + 8 * s] = active[s] ? det_exp(lam0[s] + 0.5 * nu0[s]) : 0.0;
+                    dsh[gl + G * s] = active[s] ? det_exp(lam0[s] + 0.5 * nu0[s]) : 0.0;
                 }
                 __syncwarp(gmask);
 #pragma unroll
@@ -91,7 +102,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
                     for (int i = blo[s]; i < bhi[s]; ++i) zeta += dsh[i];
                     const double Ndm = active[s] ? p.N[dcur * M + mod[s]] : 0.0;
                     cN[s] = active[s] ? Ndm / zeta : 0.0;
-                    if (active[s] && gl + 8 * s == blo[s]) p.zeta[dcur * M + mod[s]] = zeta;
+                    if (active[s] && gl + G * s == blo[s]) p.zeta[dcur * M + mod[s]] = zeta;
                     x[s] = nu0[s];
                     other[s] = lam0[s];
                 }
@@ -100,7 +111,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
                 // λ's problem: the new ν, the old ζ (both written by the ν kernel), the old sumθ (:454)
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
-                    const long long base = dcur * MK + gl + 8 * s;
+                    const long long base = dcur * MK + gl + G * s;
                     x[s] = active[s] ? p.lam_prev[base] : 0.0;
                     other[s] = active[s] ? 0.5 * p.nu[base] : 0.75;
                     sth[s] = active[s] ? p.sumtheta[base] : 0.0;
@@ -159,7 +170,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
                 diff[s] = xe[s] - muj[s];
-                dsh[gl + 8 * s] = active[s] ? diff[s] : 0.0;
+                dsh[gl + G * s] = active[s] ? diff[s] : 0.0;
             }
             __syncwarp(gmask);
             const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
@@ -171,7 +182,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
                 const double2 dv = dv2[i];
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
-                    const double2 sv = reinterpret_cast<const double2 *>(ST + (gl + 8 * s) * STRIDE)[i];
+                    const double2 sv = reinterpret_cast<const double2 *>(ST + (gl + G * s) * STRIDE)[i];
                     q[s] = fma(sv.x, dv.x, q[s]);
                     qo[s] = fma(sv.y, dv.y, qo[s]);
                 }
@@ -201,12 +212,12 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
             okabs = okabs && !(adl[s] > 1e-4);
         }
         __syncwarp();
-        double gterm = slot_sum<CPL>(gl_), wterm = slot_sum<CPL>(wl_), t = slot_sum<CPL>(tl);
+        double gterm = slot_sum_g<CPL>(gl_), wterm = slot_sum_g<CPL>(wl_), t = slot_sum_g<CPL>(tl);
         group_tree_sum3<G>(gterm, wterm, t, lane);
         const double f = -t;
         const double gval = fmin + gterm;
         const bool inner_done = !init && (gval >= f);
-        double dn = slot_sum<CPL>(adl), xn = slot_sum<CPL>(xnl);
+        double dn = slot_sum_g<CPL>(adl), xn = slot_sum_g<CPL>(xnl);
         if (__any_sync(FULLMASK, busy && inner_done)) {
             dn = group_tree_sum<G>(dn);
             xn = group_tree_sum<G>(xn);
@@ -264,7 +275,7 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
             double *dst = NU ? p.nu : p.lam;
 #pragma unroll
             for (int s = 0; s < CPL; ++s)
-                if (active[s]) { dst[dcur * MK + gl + 8 * s] = x[s]; dd_add(acch[s], accl[s], x[s]); }
+                if (active[s]) { dst[dcur * MK + gl + G * s] = x[s]; dd_add(acch[s], accl[s], x[s]); }
             if (gl == 0) (NU ? p.nev_nu : p.nev_lam)[dcur] = nev;
             busy = false;
         }
@@ -272,9 +283,9 @@ __global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_phase(MmctmDev 
 #pragma unroll
     for (int s = 0; s < CPL; ++s) red[warp][s][lane] = make_double2(acch[s], accl[s]);
     __syncthreads();
-    // coordinate j = gl + 8 s: sum over warps and over the four groups; partial: [grid][2 MK], Σλ then Σν
+    // coordinate j = gl + G s: sum over warps and over the four groups; partial: [grid][2 MK], Σλ then Σν
     for (int j = threadIdx.x; j < MK; j += blockDim.x) {
-        const int s = j / 8, l = j % 8;
+        const int s = j / G, l = j % G;
         double hi = 0.0, lo = 0.0;
         for (int wv = 0; wv < NW; ++wv)
             for (int gg = 0; gg < NG; ++gg) {

@@ -89,7 +89,7 @@ struct MmctmHost {
     size_t smem_theta[MAXM] = {0}, smem_ll[MAXM] = {0};
     int grid_solve = 0, grid_post = 0, grid_mom = 0, grid_zeta = 0;
     bool solve_multi = false;          // 16 < sum(K) <= 32: k_solve_multi (4 samples per warp) instead of k_solve
-    bool solve_split = false;          // 16 < sum(K) <= 32: k_solve_phase, one kernel per LD_MMA phase (experimental)
+    int solve_split = 0;               // 16 < sum(K) <= 32: k_solve_phase, one kernel per LD_MMA phase (experimental); 8 or 16 = lanes per sample
     bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
     size_t smem_solve = 0;
     double2 *part_mom = nullptr;
@@ -635,7 +635,7 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         const char *e = getenv("MMSIG_SOLVE");
         mm.solve_multi = e && !strcmp(e, "multi");
         // MMSIG_SOLVE=split: the same packing with one kernel per phase (mmctm_split.cuh); experimental
-        mm.solve_split = e && !strcmp(e, "split") && p.MK > 16 && p.MK <= 32;
+        mm.solve_split = (e && p.MK > 16 && p.MK <= 32) ? (!strcmp(e, "split") ? 8 : (!strcmp(e, "split16") ? 16 : 0)) : 0;
     }
     CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
@@ -645,14 +645,15 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         int nb = 0;
         if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
         else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
-        else if (mm.solve_split && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<3, PH_LAM>, 128, 0));
-        else if (mm.solve_split) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<4, PH_LAM>, 128, 0));
+        else if (mm.solve_split == 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<16, 2, PH_LAM>, 128, 0));
+        else if (mm.solve_split && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<8, 3, PH_LAM>, 128, 0));
+        else if (mm.solve_split) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<8, 4, PH_LAM>, 128, 0));
         else if (mm.solve_multi && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<3>, 128, 0));
         else if (mm.solve_multi) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<4>, 128, 0));
         else MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
         {
             // samples per block: 8 warps x 1, 2 or 4 (packed), or 4 warps x 4 (multi)
-            const int spb = p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : ((mm.solve_multi || mm.solve_split) ? 16 : 8));
+            const int spb = p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : (mm.solve_split == 16 ? 8 : ((mm.solve_multi || mm.solve_split) ? 16 : 8)));
             mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1),
                                                                             (D + spb - 1) / spb));
         }
@@ -931,12 +932,14 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         else if (q.MK <= 16) k_solve_pack<16><<<cap(mm.grid_solve, 16), 256, 0, h->stream>>>(q, mm.part_solve);
         else if (mm.solve_split) {
             // ν for every sample, then λ (which reads the new ν and the ζ the first kernel stored)
-            const int gs = cap(mm.grid_solve, 16);
-            if (q.MK <= 24) k_solve_phase<3, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            else k_solve_phase<4, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
+            const int gs = cap(mm.grid_solve, mm.solve_split == 16 ? 8 : 16);
+            if (mm.solve_split == 16) k_solve_phase<16, 2, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
+            else if (q.MK <= 24) k_solve_phase<8, 3, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
+            else k_solve_phase<8, 4, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
             cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);
-            if (q.MK <= 24) k_solve_phase<3, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            else k_solve_phase<4, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
+            if (mm.solve_split == 16) k_solve_phase<16, 2, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
+            else if (q.MK <= 24) k_solve_phase<8, 3, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
+            else k_solve_phase<8, 4, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
         }
         else if (mm.solve_multi && q.MK <= 24) k_solve_multi<3><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
         else if (mm.solve_multi) k_solve_multi<4><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);

@@ -5,7 +5,7 @@
 D=${1:-1000000}
 mkdir -p gpurun_out
 MMSIG_EXPERIMENTAL=1 python -m pytest tests/test_gpu_mmctm.py -q -m gpu -k "split_phase or multi_sample" 2>&1 | tail -5 | tee gpurun_out/ab_split_parity.log
-for v in default multi split; do
+for v in default multi split split16; do
   if [ "$v" = default ]; then unset MMSIG_SOLVE; else export MMSIG_SOLVE=$v; fi
   python bench.py --samples $D --steps 5 --warmup 3 --no-cpu --e2e-steps 1 > gpurun_out/ab_solve_${v}.json 2> gpurun_out/ab_solve_${v}.err
   python - <<PY

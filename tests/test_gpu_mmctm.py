@@ -262,10 +262,12 @@ def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
 
 @pytest.mark.skipif(os.environ.get("MMSIG_EXPERIMENTAL") != "1",
                     reason="experimental kernels (not yet measured on a GPU): run with MMSIG_EXPERIMENTAL=1")
-def test_split_phase_solver_is_bit_identical(monkeypatch):
-    """MMSIG_SOLVE=split (csrc/mmctm_split.cuh): update_ν! for every sample, then update_λ!, as two kernels with
-    the packing of k_solve_multi; same arithmetic, so bit-identical, including the per-sample evaluation counts."""
-    monkeypatch.setenv("MMSIG_SOLVE", "split")
+@pytest.mark.parametrize("variant", ["split", "split16"])
+def test_split_phase_solver_is_bit_identical(monkeypatch, variant):
+    """MMSIG_SOLVE=split / split16 (csrc/mmctm_split.cuh): update_ν! for every sample, then update_λ!, as two
+    kernels with four (8 lanes x 3-4 coordinates) or two (16 lanes x 2 coordinates) samples per warp; same
+    arithmetic, so bit-identical, including the per-sample evaluation counts."""
+    monkeypatch.setenv("MMSIG_SOLVE", variant)
     for K, V in (([10, 8, 6], [96, 32, 83]), ([16, 16], [40, 7]), ([9, 8], [30, 20])):
         counts = small_synth(400, K, V, empty_frac=0.05)
         g0 = mmsig.synth.init_gamma(K, V)
