@@ -1,4 +1,4 @@
-// mmctm_split.cuh -- EXPERIMENTAL (MMSIG_SOLVE=split, off by default, not yet measured): the E-step's two
+// mmctm_split.cuh -- EXPERIMENTAL (compiled only with make EXP=1 -> libmmsig_exp.so; MMSIG_SOLVE=split | split16; not yet measured): the E-step's two
 // LD_MMA solves as two kernels, update_ν! (src/MMCTM.jl:156-170) for every sample, then update_λ!
 // (:127-143), each with four samples per warp and CPL = 3 or 4 coordinates per lane as k_solve_multi
 // (mmctm_pack.cuh).

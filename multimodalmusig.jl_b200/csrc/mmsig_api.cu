@@ -17,7 +17,9 @@
 #include "theta_tile.cuh"
 #include "mmctm_wide.cuh"
 #include "mmctm_pack.cuh"
+#ifdef MMSIG_EXPERIMENTAL_SPLIT          // make EXP=1: the split-phase solver, not part of the default build until it is measured
 #include "mmctm_split.cuh"
+#endif
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
 #include "lda_tile.cuh"
@@ -635,7 +637,9 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         const char *e = getenv("MMSIG_SOLVE");
         mm.solve_multi = e && !strcmp(e, "multi");
         // MMSIG_SOLVE=split: the same packing with one kernel per phase (mmctm_split.cuh); experimental
+#ifdef MMSIG_EXPERIMENTAL_SPLIT
         mm.solve_split = (e && p.MK > 16 && p.MK <= 32) ? (!strcmp(e, "split") ? 8 : (!strcmp(e, "split16") ? 16 : 0)) : 0;
+#endif
     }
     CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
@@ -645,9 +649,11 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         int nb = 0;
         if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
         else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
+#ifdef MMSIG_EXPERIMENTAL_SPLIT
         else if (mm.solve_split == 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<16, 2, PH_LAM>, 128, 0));
         else if (mm.solve_split && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<8, 3, PH_LAM>, 128, 0));
         else if (mm.solve_split) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<8, 4, PH_LAM>, 128, 0));
+#endif
         else if (mm.solve_multi && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<3>, 128, 0));
         else if (mm.solve_multi) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<4>, 128, 0));
         else MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
@@ -930,6 +936,7 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         if (mm.wide) k_solve_wide<<<cap(mm.grid_solve, 8), 256, mm.smem_solve, h->stream>>>(q, mm.part_solve);
         else if (q.MK <= 8) k_solve_pack<8><<<cap(mm.grid_solve, 32), 256, 0, h->stream>>>(q, mm.part_solve);
         else if (q.MK <= 16) k_solve_pack<16><<<cap(mm.grid_solve, 16), 256, 0, h->stream>>>(q, mm.part_solve);
+#ifdef MMSIG_EXPERIMENTAL_SPLIT
         else if (mm.solve_split) {
             // ν for every sample, then λ (which reads the new ν and the ζ the first kernel stored)
             const int gs = cap(mm.grid_solve, mm.solve_split == 16 ? 8 : 16);
@@ -941,6 +948,7 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
             else if (q.MK <= 24) k_solve_phase<8, 3, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
             else k_solve_phase<8, 4, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
         }
+#endif
         else if (mm.solve_multi && q.MK <= 24) k_solve_multi<3><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
         else if (mm.solve_multi) k_solve_multi<4><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
         else MK_DISPATCH(q.MK, (k_solve<MKP><<<cap(mm.grid_solve, 8), 256, 0, h->stream>>>(q, mm.part_solve)));

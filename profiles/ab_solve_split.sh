@@ -4,6 +4,9 @@
 #   bash profiles/ab_solve_split.sh [samples]
 D=${1:-1000000}
 mkdir -p gpurun_out
+# the experimental kernels are not in the default build: make EXP=1 writes libmmsig_exp.so next to libmmsig.so
+make -C multimodalmusig.jl_b200/csrc -s EXP=1 || exit 1
+export MMSIG_LIB=$PWD/multimodalmusig.jl_b200/libmmsig_exp.so
 MMSIG_EXPERIMENTAL=1 python -m pytest tests/test_gpu_mmctm.py -q -m gpu -k "split_phase or multi_sample" 2>&1 | tail -5 | tee gpurun_out/ab_split_parity.log
 for v in default multi split split16; do
   if [ "$v" = default ]; then unset MMSIG_SOLVE; else export MMSIG_SOLVE=$v; fi

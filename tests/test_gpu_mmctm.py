@@ -261,7 +261,8 @@ def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
 
 
 @pytest.mark.skipif(os.environ.get("MMSIG_EXPERIMENTAL") != "1",
-                    reason="experimental kernels (not yet measured on a GPU): run with MMSIG_EXPERIMENTAL=1")
+                    reason="experimental kernels, not in the default build: make EXP=1, MMSIG_LIB=.../libmmsig_exp.so, "
+                           "MMSIG_EXPERIMENTAL=1 (profiles/ab_solve_split.sh)")
 @pytest.mark.parametrize("variant", ["split", "split16"])
 def test_split_phase_solver_is_bit_identical(monkeypatch, variant):
     """MMSIG_SOLVE=split / split16 (csrc/mmctm_split.cuh): update_ν! for every sample, then update_λ!, as two
