@@ -149,3 +149,32 @@ def test_ilda_elbo_table_terms(arith):
         p += K * (gammaln(J * eta[i]) - J * gammaln(eta[i])) + (eta[i] - 1) * Eb.sum()
         q = gammaln(lam).sum() - gammaln(lam.sum(1)).sum() - ((lam - 1) * Eb).sum()
     np.testing.assert_allclose([t[0], t[4]], [p, q], rtol=1e-11)
+
+
+@pytest.mark.parametrize("arith", ARITHS)
+def test_loglikelihoods_numpy(arith):
+    """calculate_loglikelihoods (src/MMCTM.jl:384-448) and LDA's (src/LDA.jl:174-188) on data with empty rows:
+    ll_m = Σ_d Σ_w n log(props_d · ϕ[:, v]) / Σ_d N_dm."""
+    K, V, D = [3, 4], [12, 9], 150
+    counts = small_synth(D, K, V, empty_frac=0.1)
+    o = orc.OracleMMCTM(K, [0.1, 0.3], V, counts, mmsig.synth.init_gamma(K, V), arith=arith, nthreads=4)
+    ll = None
+    for _ in range(2):
+        ll = o.iterate()
+    koff = np.concatenate([[0], np.cumsum(K)])
+    goff = np.concatenate([[0], np.cumsum(np.array(K) * np.array(V))])
+    for m in range(2):
+        rp, term, cnt = counts[m]
+        assert np.any(np.diff(rp) == 0)                                        # the empty rows are there
+        d_of = _expand(rp)
+        ph = o.phi[goff[m]:goff[m + 1]].reshape(K[m], V[m])
+        pr = o.props[:, koff[m]:koff[m + 1]]
+        pw = np.einsum("wk,kw->w", pr[d_of], ph[:, term])
+        np.testing.assert_allclose(ll[m], (cnt * np.log(pw)).sum() / cnt.sum(), rtol=1e-12)
+    csr = small_synth(300, [5], [20], empty_frac=0.1)[0]
+    l = orc.OracleLDA(5, 0.1, 0.2, 20, csr, mmsig.synth.init_lda_lambda(5, 20), arith=arith, nthreads=4)
+    for _ in range(2):
+        v = l.iterate()
+    rp, term, cnt = csr
+    pw = np.einsum("wk,kw->w", l.theta[_expand(rp)], l.beta[:, term])
+    np.testing.assert_allclose(v, (cnt * np.log(pw)).sum() / cnt.sum(), rtol=1e-12)
