@@ -1,4 +1,4 @@
-"""The oracle's ELBOs against a second, vectorised numpy statement of the same seven terms
+"""The oracle against a second, vectorised numpy statement: the ELBOs (seven terms each)
 (MMCTM: reference src/MMCTM.jl:271-382; LDA: src/LDA.jl:114-172), evaluated on the oracle's own
 state after a few iterations.  The reference's tests only check the sign of the ELBO; the CUDA path
 is held to the oracle's value (1e-12), so the oracle's transcription is cross-checked here."""
@@ -178,3 +178,36 @@ def test_loglikelihoods_numpy(arith):
     rp, term, cnt = csr
     pw = np.einsum("wk,kw->w", l.theta[_expand(rp)], l.beta[:, term])
     np.testing.assert_allclose(v, (cnt * np.log(pw)).sum() / cnt.sum(), rtol=1e-12)
+
+
+@pytest.mark.parametrize("arith", ARITHS)
+def test_mstep_numpy(arith):
+    """The M-step of one iteration (src/MMCTM.jl:200-250, :145-154) recomputed with numpy from the oracle's own
+    per-sample results (λ, ν, θ): μ, Σ, invΣ, γ, Elnϕ, ϕ, props."""
+    from scipy.special import digamma
+    K, V, D = [3, 4], [12, 9], 200
+    counts = small_synth(D, K, V, empty_frac=0.05)
+    al = [0.1, 0.3]
+    o = orc.OracleMMCTM(K, al, V, counts, mmsig.synth.init_gamma(K, V), arith=arith, nthreads=4)
+    for _ in range(2):
+        o.iterate()
+    lam, nu = o.lam, o.nu
+    mu = lam.mean(0)
+    np.testing.assert_allclose(o.mu, mu, rtol=1e-12, atol=1e-14)
+    diff = lam - mu
+    Sig = (np.diag(nu.sum(0)) + diff.T @ diff) / D
+    np.testing.assert_allclose(o.Sigma, Sig, rtol=1e-11, atol=1e-13)
+    np.testing.assert_allclose(o.invSigma, np.linalg.inv(Sig), rtol=1e-9, atol=1e-11)
+    koff = np.concatenate([[0], np.cumsum(K)])
+    goff = np.concatenate([[0], np.cumsum(np.array(K) * np.array(V))])
+    for m in range(2):
+        rp, term, cnt = counts[m]
+        g = np.full((K[m], V[m]), al[m])
+        np.add.at(g.T, term, o.theta(m) * cnt[:, None])
+        og = o.gamma[goff[m]:goff[m + 1]].reshape(K[m], V[m])
+        np.testing.assert_allclose(og, g, rtol=1e-11)
+        np.testing.assert_allclose(o.Elnphi[goff[m]:goff[m + 1]].reshape(K[m], V[m]),
+                                   digamma(og) - digamma(og.sum(1))[:, None], rtol=1e-10, atol=1e-11)
+        np.testing.assert_allclose(o.phi[goff[m]:goff[m + 1]].reshape(K[m], V[m]), og / og.sum(1)[:, None], rtol=1e-13)
+        e = np.exp(lam[:, koff[m]:koff[m + 1]])
+        np.testing.assert_allclose(o.props[:, koff[m]:koff[m + 1]], e / e.sum(1)[:, None], rtol=1e-12)
