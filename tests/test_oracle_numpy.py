@@ -211,3 +211,42 @@ def test_mstep_numpy(arith):
         np.testing.assert_allclose(o.phi[goff[m]:goff[m + 1]].reshape(K[m], V[m]), og / og.sum(1)[:, None], rtol=1e-13)
         e = np.exp(lam[:, koff[m]:koff[m + 1]])
         np.testing.assert_allclose(o.props[:, koff[m]:koff[m + 1]], e / e.sum(1)[:, None], rtol=1e-12)
+
+
+@pytest.mark.parametrize("arith", ARITHS)
+def test_feature_table_msteps_numpy(arith):
+    """update_γ! of the IMMCTM (src/IMMCTM.jl:197-221) and update_λ! of the ILDA (src/ILDA.jl:105-125) on random data:
+    table_k,i,j = prior_i + Σ over the nonzeros whose term carries value j of feature i of n·(θ or ϕ)_k."""
+    K, shapes, D = [3, 2], [(3, 4), (2, 3)], 150
+    feats = [_grid_features(s) for s in shapes]
+    V = [f.shape[0] for f in feats]
+    counts = small_synth(D, K, V, empty_frac=0.05)
+    alphaf = [[0.1, 0.4], [0.2, 0.3]]
+    T = sum(k * sum(s) for k, s in zip(K, shapes))
+    o = orc.OracleIMMCTM(K, alphaf, feats, counts, np.random.default_rng(4).integers(1, 101, T).astype(float),
+                         arith=arith, nthreads=4)
+    for _ in range(2):
+        o.iterate()
+    for m in range(2):
+        rp, term, cnt = counts[m]
+        nth = o.theta(m) * cnt[:, None]
+        for k in range(K[m]):
+            for i, J in enumerate(shapes[m]):
+                want = np.full(J, alphaf[m][i])
+                np.add.at(want, feats[m][term, i], nth[:, k])
+                np.testing.assert_allclose(o.table(o.gammaf, m, k, i), want, rtol=1e-11)
+    K1, shape = 4, (3, 5)
+    feat = _grid_features(shape)
+    csr = small_synth(200, [K1], [feat.shape[0]], empty_frac=0.05)[0]
+    eta = [0.2, 0.6]
+    l = orc.OracleILDA(K1, 0.1, eta, feat, csr, np.random.default_rng(6).integers(1, 101, K1 * sum(shape)).astype(float),
+                       arith=arith, nthreads=4)
+    for _ in range(2):
+        l.iterate()
+    rp, term, cnt = csr
+    nph = l.phi * cnt[:, None]
+    for k in range(K1):
+        for i, J in enumerate(shape):
+            want = np.full(J, eta[i])
+            np.add.at(want, feat[term, i], nph[:, k])
+            np.testing.assert_allclose(l.table(l.lambdaf, k, i), want, rtol=1e-11)
