@@ -1,0 +1,356 @@
+// mmctm_lean.cuh -- the E-step's two LD_MMA solves for sum(K) <= 32: update_ν! (src/MMCTM.jl:156-170)
+// for every sample, then update_λ! (:127-143), one kernel per phase, G lanes per sample and CPL
+// coordinates per lane (coordinate j on lane j % G of its group, slot j / G), 32 / G samples per warp.
+//
+// Why this shape (measured, profiles/r02_solve_ab.md): k_solve (one sample per warp, lane = coordinate)
+// spends 390 warp-instructions per objective evaluation, 36 % of them FP64, on 24 of 32 lanes at
+// sum(K) = 24; it is bound by instruction issue, not by the FP64 pipe.  Packing a sample into 8 (or 4)
+// lanes fills every lane, shares each reduction and each piece of scalar LD_MMA bookkeeping between 4
+// (or 8) samples and gives every lane CPL independent dependency chains.  One phase per kernel keeps
+// the samples of a warp in the same objective.  LD_MMA's data-dependent inner / outer loops are
+// flattened into ONE objective evaluation per trip with select-only state transitions: there is no
+// separate "first evaluation" path (the first trip proposes from a zero gradient, i.e. stays at x0),
+// no per-trip copies of the iterate (x, g change by selects; xprev / xprevprev / sigma only on an outer
+// step) and the only branches are warp-uniform (any group needs a sample / ends an inner loop).
+//
+// Arithmetic is k_solve's (DET specification) operation for operation; the 32-leaf
+// tree sum becomes: slots of a lane in the order of the tree's top levels, then the G-lane butterfly.
+// Results are bit-identical to k_solve, k_solve_pack and the oracle, evaluation counts included.
+#pragma once
+#include "mmctm_pack.cuh"
+
+namespace mmsig {
+
+#ifndef LEAN_MIN_BLOCKS
+#define LEAN_MIN_BLOCKS 3
+#endif
+
+// sum of a lane's CPL slot values in the order of the 32-leaf tree's top levels: slot s holds leaf
+// gl + G s, so tree level 16 / G pairs slot s with s ^ (NS / 2), the next level with s ^ (NS / 4), ...
+// (an absent slot is an exact + 0)
+template <int G, int CPL>
+__device__ __forceinline__ double lean_slot_sum(const double (&v)[CPL]) {
+    constexpr int NS = 32 / G;
+    double w[NS];
+#pragma unroll
+    for (int s = 0; s < NS; ++s) w[s] = s < CPL ? v[s] : 0.0;
+#pragma unroll
+    for (int off = NS / 2; off >= 1; off >>= 1)
+#pragma unroll
+        for (int s = 0; s < off; ++s)
+            if (s + off < CPL) w[s] = w[s] + w[s + off];
+    return w[0];
+}
+
+template <int G>
+__device__ __forceinline__ double lean_shfl_xor(double v, int off) {
+    return shfl_xor_d(v, off);
+}
+
+// the three group sums of one trip; every lane of a group ends with the same bits
+template <int G>
+__device__ __forceinline__ void lean_sum3(double &a, double &b, double &c, int lane) {
+    if (G >= 8) {
+        group_tree_sum3<G>(a, b, c, lane);
+    } else {
+#pragma unroll
+        for (int off = G / 2; off >= 1; off >>= 1) {
+            const double ta = shfl_xor_d(a, off), tb = shfl_xor_d(b, off), tc = shfl_xor_d(c, off);
+            a = a + ta;
+            b = b + tb;
+            c = c + tc;
+        }
+    }
+}
+
+template <int G, int CPL, int PH>
+__global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p, double2 *partial) {
+    constexpr bool NU = PH == PH_NU;
+    constexpr int NG = 32 / G, MKP = G * CPL, STRIDE = 34, NW = 4;       // NW warps per block
+    static_assert(MKP <= 32 && (G == 4 || G == 8 || G == 16), "one 32-leaf tree per sample");
+    __shared__ __align__(16) double ST[NU ? 2 : 32 * STRIDE];            // invΣ rows: λ phase only
+    __shared__ __align__(16) double dsh_all[NW][NG][STRIDE];
+    __shared__ double2 red[NW][CPL][32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int grp = lane / G, gl = lane % G;
+    const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
+    const int MK = p.MK, M = p.M;
+    double *dsh = dsh_all[warp][grp];
+    if (!NU)
+        for (int t = threadIdx.x; t < 32 * STRIDE; t += blockDim.x) {
+            const int j = t / STRIDE, i = t % STRIDE;
+            ST[t] = (i < MK && j < MK) ? p.invSigma[j * MK + i] : 0.0;
+        }
+    for (int i = gl; i < STRIDE; i += G) dsh[i] = 0.0;
+    __syncthreads();
+    bool active[CPL];
+    int mod[CPL], blo[CPL], bhi[CPL];
+    double cst[CPL];                                  // ν: -0.5 invΣ_jj ; λ: μ_j
+    double Sjj[CPL];
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) {
+        const int j = gl + G * s;
+        active[s] = j < MK;
+        mod[s] = 0;
+        for (int m = 0; m < M; ++m)
+            if (j >= p.koff[m]) mod[s] = m;
+        blo[s] = p.koff[mod[s]];
+        bhi[s] = p.koff[mod[s] + 1];
+        Sjj[s] = active[s] ? p.invSigma[j * MK + j] : 0.0;
+        cst[s] = NU ? -0.5 * Sjj[s] : (active[s] ? p.mu[j] : 0.0);
+    }
+    // iterate (per lane and slot) and LD_MMA scalars (identical in the lanes of a group)
+    double x[CPL], g[CPL], xp[CPL], xpp[CPL], sig[CPL], isig[CPL];
+    double cN[CPL], hcN[CPL], sth[CPL], oth[CPL];
+    double acch[CPL], accl[CPL];                      // Σ of this phase's result (dd)
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) {
+        x[s] = xp[s] = xpp[s] = NU ? 1.5 : cst[s];
+        g[s] = 0.0;
+        sig[s] = isig[s] = 1.0;
+        cN[s] = hcN[s] = sth[s] = oth[s] = 0.0;
+        acch[s] = accl[s] = 0.0;
+    }
+    const double INF = __longlong_as_double(0x7ff0000000000000LL);
+    double fmin = INF, rho = 1.0;
+    int k = 1, nev = 0;
+    bool first = false, need = true, alive = true;
+    long long dcur = -1;
+    const double lb = NU ? 1e-7 : -INF;
+    const int stop_rule = p.stop_rule;
+
+    while (true) {
+        // ---- groups whose solve ended store it and take their next sample (warp-uniform branch)
+        if (__any_sync(FULLMASK, need)) {
+            if (need) {
+                if (alive) {
+                    dcur = next_sample(p.work, gmask, grp * G, gl == 0);
+                    if (dcur >= p.D) alive = false;
+                }
+                if (alive) {
+                    if (NU) {
+                        // ζ from the old λ, ν (src/MMCTM.jl:450-452), then ν's problem
+                        double nu0[CPL];
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const long long base = dcur * MK + gl + G * s;
+                            oth[s] = active[s] ? p.lam_prev[base] : 0.0;
+                            nu0[s] = active[s] ? p.nu[base] : 1.5;
+                            dsh[gl + G * s] = active[s] ? det_exp(oth[s] + 0.5 * nu0[s]) : 0.0;
+                        }
+                        __syncwarp(gmask);
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            double zeta = 0.0;
+                            for (int i = blo[s]; i < bhi[s]; ++i) zeta += dsh[i];
+                            const double Ndm = active[s] ? p.N[dcur * M + mod[s]] : 0.0;
+                            cN[s] = active[s] ? Ndm / zeta : 0.0;
+                            hcN[s] = cN[s] / 2;
+                            if (active[s] && gl + G * s == blo[s]) p.zeta[dcur * M + mod[s]] = zeta;
+                            x[s] = nu0[s];
+                        }
+                        __syncwarp(gmask);
+                    } else {
+                        // λ's problem: the new ν, the old ζ (both written by the ν kernel), the old sumθ (:454)
+#pragma unroll
+                        for (int s = 0; s < CPL; ++s) {
+                            const long long base = dcur * MK + gl + G * s;
+                            x[s] = active[s] ? p.lam_prev[base] : 0.0;
+                            oth[s] = active[s] ? 0.5 * p.nu[base] : 0.0;
+                            sth[s] = active[s] ? p.sumtheta[base] : 0.0;
+                            const double Ndm = active[s] ? p.N[dcur * M + mod[s]] : 0.0;
+                            const double zeta = active[s] ? p.zeta[dcur * M + mod[s]] : 1.0;
+                            cN[s] = active[s] ? Ndm / zeta : 0.0;
+                        }
+                    }
+                    first = true;
+                    fmin = 0.0;
+                } else {
+                    // no sample left: a fixed point of the state machine (zero gradient: the proposal never moves;
+                    // fmin = +inf: every trip "ends an inner loop" and "stops", and a dead group's stop is ignored)
+#pragma unroll
+                    for (int s = 0; s < CPL; ++s) {
+                        x[s] = NU ? 1.5 : cst[s];
+                        cN[s] = hcN[s] = sth[s] = oth[s] = 0.0;
+                    }
+                    first = false;
+                    fmin = INF;
+                }
+#pragma unroll
+                for (int s = 0; s < CPL; ++s) {
+                    g[s] = 0.0;
+                    xp[s] = xpp[s] = x[s];
+                    sig[s] = isig[s] = 1.0;
+                }
+                rho = 1.0;
+                k = 1;
+                nev = 0;
+                need = false;
+            }
+            if (!__any_sync(FULLMASK, alive)) break;
+        }
+
+        // ---- propose the next point (NLopt mma.c inner iteration, m = 0 constraints).  On a solve's first
+        // trip g = 0, so the proposal is x itself and the trip evaluates the starting point.
+        double xe[CPL], gt[CPL], wt[CPL];
+        const double hr = 0.5 * rho;
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            double u = g[s];
+            const double v = fabs(g[s]) * sig[s] + hr;
+            const double sigma2 = sig[s] * sig[s];
+            u *= sigma2;
+            const double qv = fast_div(u, v);
+            const double r = qv * isig[s];                  // DET: (u / v)(1 / sigma)
+            const double om = fabs(1 - r * r);
+            const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
+            double dx = fast_div(qv, -1 - sq);
+            double xc = x[s] + dx;
+            const double mv = 0.9 * sig[s], xhi = x[s] + mv, xlo = x[s] - mv;
+            xc = xc > xhi ? xhi : (xc < xlo ? xlo : xc);
+            if (NU) xc = (!first && xc < lb) ? lb : xc;          // the starting point is evaluated as given
+            dx = xc - x[s];
+            const double dx2 = dx * dx;
+            const double denominv = fast_rcp(sigma2 - dx2);       // |dx| <= 0.9 sigma
+            const double cc = sigma2 * dx;
+            gt[s] = (g[s] * cc + v * dx2) * denominv;
+            wt[s] = 0.5 * dx2 * denominv;
+            xe[s] = xc;
+        }
+        // ---- lane-local part of the objective at xe (src/common.jl:11-36)
+        double tl[CPL], gcur[CPL];
+        if (NU) {
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const double e = det_exp(oth[s] + 0.5 * xe[s]);
+                const double grad = (cst[s] - hcN[s] * e) + fast_rcp(2 * xe[s]);
+                tl[s] = (-0.5 * (xe[s] * Sjj[s]) - cN[s] * e) + det_log(xe[s]) / 2;
+                gcur[s] = -grad;
+            }
+        } else {
+            double diff[CPL];
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                diff[s] = xe[s] - cst[s];
+                dsh[gl + G * s] = active[s] ? diff[s] : 0.0;
+            }
+            __syncwarp();
+            const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
+            double q[CPL], qo[CPL];                     // DET: even / odd index chains, then one add
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) { q[s] = 0.0; qo[s] = 0.0; }
+#pragma unroll 4
+            for (int i = 0; i < MKP / 2; ++i) {
+                const double2 dv = dv2[i];
+#pragma unroll
+                for (int s = 0; s < CPL; ++s) {
+                    const double2 sv = reinterpret_cast<const double2 *>(ST + (gl + G * s) * STRIDE)[i];
+                    q[s] = fma(sv.x, dv.x, q[s]);
+                    qo[s] = fma(sv.y, dv.y, qo[s]);
+                }
+            }
+            __syncwarp();
+#pragma unroll
+            for (int s = 0; s < CPL; ++s) {
+                const double qq = q[s] + qo[s];
+                const double e = det_exp(xe[s] + oth[s]);
+                const double ce = cN[s] * e;
+                const double grad = (-qq + sth[s]) - ce;
+                const double a = qq * diff[s], b = xe[s] * sth[s];
+                tl[s] = (b - 0.5 * a) - ce;
+                gcur[s] = -grad;
+            }
+        }
+        double adl[CPL], xnl[CPL];
+        bool ok26 = true, okabs = true;
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            if (!active[s]) { tl[s] = 0.0; gcur[s] = 0.0; }
+            const double ax = fabs(xe[s]);
+            adl[s] = active[s] ? fabs(xe[s] - xp[s]) : 0.0;
+            xnl[s] = active[s] ? ax : 0.0;
+            okabs = okabs && !(adl[s] > 1e-4);
+            if (stop_rule == 1)
+                ok26 = ok26 && (!active[s] || adl[s] < 1e-4 || adl[s] < 1e-4 * (ax + fabs(xp[s])) * 0.5 || xe[s] == xp[s]);
+        }
+        // ---- the three group sums in one pass
+        double gterm = lean_slot_sum<G, CPL>(gt), wterm = lean_slot_sum<G, CPL>(wt), t = lean_slot_sum<G, CPL>(tl);
+        lean_sum3<G>(gterm, wterm, t, lane);
+        const double f = -t;
+        const double gval = fmin + gterm;
+        const bool inner_done = !first && (gval >= f);
+        // x-tolerance (NLopt stop.c) on (xcur, xprev), needed only when an inner loop ends
+        bool stop = false;
+        if (__any_sync(FULLMASK, inner_done)) {
+            if (stop_rule == 1) {
+                stop = group_all<G>(ok26, lane);
+            } else {
+                double dn = lean_slot_sum<G, CPL>(adl), xn = lean_slot_sum<G, CPL>(xnl);
+#pragma unroll
+                for (int off = G / 2; off >= 1; off >>= 1) {
+                    const double ta = shfl_xor_d(dn, off), tb = shfl_xor_d(xn, off);
+                    dn = dn + ta;
+                    xn = xn + tb;
+                }
+                stop = (dn <= 1e-4 * xn) || group_all<G>(okabs, lane);
+            }
+        }
+        // ---- state transitions: selects on group-uniform predicates
+        const bool better = alive && (first || f < fmin);
+        ++nev;
+        fmin = better ? f : fmin;
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            x[s] = better ? xe[s] : x[s];
+            g[s] = better ? gcur[s] : g[s];
+        }
+        const bool finish = alive && ((inner_done && stop) || nev >= MMA_MAXEVAL);
+        const bool outer = alive && inner_done && !finish;
+        if (!first && !inner_done && f > gval) {                 // rho grows inside an inner loop
+            const double r1 = 10 * rho, r2 = 1.1 * (rho + guarded_div(f - gval, wterm));
+            rho = r1 < r2 ? r1 : r2;
+        }
+        first = false;
+        if (__any_sync(FULLMASK, outer)) {
+            if (outer) {
+                rho = 0.1 * rho > 1e-5 ? 0.1 * rho : 1e-5;
+#pragma unroll
+                for (int s = 0; s < CPL; ++s) {
+                    if (k > 1) {
+                        const double s2 = (xe[s] - xp[s]) * (xp[s] - xpp[s]);
+                        const double gam = s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
+                        sig[s] = sig[s] * gam;
+                        isig[s] = fast_rcp(sig[s]);
+                    }
+                    xpp[s] = xp[s];
+                    xp[s] = xe[s];
+                }
+                ++k;
+            }
+        }
+        if (finish) {
+            double *dst = NU ? p.nu : p.lam;
+#pragma unroll
+            for (int s = 0; s < CPL; ++s)
+                if (active[s]) { dst[dcur * MK + gl + G * s] = x[s]; dd_add(acch[s], accl[s], x[s]); }
+            if (gl == 0) (NU ? p.nev_nu : p.nev_lam)[dcur] = nev;
+            need = true;
+        }
+    }
+#pragma unroll
+    for (int s = 0; s < CPL; ++s) red[warp][s][lane] = make_double2(acch[s], accl[s]);
+    __syncthreads();
+    // coordinate j = gl + G s: sum over warps and over the groups; partial: [grid][2 MK], Σλ then Σν
+    for (int j = threadIdx.x; j < MK; j += blockDim.x) {
+        const int s = j / G, l = j % G;
+        double hi = 0.0, lo = 0.0;
+        for (int wv = 0; wv < NW; ++wv)
+            for (int gg = 0; gg < NG; ++gg) {
+                const double2 v = red[wv][s][gg * G + l];
+                dd_merge(hi, lo, v.x, v.y);
+            }
+        put_partial(partial + (size_t)blockIdx.x * 2 * MK + (NU ? MK : 0) + j, hi, lo, p.accum);
+    }
+}
+
+}  // namespace mmsig

@@ -20,6 +20,7 @@
 #ifdef MMSIG_EXPERIMENTAL_SPLIT          // make EXP=1: the split-phase solver, not part of the default build until it is measured
 #include "mmctm_split.cuh"
 #endif
+#include "mmctm_lean.cuh"
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
 #include "lda_tile.cuh"
@@ -92,6 +93,7 @@ struct MmctmHost {
     int grid_solve = 0, grid_post = 0, grid_mom = 0, grid_zeta = 0;
     bool solve_multi = false;          // 16 < sum(K) <= 32: k_solve_multi (4 samples per warp) instead of k_solve
     int solve_split = 0;               // 16 < sum(K) <= 32: k_solve_phase, one kernel per LD_MMA phase (experimental); 8 or 16 = lanes per sample
+    int solve_lean = 0;                // sum(K) <= 32: k_solve_lean, one kernel per LD_MMA phase, G = 4 or 8 lanes per sample (mmctm_lean.cuh)
     bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
     size_t smem_solve = 0;
     double2 *part_mom = nullptr;
@@ -395,10 +397,13 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
         const long long beg = rowptr[d], end = rowptr[d + 1];
         long long s = 0;
         for (long long w = beg + lane; w < end; w += 32) {
-            const int t = term[w], c = count[w];
-            if (t < 0 || t >= V) bad |= 1;
-            if (c <= 0) bad |= 2;
+            int t = term[w], c = count[w];
             if (w > beg && term[w - 1] >= t) bad |= 4;
+            // a bad entry is flagged AND neutralised (term 0, count 0): mmsig_mmctm_fit_host launches the
+            // E-step of a chunk before the flags are read, and the tile kernels index shared memory with
+            // the term (a term < 0 or >= 65536 would also alias into the slot-tag bits)
+            if (t < 0 || t >= V) { bad |= 1; t = 0; c = 0; }
+            if (c <= 0) { bad |= 2; c = 0; }
             rec[w] = make_int2(tag ? (t | (int)(((tag_base + d) & 31) << 16)) : t, c);
             s += c;
         }
@@ -536,6 +541,23 @@ static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, int V, lon
         else { constexpr int MKP = 32; EXPR; }                    \
     } while (0)
 
+// k_solve_lean instance for (lanes per sample G, sum(K)): CPL = ceil(sum(K) / G) coordinates per lane
+#define LEAN_DISPATCH(G_, MK_, PH_, EXPR)                                                        \
+    do {                                                                                         \
+        if ((G_) == 8) {                                                                         \
+            if ((MK_) <= 8) { constexpr int LG = 8, LC = 1, LP = PH_; EXPR; }                    \
+            else if ((MK_) <= 16) { constexpr int LG = 8, LC = 2, LP = PH_; EXPR; }              \
+            else if ((MK_) <= 24) { constexpr int LG = 8, LC = 3, LP = PH_; EXPR; }              \
+            else { constexpr int LG = 8, LC = 4, LP = PH_; EXPR; }                               \
+        } else {                                                                                 \
+            if ((MK_) <= 8) { constexpr int LG = 4, LC = 2, LP = PH_; EXPR; }                    \
+            else if ((MK_) <= 12) { constexpr int LG = 4, LC = 3, LP = PH_; EXPR; }              \
+            else if ((MK_) <= 16) { constexpr int LG = 4, LC = 4, LP = PH_; EXPR; }              \
+            else if ((MK_) <= 20) { constexpr int LG = 4, LC = 5, LP = PH_; EXPR; }              \
+            else { constexpr int LG = 4, LC = 6, LP = PH_; EXPR; }                               \
+        }                                                                                        \
+    } while (0)
+
 // Shape-dependent part of set_data: allocations and launch plans for (D, D_total, M, K, V, nnz_m).
 // *same_out: the resident shape matched and everything was kept.  Counts are not touched.
 static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K, const int32_t *V,
@@ -640,6 +662,9 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
 #ifdef MMSIG_EXPERIMENTAL_SPLIT
         mm.solve_split = (e && p.MK > 16 && p.MK <= 32) ? (!strcmp(e, "split") ? 8 : (!strcmp(e, "split16") ? 16 : 0)) : 0;
 #endif
+        // MMSIG_SOLVE=lean8 | lean4: k_solve_lean with 8 / 4 lanes per sample (mmctm_lean.cuh)
+        mm.solve_lean = (e && p.MK <= 32) ? (!strcmp(e, "lean8") ? 8 : (!strcmp(e, "lean4") ? 4 : 0)) : 0;
+        if (mm.solve_lean == 4 && p.MK > 24) mm.solve_lean = 8;
     }
     CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
@@ -647,7 +672,8 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     };
     if (!mm.wide) {
         int nb = 0;
-        if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
+        if (mm.solve_lean) LEAN_DISPATCH(mm.solve_lean, p.MK, PH_LAM, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_lean<LG, LC, LP>, 128, 0)));
+        else if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
         else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
 #ifdef MMSIG_EXPERIMENTAL_SPLIT
         else if (mm.solve_split == 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<16, 2, PH_LAM>, 128, 0));
@@ -659,7 +685,8 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         else MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
         {
             // samples per block: 8 warps x 1, 2 or 4 (packed), or 4 warps x 4 (multi)
-            const int spb = p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : (mm.solve_split == 16 ? 8 : ((mm.solve_multi || mm.solve_split) ? 16 : 8)));
+            const int spb = mm.solve_lean ? 4 * (32 / mm.solve_lean)
+                          : p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : (mm.solve_split == 16 ? 8 : ((mm.solve_multi || mm.solve_split) ? 16 : 8)));
             mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1),
                                                                             (D + spb - 1) / spb));
         }
@@ -934,6 +961,13 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
     {
         LaunchScope ls(h, "k_solve");
         if (mm.wide) k_solve_wide<<<cap(mm.grid_solve, 8), 256, mm.smem_solve, h->stream>>>(q, mm.part_solve);
+        else if (mm.solve_lean) {
+            // ν for every sample, then λ (which reads the new ν and the ζ the first kernel stored)
+            const int gs = cap(mm.grid_solve, 4 * (32 / mm.solve_lean));
+            LEAN_DISPATCH(mm.solve_lean, q.MK, PH_NU, (k_solve_lean<LG, LC, LP><<<gs, 128, 0, h->stream>>>(q, mm.part_solve)));
+            cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);
+            LEAN_DISPATCH(mm.solve_lean, q.MK, PH_LAM, (k_solve_lean<LG, LC, LP><<<gs, 128, 0, h->stream>>>(q, mm.part_solve)));
+        }
         else if (q.MK <= 8) k_solve_pack<8><<<cap(mm.grid_solve, 32), 256, 0, h->stream>>>(q, mm.part_solve);
         else if (q.MK <= 16) k_solve_pack<16><<<cap(mm.grid_solve, 16), 256, 0, h->stream>>>(q, mm.part_solve);
 #ifdef MMSIG_EXPERIMENTAL_SPLIT

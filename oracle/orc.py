@@ -204,6 +204,20 @@ class OracleMMCTM:
         nnz = int(self._keep[m][0][-1])
         return _view(self.p.contents.theta[m], (nnz, int(self.K[m])))
 
+    def set_state(self, gamma, lam, nu, mu, Sigma, invSigma):
+        """Overwrite the model state (what `fit!` reads from the struct, src/MMCTM.jl:1-27) and re-derive
+        Elnphi (:78-79) and zeta (:85-86) in this oracle's arithmetic: two oracles (or an oracle and the
+        device) can then take one iteration from an IDENTICAL state at any point of a fit."""
+        self.gamma[:] = np.asarray(gamma, float).reshape(-1)
+        self.lam[:] = np.asarray(lam, float).reshape(self.D, self.MK)
+        self.nu[:] = np.asarray(nu, float).reshape(self.D, self.MK)
+        self.mu[:] = np.asarray(mu, float).reshape(-1)
+        self.Sigma[:] = np.asarray(Sigma, float).reshape(self.MK, self.MK)
+        self.invSigma[:] = np.asarray(invSigma, float).reshape(self.MK, self.MK)
+        self.L.orc_mmctm_update_Elnphi(self.p)
+        for d in range(self.D):
+            self.L.orc_mmctm_update_zeta(self.p, d)
+
     def N(self):
         return np.ctypeslib.as_array(self.p.contents.N, shape=(self.D * self.M,)).reshape(self.D, self.M)
 

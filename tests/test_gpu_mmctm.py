@@ -147,22 +147,76 @@ def test_set_state_continues_a_fit(brca):
     a.close(); b.close()
 
 
-def test_against_literal_oracle_statistics(brca):
-    """The literal oracle (glibc exp/log, sequential sums) differs from the pinned arithmetic by
-    rounding only; where MMA takes the same number of evaluations the results agree closely, and the
-    aggregate quantities agree to the level the flipped samples allow."""
-    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
-    g0 = mmsig.synth.init_gamma(K, V)
-    o = oracle_mmctm(K, alpha, V, brca, g0, arith=orc.ARITH_LITERAL)
-    g = mmsig.MMCTM(K, alpha, brca, V=V, gamma0=g0)
-    ll_o, ll_g = o.iterate(), g.iterate()
+# Measured distance between the pinned arithmetic (what the device computes, bit for bit) and the LITERAL
+# restatement of the reference (glibc exp / log, sequential sums), one E+M iteration from an identical state
+# (DESIGN.md section 2 holds the table; tests/test_literal_vs_det_cpu.py asserts the same figures on the CPU).
+# First iteration: brca-eu 5 of 560 samples take another MMA trace, config-4 shape none of 2000.
+LITERAL_FIRST = dict(same=0.99, dlam=1e-7, dnu=1e-7, phi=1e-13, ll=1e-11, mu=1e-8, sigma=1e-7)
+# From the literal oracle's state after 6 / 12 iterations: the conditioning of MMA's stop grows with the fit
+# (cond(Sigma)), more samples flip; phi (a function of the OLD lambda only) and the LL stay tight.
+LITERAL_LATER = dict(same=0.95, phi=1e-13, ll=1e-6)
+
+
+def _literal_stats(o, g, ll_o, ll_g):
     nn, nl = g.evals()
     same = (nn == o.nev_nu) & (nl == o.nev_lambda)
-    assert same.mean() > 0.9
     s = g.state()
-    assert np.abs(s["lam"] - o.lam)[same].max() < 1e-6
-    assert rel_err(ll_g, ll_o) < 1e-6
-    assert rel_err(s["phi"], o.phi) < 1e-5
+    dl = np.abs(s["lam"] - o.lam).max(axis=1)
+    dn = (np.abs(s["nu"] - o.nu) / np.abs(o.nu)).max(axis=1)
+    return dict(same=float(same.mean()), diverged=int((~same).sum()), dlam=float(dl[same].max()), dnu=float(dn[same].max()),
+                phi=rel_err(s["phi"], o.phi), ll=rel_err(ll_g, ll_o), mu=norm_err(s["mu"], o.mu),
+                sigma=norm_err(s["Sigma"], o.Sigma))
+
+
+def _assert_literal(st, lim):
+    assert st["same"] >= lim["same"], st
+    for k in lim:
+        if k != "same":
+            assert st[k] <= lim[k], (k, st)
+
+
+@pytest.mark.parametrize("case", ["brca", "config4"])
+def test_against_literal_oracle_statistics(brca, case):
+    """Device path against the LITERAL oracle, first iteration from the constructor state, at the measured
+    figures: >= 99 % of the samples take the same MMA trace (same evaluation counts); among those
+    |dlambda| <= 1e-7, rel dnu <= 1e-7; phi <= 1e-13, LL <= 1e-11, mu <= 1e-8, Sigma <= 1e-7 (north_star's 1e-12
+    holds for phi and the LL only: lambda, nu are where LD_MMA stops at xtol 1e-4, not an optimum)."""
+    if case == "brca":
+        K, V, counts = [7, 7], [96, 48], brca
+    else:
+        K, V = [10, 8, 6], [96, 32, 83]
+        counts = small_synth(2000, K, V, empty_frac=0.05)
+    alpha = [0.1] * len(K)
+    g0 = mmsig.synth.init_gamma(K, V)
+    o = oracle_mmctm(K, alpha, V, counts, g0, arith=orc.ARITH_LITERAL)
+    g = mmsig.MMCTM(K, alpha, counts, V=V, gamma0=g0)
+    ll_o, ll_g = o.iterate(), g.iterate()
+    st = _literal_stats(o, g, ll_o, ll_g)
+    print("literal-vs-device, first iteration,", case, st)
+    _assert_literal(st, LITERAL_FIRST)
+    g.close()
+
+
+@pytest.mark.parametrize("case,iters", [("brca", 12), ("config4", 6)])
+def test_against_literal_oracle_later_iteration(brca, case, iters):
+    """The same comparison from the LITERAL oracle's own state after `iters` iterations (identical state on
+    both sides through set_state): what a user of the reference would see between two builds of it."""
+    if case == "brca":
+        K, V, counts = [7, 7], [96, 48], brca
+    else:
+        K, V = [10, 8, 6], [96, 32, 83]
+        counts = small_synth(2000, K, V, empty_frac=0.05)
+    alpha = [0.1] * len(K)
+    g0 = mmsig.synth.init_gamma(K, V)
+    o = oracle_mmctm(K, alpha, V, counts, g0, arith=orc.ARITH_LITERAL)
+    for _ in range(iters):
+        o.iterate()
+    g = mmsig.MMCTM(K, alpha, counts, V=V, gamma0=g0)
+    g.set_state(o.gamma.copy(), lam=o.lam.copy(), nu=o.nu.copy(), mu=o.mu.copy(), Sigma=o.Sigma.copy(), invSigma=o.invSigma.copy())
+    ll_o, ll_g = o.iterate(), g.iterate()
+    st = _literal_stats(o, g, ll_o, ll_g)
+    print("literal-vs-device, iteration %d," % (iters + 1), case, st)
+    _assert_literal(st, LITERAL_LATER)
     g.close()
 
 
@@ -260,6 +314,37 @@ def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
         g.close()
 
 
+@pytest.mark.parametrize("variant", ["lean8", "lean4", "warp"])
+def test_solver_layouts_are_bit_identical(monkeypatch, variant):
+    """MMSIG_SOLVE selects the lane layout of the LD_MMA kernels for sum(K) <= 32: lean8 / lean4 (csrc/mmctm_lean.cuh:
+    one kernel per phase, 8 / 4 lanes per sample, several coordinates per lane) or warp (k_solve / k_solve_pack: one
+    kernel, one coordinate per lane).  Same arithmetic, so every layout is bit-identical to the oracle, per-sample
+    evaluation counts included; edge shapes: sum(K) = 32 (no padding lane), 5 (mostly padding), empty rows."""
+    monkeypatch.setenv("MMSIG_SOLVE", variant)
+    for K, V, D in (([10, 8, 6], [96, 32, 83], 700), ([16, 16], [40, 7], 300), ([9, 8], [30, 20], 300), ([10], [96], 500),
+                    ([7, 7], [96, 32], 400), ([3, 2], [10, 6], 67), ([12, 12, 5], [30, 20, 9], 200)):
+        counts = small_synth(D, K, V, empty_frac=0.05)
+        g0 = mmsig.synth.init_gamma(K, V)
+        o, g = _pair(K, [0.1] * len(K), V, counts, g0)
+        for _ in range(3):
+            ll_o, ll_g = o.iterate(), g.iterate()
+            _check_iteration(o, g, ll_o, ll_g)
+        g.close()
+    # stop rule of NLopt <= 2.6 and a starting nu below LD_MMA's lower bound (evaluated as given, then clamped)
+    K, V = [10, 8, 6], [96, 32, 83]
+    counts = small_synth(300, K, V, empty_frac=0.05)
+    g0 = mmsig.synth.init_gamma(K, V)
+    o, g = _pair(K, [0.1] * 3, V, counts, g0, stop_rule=1)
+    nu0 = np.ones((300, 24)); nu0[::7, ::5] = 1e-9
+    lam0 = np.zeros((300, 24))
+    o.set_state(g0, lam0, nu0, np.zeros(24), np.eye(24), np.eye(24))
+    g.set_state(g0, lam=lam0, nu=nu0)
+    for _ in range(2):
+        ll_o, ll_g = o.iterate(), g.iterate()
+        _check_iteration(o, g, ll_o, ll_g)
+    g.close()
+
+
 @pytest.mark.skipif(os.environ.get("MMSIG_EXPERIMENTAL") != "1",
                     reason="experimental kernels, not in the default build: make EXP=1, MMSIG_LIB=.../libmmsig_exp.so, "
                            "MMSIG_EXPERIMENTAL=1 (profiles/ab_solve_split.sh)")
@@ -331,4 +416,15 @@ def test_fit_host_rejects_bad_counts():
         m.fit_host(bad2, g0, maxiter=1)
     hist, _ = m.fit_host(counts, g0, maxiter=2)        # the handle recovers
     assert np.isfinite(hist).all()
+    # terms far outside the tile (negative, aliasing into the slot-tag bits of a record, huge): fit_host
+    # launches a chunk's E-step before it reads the validation flags, so the packing kernel has to
+    # neutralise such a record, not only flag it (an out-of-bounds shared-memory write would poison the context)
+    for t_bad in (-1, 65535, 70000, 0x7fff0000, -(2 ** 31)):
+        bad3 = [(r.copy(), t.copy(), c.copy()) for r, t, c in counts]
+        w = int(bad3[0][0][7 + 1]) - 1                 # last nonzero of row 7 (keeps the row ascending unless negative)
+        bad3[0][1][w] = t_bad
+        with pytest.raises(mmsig.capi.MmsigError):
+            m.fit_host(bad3, g0, maxiter=1)
+        hist, _ = m.fit_host(counts, g0, maxiter=1)    # no sticky error: the same handle still works
+        assert np.isfinite(hist).all()
     m.close()
