@@ -79,6 +79,69 @@ int32_t     mmsig_synchronize(mmsig_handle *h);
 int32_t mmsig_comm_unique_id(uint8_t id_out[128]);
 int32_t mmsig_comm_init(mmsig_handle *h, const uint8_t id[128], int32_t rank, int32_t nranks);
 
+/* ---- multi-GPU from ONE process: a group of devices -------------------------------------------
+ * The reference's only parallelism is `addprocs` + `pmap` over independent restarts
+ * (scripts/run_mmctm.jl:8-11,99-111); fit! itself is serial (src/MMCTM.jl:463-465).  A group serves a single
+ * caller (julia/MMSigB200.jl: fit!(model; devices=0:7), fit_restarts(...; devices=0:7)) with both patterns:
+ *   - one fit with the samples sharded over the devices (contiguous shards balanced by nonzeros); per iteration
+ *     the members exchange the same two packed buffers of double-double partial sums as above, by peer stores
+ *     over NVLink into each other's exchange arenas + stream-ordered events (no NCCL, no host staging), and
+ *     every member reduces them in rank order: all devices hold bit-identical globals, and the result is
+ *     bit-identical to the one-GPU fit;
+ *   - restarts dealt over the devices, each device holding the whole corpus, no communication.
+ * The group runs one host thread per device inside each call; calls block; a group is not thread-safe.
+ * All arrays are those of the one-handle calls for the WHOLE corpus (the library shards them).  The same
+ * device may be listed more than once (several shards on one GPU: how a one-GPU box tests this path);
+ * distinct devices need peer access to one another. */
+typedef struct mmsig_group mmsig_group;
+int32_t     mmsig_group_create(const mmsig_config *cfg, int32_t n_devices, const int32_t *device_ids, mmsig_group **out);
+int32_t     mmsig_group_destroy(mmsig_group *g);
+const char *mmsig_group_last_error(const mmsig_group *g);     /* g may be NULL: last create error */
+int32_t     mmsig_group_size(const mmsig_group *g);
+/* member i's handle, for the instrumentation calls only (mmsig_launch_count, mmsig_kernel_times) */
+mmsig_handle *mmsig_group_member(mmsig_group *g, int32_t i);
+int32_t mmsig_group_mmctm_set_data(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+                                   const int64_t *const *rowptr, const int32_t *const *term,
+                                   const int32_t *const *count);
+int32_t mmsig_group_mmctm_set_state(mmsig_group *g, const double *alpha, const double *gamma, const double *lambda,
+                                    const double *nu, const double *mu, const double *Sigma, const double *invSigma);
+int32_t mmsig_group_mmctm_iterate(mmsig_group *g, uint32_t flags, double *ll_out);
+int32_t mmsig_group_mmctm_fit(mmsig_group *g, int32_t maxiter, double tol, uint32_t flags, double *ll_hist,
+                              int32_t *n_iter, int32_t *converged);
+int32_t mmsig_group_mmctm_elbo(mmsig_group *g, double *elbo, double *terms);
+int32_t mmsig_group_mmctm_get_state(mmsig_group *g, double *lambda, double *nu, double *zeta, double *mu,
+                                    double *Sigma, double *invSigma, double *gamma, double *Elnphi, double *phi,
+                                    double *props);
+int32_t mmsig_group_mmctm_get_evals(mmsig_group *g, int32_t *nev_nu, int32_t *nev_lambda);
+/* mmsig_mmctm_fit_host over the group: every device pipelines its shard's uploads behind its own E-step */
+int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+                                   const int64_t *const *rowptr, const int32_t *const *term,
+                                   const int32_t *const *count, const double *alpha, const double *gamma,
+                                   const double *lambda, const double *nu, const double *mu, const double *Sigma,
+                                   const double *invSigma, int32_t maxiter, double tol, uint32_t flags,
+                                   double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
+                                   double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
+                                   double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
+                                   double *props_out);
+/* R independent restarts dealt over the devices (restart r on member r mod n; every member holds the whole
+ * corpus; scripts/run_mmctm.jl:99-111's pmap): outputs as mmsig_mmctm_restarts; afterwards
+ * mmsig_group_mmctm_get_state / _elbo read the device that holds the best restart. */
+int32_t mmsig_group_mmctm_restarts(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+                                   const int64_t *const *rowptr, const int32_t *const *term,
+                                   const int32_t *const *count, const double *alpha, int32_t R, const double *gamma0,
+                                   int32_t maxiter, double tol, uint32_t flags, double *elbo_out, double *ll_out,
+                                   int32_t *n_iter_out, int32_t *best);
+/* LDA (src/LDA.jl:198-224) over the group */
+int32_t mmsig_group_lda_set_data(mmsig_group *g, int64_t D, int32_t K, int32_t V, const int64_t *rowptr,
+                                 const int32_t *term, const int32_t *count);
+int32_t mmsig_group_lda_set_state(mmsig_group *g, double alpha, double eta, const double *lambda,
+                                  const double *gamma_next);
+int32_t mmsig_group_lda_fit(mmsig_group *g, int32_t maxiter, double tol, double *ll_hist, int32_t *n_iter,
+                            int32_t *converged);
+int32_t mmsig_group_lda_elbo(mmsig_group *g, double *elbo, double *terms);
+int32_t mmsig_group_lda_get_state(mmsig_group *g, double *lambda, double *Elnbeta, double *beta, double *gamma,
+                                  double *Elntheta, double *theta);
+
 /* ---- count ingest: format_counts_mmctm / _ctm / _lda (reference src/utils.jl:1-36) on the device ----
  * make_count_matrix (src/utils.jl:1-7) for every sample of one modality's dense count matrix:
  * entries > 0 become (term, count) rows in ascending term order, entries <= 0 are dropped.

@@ -40,6 +40,27 @@ _SIGS = {
     "mmsig_synchronize": (C.c_int32, [C.c_void_p]),
     "mmsig_comm_unique_id": (C.c_int32, [c_u8p]),
     "mmsig_comm_init": (C.c_int32, [C.c_void_p, c_u8p, C.c_int32, C.c_int32]),
+    "mmsig_group_create": (C.c_int32, [C.POINTER(Config), C.c_int32, c_i32p, C.POINTER(C.c_void_p)]),
+    "mmsig_group_destroy": (C.c_int32, [C.c_void_p]),
+    "mmsig_group_last_error": (C.c_char_p, [C.c_void_p]),
+    "mmsig_group_size": (C.c_int32, [C.c_void_p]),
+    "mmsig_group_member": (C.c_void_p, [C.c_void_p, C.c_int32]),
+    "mmsig_group_mmctm_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)]),
+    "mmsig_group_mmctm_set_state": (C.c_int32, [C.c_void_p] + [c_dp] * 7),
+    "mmsig_group_mmctm_iterate": (C.c_int32, [C.c_void_p, C.c_uint32, c_dp]),
+    "mmsig_group_mmctm_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p]),
+    "mmsig_group_mmctm_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
+    "mmsig_group_mmctm_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 10),
+    "mmsig_group_mmctm_get_evals": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
+    "mmsig_group_mmctm_fit_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)] + [c_dp] * 7 +
+                                   [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
+    "mmsig_group_mmctm_restarts": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p), c_dp, C.c_int32, c_dp,
+                                               C.c_int32, C.c_double, C.c_uint32, c_dp, c_dp, c_i32p, c_i32p]),
+    "mmsig_group_lda_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p]),
+    "mmsig_group_lda_set_state": (C.c_int32, [C.c_void_p, C.c_double, C.c_double, c_dp, c_dp]),
+    "mmsig_group_lda_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, c_dp, c_i32p, c_i32p]),
+    "mmsig_group_lda_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
+    "mmsig_group_lda_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 6),
     "mmsig_tsv_dims": (C.c_int32, [C.c_char_p, c_i64p, c_i64p]),
     "mmsig_tsv_read": (C.c_int32, [C.c_char_p, C.c_int64, C.c_int64, c_i32p]),
     "mmsig_format_counts": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_int32, C.c_int32, c_i64p, c_i64p]),
@@ -181,6 +202,49 @@ class Handle:
         if k < 0:
             self.check(k)
         return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(k)}
+
+
+class Group:
+    """Owns one mmsig_group: several GPUs driven from this process (include/mmsig.h)."""
+
+    def __init__(self, devices, stop_rule=STOP_NLOPT27, profile=False):
+        self.lib = load()
+        self.devices = [int(d) for d in devices]
+        cfg = Config(device=self.devices[0], stop_rule=stop_rule, profile=int(profile))
+        ids = np.asarray(self.devices, np.int32)
+        gp = C.c_void_p()
+        rc = self.lib.mmsig_group_create(C.byref(cfg), len(self.devices), ids.ctypes.data_as(c_i32p), C.byref(gp))
+        if rc != 0:
+            raise MmsigError(rc, (self.lib.mmsig_group_last_error(None) or b"").decode())
+        self.g = gp
+
+    def check(self, rc):
+        if rc != 0:
+            raise MmsigError(rc, (self.lib.mmsig_group_last_error(self.g) or b"").decode())
+
+    def close(self):
+        if getattr(self, "g", None):
+            self.lib.mmsig_group_destroy(self.g)
+            self.g = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def launch_count(self):
+        return sum(int(self.lib.mmsig_launch_count(C.c_void_p(self.lib.mmsig_group_member(self.g, i))))
+                   for i in range(len(self.devices)))
+
+    def kernel_times(self, member=0, reset=False):
+        n = 64
+        names = (C.c_char_p * n)()
+        ms = np.zeros(n)
+        cnt = np.zeros(n, dtype=np.int64)
+        h = C.c_void_p(self.lib.mmsig_group_member(self.g, member))
+        k = self.lib.mmsig_kernel_times(h, n, names, dp(ms), cnt.ctypes.data_as(c_i64p), int(reset))
+        return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(max(k, 0))}
 
 
 def comm_unique_id():

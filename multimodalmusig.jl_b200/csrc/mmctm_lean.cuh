@@ -292,7 +292,8 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
                     dn = dn + ta;
                     xn = xn + tb;
                 }
-                stop = (dn <= 1e-4 * xn) || group_all<G>(okabs, lane);
+                const bool allabs = group_all<G>(okabs, lane);      // a full-mask vote: every lane takes it (no short circuit)
+                stop = (dn <= 1e-4 * xn) || allabs;
             }
         }
         // ---- state transitions: selects on group-uniform predicates

@@ -1,12 +1,15 @@
 // mmsig_api.cu -- the C ABI of libmmsig.so (include/mmsig.h): handle, device memory, launch
 // plans, NCCL exchange, fit loops.  Host side of the MMCTM / CTM / LDA variational-EM path.
 #include <algorithm>
+#include <atomic>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <sched.h>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -125,7 +128,32 @@ struct LdaHost {
     std::vector<double> etaf_host;      // ILDA: eta per feature
 };
 
+// One process, several GPUs (include/mmsig.h "mmsig_group"): a group owns one handle per device and drives
+// each from its own host thread.  Handles of a group exchange their packed partial sums through peer memory:
+// a rank pushes its buffer into a slot of every member's exchange arena with plain stores over NVLink
+// (k_group_push), records an event, and every member's stream waits for every other member's event.  No
+// NCCL, no spin-waits; the only host-side coupling is a pthread barrier (events must be recorded before a
+// peer can wait on them).  The arena is double-buffered by call parity, so a slot is rewritten only after
+// the exchange that followed its readers.
+struct mmsig_group {
+    int n = 0;
+    std::vector<mmsig_handle *> h;
+    std::vector<int> devices;
+    struct GroupBarrier *bar = nullptr;
+    std::vector<double2 *> arena;               // [rank] current exchange arena of that member (device memory of its GPU)
+    std::vector<size_t> arena_cap;              // [rank] capacity in double2
+    std::vector<cudaEvent_t> ev;                // [rank * 2 + parity]
+    std::vector<long long> scratch;             // [rank * MAXM8 + i] host-side all-sum
+    std::vector<int> status;                    // [rank] result of the member's part of a group call
+    std::vector<long long> cut;                 // row boundaries of the shards of the resident corpus
+    int replica_best = -1;                      // after mmsig_group_mmctm_restarts: the member that holds the best restart
+    std::string err;
+};
+
 struct mmsig_handle {
+    mmsig_group *grp = nullptr;                        // member of a single-process multi-GPU group
+    int xparity = 0;                                   // exchange arena buffer of the next group gather
+    std::vector<void *> old_arenas;                    // outgrown arenas, freed with the handle
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of mmsig_mmctm_fit_host
@@ -218,8 +246,44 @@ static void resolve_pending(mmsig_handle *h) {
     h->pending.clear();
 }
 
+// ---- exchange inside a single-process group (peer memory) ------------------------------------
+// spin-then-yield barrier over the group's host threads that can be aborted: a member that fails
+// releases the others with an error instead of leaving them waiting
+struct GroupBarrier {
+    std::atomic<int> count{0}, gen{0};
+    std::atomic<bool> aborted{false};
+    int n = 1;
+    bool wait() {
+        if (aborted.load(std::memory_order_acquire)) return false;
+        const int g = gen.load(std::memory_order_acquire);
+        if (count.fetch_add(1, std::memory_order_acq_rel) + 1 == n) {
+            count.store(0, std::memory_order_relaxed);
+            gen.fetch_add(1, std::memory_order_acq_rel);
+            return true;
+        }
+        for (int spin = 0; gen.load(std::memory_order_acquire) == g; ++spin) {
+            if (aborted.load(std::memory_order_acquire)) return false;
+            if (spin > 4000) sched_yield();
+        }
+        return !aborted.load(std::memory_order_acquire);
+    }
+    void abort() { aborted.store(true, std::memory_order_release); }
+    void reset(int n_) { n = n_; count.store(0); aborted.store(false); }
+};
+
+struct PeerSlots { double2 *p[16]; int n; };
+__global__ void k_group_push(const double2 *__restrict__ src, size_t n, PeerSlots dst) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double2 v = src[i];
+        for (int r = 0; r < dst.n; ++r) dst.p[r][i] = v;          // peer stores over NVLink (own slot: local)
+    }
+}
+
+static int group_gather(mmsig_handle *h, const double2 *rank_buf, size_t n, const double2 **out);
+
 static int gather(mmsig_handle *h, const double2 *rank_buf, double2 *gath_buf, size_t n, const double2 **out) {
     if (h->nranks == 1) { *out = rank_buf; return 0; }
+    if (h->grp) return group_gather(h, rank_buf, n, out);
     LaunchScope ls(h, "ncclAllGather");
     int rc = g_nccl.AllGather(rank_buf, gath_buf, n * 2, kNcclFloat64, h->comm, h->stream);
     if (rc != 0)
@@ -363,9 +427,11 @@ extern "C" int32_t mmsig_kernel_times(mmsig_handle *h, int32_t n_max, const char
 }
 
 // sum of per-rank int64 totals (Σ_d N_dm) over ranks, on the host
+static int group_allsum(mmsig_handle *h, long long *vals, int n);
 static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
     if (h->nranks == 1) return 0;
     NEED(n <= MAXM, "allsum_ll: too many values");
+    if (h->grp) return group_allsum(h, vals, n);
     if (!h->allsum_buf) CU(cudaMalloc(&h->allsum_buf, (size_t)MAXM * (h->nranks + 1) * sizeof(long long)));   // kept: no malloc / free per call
     long long *d_in = h->allsum_buf, *d_out = h->allsum_buf + MAXM;
     CU(cudaMemcpyAsync(d_in, vals, n * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
@@ -1684,6 +1750,7 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
 }
 
 #include "ingest_api.inl"
+#include "group_api.inl"
 
 extern "C" int32_t mmsig_lda_iterate_flags(mmsig_handle *h, uint32_t flags, double *ll_out);
 #include "lda_api.inl"

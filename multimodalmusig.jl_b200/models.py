@@ -604,3 +604,122 @@ class ILDA(LDA):
         new.ll_history = new._loop(capi.FLAG_FREEZE_TOPICS, maxiter, 1e-4, verbose)
         new.elbo = new.calculate_elbo()[0]
         return new
+
+
+class MMCTMGroup:
+    """MMCTM over several GPUs of ONE process (mmsig_group_*): `fit!(model; devices=0:7)` of the Julia shim.
+    Same arrays as MMCTM for the whole corpus; the library shards the samples (contiguous, balanced by
+    nonzeros) and every device ends each iteration with bit-identical tables."""
+
+    def __init__(self, K, alpha, counts, devices, V=None, gamma0=None, rng=None, stop_rule=capi.STOP_NLOPT27, profile=False):
+        self.K = [int(k) for k in K]
+        self.M = len(self.K)
+        self.alpha = np.asarray(alpha, dtype=np.float64).copy()
+        self.V = infer_V(counts) if V is None else [int(v) for v in V]
+        self.D = len(counts[0][0]) - 1
+        self.MK = sum(self.K)
+        self.G = sum(k * v for k, v in zip(self.K, self.V))
+        if gamma0 is None:
+            rng = np.random.default_rng() if rng is None else rng
+            gamma0 = rng.integers(1, 101, size=self.G).astype(np.float64)
+        self.grp = capi.Group(devices, stop_rule=stop_rule, profile=profile)
+        self._csr(counts)
+        lib = self.grp.lib
+        self.grp.check(lib.mmsig_group_mmctm_set_data(self.grp.g, self.D, self.M, *self._kv, *self._ptrs))
+        self.set_state(gamma0)
+        self.converged, self.elbo, self.ll = False, float("nan"), None
+
+    def _csr(self, counts):
+        keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32), np.ascontiguousarray(c, np.int32))
+                for r, t, c in counts]
+        M = self.M
+        self._keep = keep
+        self._ptrs = ((capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep]),
+                      (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep]),
+                      (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep]))
+        self._K32, self._V32 = np.asarray(self.K, np.int32), np.asarray(self.V, np.int32)
+        self._kv = (self._K32.ctypes.data_as(capi.c_i32p), self._V32.ctypes.data_as(capi.c_i32p))
+
+    def set_state(self, gamma, lam=None, nu=None, mu=None, Sigma=None, invSigma=None):
+        D, MK = self.D, self.MK
+        a = [capi.f64(self.alpha, self.M), capi.f64(gamma, self.G), capi.f64(lam, D * MK), capi.f64(nu, D * MK),
+             capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_set_state(self.grp.g, *[capi.dp(x) for x in a]))
+
+    def iterate(self, updateSigma=True, flags=None):
+        ll = np.zeros(self.M)
+        if flags is None:
+            flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_iterate(self.grp.g, flags, capi.dp(ll)))
+        return ll
+
+    def fit(self, maxiter=100, tol=1e-4, updateSigma=True, verbose=False):
+        hist = np.zeros((maxiter, self.M))
+        n, conv = C.c_int32(0), C.c_int32(0)
+        flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_fit(self.grp.g, maxiter, tol, flags, capi.dp(hist), C.byref(n), C.byref(conv)))
+        hist = hist[:n.value].copy()
+        self.converged, self.ll = bool(conv.value), hist[-1].copy()
+        self.elbo = self.calculate_elbo()[0]
+        return hist
+
+    def calculate_elbo(self):
+        e, t = C.c_double(0.0), np.zeros(7)
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_elbo(self.grp.g, C.byref(e), capi.dp(t)))
+        return e.value, t
+
+    def _state_buffers(self, props=True):
+        D, MK, M, G = self.D, self.MK, self.M, self.G
+        out = {"lam": np.empty((D, MK)), "nu": np.empty((D, MK)), "zeta": np.empty((D, M)), "mu": np.empty(MK),
+               "Sigma": np.empty((MK, MK)), "invSigma": np.empty((MK, MK)), "gamma": np.empty(G), "Elnphi": np.empty(G),
+               "phi": np.empty(G)}
+        if props:
+            out["props"] = np.empty((D, MK))
+        return out
+
+    def state(self, props=True):
+        out = self._state_buffers(props)
+        order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_get_state(self.grp.g, *[capi.dp(out.get(k)) for k in order]))
+        return out
+
+    def evals(self):
+        a, b = np.zeros(self.D, np.int32), np.zeros(self.D, np.int32)
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_get_evals(self.grp.g, a.ctypes.data_as(capi.c_i32p), b.ctypes.data_as(capi.c_i32p)))
+        return a, b
+
+    def fit_host(self, counts, gamma, lam=None, nu=None, mu=None, Sigma=None, invSigma=None, maxiter=100, tol=1e-4,
+                 updateSigma=True, out=None, props=True):
+        """mmsig_group_mmctm_fit_host: the whole fit from / to host buffers over all devices of the group."""
+        self._csr(counts)
+        self.D = len(counts[0][0]) - 1
+        D, MK = self.D, self.MK
+        out = self._state_buffers(props) if out is None else out
+        a = [capi.f64(self.alpha, self.M), capi.f64(gamma, self.G), capi.f64(lam, D * MK), capi.f64(nu, D * MK),
+             capi.f64(mu, MK), capi.f64(Sigma, MK * MK), capi.f64(invSigma, MK * MK)]
+        hist = np.zeros((maxiter, self.M))
+        n, conv = C.c_int32(0), C.c_int32(0)
+        order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
+        flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_fit_host(
+            self.grp.g, D, self.M, *self._kv, *self._ptrs, *[capi.dp(x) for x in a], maxiter, tol, flags, capi.dp(hist),
+            C.byref(n), C.byref(conv), *[capi.dp(out.get(k)) for k in order]))
+        hist = hist[:n.value].copy()
+        self.converged, self.ll = bool(conv.value), hist[-1].copy()
+        return hist, out
+
+    def fit_restarts(self, gamma0s, maxiter=100, tol=1e-4, updateSigma=True):
+        """R restarts dealt over the devices (scripts/run_mmctm.jl:99-111); returns (elbo[R], ll[R, M], n_iter[R], best);
+        state() / calculate_elbo() afterwards read the best restart."""
+        g0 = capi.f64(np.asarray(gamma0s, float).reshape(-1))
+        R = g0.size // self.G
+        elbo, ll, nit, best = np.zeros(R), np.zeros((R, self.M)), np.zeros(R, np.int32), C.c_int32(-1)
+        flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
+        self.grp.check(self.grp.lib.mmsig_group_mmctm_restarts(
+            self.grp.g, self.D, self.M, *self._kv, *self._ptrs, capi.dp(capi.f64(self.alpha, self.M)), R, capi.dp(g0), maxiter, tol,
+            flags, capi.dp(elbo), capi.dp(ll), nit.ctypes.data_as(capi.c_i32p), C.byref(best)))
+        self.ll = ll[best.value].copy()
+        return elbo, ll, nit, best.value
+
+    def close(self):
+        self.grp.close()
