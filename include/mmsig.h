@@ -71,6 +71,12 @@ const char *mmsig_last_error(const mmsig_handle *h);           /* h may be NULL:
 /* run every kernel of this handle on an existing CUDA stream (a cudaStream_t, e.g. torch's) */
 int32_t     mmsig_set_stream(mmsig_handle *h, void *cuda_stream);
 int32_t     mmsig_synchronize(mmsig_handle *h);
+/* switch the per-kernel CUDA-event timing of cfg.profile on / off (mmsig_kernel_times) */
+int32_t     mmsig_set_profile(mmsig_handle *h, int32_t on);
+/* page-locked ("pinned") host memory for the caller's count / state buffers: transfers from and to it run
+ * at link speed and overlap with kernels; mmsig_mmctm_fit_host accepts pageable buffers too (slower). */
+int32_t     mmsig_host_alloc(uint64_t bytes, void **out);
+int32_t     mmsig_host_free(void *p);
 
 /* ---- multi-GPU: one handle (process) per GPU, samples sharded over ranks -----------------
  * Per iteration the ranks exchange one small packed buffer of double-double partial sums
@@ -113,6 +119,7 @@ int32_t mmsig_group_mmctm_get_state(mmsig_group *g, double *lambda, double *nu, 
                                     double *Sigma, double *invSigma, double *gamma, double *Elnphi, double *phi,
                                     double *props);
 int32_t mmsig_group_mmctm_get_evals(mmsig_group *g, int32_t *nev_nu, int32_t *nev_lambda);
+int32_t mmsig_group_mmctm_get_theta(mmsig_group *g, int32_t m, double *theta_out);
 /* mmsig_mmctm_fit_host over the group: every device pipelines its shard's uploads behind its own E-step */
 int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
                                    const int64_t *const *rowptr, const int32_t *const *term,

@@ -60,15 +60,82 @@ end
 flat_rows(v::Vector{Vector{Float64}}) = collect(reduce(vcat, v))                         # [d][j] -> D*MK row-major
 flat_tables(t::Vector{Vector{Vector{Float64}}}) = collect(reduce(vcat, [reduce(vcat, tm) for tm in t]))   # [m][k][v]
 
+# ---- several GPUs from this process: a group of devices (include/mmsig.h, mmsig_group_*) --------------
+function gcheck(g::Ptr{Cvoid}, rc::Int32)
+    if rc != 0
+        msg = unsafe_string(ccall((:mmsig_group_last_error, LIB), Cstring, (Ptr{Cvoid},), g))
+        error("libmmsig error $rc: $msg")
+    end
+end
+
+function create_group(devices; stop_rule=0)
+    ids = Int32.(collect(devices))
+    cfg = Ref(MmsigConfig(ids[1], Int32(stop_rule), Int32(0), ntuple(_ -> Int32(0), 5)))
+    g = Ref{Ptr{Cvoid}}(C_NULL)
+    rc = ccall((:mmsig_group_create, LIB), Int32, (Ref{MmsigConfig}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), cfg, length(ids), ids, g)
+    gcheck(C_NULL, rc)
+    return g[]
+end
+
+destroy_group(g) = ccall((:mmsig_group_destroy, LIB), Int32, (Ptr{Cvoid},), g)
+
+# flat device results -> the nested vectors of the struct (shapes preserved)
+function scatter_state!(model::MMCTM, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props)
+    D, M, MK = model.D, model.M, sum(model.K)
+    for d in 1:D
+        model.λ[d] .= @view λ[(d - 1) * MK + 1:d * MK]
+        model.ν[d] .= @view ν[(d - 1) * MK + 1:d * MK]
+        model.ζ[d] .= @view ζ[(d - 1) * M + 1:d * M]
+        off = 0
+        for m in 1:M
+            model.props[d][m] = props[(d - 1) * MK + off + 1:(d - 1) * MK + off + model.K[m]]
+            off += model.K[m]
+        end
+    end
+    model.μ .= μ
+    model.Σ .= transpose(reshape(Σ, MK, MK)); model.invΣ .= transpose(reshape(invΣ, MK, MK))
+    o = 0
+    for m in 1:M, k in 1:model.K[m]
+        r = (o + 1):(o + model.V[m])
+        model.γ[m][k] .= @view γ[r]; model.Elnϕ[m][k] .= @view Elnϕ[r]; model.ϕ[m][k] .= @view ϕ[r]
+        o += model.V[m]
+    end
+end
+
+# model.θ[d][m] (K_m x nnz_dm, src/MMCTM.jl:17,52-57): the library never stores θ; it is recomputed from the λ / Elnϕ
+# of the last E-step on request, while the handle (or group) is still alive
+function materialize_theta!(model::MMCTM, h::Ptr{Cvoid}, grouped::Bool)
+    for m in 1:model.M
+        nnz = sum(size(model.X[d][m], 1) for d in 1:model.D)
+        buf = zeros(model.K[m] * nnz)                                   # [w][k] row-major == K_m x nnz column-major
+        if grouped
+            gcheck(h, ccall((:mmsig_group_mmctm_get_theta, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), h, m - 1, buf))
+        else
+            check(h, ccall((:mmsig_mmctm_get_theta, LIB), Int32, (Ptr{Cvoid}, Int32, Ptr{Float64}), h, m - 1, buf))
+        end
+        o = 0
+        for d in 1:model.D
+            n = size(model.X[d][m], 1)
+            model.θ[d][m] = reshape(buf[o + 1:o + model.K[m] * n], model.K[m], n)
+            o += model.K[m] * n
+        end
+    end
+end
+
+# fit!(model; ...) (src/MMCTM.jl:457-494).  Extra keywords: `device` (one GPU), or `devices=0:7` (the samples of this
+# fit sharded over several GPUs of this process, bit-identical results), `materialize_θ=true` to fill model.θ.
 function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true,
-              device=0, stop_rule=0)
+              device=0, devices=nothing, stop_rule=0, materialize_θ=false)
     D, M, MK = model.D, model.M, sum(model.K)
     rowptr, term, count = flatten_counts(model.X, M)
     K32, V32 = Int32.(model.K), Int32.(model.V)
     λ, ν = flat_rows(model.λ), flat_rows(model.ν)
     γ = flat_tables(model.γ)
     Σ, invΣ = collect(transpose(model.Σ)), collect(transpose(model.invΣ))               # row-major
-    h = create(device=device, stop_rule=stop_rule)
+    grouped = devices !== nothing && length(devices) > 1
+    h = grouped ? create_group(devices; stop_rule=stop_rule) :
+                  create(device=(devices === nothing ? device : first(devices)), stop_rule=stop_rule)
+    chk = grouped ? gcheck : check
     ll = Vector{Float64}[]
     try
         flags = UInt32((updateΣ ? 1 : 0) | (autoα ? 16 : 0))
@@ -80,26 +147,50 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
                 # one call: counts + state in, the whole loop of src/MMCTM.jl:462-489, state out, with
                 # the host<->device copies pipelined behind the E-step (mmsig_mmctm_fit_host)
                 hist = zeros(M, maxiter); nit = Ref{Int32}(0); conv = Ref{Int32}(0)
-                check(h, ccall((:mmsig_mmctm_fit_host, LIB), Int32,
-                    (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}},
-                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                     Int32, Float64, UInt32, Ptr{Float64}, Ref{Int32}, Ref{Int32},
-                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
-                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                    h, D, D, M, K32, V32, rp, tp, cp, model.α, γ, λ, ν, model.μ, Σ, invΣ,
-                    maxiter, tol, flags, hist, nit, conv, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+                if grouped
+                    chk(h, ccall((:mmsig_group_mmctm_fit_host, LIB), Int32,
+                        (Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Int32, Float64, UInt32, Ptr{Float64}, Ref{Int32}, Ref{Int32},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        h, D, M, K32, V32, rp, tp, cp, model.α, γ, λ, ν, model.μ, Σ, invΣ,
+                        maxiter, tol, flags, hist, nit, conv, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+                else
+                    chk(h, ccall((:mmsig_mmctm_fit_host, LIB), Int32,
+                        (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Int32, Float64, UInt32, Ptr{Float64}, Ref{Int32}, Ref{Int32},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        h, D, D, M, K32, V32, rp, tp, cp, model.α, γ, λ, ν, model.μ, Σ, invΣ,
+                        maxiter, tol, flags, hist, nit, conv, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+                end
                 ll = [hist[:, i] for i in 1:nit[]]
                 model.converged = conv[] != 0
             else
-                check(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
-                    (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
-                    h, D, D, M, K32, V32, rp, tp, cp))
-                check(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
-                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
-                    h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
+                if grouped
+                    chk(h, ccall((:mmsig_group_mmctm_set_data, LIB), Int32,
+                        (Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                        h, D, M, K32, V32, rp, tp, cp))
+                    chk(h, ccall((:mmsig_group_mmctm_set_state, LIB), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
+                else
+                    chk(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
+                        (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                        h, D, D, M, K32, V32, rp, tp, cp))
+                    chk(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        h, model.α, γ, λ, ν, model.μ, Σ, invΣ))
+                end
                 llbuf = zeros(M)
                 for iter in 1:maxiter                                   # src/MMCTM.jl:462-489
-                    check(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+                    if grouped
+                        chk(h, ccall((:mmsig_group_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+                    else
+                        chk(h, ccall((:mmsig_mmctm_iterate, LIB), Int32, (Ptr{Cvoid}, UInt32, Ptr{Float64}), h, flags, llbuf))
+                    end
                     push!(ll, copy(llbuf))
                     println("$iter\tLog-likelihoods: ", join(ll[end], ", "))      # src/MMCTM.jl:482
                     if length(ll) > 10 && check_convergence(ll, tol=tol)
@@ -107,40 +198,95 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
                         break
                     end
                 end
-                check(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
+                if grouped
+                    chk(h, ccall((:mmsig_group_mmctm_get_state, LIB), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+                else
+                    chk(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
+                        (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                         Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                        h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+                end
+            end
+        end
+        if grouped
+            chk(h, ccall((:mmsig_group_mmctm_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
+        else
+            chk(h, ccall((:mmsig_mmctm_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
+        end
+        scatter_state!(model, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props)
+        materialize_θ && materialize_theta!(model, h, grouped)           # otherwise model.θ keeps its previous value
+        if autoα && !grouped
+            chk(h, ccall((:mmsig_mmctm_get_alpha, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, model.α))
+        elseif autoα
+            h0 = ccall((:mmsig_group_member, LIB), Ptr{Cvoid}, (Ptr{Cvoid}, Int32), h, 0)      # α is identical on every member
+            check(h0, ccall((:mmsig_mmctm_get_alpha, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h0, model.α))
+        end
+        model.elbo = elbo[]
+        model.ll = ll[end]
+    finally
+        grouped ? destroy_group(h) : destroy(h)
+    end
+    return ll
+end
+
+# "fit many models and pick the best one" (README.md:42; scripts/run_mmctm.jl:77-111): R restarts from the rows of
+# γ0s (each a flat [m][k][v] table, e.g. flat_tables(MMCTM(K, α, X).γ)), on one GPU or dealt over `devices`
+# (restart r on device r mod n, no communication).  The best restart's state (arg-max ELBO) is loaded into `model`;
+# returns (elbo per restart, final log-likelihoods per restart, iterations per restart, index of the best).
+function fit_restarts!(model::MMCTM, γ0s::Vector{Vector{Float64}}; maxiter=100, tol=1e-4, updateΣ=true,
+                       device=0, devices=nothing, stop_rule=0)
+    D, M, MK = model.D, model.M, sum(model.K)
+    R = length(γ0s)
+    rowptr, term, count = flatten_counts(model.X, M)
+    K32, V32 = Int32.(model.K), Int32.(model.V)
+    g0 = collect(reduce(vcat, γ0s))
+    G = length(γ0s[1])
+    grouped = devices !== nothing && length(devices) > 1
+    h = grouped ? create_group(devices; stop_rule=stop_rule) :
+                  create(device=(devices === nothing ? device : first(devices)), stop_rule=stop_rule)
+    chk = grouped ? gcheck : check
+    elbos = zeros(R); lls = zeros(M, R); nits = zeros(Int32, R); best = Ref{Int32}(-1)
+    try
+        flags = UInt32(updateΣ ? 1 : 0)
+        λ = zeros(D * MK); ν = zeros(D * MK); ζ = zeros(D * M); μ = zeros(MK); Σ = zeros(MK * MK); invΣ = zeros(MK * MK)
+        γ = zeros(G); Elnϕ = zeros(G); ϕ = zeros(G); props = zeros(D * MK)
+        GC.@preserve rowptr term count begin
+            rp = [pointer(r) for r in rowptr]; tp = [pointer(t) for t in term]; cp = [pointer(c) for c in count]
+            if grouped
+                chk(h, ccall((:mmsig_group_mmctm_restarts, LIB), Int32,
+                    (Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}, Ptr{Float64},
+                     Int32, Ptr{Float64}, Int32, Float64, UInt32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ref{Int32}),
+                    h, D, M, K32, V32, rp, tp, cp, model.α, R, g0, maxiter, tol, flags, elbos, lls, nits, best))
+                chk(h, ccall((:mmsig_group_mmctm_get_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                     Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
+            else
+                chk(h, ccall((:mmsig_mmctm_set_data, LIB), Int32,
+                    (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{Int32}}, Ptr{Ptr{Int32}}),
+                    h, D, D, M, K32, V32, rp, tp, cp))
+                chk(h, ccall((:mmsig_mmctm_set_state, LIB), Int32,
+                    (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                    h, model.α, g0, C_NULL, C_NULL, C_NULL, C_NULL, C_NULL))
+                chk(h, ccall((:mmsig_mmctm_restarts, LIB), Int32,
+                    (Ptr{Cvoid}, Int32, Ptr{Float64}, Int32, Float64, UInt32, Ptr{Float64}, Ptr{Float64}, Ptr{Int32}, Ref{Int32}),
+                    h, R, g0, maxiter, tol, flags, elbos, lls, nits, best))
+                chk(h, ccall((:mmsig_mmctm_get_state, LIB), Int32,
                     (Ptr{Cvoid}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
                      Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
                     h, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props))
             end
         end
-        check(h, ccall((:mmsig_mmctm_elbo, LIB), Int32, (Ptr{Cvoid}, Ref{Float64}, Ptr{Float64}), h, elbo, C_NULL))
-        # scatter back into the nested vectors (shapes preserved)
-        for d in 1:D
-            model.λ[d] .= @view λ[(d - 1) * MK + 1:d * MK]
-            model.ν[d] .= @view ν[(d - 1) * MK + 1:d * MK]
-            model.ζ[d] .= @view ζ[(d - 1) * M + 1:d * M]
-            off = 0
-            for m in 1:M
-                model.props[d][m] .= @view props[(d - 1) * MK + off + 1:(d - 1) * MK + off + model.K[m]]
-                off += model.K[m]
-            end
-        end
-        model.μ .= μ
-        model.Σ .= transpose(reshape(Σ, MK, MK)); model.invΣ .= transpose(reshape(invΣ, MK, MK))
-        o = 0
-        for m in 1:M, k in 1:model.K[m]
-            r = (o + 1):(o + model.V[m])
-            model.γ[m][k] .= @view γ[r]; model.Elnϕ[m][k] .= @view Elnϕ[r]; model.ϕ[m][k] .= @view ϕ[r]
-            o += model.V[m]
-        end
-        # model.θ is materialised lazily: materialize_theta!(model, h) before destroy if wanted
-        autoα && check(h, ccall((:mmsig_mmctm_get_alpha, LIB), Int32, (Ptr{Cvoid}, Ptr{Float64}), h, model.α))
-        model.elbo = elbo[]
-        model.ll = ll[end]
+        scatter_state!(model, λ, ν, ζ, μ, Σ, invΣ, γ, Elnϕ, ϕ, props)
+        model.elbo = elbos[best[] + 1]
+        model.ll = lls[:, best[] + 1]
     finally
-        destroy(h)
+        grouped ? destroy_group(h) : destroy(h)
     end
-    return ll
+    return elbos, [lls[:, r] for r in 1:R], Int.(nits), Int(best[]) + 1
 end
 
 # ---- fit_heldout / transform (src/MMCTM.jl:554-586, :511-552): the same E-step with the topics and

@@ -38,6 +38,9 @@ _SIGS = {
     "mmsig_last_error": (C.c_char_p, [C.c_void_p]),
     "mmsig_set_stream": (C.c_int32, [C.c_void_p, C.c_void_p]),
     "mmsig_synchronize": (C.c_int32, [C.c_void_p]),
+    "mmsig_set_profile": (C.c_int32, [C.c_void_p, C.c_int32]),
+    "mmsig_host_alloc": (C.c_int32, [C.c_uint64, C.POINTER(C.c_void_p)]),
+    "mmsig_host_free": (C.c_int32, [C.c_void_p]),
     "mmsig_comm_unique_id": (C.c_int32, [c_u8p]),
     "mmsig_comm_init": (C.c_int32, [C.c_void_p, c_u8p, C.c_int32, C.c_int32]),
     "mmsig_group_create": (C.c_int32, [C.POINTER(Config), C.c_int32, c_i32p, C.POINTER(C.c_void_p)]),
@@ -52,6 +55,7 @@ _SIGS = {
     "mmsig_group_mmctm_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_group_mmctm_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 10),
     "mmsig_group_mmctm_get_evals": (C.c_int32, [C.c_void_p, c_i32p, c_i32p]),
+    "mmsig_group_mmctm_get_theta": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
     "mmsig_group_mmctm_fit_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)] + [c_dp] * 7 +
                                    [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
     "mmsig_group_mmctm_restarts": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p), c_dp, C.c_int32, c_dp,
@@ -186,6 +190,9 @@ class Handle:
     def synchronize(self):
         self.check(self.lib.mmsig_synchronize(self.h))
 
+    def set_profile(self, on):
+        self.check(self.lib.mmsig_set_profile(self.h, int(bool(on))))
+
     def comm_init(self, uid_bytes, rank, nranks):
         buf = (C.c_uint8 * 128).from_buffer_copy(bytes(uid_bytes))
         self.check(self.lib.mmsig_comm_init(self.h, buf, rank, nranks))
@@ -245,6 +252,35 @@ class Group:
         h = C.c_void_p(self.lib.mmsig_group_member(self.g, member))
         k = self.lib.mmsig_kernel_times(h, n, names, dp(ms), cnt.ctypes.data_as(c_i64p), int(reset))
         return {names[i].decode(): (float(ms[i]), int(cnt[i])) for i in range(max(k, 0))}
+
+
+def host_array(shape, dtype):
+    """numpy array in page-locked host memory owned by the library (mmsig_host_alloc); freed with the array."""
+    lib = load()
+    dtype = np.dtype(dtype)
+    n = int(np.prod(shape))
+    p = C.c_void_p()
+    rc = lib.mmsig_host_alloc(max(n, 1) * dtype.itemsize, C.byref(p))
+    if rc != 0:
+        raise MmsigError(rc, (lib.mmsig_last_error(None) or b"").decode())
+    buf = (C.c_char * (max(n, 1) * dtype.itemsize)).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=dtype, count=n).reshape(shape)
+
+    class _Owner:
+        def __init__(self, ptr):
+            self.ptr = ptr
+
+        def __del__(self):
+            try:
+                lib.mmsig_host_free(C.c_void_p(self.ptr))
+            except Exception:
+                pass
+    arr = arr.view()
+    _PINNED[id(buf)] = (buf, _Owner(p.value))
+    return arr
+
+
+_PINNED = {}
 
 
 def comm_unique_id():

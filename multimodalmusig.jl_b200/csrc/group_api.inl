@@ -232,6 +232,23 @@ static void make_shard(ShardView &sv, long long d0, long long d1, int32_t M, con
     }
 }
 
+// a member running alone on a whole corpus (replica): no exchange with the other members
+struct Detach {
+    mmsig_handle *h;
+    mmsig_group *g;
+    int rank, nranks;
+    explicit Detach(mmsig_handle *h_) : h(h_), g(h_->grp), rank(h_->rank), nranks(h_->nranks) {
+        h->grp = nullptr;
+        h->rank = 0;
+        h->nranks = 1;
+    }
+    ~Detach() {
+        h->grp = g;
+        h->rank = rank;
+        h->nranks = nranks;
+    }
+};
+
 #define GNEED(cond, msg)                                  \
     do {                                                  \
         if (!(cond)) return gfail(g, MMSIG_EINVAL, msg);  \
@@ -289,7 +306,12 @@ extern "C" int32_t mmsig_group_mmctm_fit(mmsig_group *g, int32_t maxiter, double
 
 extern "C" int32_t mmsig_group_mmctm_elbo(mmsig_group *g, double *elbo, double *terms) {
     GNEED(g, "null group");
-    if (g->replica_best >= 0) return mmsig_mmctm_elbo(g->h[g->replica_best], elbo, terms);
+    if (g->replica_best >= 0) {
+        Detach dt(g->h[g->replica_best]);
+        int rc = mmsig_mmctm_elbo(g->h[g->replica_best], elbo, terms);
+        if (rc) g->err = g->h[g->replica_best]->err;
+        return rc;
+    }
     std::vector<double> e(g->n, 0.0), t((size_t)g->n * 7, 0.0);
     int rc = group_run(g, [&](int r, mmsig_handle *h) { return (int)mmsig_mmctm_elbo(h, &e[r], t.data() + (size_t)r * 7); });
     if (rc) return rc;
@@ -302,8 +324,12 @@ extern "C" int32_t mmsig_group_mmctm_get_state(mmsig_group *g, double *lambda, d
                                                double *Sigma, double *invSigma, double *gamma, double *Elnphi, double *phi,
                                                double *props) {
     GNEED(g, "null group");
-    if (g->replica_best >= 0)            // after mmsig_group_mmctm_restarts: the best restart lives on one device, whole
-        return mmsig_mmctm_get_state(g->h[g->replica_best], lambda, nu, zeta, mu, Sigma, invSigma, gamma, Elnphi, phi, props);
+    if (g->replica_best >= 0) {          // after mmsig_group_mmctm_restarts: the best restart lives on one device, whole
+        Detach dt(g->h[g->replica_best]);
+        int rc = mmsig_mmctm_get_state(g->h[g->replica_best], lambda, nu, zeta, mu, Sigma, invSigma, gamma, Elnphi, phi, props);
+        if (rc) g->err = g->h[g->replica_best]->err;
+        return rc;
+    }
     GNEED(g->cut.size() == (size_t)g->n + 1, "mmsig_group_mmctm_set_data first");
     const int MK = g->h[0]->mm.p.MK, M = g->h[0]->mm.p.M;
     return group_run(g, [&](int r, mmsig_handle *h) {
@@ -320,6 +346,20 @@ extern "C" int32_t mmsig_group_mmctm_get_evals(mmsig_group *g, int32_t *nev_nu, 
     return group_run(g, [&](int r, mmsig_handle *h) {
         return (int)mmsig_mmctm_get_evals(h, nev_nu ? nev_nu + g->cut[r] : nullptr, nev_lambda ? nev_lambda + g->cut[r] : nullptr);
     });
+}
+
+// model.θ[d][m] of modality m for all samples (nnz_m x K_m, [w][k]): every member recomputes its shard's rows
+extern "C" int32_t mmsig_group_mmctm_get_theta(mmsig_group *g, int32_t m, double *theta_out) {
+    GNEED(g && theta_out, "null argument");
+    if (g->replica_best >= 0) {
+        Detach dt(g->h[g->replica_best]);
+        return mmsig_mmctm_get_theta(g->h[g->replica_best], m, theta_out);
+    }
+    GNEED(g->cut.size() == (size_t)g->n + 1 && g->h[0]->mm.has_state, "mmsig_group_mmctm_set_data / _set_state first");
+    GNEED(m >= 0 && m < g->h[0]->mm.p.M, "bad modality");
+    std::vector<size_t> off(g->n + 1, 0);
+    for (int r = 0; r < g->n; ++r) off[r + 1] = off[r] + (size_t)g->h[r]->mm.nnz[m] * g->h[r]->mm.p.K[m];
+    return group_run(g, [&](int r, mmsig_handle *h) { return (int)mmsig_mmctm_get_theta(h, m, theta_out + off[r]); });
 }
 
 // fit! from and to host buffers over all devices of the group: mmsig_mmctm_fit_host per shard, each device
@@ -382,12 +422,7 @@ extern "C" int32_t mmsig_group_mmctm_restarts(mmsig_group *g, int64_t D, int32_t
         std::vector<int> mine;
         for (int i = r; i < R; i += g->n) mine.push_back(i);
         if (mine.empty()) return 0;
-        // a replica: this member runs alone on the whole corpus
-        mmsig_group *keep = h->grp;
-        const int krank = h->rank, kn = h->nranks;
-        h->grp = nullptr;
-        h->rank = 0;
-        h->nranks = 1;
+        Detach dt(h);                        // a replica: this member runs alone on the whole corpus
         int rcl = mmsig_mmctm_set_data(h, D, D, M, K, V, rowptr, term, count);
         if (!rcl) rcl = mmsig_mmctm_set_state(h, alpha, gamma0 + (size_t)mine[0] * G, nullptr, nullptr, nullptr, nullptr, nullptr);
         if (!rcl) {
@@ -405,9 +440,6 @@ extern "C" int32_t mmsig_group_mmctm_restarts(mmsig_group *g, int64_t D, int32_t
                 lbest[r] = mine[b];
             }
         }
-        h->grp = keep;
-        h->rank = krank;
-        h->nranks = kn;
         return rcl;
     });
     if (rc) return rc;

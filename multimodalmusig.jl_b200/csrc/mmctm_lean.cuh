@@ -70,7 +70,10 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
     static_assert(MKP <= 32 && (G == 4 || G == 8 || G == 16), "one 32-leaf tree per sample");
     __shared__ __align__(16) double ST[NU ? 2 : 32 * STRIDE];            // invΣ rows: λ phase only
     __shared__ __align__(16) double dsh_all[NW][NG][STRIDE];
-    __shared__ double2 red[NW][CPL][32];
+    __shared__ double2 red[NW][CPL][32];                                 // Σ of this phase's result per lane and slot (dd), updated when a solve ends
+    // per-sample values read once per trip (or less) live in shared memory, not in registers: the kernel is bound by
+    // fixed-latency stalls at 3 warps per scheduler (ncu, profiles/r02a), and 128 registers admit a fourth
+    __shared__ double ctx_c[CPL][NW * 32], ctx_o[CPL][NW * 32], ctx_s[NU ? 1 : CPL][NW * 32], ctx_xpp[CPL][NW * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int grp = lane / G, gl = lane % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
@@ -83,33 +86,24 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
         }
     for (int i = gl; i < STRIDE; i += G) dsh[i] = 0.0;
     __syncthreads();
+    const int tid = threadIdx.x;
     bool active[CPL];
-    int mod[CPL], blo[CPL], bhi[CPL];
     double cst[CPL];                                  // ν: -0.5 invΣ_jj ; λ: μ_j
-    double Sjj[CPL];
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
         const int j = gl + G * s;
         active[s] = j < MK;
-        mod[s] = 0;
-        for (int m = 0; m < M; ++m)
-            if (j >= p.koff[m]) mod[s] = m;
-        blo[s] = p.koff[mod[s]];
-        bhi[s] = p.koff[mod[s] + 1];
-        Sjj[s] = active[s] ? p.invSigma[j * MK + j] : 0.0;
-        cst[s] = NU ? -0.5 * Sjj[s] : (active[s] ? p.mu[j] : 0.0);
+        const double Sjj = active[s] ? p.invSigma[j * MK + j] : 0.0;
+        cst[s] = NU ? -0.5 * Sjj : (active[s] ? p.mu[j] : 0.0);
+        red[warp][s][lane] = make_double2(0.0, 0.0);
     }
     // iterate (per lane and slot) and LD_MMA scalars (identical in the lanes of a group)
-    double x[CPL], g[CPL], xp[CPL], xpp[CPL], sig[CPL], isig[CPL];
-    double cN[CPL], hcN[CPL], sth[CPL], oth[CPL];
-    double acch[CPL], accl[CPL];                      // Σ of this phase's result (dd)
+    double x[CPL], g[CPL], xp[CPL], sig[CPL], isig[CPL];
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
-        x[s] = xp[s] = xpp[s] = NU ? 1.5 : cst[s];
+        x[s] = xp[s] = NU ? 1.5 : cst[s];
         g[s] = 0.0;
         sig[s] = isig[s] = 1.0;
-        cN[s] = hcN[s] = sth[s] = oth[s] = 0.0;
-        acch[s] = accl[s] = 0.0;
     }
     const double INF = __longlong_as_double(0x7ff0000000000000LL);
     double fmin = INF, rho = 1.0;
@@ -134,19 +128,23 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
                             const long long base = dcur * MK + gl + G * s;
-                            oth[s] = active[s] ? p.lam_prev[base] : 0.0;
+                            const double lam0 = active[s] ? p.lam_prev[base] : 0.0;
                             nu0[s] = active[s] ? p.nu[base] : 1.5;
-                            dsh[gl + G * s] = active[s] ? det_exp(oth[s] + 0.5 * nu0[s]) : 0.0;
+                            ctx_o[s][tid] = lam0;
+                            dsh[gl + G * s] = active[s] ? det_exp(lam0 + 0.5 * nu0[s]) : 0.0;
                         }
                         __syncwarp(gmask);
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
+                            int mod = 0;
+                            for (int m = 0; m < M; ++m)
+                                if (gl + G * s >= p.koff[m]) mod = m;
+                            const int blo = p.koff[mod], bhi = p.koff[mod + 1];
                             double zeta = 0.0;
-                            for (int i = blo[s]; i < bhi[s]; ++i) zeta += dsh[i];
-                            const double Ndm = active[s] ? p.N[dcur * M + mod[s]] : 0.0;
-                            cN[s] = active[s] ? Ndm / zeta : 0.0;
-                            hcN[s] = cN[s] / 2;
-                            if (active[s] && gl + G * s == blo[s]) p.zeta[dcur * M + mod[s]] = zeta;
+                            for (int i = blo; i < bhi; ++i) zeta += dsh[i];
+                            const double Ndm = active[s] ? p.N[dcur * M + mod] : 0.0;
+                            ctx_c[s][tid] = active[s] ? Ndm / zeta : 0.0;
+                            if (active[s] && gl + G * s == blo) p.zeta[dcur * M + mod] = zeta;
                             x[s] = nu0[s];
                         }
                         __syncwarp(gmask);
@@ -155,12 +153,15 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
                             const long long base = dcur * MK + gl + G * s;
+                            int mod = 0;
+                            for (int m = 0; m < M; ++m)
+                                if (gl + G * s >= p.koff[m]) mod = m;
                             x[s] = active[s] ? p.lam_prev[base] : 0.0;
-                            oth[s] = active[s] ? 0.5 * p.nu[base] : 0.0;
-                            sth[s] = active[s] ? p.sumtheta[base] : 0.0;
-                            const double Ndm = active[s] ? p.N[dcur * M + mod[s]] : 0.0;
-                            const double zeta = active[s] ? p.zeta[dcur * M + mod[s]] : 1.0;
-                            cN[s] = active[s] ? Ndm / zeta : 0.0;
+                            ctx_o[s][tid] = active[s] ? 0.5 * p.nu[base] : 0.0;
+                            ctx_s[NU ? 0 : s][tid] = active[s] ? p.sumtheta[base] : 0.0;
+                            const double Ndm = active[s] ? p.N[dcur * M + mod] : 0.0;
+                            const double zeta = active[s] ? p.zeta[dcur * M + mod] : 1.0;
+                            ctx_c[s][tid] = active[s] ? Ndm / zeta : 0.0;
                         }
                     }
                     first = true;
@@ -171,7 +172,9 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                     for (int s = 0; s < CPL; ++s) {
                         x[s] = NU ? 1.5 : cst[s];
-                        cN[s] = hcN[s] = sth[s] = oth[s] = 0.0;
+                        ctx_c[s][tid] = 0.0;
+                        ctx_o[s][tid] = 0.0;
+                        ctx_s[NU ? 0 : s][tid] = 0.0;
                     }
                     first = false;
                     fmin = INF;
@@ -179,7 +182,8 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
                     g[s] = 0.0;
-                    xp[s] = xpp[s] = x[s];
+                    xp[s] = x[s];
+                    ctx_xpp[s][tid] = x[s];
                     sig[s] = isig[s] = 1.0;
                 }
                 rho = 1.0;
@@ -222,9 +226,12 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
         if (NU) {
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
-                const double e = det_exp(oth[s] + 0.5 * xe[s]);
-                const double grad = (cst[s] - hcN[s] * e) + fast_rcp(2 * xe[s]);
-                tl[s] = (-0.5 * (xe[s] * Sjj[s]) - cN[s] * e) + det_log(xe[s]) / 2;
+                // src/common.jl:25-36 with the exact power-of-two scalings folded: (c / 2) e == (c e) / 2 and
+                // -0.5 (x S_jj) == x (-0.5 S_jj) bit for bit, so one product serves value and gradient
+                const double e = det_exp(ctx_o[s][tid] + 0.5 * xe[s]);
+                const double ce = ctx_c[s][tid] * e;
+                const double grad = fma(-0.5, ce, cst[s]) + fast_rcp(2 * xe[s]);
+                tl[s] = (xe[s] * cst[s] - ce) + det_log(xe[s]) / 2;
                 gcur[s] = -grad;
             }
         } else {
@@ -253,10 +260,11 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
                 const double qq = q[s] + qo[s];
-                const double e = det_exp(xe[s] + oth[s]);
-                const double ce = cN[s] * e;
-                const double grad = (-qq + sth[s]) - ce;
-                const double a = qq * diff[s], b = xe[s] * sth[s];
+                const double e = det_exp(xe[s] + ctx_o[s][tid]);
+                const double ce = ctx_c[s][tid] * e;
+                const double sth = ctx_s[NU ? 0 : s][tid];
+                const double grad = (-qq + sth) - ce;
+                const double a = qq * diff[s], b = xe[s] * sth;
                 tl[s] = (b - 0.5 * a) - ce;
                 gcur[s] = -grad;
             }
@@ -318,12 +326,12 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
                     if (k > 1) {
-                        const double s2 = (xe[s] - xp[s]) * (xp[s] - xpp[s]);
+                        const double s2 = (xe[s] - xp[s]) * (xp[s] - ctx_xpp[s][tid]);
                         const double gam = s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
                         sig[s] = sig[s] * gam;
                         isig[s] = fast_rcp(sig[s]);
                     }
-                    xpp[s] = xp[s];
+                    ctx_xpp[s][tid] = xp[s];
                     xp[s] = xe[s];
                 }
                 ++k;
@@ -333,13 +341,16 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
             double *dst = NU ? p.nu : p.lam;
 #pragma unroll
             for (int s = 0; s < CPL; ++s)
-                if (active[s]) { dst[dcur * MK + gl + G * s] = x[s]; dd_add(acch[s], accl[s], x[s]); }
+                if (active[s]) {
+                    dst[dcur * MK + gl + G * s] = x[s];
+                    double2 a = red[warp][s][lane];
+                    dd_add(a.x, a.y, x[s]);
+                    red[warp][s][lane] = a;
+                }
             if (gl == 0) (NU ? p.nev_nu : p.nev_lam)[dcur] = nev;
             need = true;
         }
     }
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) red[warp][s][lane] = make_double2(acch[s], accl[s]);
     __syncthreads();
     // coordinate j = gl + G s: sum over warps and over the groups; partial: [grid][2 MK], Σλ then Σν
     for (int j = threadIdx.x; j < MK; j += blockDim.x) {

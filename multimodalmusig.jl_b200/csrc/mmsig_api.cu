@@ -380,6 +380,33 @@ extern "C" int32_t mmsig_synchronize(mmsig_handle *h) {
     return 0;
 }
 
+extern "C" int32_t mmsig_set_profile(mmsig_handle *h, int32_t on) {
+    NEED(h, "null handle");
+    CU(cudaSetDevice(h->device));
+    CU(cudaStreamSynchronize(h->stream));
+    resolve_pending(h);
+    h->profile = on != 0;
+    return 0;
+}
+
+// page-locked host memory for the caller's buffers: copies from / to it run at link speed and overlap
+// with kernels (pageable buffers are staged by the driver, chunk by chunk)
+extern "C" int32_t mmsig_host_alloc(uint64_t bytes, void **out) {
+    mmsig_handle *h = nullptr;
+    NEED(out, "null argument");
+    void *p = nullptr;
+    cudaError_t e = cudaHostAlloc(&p, std::max<uint64_t>(bytes, 1), cudaHostAllocPortable);
+    if (e != cudaSuccess) return fail(h, e == cudaErrorMemoryAllocation ? MMSIG_ENOMEM : MMSIG_ENODEV, std::string("cudaHostAlloc: ") + cudaGetErrorString(e));
+    *out = p;
+    return 0;
+}
+extern "C" int32_t mmsig_host_free(void *p) {
+    mmsig_handle *h = nullptr;
+    if (!p) return 0;
+    CU(cudaFreeHost(p));
+    return 0;
+}
+
 extern "C" int32_t mmsig_comm_unique_id(uint8_t id_out[128]) {
     mmsig_handle *h = nullptr;
     std::string err;
@@ -618,9 +645,7 @@ static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, int V, lon
         } else {                                                                                 \
             if ((MK_) <= 8) { constexpr int LG = 4, LC = 2, LP = PH_; EXPR; }                    \
             else if ((MK_) <= 12) { constexpr int LG = 4, LC = 3, LP = PH_; EXPR; }              \
-            else if ((MK_) <= 16) { constexpr int LG = 4, LC = 4, LP = PH_; EXPR; }              \
-            else if ((MK_) <= 20) { constexpr int LG = 4, LC = 5, LP = PH_; EXPR; }              \
-            else { constexpr int LG = 4, LC = 6, LP = PH_; EXPR; }                               \
+            else { constexpr int LG = 4, LC = 4, LP = PH_; EXPR; }                               \
         }                                                                                        \
     } while (0)
 
@@ -730,7 +755,7 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
 #endif
         // MMSIG_SOLVE=lean8 | lean4: k_solve_lean with 8 / 4 lanes per sample (mmctm_lean.cuh)
         mm.solve_lean = (e && p.MK <= 32) ? (!strcmp(e, "lean8") ? 8 : (!strcmp(e, "lean4") ? 4 : 0)) : 0;
-        if (mm.solve_lean == 4 && p.MK > 24) mm.solve_lean = 8;
+        if (mm.solve_lean == 4 && p.MK > 16) mm.solve_lean = 8;            // 4 lanes x (> 4 coordinates) spills: measured 43 ms against 23 ms at sum(K) = 24
     }
     CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
