@@ -22,7 +22,7 @@
 namespace mmsig {
 
 #ifndef LEAN_MIN_BLOCKS
-#define LEAN_MIN_BLOCKS 3
+#define LEAN_MIN_BLOCKS 4          // 126 registers, no spills; measured 20.8 ms against 23.4 ms at 3 (160 registers) and 20.4 ms at 5 (96, spills)
 #endif
 
 // sum of a lane's CPL slot values in the order of the 32-leaf tree's top levels: slot s holds leaf
@@ -63,39 +63,71 @@ __device__ __forceinline__ void lean_sum3(double &a, double &b, double &c, int l
     }
 }
 
+#ifndef LEAN_MV_UNROLL
+#define LEAN_MV_UNROLL 4
+#endif
+constexpr int kLeanMvUnroll = LEAN_MV_UNROLL;
+
+// asynchronous 8-byte copy global -> shared (LDGSTS): the next sample's inputs travel while the current one is solved
+__device__ __forceinline__ void cp_async8(double *smem_dst, const double *gmem_src) {
+    const unsigned a = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(a), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
+// dynamic shared memory of k_solve_lean<G, CPL, PH> (doubles): invΣ rows (λ phase) | per-group Δ vectors | dd sums of
+// the results | per-sample context (c, other, [sumθ], xprevprev) | staging of the next sample's inputs
 template <int G, int CPL, int PH>
+constexpr size_t lean_smem_doubles() {
+    constexpr bool NU = PH == PH_NU;
+    return (NU ? 0 : G * CPL * 34) + 4 * (32 / G) * 34 + 2 * 4 * CPL * 32 + (NU ? 3 : 4) * CPL * 128 + (NU ? 3 : 5) * CPL * 128;
+}
+
+// FULL: sum(K) == G * CPL, no padding coordinate -- every "active" mask is compile-time true
+template <int G, int CPL, int PH, bool FULL>
 __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p, double2 *partial) {
     constexpr bool NU = PH == PH_NU;
     constexpr int NG = 32 / G, MKP = G * CPL, STRIDE = 34, NW = 4;       // NW warps per block
+    constexpr int NSTG = NU ? 3 : 5;                                     // staged inputs per coordinate: ν: λ, ν, N ; λ: λ, ν, sumθ, N, ζ
     static_assert(MKP <= 32 && (G == 4 || G == 8 || G == 16), "one 32-leaf tree per sample");
-    __shared__ __align__(16) double ST[NU ? 2 : 32 * STRIDE];            // invΣ rows: λ phase only
-    __shared__ __align__(16) double dsh_all[NW][NG][STRIDE];
-    __shared__ double2 red[NW][CPL][32];                                 // Σ of this phase's result per lane and slot (dd), updated when a solve ends
+    extern __shared__ __align__(16) double lean_smem[];
+    double *ST = lean_smem;                                              // invΣ rows: λ phase only
+    double *dsh_base = ST + (NU ? 0 : MKP * STRIDE);                     // [NW][NG][STRIDE]
+    double2 *red = reinterpret_cast<double2 *>(dsh_base + NW * NG * STRIDE);   // [NW][CPL][32]: Σ of this phase's result per lane and slot (dd)
     // per-sample values read once per trip (or less) live in shared memory, not in registers: the kernel is bound by
-    // fixed-latency stalls at 3 warps per scheduler (ncu, profiles/r02a), and 128 registers admit a fourth
-    __shared__ double ctx_c[CPL][NW * 32], ctx_o[CPL][NW * 32], ctx_s[NU ? 1 : CPL][NW * 32], ctx_xpp[CPL][NW * 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // fixed-latency stalls, and <= 128 registers admit four to five blocks per SM (ncu: profiles/r02_solve_summary.md)
+    double *ctx_c = reinterpret_cast<double *>(red + NW * CPL * 32);     // [CPL][128] N_dm / ζ_dm
+    double *ctx_o = ctx_c + CPL * 128;                                   // ν: λ_j ; λ: ν_j / 2
+    double *ctx_xpp = ctx_o + CPL * 128;                                 // xprevprev
+    double *ctx_s = ctx_xpp + CPL * 128;                                 // λ: sumθ_j
+    double *stage = ctx_s + (NU ? 0 : CPL * 128);                        // [NSTG][CPL][128]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, tid = threadIdx.x;
     const int grp = lane / G, gl = lane % G;
     const unsigned gmask = (G == 32) ? 0xffffffffu : (((1u << G) - 1u) << (grp * G));
     const int MK = p.MK, M = p.M;
-    double *dsh = dsh_all[warp][grp];
+    double *dsh = dsh_base + (warp * NG + grp) * STRIDE;
     if (!NU)
-        for (int t = threadIdx.x; t < 32 * STRIDE; t += blockDim.x) {
+        for (int t = threadIdx.x; t < MKP * STRIDE; t += blockDim.x) {
             const int j = t / STRIDE, i = t % STRIDE;
             ST[t] = (i < MK && j < MK) ? p.invSigma[j * MK + i] : 0.0;
         }
     for (int i = gl; i < STRIDE; i += G) dsh[i] = 0.0;
     __syncthreads();
-    const int tid = threadIdx.x;
+    constexpr bool full = FULL;
     bool active[CPL];
+    int mod[CPL];
     double cst[CPL];                                  // ν: -0.5 invΣ_jj ; λ: μ_j
 #pragma unroll
     for (int s = 0; s < CPL; ++s) {
         const int j = gl + G * s;
-        active[s] = j < MK;
+        active[s] = FULL || j < MK;
+        mod[s] = 0;
+        for (int m = 0; m < M; ++m)
+            if (j >= p.koff[m]) mod[s] = m;
         const double Sjj = active[s] ? p.invSigma[j * MK + j] : 0.0;
         cst[s] = NU ? -0.5 * Sjj : (active[s] ? p.mu[j] : 0.0);
-        red[warp][s][lane] = make_double2(0.0, 0.0);
+        red[(warp * CPL + s) * 32 + lane] = make_double2(0.0, 0.0);
     }
     // iterate (per lane and slot) and LD_MMA scalars (identical in the lanes of a group)
     double x[CPL], g[CPL], xp[CPL], sig[CPL], isig[CPL];
@@ -109,42 +141,62 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
     double fmin = INF, rho = 1.0;
     int k = 1, nev = 0;
     bool first = false, need = true, alive = true;
-    long long dcur = -1;
     const double lb = NU ? 1e-7 : -INF;
     const int stop_rule = p.stop_rule;
 
+    // Sample pipeline of a group: dcur is being solved, dstage has its inputs in flight to (or already in) the
+    // staging slots, `ticket` is the atomic counter value this group's leader drew at the previous refill (read at
+    // the next one, so neither the atomic nor the loads are ever waited for while a solve could run).
+    auto stage_issue = [&](long long d) {
+#pragma unroll
+        for (int s = 0; s < CPL; ++s) {
+            if (!active[s]) continue;
+            const long long base = d * MK + gl + G * s;
+            cp_async8(stage + (0 * CPL + s) * 128 + tid, p.lam_prev + base);
+            cp_async8(stage + (1 * CPL + s) * 128 + tid, p.nu + base);
+            cp_async8(stage + (2 * CPL + s) * 128 + tid, p.N + d * M + mod[s]);
+            if (!NU) {
+                cp_async8(stage + (3 * CPL + s) * 128 + tid, p.sumtheta + base);
+                cp_async8(stage + (4 * CPL + s) * 128 + tid, p.zeta + d * M + mod[s]);
+            }
+        }
+        cp_async_commit();
+    };
+    long long dcur = -1;
+    long long dstage = next_sample(p.work, gmask, grp * G, gl == 0);
+    if (dstage < p.D) stage_issue(dstage);
+    unsigned long long ticket = 0;
+    if (gl == 0) ticket = atomicAdd(p.work, 1ULL);
+
     while (true) {
-        // ---- groups whose solve ended store it and take their next sample (warp-uniform branch)
+        // ---- groups whose solve ended take their next sample (warp-uniform branch)
         if (__any_sync(FULLMASK, need)) {
             if (need) {
                 if (alive) {
-                    dcur = next_sample(p.work, gmask, grp * G, gl == 0);
+                    dcur = dstage;
                     if (dcur >= p.D) alive = false;
                 }
                 if (alive) {
+                    cp_async_wait_all();                       // this lane's staged inputs of dcur have landed
                     if (NU) {
                         // ζ from the old λ, ν (src/MMCTM.jl:450-452), then ν's problem
                         double nu0[CPL];
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
-                            const long long base = dcur * MK + gl + G * s;
-                            const double lam0 = active[s] ? p.lam_prev[base] : 0.0;
-                            nu0[s] = active[s] ? p.nu[base] : 1.5;
-                            ctx_o[s][tid] = lam0;
+                            const double lam0 = active[s] ? stage[(0 * CPL + s) * 128 + tid] : 0.0;
+                            nu0[s] = active[s] ? stage[(1 * CPL + s) * 128 + tid] : 1.5;
+                            ctx_o[s * 128 + tid] = lam0;
                             dsh[gl + G * s] = active[s] ? det_exp(lam0 + 0.5 * nu0[s]) : 0.0;
                         }
                         __syncwarp(gmask);
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
-                            int mod = 0;
-                            for (int m = 0; m < M; ++m)
-                                if (gl + G * s >= p.koff[m]) mod = m;
-                            const int blo = p.koff[mod], bhi = p.koff[mod + 1];
+                            const int blo = p.koff[mod[s]], bhi = p.koff[mod[s] + 1];
                             double zeta = 0.0;
                             for (int i = blo; i < bhi; ++i) zeta += dsh[i];
-                            const double Ndm = active[s] ? p.N[dcur * M + mod] : 0.0;
-                            ctx_c[s][tid] = active[s] ? Ndm / zeta : 0.0;
-                            if (active[s] && gl + G * s == blo) p.zeta[dcur * M + mod] = zeta;
+                            const double Ndm = active[s] ? stage[(2 * CPL + s) * 128 + tid] : 0.0;
+                            ctx_c[s * 128 + tid] = active[s] ? Ndm / zeta : 0.0;
+                            if (active[s] && gl + G * s == blo) p.zeta[dcur * M + mod[s]] = zeta;
                             x[s] = nu0[s];
                         }
                         __syncwarp(gmask);
@@ -152,16 +204,12 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
                         // λ's problem: the new ν, the old ζ (both written by the ν kernel), the old sumθ (:454)
 #pragma unroll
                         for (int s = 0; s < CPL; ++s) {
-                            const long long base = dcur * MK + gl + G * s;
-                            int mod = 0;
-                            for (int m = 0; m < M; ++m)
-                                if (gl + G * s >= p.koff[m]) mod = m;
-                            x[s] = active[s] ? p.lam_prev[base] : 0.0;
-                            ctx_o[s][tid] = active[s] ? 0.5 * p.nu[base] : 0.0;
-                            ctx_s[NU ? 0 : s][tid] = active[s] ? p.sumtheta[base] : 0.0;
-                            const double Ndm = active[s] ? p.N[dcur * M + mod] : 0.0;
-                            const double zeta = active[s] ? p.zeta[dcur * M + mod] : 1.0;
-                            ctx_c[s][tid] = active[s] ? Ndm / zeta : 0.0;
+                            x[s] = active[s] ? stage[(0 * CPL + s) * 128 + tid] : 0.0;
+                            ctx_o[s * 128 + tid] = active[s] ? 0.5 * stage[(1 * CPL + s) * 128 + tid] : 0.0;
+                            ctx_s[s * 128 + tid] = active[s] ? stage[(3 * CPL + s) * 128 + tid] : 0.0;
+                            const double Ndm = active[s] ? stage[(2 * CPL + s) * 128 + tid] : 0.0;
+                            const double zeta = active[s] ? stage[(4 * CPL + s) * 128 + tid] : 1.0;
+                            ctx_c[s * 128 + tid] = active[s] ? Ndm / zeta : 0.0;
                         }
                     }
                     first = true;
@@ -172,18 +220,26 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                     for (int s = 0; s < CPL; ++s) {
                         x[s] = NU ? 1.5 : cst[s];
-                        ctx_c[s][tid] = 0.0;
-                        ctx_o[s][tid] = 0.0;
-                        ctx_s[NU ? 0 : s][tid] = 0.0;
+                        ctx_c[s * 128 + tid] = 0.0;
+                        ctx_o[s * 128 + tid] = 0.0;
+                        if (!NU) ctx_s[s * 128 + tid] = 0.0;
                     }
                     first = false;
                     fmin = INF;
+                }
+                // refill the pipeline: the ticket drawn at the previous refill becomes the staged sample, a new ticket is drawn
+                {
+                    const unsigned hi = (unsigned)__shfl_sync(gmask, (int)(ticket >> 32), grp * G);
+                    const unsigned lo = (unsigned)__shfl_sync(gmask, (int)(ticket & 0xffffffffu), grp * G);
+                    dstage = (long long)(((unsigned long long)hi << 32) | lo);
+                    if (alive && dstage < p.D) stage_issue(dstage);
+                    if (alive && gl == 0) ticket = atomicAdd(p.work, 1ULL);
                 }
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
                     g[s] = 0.0;
                     xp[s] = x[s];
-                    ctx_xpp[s][tid] = x[s];
+                    ctx_xpp[s * 128 + tid] = x[s];
                     sig[s] = isig[s] = 1.0;
                 }
                 rho = 1.0;
@@ -228,8 +284,8 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
             for (int s = 0; s < CPL; ++s) {
                 // src/common.jl:25-36 with the exact power-of-two scalings folded: (c / 2) e == (c e) / 2 and
                 // -0.5 (x S_jj) == x (-0.5 S_jj) bit for bit, so one product serves value and gradient
-                const double e = det_exp(ctx_o[s][tid] + 0.5 * xe[s]);
-                const double ce = ctx_c[s][tid] * e;
+                const double e = det_exp(ctx_o[s * 128 + tid] + 0.5 * xe[s]);
+                const double ce = ctx_c[s * 128 + tid] * e;
                 const double grad = fma(-0.5, ce, cst[s]) + fast_rcp(2 * xe[s]);
                 tl[s] = (xe[s] * cst[s] - ce) + det_log(xe[s]) / 2;
                 gcur[s] = -grad;
@@ -239,14 +295,14 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
                 diff[s] = xe[s] - cst[s];
-                dsh[gl + G * s] = active[s] ? diff[s] : 0.0;
+                dsh[gl + G * s] = (full || active[s]) ? diff[s] : 0.0;
             }
             __syncwarp();
             const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
             double q[CPL], qo[CPL];                     // DET: even / odd index chains, then one add
 #pragma unroll
             for (int s = 0; s < CPL; ++s) { q[s] = 0.0; qo[s] = 0.0; }
-#pragma unroll 4
+#pragma unroll kLeanMvUnroll
             for (int i = 0; i < MKP / 2; ++i) {
                 const double2 dv = dv2[i];
 #pragma unroll
@@ -260,9 +316,9 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
             for (int s = 0; s < CPL; ++s) {
                 const double qq = q[s] + qo[s];
-                const double e = det_exp(xe[s] + ctx_o[s][tid]);
-                const double ce = ctx_c[s][tid] * e;
-                const double sth = ctx_s[NU ? 0 : s][tid];
+                const double e = det_exp(xe[s] + ctx_o[s * 128 + tid]);
+                const double ce = ctx_c[s * 128 + tid] * e;
+                const double sth = ctx_s[s * 128 + tid];
                 const double grad = (-qq + sth) - ce;
                 const double a = qq * diff[s], b = xe[s] * sth;
                 tl[s] = (b - 0.5 * a) - ce;
@@ -273,10 +329,10 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
         bool ok26 = true, okabs = true;
 #pragma unroll
         for (int s = 0; s < CPL; ++s) {
-            if (!active[s]) { tl[s] = 0.0; gcur[s] = 0.0; }
+            if (!full && !active[s]) { tl[s] = 0.0; gcur[s] = 0.0; }
             const double ax = fabs(xe[s]);
-            adl[s] = active[s] ? fabs(xe[s] - xp[s]) : 0.0;
-            xnl[s] = active[s] ? ax : 0.0;
+            adl[s] = (full || active[s]) ? fabs(xe[s] - xp[s]) : 0.0;
+            xnl[s] = (full || active[s]) ? ax : 0.0;
             okabs = okabs && !(adl[s] > 1e-4);
             if (stop_rule == 1)
                 ok26 = ok26 && (!active[s] || adl[s] < 1e-4 || adl[s] < 1e-4 * (ax + fabs(xp[s])) * 0.5 || xe[s] == xp[s]);
@@ -326,12 +382,12 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
 #pragma unroll
                 for (int s = 0; s < CPL; ++s) {
                     if (k > 1) {
-                        const double s2 = (xe[s] - xp[s]) * (xp[s] - ctx_xpp[s][tid]);
+                        const double s2 = (xe[s] - xp[s]) * (xp[s] - ctx_xpp[s * 128 + tid]);
                         const double gam = s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
                         sig[s] = sig[s] * gam;
                         isig[s] = fast_rcp(sig[s]);
                     }
-                    ctx_xpp[s][tid] = xp[s];
+                    ctx_xpp[s * 128 + tid] = xp[s];
                     xp[s] = xe[s];
                 }
                 ++k;
@@ -343,9 +399,9 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
             for (int s = 0; s < CPL; ++s)
                 if (active[s]) {
                     dst[dcur * MK + gl + G * s] = x[s];
-                    double2 a = red[warp][s][lane];
+                    double2 a = red[(warp * CPL + s) * 32 + lane];
                     dd_add(a.x, a.y, x[s]);
-                    red[warp][s][lane] = a;
+                    red[(warp * CPL + s) * 32 + lane] = a;
                 }
             if (gl == 0) (NU ? p.nev_nu : p.nev_lam)[dcur] = nev;
             need = true;
@@ -358,7 +414,7 @@ __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p,
         double hi = 0.0, lo = 0.0;
         for (int wv = 0; wv < NW; ++wv)
             for (int gg = 0; gg < NG; ++gg) {
-                const double2 v = red[wv][s][gg * G + l];
+                const double2 v = red[(wv * CPL + s) * 32 + gg * G + l];
                 dd_merge(hi, lo, v.x, v.y);
             }
         put_partial(partial + (size_t)blockIdx.x * 2 * MK + (NU ? MK : 0) + j, hi, lo, p.accum);

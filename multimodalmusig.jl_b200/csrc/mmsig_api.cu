@@ -634,18 +634,24 @@ static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, int V, lon
         else { constexpr int MKP = 32; EXPR; }                    \
     } while (0)
 
-// k_solve_lean instance for (lanes per sample G, sum(K)): CPL = ceil(sum(K) / G) coordinates per lane
+// k_solve_lean instance for (lanes per sample G, sum(K)): CPL = ceil(sum(K) / G) coordinates per lane; FULL when no
+// coordinate is padding (8 lanes only: the tuned shapes sum(K) = 8, 16, 24, 32)
+#define LEAN_CASE(G_, C_, MK_, PH_, EXPR)                                                                        \
+    do {                                                                                                         \
+        if ((G_) == 8 && (MK_) == 8 * (C_)) { constexpr int LG = G_, LC = C_, LP = PH_; constexpr bool LF = true; EXPR; } \
+        else { constexpr int LG = G_, LC = C_, LP = PH_; constexpr bool LF = false; EXPR; }                     \
+    } while (0)
 #define LEAN_DISPATCH(G_, MK_, PH_, EXPR)                                                        \
     do {                                                                                         \
         if ((G_) == 8) {                                                                         \
-            if ((MK_) <= 8) { constexpr int LG = 8, LC = 1, LP = PH_; EXPR; }                    \
-            else if ((MK_) <= 16) { constexpr int LG = 8, LC = 2, LP = PH_; EXPR; }              \
-            else if ((MK_) <= 24) { constexpr int LG = 8, LC = 3, LP = PH_; EXPR; }              \
-            else { constexpr int LG = 8, LC = 4, LP = PH_; EXPR; }                               \
+            if ((MK_) <= 8) LEAN_CASE(8, 1, MK_, PH_, EXPR);                                     \
+            else if ((MK_) <= 16) LEAN_CASE(8, 2, MK_, PH_, EXPR);                               \
+            else if ((MK_) <= 24) LEAN_CASE(8, 3, MK_, PH_, EXPR);                               \
+            else LEAN_CASE(8, 4, MK_, PH_, EXPR);                                                \
         } else {                                                                                 \
-            if ((MK_) <= 8) { constexpr int LG = 4, LC = 2, LP = PH_; EXPR; }                    \
-            else if ((MK_) <= 12) { constexpr int LG = 4, LC = 3, LP = PH_; EXPR; }              \
-            else { constexpr int LG = 4, LC = 4, LP = PH_; EXPR; }                               \
+            if ((MK_) <= 8) { constexpr int LG = 4, LC = 2, LP = PH_; constexpr bool LF = false; EXPR; }        \
+            else if ((MK_) <= 12) { constexpr int LG = 4, LC = 3, LP = PH_; constexpr bool LF = false; EXPR; }  \
+            else { constexpr int LG = 4, LC = 4, LP = PH_; constexpr bool LF = false; EXPR; }                   \
         }                                                                                        \
     } while (0)
 
@@ -763,7 +769,12 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     };
     if (!mm.wide) {
         int nb = 0;
-        if (mm.solve_lean) LEAN_DISPATCH(mm.solve_lean, p.MK, PH_LAM, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_lean<LG, LC, LP>, 128, 0)));
+        if (mm.solve_lean) {
+            LEAN_DISPATCH(mm.solve_lean, p.MK, PH_NU, CU(allow_max_smem(h, k_solve_lean<LG, LC, LP, LF>)));
+            LEAN_DISPATCH(mm.solve_lean, p.MK, PH_LAM, CU(allow_max_smem(h, k_solve_lean<LG, LC, LP, LF>)));
+            LEAN_DISPATCH(mm.solve_lean, p.MK, PH_LAM, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_lean<LG, LC, LP, LF>, 128,
+                                                                                                         lean_smem_doubles<LG, LC, LP>() * sizeof(double))));
+        }
         else if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
         else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
 #ifdef MMSIG_EXPERIMENTAL_SPLIT
@@ -1055,9 +1066,10 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         else if (mm.solve_lean) {
             // ν for every sample, then λ (which reads the new ν and the ζ the first kernel stored)
             const int gs = cap(mm.grid_solve, 4 * (32 / mm.solve_lean));
-            LEAN_DISPATCH(mm.solve_lean, q.MK, PH_NU, (k_solve_lean<LG, LC, LP><<<gs, 128, 0, h->stream>>>(q, mm.part_solve)));
+            LEAN_DISPATCH(mm.solve_lean, q.MK, PH_NU, (k_solve_lean<LG, LC, LP, LF><<<gs, 128, lean_smem_doubles<LG, LC, LP>() * sizeof(double), h->stream>>>(q, mm.part_solve)));
             cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);
-            LEAN_DISPATCH(mm.solve_lean, q.MK, PH_LAM, (k_solve_lean<LG, LC, LP><<<gs, 128, 0, h->stream>>>(q, mm.part_solve)));
+            h->launches++;
+            LEAN_DISPATCH(mm.solve_lean, q.MK, PH_LAM, (k_solve_lean<LG, LC, LP, LF><<<gs, 128, lean_smem_doubles<LG, LC, LP>() * sizeof(double), h->stream>>>(q, mm.part_solve)));
         }
         else if (q.MK <= 8) k_solve_pack<8><<<cap(mm.grid_solve, 32), 256, 0, h->stream>>>(q, mm.part_solve);
         else if (q.MK <= 16) k_solve_pack<16><<<cap(mm.grid_solve, 16), 256, 0, h->stream>>>(q, mm.part_solve);

@@ -22,6 +22,18 @@ def test_reference_arm_prints_one_json_line():
     assert j["value"] > 0 and j["cpu_baseline"]["kind"] == "port" and j["cpu_baseline"]["cores"] >= 1
     assert j["e2e"]["h2d_bytes_per_step"] == 0 and j["e2e"]["d2h_bytes_per_step"] == 0
     assert "workload" in j["config"] and "model" not in j["config"]
+    # the sample is the whole (3000-sample) workload here: nothing extrapolated, and the line says so
+    assert j["extrapolated"] is False and j["sample_D"] == 3000 and j["cpu_baseline"]["extrapolated"] is False
+
+
+def test_reference_arm_other_configs():
+    for cfgno, metric in ((2, "lda_em_iterations_per_sec"), (3, "mmctm_em_iterations_per_sec")):
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--config", str(cfgno), "--steps", "1",
+                            "--warmup", "0", "--samples", "40000", "--cpu-budget-s", "2"], capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-2000:]
+        j = json.loads([l for l in r.stdout.splitlines() if l.strip()][0])
+        assert j["metric"] == metric and j["value"] > 0 and j["sample_D"] <= 40000
+        assert j["extrapolated"] == (j["sample_D"] < 40000)
 
 
 def test_product_arm_refuses_to_run_without_a_gpu():
