@@ -130,6 +130,14 @@ int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t M, const i
                                    double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
                                    double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
                                    double *props_out);
+int32_t mmsig_group_mmctm_fit_host_packed(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+                                          const int64_t *const *rowptr, const uint32_t *const *rec, const double *alpha,
+                                          const double *gamma, const double *lambda, const double *nu, const double *mu,
+                                          const double *Sigma, const double *invSigma, int32_t maxiter, double tol,
+                                          uint32_t flags, double *ll_hist, int32_t *n_iter, int32_t *converged,
+                                          double *lambda_out, double *nu_out, double *zeta_out, double *mu_out,
+                                          double *Sigma_out, double *invSigma_out, double *gamma_out, double *Elnphi_out,
+                                          double *phi_out, double *props_out);
 /* R independent restarts dealt over the devices (restart r on member r mod n; every member holds the whole
  * corpus; scripts/run_mmctm.jl:99-111's pmap): outputs as mmsig_mmctm_restarts; afterwards
  * mmsig_group_mmctm_get_state / _elbo read the device that holds the best restart. */
@@ -218,6 +226,19 @@ int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_
                              double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
                              double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
                              double *props_out);
+/* The same call with 4-byte count records, which halves the host -> device traffic of the counts (the transfer an
+ * end-to-end fit! of a million samples is bound by): rec[m][w] = term | count << 10 (term < 1024, count < 2^22;
+ * mmsig_pack_records builds them and answers MMSIG_ELIMIT when a value does not fit).  julia/MMSigB200.jl's
+ * flatten_counts writes this form directly. */
+int32_t mmsig_mmctm_fit_host_packed(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                    const int32_t *V, const int64_t *const *rowptr, const uint32_t *const *rec,
+                                    const double *alpha, const double *gamma, const double *lambda, const double *nu,
+                                    const double *mu, const double *Sigma, const double *invSigma, int32_t maxiter,
+                                    double tol, uint32_t flags, double *ll_hist, int32_t *n_iter, int32_t *converged,
+                                    double *lambda_out, double *nu_out, double *zeta_out, double *mu_out,
+                                    double *Sigma_out, double *invSigma_out, double *gamma_out, double *Elnphi_out,
+                                    double *phi_out, double *props_out);
+int32_t mmsig_pack_records(int64_t nnz, const int32_t *term, const int32_t *count, uint32_t *rec);
 /* calculate_elbo (src/MMCTM.jl:271-382) with the staleness of :490: θ, ζ, sumθ from the last
  * E-step, everything else current.  terms[7] = ElnPϕ, ElnPη, ElnPZ, ElnPX, ElnQϕ, ElnQη, ElnQZ. */
 int32_t mmsig_mmctm_elbo(mmsig_handle *h, double *elbo, double *terms);

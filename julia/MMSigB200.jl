@@ -57,6 +57,52 @@ function flatten_counts(X::Vector{Vector{Matrix{Int}}}, M::Int)
     return rowptr, term, count
 end
 
+# Page-locked ("pinned") host vectors owned by the library (mmsig_host_alloc): copies from / to them run at link
+# speed and overlap with kernels, ordinary Julia Vectors are staged by the driver (slower; bench.py prints both).
+function pinned_vector(::Type{T}, n::Integer) where T
+    p = Ref{Ptr{Cvoid}}(C_NULL)
+    check(C_NULL, ccall((:mmsig_host_alloc, LIB), Int32, (UInt64, Ref{Ptr{Cvoid}}), UInt64(max(n, 1) * sizeof(T)), p))
+    return unsafe_wrap(Array, Ptr{T}(p[]), n; own=false)
+end
+host_free(v::Array) = ccall((:mmsig_host_free, LIB), Int32, (Ptr{Cvoid},), pointer(v))
+
+# X[d][m] -> row pointers + 4-byte records term | count << 10 in pinned memory (mmsig_mmctm_fit_host_packed: half the
+# host -> device traffic of the counts); `nothing` when a term needs more than 10 bits or a count more than 22
+function flatten_counts_packed(X::Vector{Vector{Matrix{Int}}}, M::Int)
+    D = length(X)
+    rowptr = [pinned_vector(Int64, D + 1) for m in 1:M]
+    for m in 1:M
+        rowptr[m][1] = 0
+        for d in 1:D
+            rowptr[m][d + 1] = rowptr[m][d] + size(X[d][m], 1)
+        end
+    end
+    rec = [pinned_vector(UInt32, rowptr[m][end]) for m in 1:M]
+    fits = true
+    for m in 1:M, d in 1:D
+        o = rowptr[m][d]
+        for w in 1:size(X[d][m], 1)
+            t, c = X[d][m][w, 1] - 1, X[d][m][w, 2]
+            fits &= (0 <= t < 1024) & (0 < c < 4194304)
+            rec[m][o + w] = UInt32(t & 1023) | (UInt32(c & 4194303) << 10)
+        end
+    end
+    if !fits
+        foreach(host_free, rowptr); foreach(host_free, rec)
+        return nothing
+    end
+    return rowptr, rec
+end
+
+function flat_rows_pinned(v::Vector{Vector{Float64}})                                   # [d][j] -> D*MK row-major, pinned
+    MK = length(v[1])
+    out = pinned_vector(Float64, length(v) * MK)
+    for d in 1:length(v)
+        out[(d - 1) * MK + 1:d * MK] .= v[d]
+    end
+    return out
+end
+
 flat_rows(v::Vector{Vector{Float64}}) = collect(reduce(vcat, v))                         # [d][j] -> D*MK row-major
 flat_tables(t::Vector{Vector{Vector{Float64}}}) = collect(reduce(vcat, [reduce(vcat, tm) for tm in t]))   # [m][k][v]
 
@@ -143,7 +189,43 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
         elbo = Ref(0.0)
         GC.@preserve rowptr term count begin
             rp = [pointer(r) for r in rowptr]; tp = [pointer(t) for t in term]; cp = [pointer(c) for c in count]
-            if !verbose
+            packed = verbose ? nothing : flatten_counts_packed(model.X, M)
+            if !verbose && packed !== nothing
+                # one call, 4-byte count records and page-locked buffers: what an end-to-end fit! of a large corpus is bound by
+                # is the host -> device link (mmsig_mmctm_fit_host_packed)
+                prow, prec = packed
+                hist = zeros(M, maxiter); nit = Ref{Int32}(0); conv = Ref{Int32}(0)
+                λp, νp = flat_rows_pinned(model.λ), flat_rows_pinned(model.ν)
+                ζp = pinned_vector(Float64, D * M); pp = pinned_vector(Float64, D * MK)
+                try
+                    rpp = [pointer(r) for r in prow]; xp = [pointer(x) for x in prec]
+                    if grouped
+                        chk(h, ccall((:mmsig_group_mmctm_fit_host_packed, LIB), Int32,
+                            (Ptr{Cvoid}, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{UInt32}},
+                             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                             Int32, Float64, UInt32, Ptr{Float64}, Ref{Int32}, Ref{Int32},
+                             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                            h, D, M, K32, V32, rpp, xp, model.α, γ, λp, νp, model.μ, Σ, invΣ,
+                            maxiter, tol, flags, hist, nit, conv, λp, νp, ζp, μ, Σ, invΣ, γ, Elnϕ, ϕ, pp))
+                    else
+                        chk(h, ccall((:mmsig_mmctm_fit_host_packed, LIB), Int32,
+                            (Ptr{Cvoid}, Int64, Int64, Int32, Ptr{Int32}, Ptr{Int32}, Ptr{Ptr{Int64}}, Ptr{Ptr{UInt32}},
+                             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                             Int32, Float64, UInt32, Ptr{Float64}, Ref{Int32}, Ref{Int32},
+                             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64},
+                             Ptr{Float64}, Ptr{Float64}, Ptr{Float64}, Ptr{Float64}),
+                            h, D, D, M, K32, V32, rpp, xp, model.α, γ, λp, νp, model.μ, Σ, invΣ,
+                            maxiter, tol, flags, hist, nit, conv, λp, νp, ζp, μ, Σ, invΣ, γ, Elnϕ, ϕ, pp))
+                    end
+                    λ .= λp; ν .= νp; ζ .= ζp; props .= pp
+                finally
+                    foreach(host_free, prow); foreach(host_free, prec)
+                    host_free(λp); host_free(νp); host_free(ζp); host_free(pp)
+                end
+                ll = [hist[:, i] for i in 1:nit[]]
+                model.converged = conv[] != 0
+            elseif !verbose
                 # one call: counts + state in, the whole loop of src/MMCTM.jl:462-489, state out, with
                 # the host<->device copies pipelined behind the E-step (mmsig_mmctm_fit_host)
                 hist = zeros(M, maxiter); nit = Ref{Int32}(0); conv = Ref{Int32}(0)

@@ -13,6 +13,7 @@ c_dp = C.POINTER(C.c_double)
 c_i32p = C.POINTER(C.c_int32)
 c_i64p = C.POINTER(C.c_int64)
 c_u8p = C.POINTER(C.c_uint8)
+c_u32p = C.POINTER(C.c_uint32)
 
 FLAG_UPDATE_SIGMA, FLAG_FREEZE_TOPICS, FLAG_FREEZE_MU, FLAG_UNSMOOTHED, FLAG_AUTO_ALPHA = 1, 2, 4, 8, 16
 STOP_NLOPT27, STOP_NLOPT26 = 0, 1
@@ -58,6 +59,8 @@ _SIGS = {
     "mmsig_group_mmctm_get_theta": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
     "mmsig_group_mmctm_fit_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)] + [c_dp] * 7 +
                                    [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
+    "mmsig_group_mmctm_fit_host_packed": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_u32p)] +
+                                          [c_dp] * 7 + [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
     "mmsig_group_mmctm_restarts": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, c_i32p, c_i32p, C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p), c_dp, C.c_int32, c_dp,
                                                C.c_int32, C.c_double, C.c_uint32, c_dp, c_dp, c_i32p, c_i32p]),
     "mmsig_group_lda_set_data": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p]),
@@ -83,6 +86,10 @@ _SIGS = {
     "mmsig_mmctm_fit_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
                                          C.POINTER(c_i64p), C.POINTER(c_i32p), C.POINTER(c_i32p)] + [c_dp] * 7 +
                              [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
+    "mmsig_mmctm_fit_host_packed": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, c_i32p, c_i32p,
+                                                C.POINTER(c_i64p), C.POINTER(c_u32p)] + [c_dp] * 7 +
+                                    [C.c_int32, C.c_double, C.c_uint32, c_dp, c_i32p, c_i32p] + [c_dp] * 10),
+    "mmsig_pack_records": (C.c_int32, [C.c_int64, c_i32p, c_i32p, c_u32p]),
     "mmsig_mmctm_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_mmctm_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 10),
     "mmsig_mmctm_get_theta": (C.c_int32, [C.c_void_p, C.c_int32, c_dp]),
@@ -281,6 +288,18 @@ def host_array(shape, dtype):
 
 
 _PINNED = {}
+
+
+def pack_records(term, count, out=None):
+    """(term, count) int32 arrays -> the 4-byte records of mmsig_mmctm_fit_host_packed (mmsig_pack_records)."""
+    lib = load()
+    term = np.ascontiguousarray(term, np.int32)
+    count = np.ascontiguousarray(count, np.int32)
+    rec = np.empty(term.size, np.uint32) if out is None else out
+    rc = lib.mmsig_pack_records(term.size, term.ctypes.data_as(c_i32p), count.ctypes.data_as(c_i32p), rec.ctypes.data_as(c_u32p))
+    if rc != 0:
+        raise MmsigError(rc, (lib.mmsig_last_error(None) or b"").decode())
+    return rec
 
 
 def comm_unique_id():

@@ -364,7 +364,7 @@ extern "C" int32_t mmsig_group_mmctm_get_theta(mmsig_group *g, int32_t m, double
 
 // fit! from and to host buffers over all devices of the group: mmsig_mmctm_fit_host per shard, each device
 // pipelining its own uploads behind its own E-step
-extern "C" int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+static int group_fit_host_impl(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
                                               const int64_t *const *rowptr, const int32_t *const *term,
                                               const int32_t *const *count, const double *alpha, const double *gamma,
                                               const double *lambda, const double *nu, const double *mu, const double *Sigma,
@@ -372,8 +372,8 @@ extern "C" int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t
                                               double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
                                               double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
                                               double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
-                                              double *props_out) {
-    GNEED(g && K && V && rowptr && term && count && alpha && gamma, "null argument");
+                                              double *props_out, bool packed) {
+    GNEED(g && K && V && rowptr && term && (count || packed) && alpha && gamma, "null argument");
     GNEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
     if (M < 1 || M > MAXM) return gfail(g, MMSIG_ELIMIT, "1 <= M <= 8 modalities supported");
     int rc = group_shard(g, D, M, rowptr);
@@ -385,20 +385,47 @@ extern "C" int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t
     std::vector<int> nit(g->n, 0), conv(g->n, 0);
     rc = group_run(g, [&](int r, mmsig_handle *h) {
         ShardView sv;
-        make_shard(sv, g->cut[r], g->cut[r + 1], M, rowptr, term, count);
+        std::vector<const int32_t *> nocount(M, nullptr);
+        make_shard(sv, g->cut[r], g->cut[r + 1], M, rowptr, term, packed ? nocount.data() : count);
         const size_t off = (size_t)sv.d0 * MK, offz = (size_t)sv.d0 * M;
         const bool z = r == 0;
-        return (int)mmsig_mmctm_fit_host(h, sv.d1 - sv.d0, D, M, K, V, sv.rowptr.data(), sv.term.data(), sv.count.data(), alpha, gamma,
+        return (int)mmctm_fit_host_impl(h, sv.d1 - sv.d0, D, M, K, V, sv.rowptr.data(), sv.term.data(), packed ? nullptr : sv.count.data(), alpha, gamma,
                                          lambda ? lambda + off : nullptr, nu ? nu + off : nullptr, mu, Sigma, invSigma, maxiter, tol, flags,
                                          z ? ll_hist : hist[r].data(), &nit[r], &conv[r], lambda_out ? lambda_out + off : nullptr,
                                          nu_out ? nu_out + off : nullptr, zeta_out ? zeta_out + offz : nullptr, z ? mu_out : nullptr,
                                          z ? Sigma_out : nullptr, z ? invSigma_out : nullptr, z ? gamma_out : nullptr,
-                                         z ? Elnphi_out : nullptr, z ? phi_out : nullptr, props_out ? props_out + off : nullptr);
+                                         z ? Elnphi_out : nullptr, z ? phi_out : nullptr, props_out ? props_out + off : nullptr, packed);
     });
     if (rc) return rc;
     if (n_iter) *n_iter = nit[0];
     if (converged) *converged = conv[0];
     return 0;
+}
+
+extern "C" int32_t mmsig_group_mmctm_fit_host(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+                                              const int64_t *const *rowptr, const int32_t *const *term,
+                                              const int32_t *const *count, const double *alpha, const double *gamma,
+                                              const double *lambda, const double *nu, const double *mu, const double *Sigma,
+                                              const double *invSigma, int32_t maxiter, double tol, uint32_t flags,
+                                              double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
+                                              double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
+                                              double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
+                                              double *props_out) {
+    return group_fit_host_impl(g, D, M, K, V, rowptr, term, count, alpha, gamma, lambda, nu, mu, Sigma, invSigma, maxiter, tol, flags,
+                               ll_hist, n_iter, converged, lambda_out, nu_out, zeta_out, mu_out, Sigma_out, invSigma_out, gamma_out,
+                               Elnphi_out, phi_out, props_out, false);
+}
+extern "C" int32_t mmsig_group_mmctm_fit_host_packed(mmsig_group *g, int64_t D, int32_t M, const int32_t *K, const int32_t *V,
+                                                     const int64_t *const *rowptr, const uint32_t *const *rec, const double *alpha,
+                                                     const double *gamma, const double *lambda, const double *nu, const double *mu,
+                                                     const double *Sigma, const double *invSigma, int32_t maxiter, double tol,
+                                                     uint32_t flags, double *ll_hist, int32_t *n_iter, int32_t *converged,
+                                                     double *lambda_out, double *nu_out, double *zeta_out, double *mu_out,
+                                                     double *Sigma_out, double *invSigma_out, double *gamma_out, double *Elnphi_out,
+                                                     double *phi_out, double *props_out) {
+    return group_fit_host_impl(g, D, M, K, V, rowptr, reinterpret_cast<const int32_t *const *>(rec), nullptr, alpha, gamma, lambda, nu, mu,
+                               Sigma, invSigma, maxiter, tol, flags, ll_hist, n_iter, converged, lambda_out, nu_out, zeta_out, mu_out,
+                               Sigma_out, invSigma_out, gamma_out, Elnphi_out, phi_out, props_out, true);
 }
 
 // Independent restarts dealt over the devices (scripts/run_mmctm.jl:99-111 `pmap(fit_restart, ...)`; README.md:42):

@@ -48,9 +48,6 @@ __device__ __forceinline__ bool group_all(bool pred, int lane) {
 }
 
 constexpr int PH_IDLE = 0, PH_NU = 1, PH_LAM = 2;
-#ifndef MULTI_MIN_BLOCKS
-#define MULTI_MIN_BLOCKS 3
-#endif
 
 template <int G>
 __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *partial) {
@@ -256,287 +253,6 @@ __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *part
                 for (int gg = 0; gg < NG; ++gg) dd_merge(hi, lo, red[wv][which][gg * G + lane].x, red[wv][which][gg * G + lane].y);
             put_partial(partial + (size_t)blockIdx.x * 2 * MK + which * MK + lane, hi, lo, p.accum);
         }
-    }
-}
-
-// ------------------------------------------------------------------------------------------
-// 16 < ΣK_m <= 32: groups of 8 lanes, CPL = 3 or 4 coordinates per lane (coordinate j on lane
-// j % 8 of its group, slot j / 8), four samples per warp.  The 32-leaf tree becomes: slots
-// (0 + 2) + (1 + 3) inside the lane -- its levels 16 and 8 -- then the 8-lane butterfly (levels
-// 4, 2, 1): bit-identical.  Compared with one coordinate per lane this fills every lane (24 of
-// 32 were busy at ΣK_m = 24) and shares each reduction and each piece of scalar MMA bookkeeping
-// between four samples.
-// ------------------------------------------------------------------------------------------
-template <int CPL>
-__device__ __forceinline__ double slot_sum(const double (&v)[CPL]) {
-    if (CPL == 3) return (v[0] + v[2]) + v[1];
-    return (v[0] + v[2]) + (v[1] + v[CPL - 1]);          // CPL == 4
-}
-
-template <int CPL>
-__global__ void __launch_bounds__(128, MULTI_MIN_BLOCKS) k_solve_multi(MmctmDev p, double2 *partial) {
-    constexpr int G = 8, NG = 4, MKP = 8 * CPL, STRIDE = 34, NW = 4;     // NW warps per block
-    __shared__ __align__(16) double ST[32 * STRIDE];
-    __shared__ __align__(16) double dsh_all[NW][NG][STRIDE];
-    __shared__ double2 red[NW][2 * CPL][32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int grp = lane / G, gl = lane % G;
-    const unsigned gmask = 0xffu << (grp * G);
-    const int MK = p.MK, M = p.M;
-    double *dsh = dsh_all[warp][grp];
-    for (int t = threadIdx.x; t < 32 * STRIDE; t += blockDim.x) {
-        const int j = t / STRIDE, i = t % STRIDE;
-        ST[t] = (i < MK && j < MK) ? p.invSigma[j * MK + i] : 0.0;
-    }
-    for (int i = gl; i < STRIDE; i += G) dsh[i] = 0.0;
-    __syncthreads();
-    bool active[CPL];
-    int mod[CPL], blo[CPL], bhi[CPL];
-    double Sjj[CPL], muj[CPL];
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-        const int j = gl + 8 * s;
-        active[s] = j < MK;
-        mod[s] = 0;
-        for (int m = 0; m < M; ++m)
-            if (j >= p.koff[m]) mod[s] = m;
-        blo[s] = p.koff[mod[s]];
-        bhi[s] = p.koff[mod[s] + 1];
-        Sjj[s] = active[s] ? p.invSigma[j * MK + j] : 0.0;
-        muj[s] = active[s] ? p.mu[j] : 0.0;
-    }
-    int phase = PH_IDLE, k = 0, nev = 0, nev_nu = 0;
-    bool init = false;
-    double x[CPL], g[CPL], xcur[CPL], xprev[CPL], xprevprev[CPL], sigma[CPL];
-    double cN[CPL], sth[CPL], other[CPL], lam0[CPL];
-    double acc[4][CPL];                              // Σλ hi/lo, Σν hi/lo
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-        x[s] = g[s] = xcur[s] = xprev[s] = xprevprev[s] = 0.0;
-        sigma[s] = 1.0;
-        cN[s] = sth[s] = other[s] = lam0[s] = 0.0;
-        acc[0][s] = acc[1][s] = acc[2][s] = acc[3][s] = 0.0;
-    }
-    double fmin = 0.0, rho = 1.0;
-    long long dcur = -1;
-    bool exhausted = false;
-
-    while (true) {
-        if (phase == PH_IDLE && !exhausted) {
-            dcur = next_sample(p.work, gmask, grp * G, gl == 0);
-            if (dcur >= p.D) exhausted = true;
-        }
-        if (phase == PH_IDLE && !exhausted) {
-            double nu0[CPL];
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) {
-                const long long base = dcur * MK + gl + 8 * s;
-                lam0[s] = active[s] ? p.lam_prev[base] : 0.0;
-                nu0[s] = active[s] ? p.nu[base] : 1.5;
-                sth[s] = active[s] ? p.sumtheta[base] : 0.0;
-                dsh[gl + 8 * s] = active[s] ? det_exp(lam0[s] + 0.5 * nu0[s]) : 0.0;
-            }
-            __syncwarp(gmask);
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) {
-                double zeta = 0.0;
-                for (int i = blo[s]; i < bhi[s]; ++i) zeta += dsh[i];
-                const double Ndm = active[s] ? p.N[dcur * M + mod[s]] : 0.0;
-                cN[s] = active[s] ? Ndm / zeta : 0.0;
-                if (active[s] && gl + 8 * s == blo[s]) p.zeta[dcur * M + mod[s]] = zeta;
-                x[s] = nu0[s];
-                other[s] = lam0[s];
-            }
-            __syncwarp(gmask);
-            phase = PH_NU;
-            init = true;
-        }
-        if (!__any_sync(FULLMASK, phase != PH_IDLE)) break;
-        const bool busy = phase != PH_IDLE;
-
-        double xe[CPL], gl_[CPL], wl_[CPL];
-#pragma unroll
-        for (int s = 0; s < CPL; ++s) { xe[s] = x[s]; gl_[s] = 0.0; wl_[s] = 0.0; }
-        if (busy && !init) {
-            const double lb = (phase == PH_NU) ? 1e-7 : -__longlong_as_double(0x7ff0000000000000LL);
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) {
-                double u = g[s];
-                const double v = fabs(g[s]) * sigma[s] + 0.5 * rho;
-                const double sigma2 = sigma[s] * sigma[s];
-                u *= sigma2;
-                const double qv = fast_div(u, v);
-                const double r = qv * fast_rcp(sigma[s]);      // DET: (u / v)(1 / sigma)
-                const double om = fabs(1 - r * r);
-                const double sq = fast_sqrt(om < 0x1p-200 ? 0x1p-200 : om);   // om is 0 or >= 2^-53: sqrt(0) -> 2^-100, and -1 - 2^-100 == -1
-                double dx = fast_div(qv, -1 - sq);
-                double xc = x[s] + dx;
-                if (xc > x[s] + 0.9 * sigma[s]) xc = x[s] + 0.9 * sigma[s];
-                else if (xc < x[s] - 0.9 * sigma[s]) xc = x[s] - 0.9 * sigma[s];
-                if (xc < lb) xc = lb;
-                if (!active[s]) xc = x[s];
-                dx = xc - x[s];
-                const double dx2 = dx * dx;
-                const double denominv = fast_rcp(sigma2 - dx2);       // |dx| <= 0.9 sigma
-                const double cc = sigma2 * dx;
-                gl_[s] = (g[s] * cc + (fabs(g[s]) * sigma[s] + 0.5 * rho) * dx2) * denominv;
-                wl_[s] = 0.5 * dx2 * denominv;
-                xe[s] = xc;
-            }
-        }
-        double tl[CPL], gcur[CPL];
-#pragma unroll
-        for (int s = 0; s < CPL; ++s) { tl[s] = 0.0; gcur[s] = 1.0; }
-        if (phase == PH_NU) {
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) {
-                const double e = det_exp(other[s] + 0.5 * xe[s]);
-                const double grad = (-0.5 * Sjj[s] - (cN[s] / 2) * e) + fast_rcp(2 * xe[s]);
-                tl[s] = (-0.5 * (xe[s] * Sjj[s]) - cN[s] * e) + det_log(xe[s]) / 2;
-                gcur[s] = -grad;
-            }
-        } else if (phase == PH_LAM) {
-            double diff[CPL];
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) {
-                diff[s] = xe[s] - muj[s];
-                dsh[gl + 8 * s] = active[s] ? diff[s] : 0.0;
-            }
-            __syncwarp(gmask);
-            const double2 *dv2 = reinterpret_cast<const double2 *>(dsh);
-            double q[CPL], qo[CPL];                     // DET: even / odd index chains, then one add
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) { q[s] = 0.0; qo[s] = 0.0; }
-#pragma unroll 4
-            for (int i = 0; i < MKP / 2; ++i) {
-                const double2 dv = dv2[i];
-#pragma unroll
-                for (int s = 0; s < CPL; ++s) {
-                    const double2 sv = reinterpret_cast<const double2 *>(ST + (gl + 8 * s) * STRIDE)[i];
-                    q[s] = fma(sv.x, dv.x, q[s]);
-                    qo[s] = fma(sv.y, dv.y, qo[s]);
-                }
-            }
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) q[s] = q[s] + qo[s];
-            __syncwarp(gmask);
-#pragma unroll
-            for (int s = 0; s < CPL; ++s) {
-                const double e = det_exp(xe[s] + other[s]);
-                const double ce = cN[s] * e;
-                const double grad = (-q[s] + sth[s]) - ce;
-                const double a = q[s] * diff[s], b = xe[s] * sth[s];
-                tl[s] = (b - 0.5 * a) - ce;
-                gcur[s] = -grad;
-            }
-        }
-        double adl[CPL], xnl[CPL];
-        bool ok26 = true, okabs = true;
-#pragma unroll
-        for (int s = 0; s < CPL; ++s) {
-            if (!active[s] || !busy) { tl[s] = 0.0; gcur[s] = 1.0; }
-            adl[s] = (active[s] && busy && !init) ? fabs(xe[s] - xprev[s]) : 0.0;
-            xnl[s] = (active[s] && busy) ? fabs(xe[s]) : 0.0;
-            ok26 = ok26 && (!active[s] || adl[s] < 1e-4 || adl[s] < 1e-4 * (fabs(xe[s]) + fabs(xprev[s])) * 0.5 ||
-                            xe[s] == xprev[s]);
-            okabs = okabs && !(adl[s] > 1e-4);
-        }
-        __syncwarp();
-        double gterm = slot_sum<CPL>(gl_), wterm = slot_sum<CPL>(wl_), t = slot_sum<CPL>(tl);
-        group_tree_sum3<G>(gterm, wterm, t, lane);
-        const double f = -t;
-        const double gval = fmin + gterm;
-        const bool inner_done = !init && (gval >= f);
-        double dn = slot_sum<CPL>(adl), xn = slot_sum<CPL>(xnl);
-        if (__any_sync(FULLMASK, busy && inner_done)) {
-            dn = group_tree_sum<G>(dn);
-            xn = group_tree_sum<G>(xn);
-        }
-        const bool all26 = group_all<G>(ok26, lane);
-        const bool allabs = group_all<G>(okabs, lane);
-        bool finish = false;
-        if (busy) {
-            if (init) {
-                fmin = f;
-                nev = 1;
-                k = 1;
-                rho = 1.0;
-                init = false;
-#pragma unroll
-                for (int s = 0; s < CPL; ++s) {
-                    g[s] = gcur[s];
-                    xcur[s] = xprev[s] = xprevprev[s] = x[s];
-                    sigma[s] = 1.0;
-                }
-            } else {
-                ++nev;
-                const bool better = f < fmin;
-                if (better) fmin = f;
-#pragma unroll
-                for (int s = 0; s < CPL; ++s) {
-                    xcur[s] = xe[s];
-                    if (better) { x[s] = xe[s]; g[s] = gcur[s]; }
-                }
-                if (nev >= MMA_MAXEVAL) finish = true;
-                else if (inner_done) {
-                    const bool stop = (p.stop_rule == 1) ? all26 : ((dn <= 1e-4 * xn) || allabs);
-                    if (stop) finish = true;
-                    else {
-                        rho = 0.1 * rho > 1e-5 ? 0.1 * rho : 1e-5;
-#pragma unroll
-                        for (int s = 0; s < CPL; ++s) {
-                            if (k > 1) {
-                                const double s2 = (xcur[s] - xprev[s]) * (xprev[s] - xprevprev[s]);
-                                sigma[s] *= s2 < 0 ? 0.7 : (s2 > 0 ? 1.2 : 1.0);
-                            }
-                            xprevprev[s] = xprev[s];
-                            xprev[s] = xcur[s];
-                        }
-                        ++k;
-                    }
-                } else if (f > gval) {
-                    const double r1 = 10 * rho, r2 = 1.1 * (rho + guarded_div(f - gval, wterm));
-                    rho = r1 < r2 ? r1 : r2;
-                }
-            }
-        }
-        if (finish) {
-            if (phase == PH_NU) {
-                nev_nu = nev;
-#pragma unroll
-                for (int s = 0; s < CPL; ++s) {
-                    const double nu_new = x[s];
-                    if (active[s]) { p.nu[dcur * MK + gl + 8 * s] = nu_new; dd_add(acc[2][s], acc[3][s], nu_new); }
-                    other[s] = 0.5 * nu_new;
-                    x[s] = lam0[s];
-                }
-                phase = PH_LAM;
-                init = true;
-            } else {
-#pragma unroll
-                for (int s = 0; s < CPL; ++s)
-                    if (active[s]) { p.lam[dcur * MK + gl + 8 * s] = x[s]; dd_add(acc[0][s], acc[1][s], x[s]); }
-                if (gl == 0) { p.nev_nu[dcur] = nev_nu; p.nev_lam[dcur] = nev; }
-                phase = PH_IDLE;
-            }
-        }
-    }
-#pragma unroll
-    for (int s = 0; s < CPL; ++s) {
-        red[warp][s][lane] = make_double2(acc[0][s], acc[1][s]);
-        red[warp][CPL + s][lane] = make_double2(acc[2][s], acc[3][s]);
-    }
-    __syncthreads();
-    // coordinate j = gl + 8 s: sum over warps and over the four groups
-    for (int t = threadIdx.x; t < 2 * MK; t += blockDim.x) {
-        const int which = t / MK, j = t % MK, s = j / 8, l = j % 8;
-        double hi = 0.0, lo = 0.0;
-        for (int wv = 0; wv < NW; ++wv)
-            for (int gg = 0; gg < NG; ++gg) {
-                const double2 v = red[wv][which * CPL + s][gg * G + l];
-                dd_merge(hi, lo, v.x, v.y);
-            }
-        put_partial(partial + (size_t)blockIdx.x * 2 * MK + which * MK + j, hi, lo, p.accum);
     }
 }
 

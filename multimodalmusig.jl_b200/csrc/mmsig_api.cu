@@ -20,9 +20,6 @@
 #include "theta_tile.cuh"
 #include "mmctm_wide.cuh"
 #include "mmctm_pack.cuh"
-#ifdef MMSIG_EXPERIMENTAL_SPLIT          // make EXP=1: the split-phase solver, not part of the default build until it is measured
-#include "mmctm_split.cuh"
-#endif
 #include "mmctm_lean.cuh"
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
@@ -94,9 +91,7 @@ struct MmctmHost {
     int grid_theta[MAXM] = {0}, W_theta[MAXM] = {0}, grid_ll[MAXM] = {0};
     size_t smem_theta[MAXM] = {0}, smem_ll[MAXM] = {0};
     int grid_solve = 0, grid_post = 0, grid_mom = 0, grid_zeta = 0;
-    bool solve_multi = false;          // 16 < sum(K) <= 32: k_solve_multi (4 samples per warp) instead of k_solve
-    int solve_split = 0;               // 16 < sum(K) <= 32: k_solve_phase, one kernel per LD_MMA phase (experimental); 8 or 16 = lanes per sample
-    int solve_lean = 0;                // sum(K) <= 32: k_solve_lean, one kernel per LD_MMA phase, G = 4 or 8 lanes per sample (mmctm_lean.cuh)
+    int solve_lean = 0;                // sum(K) <= 32: k_solve_lean, one kernel per LD_MMA phase, G = 4 or 8 lanes per sample (mmctm_lean.cuh); 0: one coordinate per lane (k_solve / k_solve_pack)
     bool wide = false;                 // 32 < sum(K) <= 64: two coordinates per lane (mmctm_wide.cuh)
     size_t smem_solve = 0;
     double2 *part_mom = nullptr;
@@ -158,6 +153,7 @@ struct mmsig_handle {
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of mmsig_mmctm_fit_host
     long long *allsum_buf = nullptr;                   // scratch of allsum_ll (multi-rank totals)
+    double *ll_pinned = nullptr;                       // page-locked landing zone of the log-likelihoods of the sync-free iterations
     int2 *fmt_rec = nullptr;                           // records of the last mmsig_format_counts
     long long fmt_nnz = -1;
     bool own_stream = false;
@@ -357,6 +353,7 @@ extern "C" int32_t mmsig_destroy(mmsig_handle *h) {
     if (h->own_stream) cudaStreamDestroy(h->stream);
     cudaFree(h->fmt_rec);
     cudaFree(h->allsum_buf);
+    if (h->ll_pinned) cudaFreeHost(h->ll_pinned);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
     delete h;
@@ -490,8 +487,16 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
         const long long beg = rowptr[d], end = rowptr[d + 1];
         long long s = 0;
         for (long long w = beg + lane; w < end; w += 32) {
-            int t = term[w], c = count[w];
-            if (w > beg && term[w - 1] >= t) bad |= 4;
+            // count == nullptr: term[] holds packed records (bits 0-9 term, bits 10-31 count: mmsig_pack_records)
+            int t = term[w], c;
+            int tprev = w > beg ? term[w - 1] : -1;
+            if (count) c = count[w];
+            else {
+                c = (int)((unsigned)t >> 10);
+                t &= 1023;
+                tprev = w > beg ? (tprev & 1023) : -1;
+            }
+            if (w > beg && tprev >= t) bad |= 4;
             // a bad entry is flagged AND neutralised (term 0, count 0): mmsig_mmctm_fit_host launches the
             // E-step of a chunk before the flags are read, and the tile kernels index shared memory with
             // the term (a term < 0 or >= 65536 would also alias into the slot-tag bits)
@@ -528,11 +533,11 @@ static int ensure_countbuf(mmsig_handle *h, std::vector<void *> &pool, CountBuf 
 }
 // rows [d0, d1) of one modality: validation, (term, count) -> records, row totals
 static void pack_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d1, int V, int M, int m, double *d_N,
-                        int tag = 0) {
+                        int tag = 0, bool packed = false) {
     LaunchScope ls(h, "k_pack_rows");
     const long long Dc = d1 - d0;
     int grid = (int)std::min<long long>((Dc + 7) / 8, (long long)h->numSM * 8);
-    k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr + d0, cb.term, cb.count, Dc, V, cb.rec, d_N + d0 * M, M, m,
+    k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr + d0, cb.term, packed ? nullptr : cb.count, Dc, V, cb.rec, d_N + d0 * M, M, m,
                                                            cb.flags, (unsigned long long *)(cb.flags + 2), tag, d0);
 }
 static int flags_verdict(mmsig_handle *h, const int *hf, long long *ntot_out) {
@@ -749,19 +754,18 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     }
     mm.wide = p.MK > 32;
     {
-        // MMSIG_SOLVE=multi selects k_solve_multi (4 samples per warp, 3-4 coordinates per lane) for
-        // 16 < sum(K) <= 32.  It is bit-identical but measured SLOWER than one sample per warp on
-        // B200 (26.1 vs 21.9 ms at D = 5e5, sum(K) = 24: 168 registers, phase divergence), so it
-        // is off by default and kept for A/B measurements.
+        // Lane layout of the LD_MMA kernels for sum(K) <= 32 (all bit-identical; tests/test_gpu_mmctm.py::test_solver_layouts_are_bit_identical).
+        // Default: k_solve_lean (mmctm_lean.cuh), 4 lanes per sample up to sum(K) = 12, 8 above.  Measured on B200 at
+        // D = 1e6 (profiles/r02_solve_summary.md): sum(K) = 24: 18.8 ms against 33.7 ms for one coordinate per lane
+        // (k_solve); sum(K) = 10: 7.2 ms (4 lanes) / 9.8 ms (8 lanes) against 14.1 ms (k_solve_pack).
+        // MMSIG_SOLVE=warp | lean8 | lean4 overrides (A/B measurements).
         const char *e = getenv("MMSIG_SOLVE");
-        mm.solve_multi = e && !strcmp(e, "multi");
-        // MMSIG_SOLVE=split: the same packing with one kernel per phase (mmctm_split.cuh); experimental
-#ifdef MMSIG_EXPERIMENTAL_SPLIT
-        mm.solve_split = (e && p.MK > 16 && p.MK <= 32) ? (!strcmp(e, "split") ? 8 : (!strcmp(e, "split16") ? 16 : 0)) : 0;
-#endif
-        // MMSIG_SOLVE=lean8 | lean4: k_solve_lean with 8 / 4 lanes per sample (mmctm_lean.cuh)
-        mm.solve_lean = (e && p.MK <= 32) ? (!strcmp(e, "lean8") ? 8 : (!strcmp(e, "lean4") ? 4 : 0)) : 0;
-        if (mm.solve_lean == 4 && p.MK > 16) mm.solve_lean = 8;            // 4 lanes x (> 4 coordinates) spills: measured 43 ms against 23 ms at sum(K) = 24
+        mm.solve_lean = p.MK > 32 ? 0 : (p.MK <= 12 ? 4 : 8);
+        if (e && p.MK <= 32) {
+            if (!strcmp(e, "warp")) mm.solve_lean = 0;
+            else if (!strcmp(e, "lean8")) mm.solve_lean = 8;
+            else if (!strcmp(e, "lean4")) mm.solve_lean = p.MK <= 16 ? 4 : 8;     // 4 lanes x (> 4 coordinates) spills: 43 ms against 23 ms at sum(K) = 24
+        }
     }
     CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
@@ -777,18 +781,10 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         }
         else if (p.MK <= 8) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<8>, 256, 0));
         else if (p.MK <= 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_pack<16>, 256, 0));
-#ifdef MMSIG_EXPERIMENTAL_SPLIT
-        else if (mm.solve_split == 16) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<16, 2, PH_LAM>, 128, 0));
-        else if (mm.solve_split && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<8, 3, PH_LAM>, 128, 0));
-        else if (mm.solve_split) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_phase<8, 4, PH_LAM>, 128, 0));
-#endif
-        else if (mm.solve_multi && p.MK <= 24) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<3>, 128, 0));
-        else if (mm.solve_multi) CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve_multi<4>, 128, 0));
         else MK_DISPATCH(p.MK, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_solve<MKP>, 256, 0)));
         {
-            // samples per block: 8 warps x 1, 2 or 4 (packed), or 4 warps x 4 (multi)
-            const int spb = mm.solve_lean ? 4 * (32 / mm.solve_lean)
-                          : p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : (mm.solve_split == 16 ? 8 : ((mm.solve_multi || mm.solve_split) ? 16 : 8)));
+            // samples per block: 4 warps x 4 or 8 (lean), 8 warps x 1, 2 or 4 (one coordinate per lane)
+            const int spb = mm.solve_lean ? 4 * (32 / mm.solve_lean) : (p.MK <= 8 ? 32 : (p.MK <= 16 ? 16 : 8));
             mm.grid_solve = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1),
                                                                             (D + spb - 1) / spb));
         }
@@ -1073,21 +1069,6 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         }
         else if (q.MK <= 8) k_solve_pack<8><<<cap(mm.grid_solve, 32), 256, 0, h->stream>>>(q, mm.part_solve);
         else if (q.MK <= 16) k_solve_pack<16><<<cap(mm.grid_solve, 16), 256, 0, h->stream>>>(q, mm.part_solve);
-#ifdef MMSIG_EXPERIMENTAL_SPLIT
-        else if (mm.solve_split) {
-            // ν for every sample, then λ (which reads the new ν and the ζ the first kernel stored)
-            const int gs = cap(mm.grid_solve, mm.solve_split == 16 ? 8 : 16);
-            if (mm.solve_split == 16) k_solve_phase<16, 2, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            else if (q.MK <= 24) k_solve_phase<8, 3, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            else k_solve_phase<8, 4, PH_NU><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);
-            if (mm.solve_split == 16) k_solve_phase<16, 2, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            else if (q.MK <= 24) k_solve_phase<8, 3, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-            else k_solve_phase<8, 4, PH_LAM><<<gs, 128, 0, h->stream>>>(q, mm.part_solve);
-        }
-#endif
-        else if (mm.solve_multi && q.MK <= 24) k_solve_multi<3><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
-        else if (mm.solve_multi) k_solve_multi<4><<<cap(mm.grid_solve, 16), 128, 0, h->stream>>>(q, mm.part_solve);
         else MK_DISPATCH(q.MK, (k_solve<MKP><<<cap(mm.grid_solve, 8), 256, 0, h->stream>>>(q, mm.part_solve)));
     }
 }
@@ -1211,20 +1192,59 @@ static bool converged_vec(const double *prev, const double *cur, int M, double t
     return r < tol;
 }
 
-extern "C" int32_t mmsig_mmctm_fit(mmsig_handle *h, int32_t maxiter, double tol, uint32_t flags, double *ll_hist,
-                                   int32_t *n_iter, int32_t *converged) {
-    NEED(h, "null handle");
-    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
-    NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
-    const int M = h->mm.p.M;
-    int it = 0, conv = 0;
-    for (int iter = 1; iter <= maxiter; ++iter) {
+// Iterations first..maxiter of fit!'s loop (src/MMCTM.jl:462-489).  The convergence rule can only fire once the
+// history holds more than 10 entries (:485), so the iterations before that are enqueued back to back, their
+// log-likelihoods landing in page-locked memory, and the host synchronises once; from then on once per iteration
+// (the decision needs that iteration's LL).  hist_len: entries of ll_hist filled before `first`.
+static int mmctm_run_iterations(mmsig_handle *h, int first, int32_t maxiter, double tol, uint32_t flags, double *ll_hist,
+                                int *it_out, int *conv_out) {
+    MmctmHost &mm = h->mm;
+    const int M = mm.p.M;
+    int it = first - 1, conv = 0;
+    int iter = first;
+    if (!(flags & MMSIG_FLAG_AUTO_ALPHA)) {            // update_alpha! synchronises inside every iteration anyway
+        const int nfree = std::min<int>(maxiter, 10) - first + 1;
+        if (nfree > 1) {
+            if (!h->ll_pinned) CU(cudaHostAlloc((void **)&h->ll_pinned, (size_t)12 * (MAXM + 1) * sizeof(double), cudaHostAllocDefault));
+            int *status = reinterpret_cast<int *>(h->ll_pinned + (size_t)12 * MAXM);
+            for (int i = 0; i < nfree; ++i) {
+                int rc = mmctm_iterate_async(h, flags);
+                if (rc) return rc;
+                CU(cudaMemcpyAsync(h->ll_pinned + (size_t)i * MAXM, mm.d_ll, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                CU(cudaMemcpyAsync(status + i, mm.d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+            }
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaGetLastError());
+            for (int i = 0; i < nfree; ++i) {
+                if (status[i]) return fail(h, MMSIG_EINVAL, "Sigma is singular (inv failed)");
+                memcpy(ll_hist + (size_t)(first - 1 + i) * M, h->ll_pinned + (size_t)i * MAXM, M * sizeof(double));
+            }
+            iter = first + nfree;
+            it = iter - 1;
+        }
+    }
+    for (; iter <= maxiter; ++iter) {
         double *ll = ll_hist + (size_t)(iter - 1) * M;
         int rc = mmsig_mmctm_iterate(h, flags, ll);
         if (rc) return rc;
         it = iter;
         if (iter > 10 && converged_vec(ll - M, ll, M, tol)) { conv = 1; break; }   // src/MMCTM.jl:485
     }
+    *it_out = it;
+    *conv_out = conv;
+    return 0;
+}
+
+extern "C" int32_t mmsig_mmctm_fit(mmsig_handle *h, int32_t maxiter, double tol, uint32_t flags, double *ll_hist,
+                                   int32_t *n_iter, int32_t *converged) {
+    NEED(h, "null handle");
+    NEED(h->mm.has_state, "mmsig_mmctm_set_state first");
+    NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
+    NEED(!(h->mm.p.factored && (flags & MMSIG_FLAG_UNSMOOTHED)), "the IMMCTM has no unsmoothed E-step (no transform in src/IMMCTM.jl)");
+    CU(cudaSetDevice(h->device));
+    int it = 0, conv = 0;
+    int rc = mmctm_run_iterations(h, 1, maxiter, tol, flags, ll_hist, &it, &conv);
+    if (rc) return rc;
     if (n_iter) *n_iter = it;
     if (converged) *converged = conv;
     return 0;
@@ -1300,7 +1320,7 @@ static int pipe_chunks(long long D) {
     return (int)std::max<long long>(1, std::min<long long>({c, 64LL, (D + 31) / 32}));     // a chunk holds at least one tile of 32 samples
 }
 
-extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+static int mmctm_fit_host_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
                                         const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
                                         const int32_t *const *count, const double *alpha, const double *gamma,
                                         const double *lambda, const double *nu, const double *mu, const double *Sigma,
@@ -1308,9 +1328,9 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
                                         double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
                                         double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
                                         double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
-                                        double *props_out) {
+                                        double *props_out, bool packed) {
     NEED(h, "null handle");
-    NEED(K && V && rowptr && term && count, "null argument");
+    NEED(K && V && rowptr && term && (count || packed), "null argument");
     NEED(alpha && gamma, "alpha and gamma are required");
     NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
     CU(cudaSetDevice(h->device));
@@ -1335,7 +1355,8 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
     mm.has_state = false;
     for (int m = 0; m < M; ++m) {
         NEED(alpha[m] > 0, "alpha must be > 0");
-        NEED(rowptr[m][D] == 0 || (term[m] && count[m]), "null term / count");
+        NEED(rowptr[m][D] == 0 || (term[m] && (packed || count[m])), "null term / count");
+        NEED(!packed || V[m] <= 1024, "packed records carry 10-bit terms");
     }
     if (!h->s_in) CU(cudaStreamCreateWithFlags(&h->s_in, cudaStreamNonBlocking));
     if (!h->s_out) CU(cudaStreamCreateWithFlags(&h->s_out, cudaStreamNonBlocking));
@@ -1453,7 +1474,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
             const long long w0 = rowptr[m][d0], w1 = rowptr[m][d1];
             if (w1 > w0) {
                 CU(cudaMemcpyAsync(cb.term + w0, term[m] + w0, (size_t)(w1 - w0) * sizeof(int), cudaMemcpyHostToDevice, h->s_in));
-                CU(cudaMemcpyAsync(cb.count + w0, count[m] + w0, (size_t)(w1 - w0) * sizeof(int), cudaMemcpyHostToDevice, h->s_in));
+                if (!packed) CU(cudaMemcpyAsync(cb.count + w0, count[m] + w0, (size_t)(w1 - w0) * sizeof(int), cudaMemcpyHostToDevice, h->s_in));
             }
         }
         const size_t n = (size_t)(d1 - d0) * MK * sizeof(double);
@@ -1461,7 +1482,7 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         if (nu) CU(cudaMemcpyAsync(p.nu + d0 * MK, nu + d0 * MK, n, cudaMemcpyHostToDevice, h->s_in));
         CU(cudaEventRecord(ev_in[c], h->s_in));
         CU(cudaStreamWaitEvent(h->stream, ev_in[c], 0));
-        for (int m = 0; m < M; ++m) pack_launch(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N), 1);
+        for (int m = 0; m < M; ++m) pack_launch(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N), 1, packed);
         mmctm_estep_launch(h, chunk_view(p, d0, d1, C > 1), flags);
         if (maxiter == 1) CU(after_chunk(c));
     }
@@ -1504,7 +1525,17 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
 
     // ---- iterations 2 .. maxiter (src/MMCTM.jl:462-487)
     int it = 1, conv = 0;
-    for (int iter = 2; iter <= maxiter; ++iter) {
+    int iter0 = 2;
+    {
+        // iterations 2 .. min(10, maxiter - 1) cannot end the loop (src/MMCTM.jl:485): enqueue them without host round trips
+        const int last_free = std::min<int>(10, maxiter - (C > 1 ? 1 : 0));
+        if (last_free >= 3 && !(flags & MMSIG_FLAG_AUTO_ALPHA)) {
+            int cv = 0;
+            if ((rc = mmctm_run_iterations(h, 2, last_free, tol, flags, ll_hist, &it, &cv))) return rc;
+            iter0 = last_free + 1;
+        }
+    }
+    for (int iter = iter0; iter <= maxiter; ++iter) {
         double *ll = ll_hist + (size_t)(iter - 1) * M;
         if (iter == maxiter && C > 1) {
             // the loop ends here whatever the LL says: let the outputs leave chunk by chunk
@@ -1529,6 +1560,49 @@ extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_to
         return mmsig_mmctm_get_state(h, nullptr, nullptr, nullptr, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out, phi_out, nullptr);
     return mmsig_mmctm_get_state(h, lambda_out, nu_out, zeta_out, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out,
                                  phi_out, props_out);
+}
+
+extern "C" int32_t mmsig_mmctm_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                        const int32_t *V, const int64_t *const *rowptr, const int32_t *const *term,
+                                        const int32_t *const *count, const double *alpha, const double *gamma,
+                                        const double *lambda, const double *nu, const double *mu, const double *Sigma,
+                                        const double *invSigma, int32_t maxiter, double tol, uint32_t flags,
+                                        double *ll_hist, int32_t *n_iter, int32_t *converged, double *lambda_out,
+                                        double *nu_out, double *zeta_out, double *mu_out, double *Sigma_out,
+                                        double *invSigma_out, double *gamma_out, double *Elnphi_out, double *phi_out,
+                                        double *props_out) {
+    return mmctm_fit_host_impl(h, D, D_total, M, K, V, rowptr, term, count, alpha, gamma, lambda, nu, mu, Sigma, invSigma, maxiter, tol,
+                               flags, ll_hist, n_iter, converged, lambda_out, nu_out, zeta_out, mu_out, Sigma_out, invSigma_out,
+                               gamma_out, Elnphi_out, phi_out, props_out, false);
+}
+
+// the same with 4-byte records (half the host -> device traffic of the counts): rec[m][w] = term | count << 10
+extern "C" int32_t mmsig_mmctm_fit_host_packed(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M, const int32_t *K,
+                                               const int32_t *V, const int64_t *const *rowptr, const uint32_t *const *rec,
+                                               const double *alpha, const double *gamma, const double *lambda, const double *nu,
+                                               const double *mu, const double *Sigma, const double *invSigma, int32_t maxiter,
+                                               double tol, uint32_t flags, double *ll_hist, int32_t *n_iter, int32_t *converged,
+                                               double *lambda_out, double *nu_out, double *zeta_out, double *mu_out,
+                                               double *Sigma_out, double *invSigma_out, double *gamma_out, double *Elnphi_out,
+                                               double *phi_out, double *props_out) {
+    return mmctm_fit_host_impl(h, D, D_total, M, K, V, rowptr, reinterpret_cast<const int32_t *const *>(rec), nullptr, alpha, gamma,
+                               lambda, nu, mu, Sigma, invSigma, maxiter, tol, flags, ll_hist, n_iter, converged, lambda_out, nu_out,
+                               zeta_out, mu_out, Sigma_out, invSigma_out, gamma_out, Elnphi_out, phi_out, props_out, true);
+}
+
+// (term, count) -> packed records for mmsig_mmctm_fit_host_packed; MMSIG_ELIMIT when a term needs more than 10 bits
+// or a count more than 22 (use the unpacked entry then).  Host only.
+extern "C" int32_t mmsig_pack_records(int64_t nnz, const int32_t *term, const int32_t *count, uint32_t *rec) {
+    mmsig_handle *h = nullptr;
+    NEED(nnz >= 0 && (nnz == 0 || (term && count && rec)), "null argument");
+    unsigned bad = 0;
+    for (int64_t w = 0; w < nnz; ++w) {
+        const unsigned t = (unsigned)term[w], c = (unsigned)count[w];
+        bad |= (t >> 10) | (c >> 22);
+        rec[w] = t | (c << 10);
+    }
+    if (bad) return fail(h, MMSIG_ELIMIT, "packed records hold terms < 1024 and counts < 4194304");
+    return 0;
 }
 
 extern "C" int32_t mmsig_mmctm_get_theta(mmsig_handle *h, int32_t m, double *theta_out) {

@@ -168,8 +168,9 @@ class MMCTM:
         A = s["Sigma"][np.ix_(un, ob)] @ s["invSigma"][np.ix_(ob, ob)]
         return s["mu"][un] + (lam - s["mu"][ob]) @ A.T
 
-    def fit(self, maxiter=100, tol=1e-4, verbose=True, autoalpha=False, updateSigma=True):
-        """fit!(model; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true), src/MMCTM.jl:457-494."""
+    def fit(self, maxiter=100, tol=1e-4, verbose=True, autoalpha=False, updateSigma=True, elbo=True):
+        """fit!(model; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true), src/MMCTM.jl:457-494.
+        elbo=False skips the closing calculate_elbo (:490) -- for timing the loop alone."""
         flags = (capi.FLAG_UPDATE_SIGMA if updateSigma else 0) | (capi.FLAG_AUTO_ALPHA if autoalpha else 0)
         if verbose:
             hist = []
@@ -192,7 +193,8 @@ class MMCTM:
             a = np.zeros(self.M)
             self.h.check(self.h.lib.mmsig_mmctm_get_alpha(self.h.h, capi.dp(a)))
             self.alpha = a
-        self.elbo = self.calculate_elbo()[0]          # :490
+        if elbo:
+            self.elbo = self.calculate_elbo()[0]      # :490
         self.ll = hist[-1].copy()                     # :491
         return hist
 
@@ -203,13 +205,18 @@ class MMCTM:
         E-step chunk by chunk.  counts / gamma / lam ...: what _set_data and set_state take.
         out: optional dict of preallocated (e.g. page-locked) result arrays keyed as state().
         Returns (ll_history, out)."""
-        keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32),
-                 np.ascontiguousarray(c, np.int32)) for r, t, c in counts]
+        packed = len(counts[0]) == 2            # (rowptr, rec) with rec = capi.pack_records(term, count): 4-byte records
         M = self.M
+        if packed:
+            keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(x, np.uint32)) for r, x in counts]
+            tp = (capi.c_u32p * M)(*[k[1].ctypes.data_as(capi.c_u32p) for k in keep])
+        else:
+            keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32),
+                     np.ascontiguousarray(c, np.int32)) for r, t, c in counts]
+            tp = (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep])
+            cp = (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep])
         D = len(keep[0][0]) - 1
         rp = (capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep])
-        tp = (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep])
-        cp = (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep])
         K = np.asarray(self.K, np.int32)
         V = np.asarray(self.V, np.int32)
         MK, G = self.MK, self.G
@@ -224,10 +231,11 @@ class MMCTM:
             flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
         hist = np.zeros((maxiter, M))
         n, conv = C.c_int32(), C.c_int32()
-        self.h.check(self.h.lib.mmsig_mmctm_fit_host(
+        fn = self.h.lib.mmsig_mmctm_fit_host_packed if packed else self.h.lib.mmsig_mmctm_fit_host
+        self.h.check(fn(
             self.h.h, D, D if D_total is None else D_total, M, K.ctypes.data_as(capi.c_i32p),
-            V.ctypes.data_as(capi.c_i32p), rp, tp, cp, *[capi.dp(x) for x in a], maxiter, tol, flags, capi.dp(hist),
-            C.byref(n), C.byref(conv), *[capi.dp(out.get(k)) for k in order]))
+            V.ctypes.data_as(capi.c_i32p), rp, *((tp,) if packed else (tp, cp)), *[capi.dp(x) for x in a], maxiter, tol, flags,
+            capi.dp(hist), C.byref(n), C.byref(conv), *[capi.dp(out.get(k)) for k in order]))
         self.D = D
         self.nnz = [int(k[0][-1]) for k in keep]
         self.converged = bool(conv.value)
@@ -630,13 +638,19 @@ class MMCTMGroup:
         self.converged, self.elbo, self.ll = False, float("nan"), None
 
     def _csr(self, counts):
-        keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32), np.ascontiguousarray(c, np.int32))
-                for r, t, c in counts]
         M = self.M
+        self._packed = len(counts[0]) == 2      # (rowptr, rec): 4-byte records (capi.pack_records)
+        if self._packed:
+            keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(x, np.uint32)) for r, x in counts]
+            self._ptrs = ((capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep]),
+                          (capi.c_u32p * M)(*[k[1].ctypes.data_as(capi.c_u32p) for k in keep]))
+        else:
+            keep = [(np.ascontiguousarray(r, np.int64), np.ascontiguousarray(t, np.int32), np.ascontiguousarray(c, np.int32))
+                    for r, t, c in counts]
+            self._ptrs = ((capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep]),
+                          (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep]),
+                          (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep]))
         self._keep = keep
-        self._ptrs = ((capi.c_i64p * M)(*[k[0].ctypes.data_as(capi.c_i64p) for k in keep]),
-                      (capi.c_i32p * M)(*[k[1].ctypes.data_as(capi.c_i32p) for k in keep]),
-                      (capi.c_i32p * M)(*[k[2].ctypes.data_as(capi.c_i32p) for k in keep]))
         self._K32, self._V32 = np.asarray(self.K, np.int32), np.asarray(self.V, np.int32)
         self._kv = (self._K32.ctypes.data_as(capi.c_i32p), self._V32.ctypes.data_as(capi.c_i32p))
 
@@ -653,14 +667,15 @@ class MMCTMGroup:
         self.grp.check(self.grp.lib.mmsig_group_mmctm_iterate(self.grp.g, flags, capi.dp(ll)))
         return ll
 
-    def fit(self, maxiter=100, tol=1e-4, updateSigma=True, verbose=False):
+    def fit(self, maxiter=100, tol=1e-4, updateSigma=True, verbose=False, elbo=True):
         hist = np.zeros((maxiter, self.M))
         n, conv = C.c_int32(0), C.c_int32(0)
         flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
         self.grp.check(self.grp.lib.mmsig_group_mmctm_fit(self.grp.g, maxiter, tol, flags, capi.dp(hist), C.byref(n), C.byref(conv)))
         hist = hist[:n.value].copy()
         self.converged, self.ll = bool(conv.value), hist[-1].copy()
-        self.elbo = self.calculate_elbo()[0]
+        if elbo:
+            self.elbo = self.calculate_elbo()[0]
         return hist
 
     def calculate_elbo(self):
@@ -701,7 +716,8 @@ class MMCTMGroup:
         n, conv = C.c_int32(0), C.c_int32(0)
         order = ("lam", "nu", "zeta", "mu", "Sigma", "invSigma", "gamma", "Elnphi", "phi", "props")
         flags = capi.FLAG_UPDATE_SIGMA if updateSigma else 0
-        self.grp.check(self.grp.lib.mmsig_group_mmctm_fit_host(
+        fn = self.grp.lib.mmsig_group_mmctm_fit_host_packed if self._packed else self.grp.lib.mmsig_group_mmctm_fit_host
+        self.grp.check(fn(
             self.grp.g, D, self.M, *self._kv, *self._ptrs, *[capi.dp(x) for x in a], maxiter, tol, flags, capi.dp(hist),
             C.byref(n), C.byref(conv), *[capi.dp(out.get(k)) for k in order]))
         hist = hist[:n.value].copy()

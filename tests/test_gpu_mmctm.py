@@ -300,20 +300,6 @@ def test_two_stage_restart_orchestration():
     g.close()
 
 
-def test_multi_sample_per_warp_solver_is_bit_identical(monkeypatch):
-    """MMSIG_SOLVE=multi: the alternative k_solve for 16 < sum(K) <= 32 (4 samples per warp); off by
-    default because it measured slower, kept bit-identical."""
-    monkeypatch.setenv("MMSIG_SOLVE", "multi")
-    for K, V in (([10, 8, 6], [96, 32, 83]), ([16, 16], [40, 7])):
-        counts = small_synth(400, K, V, empty_frac=0.05)
-        g0 = mmsig.synth.init_gamma(K, V)
-        o, g = _pair(K, [0.1] * len(K), V, counts, g0)
-        for _ in range(2):
-            ll_o, ll_g = o.iterate(), g.iterate()
-            _check_iteration(o, g, ll_o, ll_g)
-        g.close()
-
-
 @pytest.mark.parametrize("variant", ["lean8", "lean4", "warp"])
 def test_solver_layouts_are_bit_identical(monkeypatch, variant):
     """MMSIG_SOLVE selects the lane layout of the LD_MMA kernels for sum(K) <= 32: lean8 / lean4 (csrc/mmctm_lean.cuh:
@@ -343,25 +329,6 @@ def test_solver_layouts_are_bit_identical(monkeypatch, variant):
         ll_o, ll_g = o.iterate(), g.iterate()
         _check_iteration(o, g, ll_o, ll_g)
     g.close()
-
-
-@pytest.mark.skipif(os.environ.get("MMSIG_EXPERIMENTAL") != "1",
-                    reason="experimental kernels, not in the default build: make EXP=1, MMSIG_LIB=.../libmmsig_exp.so, "
-                           "MMSIG_EXPERIMENTAL=1 (profiles/ab_solve_split.sh)")
-@pytest.mark.parametrize("variant", ["split", "split16"])
-def test_split_phase_solver_is_bit_identical(monkeypatch, variant):
-    """MMSIG_SOLVE=split / split16 (csrc/mmctm_split.cuh): update_ν! for every sample, then update_λ!, as two
-    kernels with four (8 lanes x 3-4 coordinates) or two (16 lanes x 2 coordinates) samples per warp; same
-    arithmetic, so bit-identical, including the per-sample evaluation counts."""
-    monkeypatch.setenv("MMSIG_SOLVE", variant)
-    for K, V in (([10, 8, 6], [96, 32, 83]), ([16, 16], [40, 7]), ([9, 8], [30, 20])):
-        counts = small_synth(400, K, V, empty_frac=0.05)
-        g0 = mmsig.synth.init_gamma(K, V)
-        o, g = _pair(K, [0.1] * len(K), V, counts, g0)
-        for _ in range(3):
-            ll_o, ll_g = o.iterate(), g.iterate()
-            _check_iteration(o, g, ll_o, ll_g)
-        g.close()
 
 
 @pytest.mark.parametrize("maxiter,chunks", [(1, 1), (1, 3), (4, 3), (14, 5)])
@@ -399,6 +366,35 @@ def test_fit_host_equals_the_four_calls(monkeypatch, maxiter, chunks):
     for k in sc:
         assert np.array_equal(sc[k], sd[k]), k
     a.close(); b.close(); c.close()
+
+
+def test_fit_host_packed_records_equal_unpacked():
+    """mmsig_mmctm_fit_host_packed (4-byte records: term | count << 10) == mmsig_mmctm_fit_host, bit for bit; values that
+    do not fit the record are refused by mmsig_pack_records."""
+    K, V, D = [5, 4, 3], [96, 32, 83], 1500
+    counts = small_synth(D, K, V, seed=3, empty_frac=0.05)
+    g0 = mmsig.synth.init_gamma(K, V)
+    a = mmsig.MMCTM(K, [0.1, 0.2, 0.3], counts, V=V, gamma0=g0)
+    ha, sa = a.fit_host(counts, g0, maxiter=3)
+    packed = [(r, mmsig.capi.pack_records(t, c)) for r, t, c in counts]
+    hb, sb = a.fit_host(packed, g0, maxiter=3)
+    assert np.array_equal(ha, hb)
+    for k in sa:
+        assert np.array_equal(sa[k], sb[k]), k
+    grp = mmsig.MMCTMGroup(K, [0.1, 0.2, 0.3], counts, [0, 0], V=V, gamma0=g0)
+    hc, sc = grp.fit_host(packed, g0, maxiter=3)
+    assert np.array_equal(ha, hc)
+    for k in sa:
+        assert np.array_equal(sa[k], sc[k]), k
+    with pytest.raises(mmsig.capi.MmsigError):
+        mmsig.capi.pack_records(np.array([3, 1024], np.int32), np.array([1, 1], np.int32))
+    with pytest.raises(mmsig.capi.MmsigError):
+        mmsig.capi.pack_records(np.array([3, 4], np.int32), np.array([1, 1 << 22], np.int32))
+    bad = [(r.copy(), x.copy()) for r, x in packed]
+    bad[0][1][5] = np.uint32(200 | (3 << 10))          # term 200 >= V[0] = 96
+    with pytest.raises(mmsig.capi.MmsigError):
+        a.fit_host(bad, g0, maxiter=1)
+    a.close(); grp.close()
 
 
 def test_fit_host_rejects_bad_counts():
