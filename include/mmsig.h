@@ -291,6 +291,12 @@ int32_t mmsig_lda_set_beta(mmsig_handle *h, const double *beta);
 int32_t mmsig_lda_iterate_flags(mmsig_handle *h, uint32_t flags, double *ll_out);
 int32_t mmsig_lda_fit(mmsig_handle *h, int32_t maxiter, double tol, double *ll_hist,
                       int32_t *n_iter, int32_t *converged);
+/* fit!(model::LDA) from and to host buffers in one call: mmsig_lda_set_data + _set_state + _fit + _get_state */
+int32_t mmsig_lda_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V, const int64_t *rowptr,
+                           const int32_t *term, const int32_t *count, double alpha, double eta, const double *lambda,
+                           const double *gamma_next, int32_t maxiter, double tol, double *ll_hist, int32_t *n_iter,
+                           int32_t *converged, double *lambda_out, double *Elnbeta_out, double *beta_out,
+                           double *gamma_out, double *Elntheta_out, double *theta_out);
 /* calculate_elbo (src/LDA.jl:114-172); terms[7] = ElnPβ, ElnPθ, ElnPZ, ElnPX, ElnQβ, ElnQθ, ElnQZ */
 int32_t mmsig_lda_elbo(mmsig_handle *h, double *elbo, double *terms);
 int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, double *beta,

@@ -108,6 +108,8 @@ _SIGS = {
     "mmsig_lda_set_beta": (C.c_int32, [C.c_void_p, c_dp]),
     "mmsig_lda_iterate_flags": (C.c_int32, [C.c_void_p, C.c_uint32, c_dp]),
     "mmsig_lda_fit": (C.c_int32, [C.c_void_p, C.c_int32, C.c_double, c_dp, c_i32p, c_i32p]),
+    "mmsig_lda_fit_host": (C.c_int32, [C.c_void_p, C.c_int64, C.c_int64, C.c_int32, C.c_int32, c_i64p, c_i32p, c_i32p, C.c_double, C.c_double,
+                                       c_dp, c_dp, C.c_int32, C.c_double, c_dp, c_i32p, c_i32p] + [c_dp] * 6),
     "mmsig_lda_elbo": (C.c_int32, [C.c_void_p, c_dp, c_dp]),
     "mmsig_lda_get_state": (C.c_int32, [C.c_void_p] + [c_dp] * 6),
     "mmsig_lda_get_phi": (C.c_int32, [C.c_void_p, c_dp]),

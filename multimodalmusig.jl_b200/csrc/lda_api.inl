@@ -289,8 +289,26 @@ extern "C" int32_t mmsig_lda_fit(mmsig_handle *h, int32_t maxiter, double tol, d
     NEED(h, "null handle");
     NEED(h->lda.has_state, "mmsig_lda_set_state first");
     NEED(maxiter >= 1 && ll_hist, "maxiter >= 1 and ll_hist required");
-    int it = 0, conv = 0;
-    for (int iter = 1; iter <= maxiter; ++iter) {
+    CU(cudaSetDevice(h->device));
+    int it = 0, conv = 0, iter = 1;
+    {
+        // the convergence rule needs more than 10 log-likelihoods (src/LDA.jl:215): the iterations before that are
+        // enqueued back to back, their log-likelihoods landing in page-locked memory, one synchronisation
+        const int nfree = std::min<int>(maxiter, 10);
+        if (nfree > 1) {
+            for (int i = 0; i < nfree; ++i) {
+                int rc = lda_iterate_async(h, 0);
+                if (rc) return rc;
+                CU(cudaMemcpyAsync(h->ll_pinned + i, h->lda.d_ll, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            }
+            CU(cudaStreamSynchronize(h->stream));
+            CU(cudaGetLastError());
+            memcpy(ll_hist, h->ll_pinned, nfree * sizeof(double));
+            iter = nfree + 1;
+            it = nfree;
+        }
+    }
+    for (; iter <= maxiter; ++iter) {
         int rc = mmsig_lda_iterate(h, &ll_hist[iter - 1]);
         if (rc) return rc;
         it = iter;
@@ -302,6 +320,24 @@ extern "C" int32_t mmsig_lda_fit(mmsig_handle *h, int32_t maxiter, double tol, d
     if (n_iter) *n_iter = it;
     if (converged) *converged = conv;
     return 0;
+}
+
+extern "C" int32_t mmsig_lda_get_state(mmsig_handle *h, double *lambda, double *Elnbeta, double *beta, double *gamma,
+                                       double *Elntheta, double *theta);
+
+// fit!(model::LDA) from and to HOST buffers in one call (src/LDA.jl:198-224): set_data + set_state + fit + get_state.
+// An LDA iteration (2.6 ms at a million samples) is far shorter than the upload of the counts, so nothing is gained by
+// chunking the first E pass behind the copies as mmsig_mmctm_fit_host does; the call saves the host round trips.
+extern "C" int32_t mmsig_lda_fit_host(mmsig_handle *h, int64_t D, int64_t D_total, int32_t K, int32_t V, const int64_t *rowptr,
+                                      const int32_t *term, const int32_t *count, double alpha, double eta, const double *lambda,
+                                      const double *gamma_next, int32_t maxiter, double tol, double *ll_hist, int32_t *n_iter,
+                                      int32_t *converged, double *lambda_out, double *Elnbeta_out, double *beta_out,
+                                      double *gamma_out, double *Elntheta_out, double *theta_out) {
+    int rc = mmsig_lda_set_data(h, D, D_total, K, V, rowptr, term, count);
+    if (rc) return rc;
+    if ((rc = mmsig_lda_set_state(h, alpha, eta, lambda, gamma_next))) return rc;
+    if ((rc = mmsig_lda_fit(h, maxiter, tol, ll_hist, n_iter, converged))) return rc;
+    return mmsig_lda_get_state(h, lambda_out, Elnbeta_out, beta_out, gamma_out, Elntheta_out, theta_out);
 }
 
 static int lda_elbo_pass(mmsig_handle *h, double *phi_dev, double2 *host_parts /*[7]*/, double *tab /*[4]*/) {

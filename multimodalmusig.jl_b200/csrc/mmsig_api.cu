@@ -338,6 +338,13 @@ extern "C" int32_t mmsig_create(const mmsig_config *cfg, mmsig_handle **out) {
         return fail(nullptr, MMSIG_ECUDA, "cannot create stream");
     }
     h->own_stream = true;
+    // page-locked landing zone of the log-likelihoods of the sync-free iterations (allocated here: cudaHostAlloc
+    // costs milliseconds and serialises across the host threads of a group)
+    if (cudaHostAlloc((void **)&h->ll_pinned, (size_t)12 * (MAXM + 1) * sizeof(double), cudaHostAllocDefault) != cudaSuccess) {
+        cudaStreamDestroy(h->stream);
+        delete h;
+        return fail(nullptr, MMSIG_ENOMEM, "cudaHostAlloc failed");
+    }
     *out = h;
     return 0;
 }
@@ -1205,7 +1212,6 @@ static int mmctm_run_iterations(mmsig_handle *h, int first, int32_t maxiter, dou
     if (!(flags & MMSIG_FLAG_AUTO_ALPHA)) {            // update_alpha! synchronises inside every iteration anyway
         const int nfree = std::min<int>(maxiter, 10) - first + 1;
         if (nfree > 1) {
-            if (!h->ll_pinned) CU(cudaHostAlloc((void **)&h->ll_pinned, (size_t)12 * (MAXM + 1) * sizeof(double), cudaHostAllocDefault));
             int *status = reinterpret_cast<int *>(h->ll_pinned + (size_t)12 * MAXM);
             for (int i = 0; i < nfree; ++i) {
                 int rc = mmctm_iterate_async(h, flags);

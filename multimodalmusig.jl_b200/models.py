@@ -509,7 +509,25 @@ class LDA:
         new.elbo = new.calculate_elbo()[0]
         return new
 
-    def fit(self, maxiter=1000, tol=1e-4, verbose=True):
+    def fit_host(self, counts, lambda0, gamma_next=None, maxiter=1000, tol=1e-4, D_total=None):
+        """fit!(model::LDA) in ONE library call from / to host arrays (mmsig_lda_fit_host).  Returns (ll_history, state)."""
+        r, t, c = (np.ascontiguousarray(counts[0], np.int64), np.ascontiguousarray(counts[1], np.int32),
+                   np.ascontiguousarray(counts[2], np.int32))
+        D, K, V = len(r) - 1, self.K, self.V
+        out = dict(lam=np.empty(K * V), Elnbeta=np.empty(K * V), beta=np.empty(K * V), gamma=np.empty((D, K)),
+                   Elntheta=np.empty((D, K)), theta=np.empty((D, K)))
+        hist = np.zeros(maxiter)
+        n, conv = C.c_int32(), C.c_int32()
+        self.h.check(self.h.lib.mmsig_lda_fit_host(
+            self.h.h, D, D if D_total is None else D_total, K, V, r.ctypes.data_as(capi.c_i64p), t.ctypes.data_as(capi.c_i32p),
+            c.ctypes.data_as(capi.c_i32p), self.alpha, self.eta, capi.dp(capi.f64(lambda0, K * V)),
+            capi.dp(capi.f64(gamma_next, D * K)), maxiter, tol, capi.dp(hist), C.byref(n), C.byref(conv),
+            *[capi.dp(out[k]) for k in ("lam", "Elnbeta", "beta", "gamma", "Elntheta", "theta")]))
+        self.D, self.nnz = D, int(r[-1])
+        self.converged, self.ll = bool(conv.value), float(hist[n.value - 1])
+        return hist[:n.value].copy(), out
+
+    def fit(self, maxiter=1000, tol=1e-4, verbose=True, elbo=True):
         """fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true), src/LDA.jl:198-224."""
         if verbose:
             hist = []
@@ -526,7 +544,8 @@ class LDA:
             self.h.check(self.h.lib.mmsig_lda_fit(self.h.h, maxiter, tol, capi.dp(buf), C.byref(n), C.byref(conv)))
             hist = buf[:n.value].copy()
             self.converged = bool(conv.value)
-        self.elbo = self.calculate_elbo()[0]
+        if elbo:
+            self.elbo = self.calculate_elbo()[0]
         self.ll = float(hist[-1])
         return hist
 

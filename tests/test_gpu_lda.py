@@ -75,3 +75,20 @@ def test_lda_fit_config2_shape(brca):
     assert abs(g.elbo - eo) <= 1e-8 * abs(eo)
     assert rel_err(g.beta, o.beta) <= 1e-9
     g.close()
+
+
+def test_lda_fit_host_equals_the_four_calls(brca):
+    """mmsig_lda_fit_host == set_data + set_state + fit + get_state, bit for bit (a handle planned for another corpus)."""
+    K, V = 20, 96
+    csr = brca[0]
+    lam0 = mmsig.synth.init_lda_lambda(K, V)
+    a = mmsig.LDA(K, 0.1, 0.1, csr, V=V, lambda0=lam0)
+    ha = a.fit(maxiter=14, tol=1e-7, verbose=False)
+    sa = a.state()
+    other = small_synth(300, [K], [V])[0]
+    b = mmsig.LDA(K, 0.1, 0.1, other, V=V, lambda0=lam0)
+    hb, sb = b.fit_host(csr, lam0, maxiter=14, tol=1e-7)
+    assert np.array_equal(ha, hb) and a.converged == b.converged
+    for k in ("lam", "Elnbeta", "beta", "gamma", "Elntheta", "theta"):
+        assert np.array_equal(np.asarray(sa[k]).reshape(-1), np.asarray(sb[k]).reshape(-1)), k
+    a.close(); b.close()
