@@ -212,7 +212,21 @@ def fp64_roofline(dom_ms, evals, Dl, MK):
             "fp64_warp_instructions_per_launch": warp_inst, "peak_source": fm["peak_source"], "model_source": fm["model_source"]}
 
 
+_T0 = time.perf_counter()
+
+
+def stage(msg):
+    """BENCH_TRACE=<seconds>: progress marks on stderr, and every thread's Python stack after that many seconds
+    (where a multi-rank run is waiting, should it ever wait)."""
+    if os.environ.get("BENCH_TRACE"):
+        sys.stderr.write("[bench rank %s %.1fs] %s\n" % (os.environ.get("RANK", "0"), time.perf_counter() - _T0, msg))
+        sys.stderr.flush()
+
+
 def main():
+    if os.environ.get("BENCH_TRACE"):
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BENCH_TRACE"]), repeat=True, file=sys.stderr)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -276,7 +290,9 @@ def bench_mmctm(args, cfg):
     D = args.samples
     per = -(-D // world)
     lo, hi = min(D, rank * per), min(D, (rank + 1) * per)
+    stage("process group up, generating samples %d..%d" % (lo, hi))
     counts = mmsig.synth.generate(D, K_CFG, V_CFG, lo=lo, hi=hi)
+    stage("counts generated")
     Dl = hi - lo
     nnz_local = sum(int(c[0][-1]) for c in counts)
     MK, M = sum(K_CFG), len(K_CFG)
@@ -315,12 +331,14 @@ def bench_mmctm(args, cfg):
     def launches():
         return model.grp.launch_count() if grouped else model.h.launch_count()
 
+    stage("model on the device")
     sampler = ClockSampler(local)
     sampler.start()
     ctx = torch.cuda.stream(stream) if stream is not None else torch.cuda.device(0)
     with ctx:
         for _ in range(args.warmup):
             model.iterate()
+        stage("warm-up done")
         barrier()
         sampler.t0 = time.perf_counter()
         l0 = launches()
@@ -333,6 +351,7 @@ def bench_mmctm(args, cfg):
         ll = model.fit(maxiter=args.steps, tol=0.0, verbose=False, elbo=False)[-1]
         if stream is not None:
             e1.record(stream)
+        stage("timed fit returned")
         barrier()
         sampler.t1 = time.perf_counter()
         # one process per GPU: CUDA events on the launching stream; the single-process group blocks in each call until
@@ -353,6 +372,7 @@ def bench_mmctm(args, cfg):
         nnz_total = float(nnz_local)
     ms_step = ms / args.steps
     value = 1000.0 / ms_step
+    stage("timed region reduced over ranks")
     st = model.state()              # the e2e leg below repeats the iteration that follows the timed ones
     # second pass with per-kernel event timing ON: the split of the step over the kernels (and what the timing costs)
     ktimes, ms_prof = {}, None
@@ -370,10 +390,13 @@ def bench_mmctm(args, cfg):
         model.h.set_profile(False)
     # a timed region shorter than ~1.5 s can fall between two nvidia-smi samples: keep the identical
     # load running, untimed, on every rank (same count everywhere: the iterations are collective)
-    n_extra = min(500, int(np.ceil(max(0.0, 1500.0 - ms - (ms_prof or 0) * args.steps) / ms_step)))
+    # ms is already the max over ranks; ms_prof is this rank's own clock, so it must not enter a count of collective calls
+    n_extra = min(500, int(np.ceil(max(0.0, 1500.0 - 2.0 * ms) / ms_step)))
+    stage("per-kernel pass done, %d extra iterations" % n_extra)
     for _ in range(n_extra):
         model.iterate()
     sampler.stop_flag.set()
+    stage("extra iterations done")
 
     # ---- e2e: public API with host buffers; H2D of counts + state, one iteration, D2H of state ----
     lam_h, t1 = pin(np.zeros((Dl, MK)))
@@ -437,8 +460,11 @@ def bench_mmctm(args, cfg):
         mmsig.capi.pack_records(t, c, out=rec)
         counts_pk.append((r, rec))
     h2d_packed = h2d - sum(c.nbytes for _, _, c in counts_p)
+    stage("e2e buffers ready")
     e2e_unpacked_ms = time_e2e(counts_p, lam_h, nu_h, out, max(1, args.e2e_steps - 1))
+    stage("e2e (unpacked) done")
     e2e_ms = time_e2e(counts_pk, lam_h, nu_h, out, args.e2e_steps)
+    stage("e2e (packed) done")
     e2e_pageable_ms = None
     if not args.no_pageable:
         # what a caller with ordinary (pageable) arrays gets, e.g. Julia Vectors that were not allocated through

@@ -304,8 +304,20 @@ __global__ void __launch_bounds__(256) k_combine(CombineSegs s, double2 *dst) {
             const int i = t - base;
             const int stride = s.stride[g] ? s.stride[g] : s.n[g];
             double hi = 0.0, lo = 0.0;
-            for (int part = lane; part < s.nparts[g]; part += 32) {
-                const double2 v = s.src[g][(size_t)part * stride + i];
+            // four loads in flight per lane, merged in part order (the order of the one-at-a-time loop)
+            const double2 *src = s.src[g] + i;
+            const int np = s.nparts[g];
+            int part = lane;
+            for (; part + 96 < np; part += 128) {
+                const double2 v0 = src[(size_t)part * stride], v1 = src[(size_t)(part + 32) * stride];
+                const double2 v2 = src[(size_t)(part + 64) * stride], v3 = src[(size_t)(part + 96) * stride];
+                dd_merge(hi, lo, v0.x, v0.y);
+                dd_merge(hi, lo, v1.x, v1.y);
+                dd_merge(hi, lo, v2.x, v2.y);
+                dd_merge(hi, lo, v3.x, v3.y);
+            }
+            for (; part < np; part += 32) {
+                const double2 v = src[(size_t)part * stride];
                 dd_merge(hi, lo, v.x, v.y);
             }
             warp_dd_allreduce(hi, lo);
@@ -599,15 +611,122 @@ __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, do
     return true;
 }
 
-// M-step, part 2 (one warp).  gathered: [nranks][MK*MK + M] dd.
+// The same factorisation and inverse for n <= NP <= 32 with the matrix in registers: lane j owns column j
+// (a[i] = A[i][j]), every loop is unrolled, rows >= n and lanes >= n are inert.  Operation for operation the
+// arithmetic of warp_lu_inverse (same pivot rule, same multiply-then-subtract per element, same order of the
+// substitution sums), so the results are bit-identical; what changes is where the operands live: no shared-memory
+// round trip and no __syncwarp between dependent steps (62 us -> a few us at n = 24).
+// elimination step K of warp_lu_inverse_reg (a template recursion instead of an unrolled loop: the body of a 32-step
+// loop of unrolled loops exceeds the compiler's full-unroll budget, and a loop that stays a loop puts a[] in local memory)
+template <int NP, int K>
+__device__ __forceinline__ void lu_reg_step(double (&a)[NP], int (&pv)[NP], bool &ok, int n, int lane) {
+    pv[K] = K;
+    if (K < n) {
+        // first index of the maximum |A[i][K]|, i >= K: lane K scans its own column
+        double best = -1.0;
+        int bi = K;
+#pragma unroll
+        for (int i = K; i < NP; ++i)
+            if (i < n) {
+                const double v = fabs(a[i]);
+                if (v > best) { best = v; bi = i; }
+            }
+        bi = __shfl_sync(FULLMASK, bi, K);
+        best = shfl_d(best, K);
+        pv[K] = bi;
+        ok = ok && best != 0.0;                  // singular: the (non-finite) result is discarded by the caller
+        // rows K <-> bi in every column
+        const double ak = a[K];
+        double ab = ak;
+#pragma unroll
+        for (int i = K + 1; i < NP; ++i)
+            if (i == bi) { ab = a[i]; a[i] = ak; }
+        a[K] = ab;
+        const double inv = 1.0 / shfl_d(a[K], K);
+#pragma unroll
+        for (int i = K + 1; i < NP; ++i)
+            if (i < n) {
+                const double l = a[i] * inv;
+                if (lane == K) a[i] = l;
+                const double lik = shfl_d(a[i], K);
+                if (lane > K) a[i] = a[i] - lik * a[K];
+            }
+    }
+    if constexpr (K + 1 < NP) lu_reg_step<NP, K + 1>(a, pv, ok, n, lane);
+}
+
+template <int NP, int K>
+__device__ __forceinline__ void lu_reg_perm(double (&b)[NP], const int (&pv)[NP], int n) {
+    if (K < n && pv[K] != K) {
+        const double bk = b[K];
+        double bp = bk;
+#pragma unroll
+        for (int i = K + 1; i < NP; ++i)
+            if (i == pv[K]) { bp = b[i]; b[i] = bk; }
+        b[K] = bp;
+    }
+    if constexpr (K + 1 < NP) lu_reg_perm<NP, K + 1>(b, pv, n);
+}
+template <int NP, int I>
+__device__ __forceinline__ void lu_reg_fwd(const double (&a)[NP], double (&b)[NP], int n) {
+    if (I < n) {
+        double s = b[I];
+#pragma unroll
+        for (int j = 0; j < I; ++j) {
+            const double lij = shfl_d(a[I], j);
+            s = s - lij * b[j];
+        }
+        b[I] = s;
+    }
+    if constexpr (I + 1 < NP) lu_reg_fwd<NP, I + 1>(a, b, n);
+}
+template <int NP, int I>
+__device__ __forceinline__ void lu_reg_bwd(const double (&a)[NP], double (&b)[NP], int n) {
+    if (I < n) {
+        double s = b[I];
+#pragma unroll
+        for (int j = I + 1; j < NP; ++j)
+            if (j < n) {
+                const double uij = shfl_d(a[I], j);
+                s = s - uij * b[j];
+            }
+        b[I] = s / shfl_d(a[I], I);
+    }
+    if constexpr (I > 0) lu_reg_bwd<NP, I - 1>(a, b, n);
+}
+
+template <int NP>
+__device__ inline bool warp_lu_inverse_reg(int n, const double *A, double *out) {
+    const int lane = threadIdx.x & 31;
+    double a[NP];
+    int pv[NP];
+    bool ok = true;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) a[i] = (i < n && lane < n) ? A[i * n + lane] : 0.0;
+    lu_reg_step<NP, 0>(a, pv, ok, n, lane);
+    // column `lane` of the inverse: P e_c, forward substitution with L (unit diagonal), back substitution with U
+    double b[NP];
+#pragma unroll
+    for (int i = 0; i < NP; ++i) b[i] = (i == lane) ? 1.0 : 0.0;
+    lu_reg_perm<NP, 0>(b, pv, n);
+    lu_reg_fwd<NP, 0>(a, b, n);
+    lu_reg_bwd<NP, NP - 1>(a, b, n);
+#pragma unroll
+    for (int i = 0; i < NP; ++i)
+        if (ok && i < n && lane < n) out[i * n + lane] = b[i];
+    return ok;
+}
+
+// M-step, part 2 (one block; the inverse on its first warp).  gathered: [nranks][MK*MK + M] dd.
 // Σ = exact_round(diag Σ_d ν + Σ_d ΔΔᵀ) / D, invΣ = inv(Σ) (src/MMCTM.jl:204-212); ll_m (:417).
-__global__ void __launch_bounds__(32) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
-                                               double *ll_out, int *status) {
-    extern __shared__ double lu_smem[];                  // A, B: MK x MK each; piv: MK ints
-    const int MK = p.MK, M = p.M, P2 = MK * MK + M, lane = threadIdx.x;
-    double *A = lu_smem, *B = lu_smem + MK * MK;
-    int *piv = reinterpret_cast<int *>(B + MK * MK);
-    for (int i = lane; i < P2; i += 32) {
+// NP: register LU for MK <= NP <= 32; NP = 0: the shared-memory LU (32 < MK <= 64).
+template <int NP>
+__global__ void __launch_bounds__(256, 1) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
+                                                double *ll_out, int *status) {
+    extern __shared__ double lu_smem[];                  // A, [B: MK x MK, piv: MK ints]
+    const int MK = p.MK, M = p.M, P2 = MK * MK + M;
+    double *A = lu_smem;
+    for (int i = threadIdx.x; i < P2; i += blockDim.x) {
         double hi = 0.0, lo = 0.0;
         for (int r = 0; r < nranks; ++r) {
             const double2 v = gathered[(size_t)r * P2 + i];
@@ -626,10 +745,17 @@ __global__ void __launch_bounds__(32) k_mstep2(MmctmDev p, const double2 *gather
             ll_out[m] = dd_round(hi, lo) / p.Ntot[m];
         }
     }
-    __syncwarp();
-    if (do_sigma) {
-        const bool ok = warp_lu_inverse(MK, A, B, piv, p.invSigma, nullptr);
-        if (lane == 0) *status = ok ? 0 : 1;
+    __syncthreads();
+    if (do_sigma && threadIdx.x < 32) {
+        bool ok;
+        if (NP > 0) {
+            ok = warp_lu_inverse_reg<(NP > 0 ? NP : 8)>(MK, A, p.invSigma);
+        } else {
+            double *B = lu_smem + MK * MK;
+            int *piv = reinterpret_cast<int *>(B + MK * MK);
+            ok = warp_lu_inverse(MK, A, B, piv, p.invSigma, nullptr);
+        }
+        if (threadIdx.x == 0) *status = ok ? 0 : 1;
     }
 }
 
