@@ -616,116 +616,16 @@ __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, do
 // arithmetic of warp_lu_inverse (same pivot rule, same multiply-then-subtract per element, same order of the
 // substitution sums), so the results are bit-identical; what changes is where the operands live: no shared-memory
 // round trip and no __syncwarp between dependent steps (62 us -> a few us at n = 24).
-// elimination step K of warp_lu_inverse_reg (a template recursion instead of an unrolled loop: the body of a 32-step
-// loop of unrolled loops exceeds the compiler's full-unroll budget, and a loop that stays a loop puts a[] in local memory)
-template <int NP, int K>
-__device__ __forceinline__ void lu_reg_step(double (&a)[NP], int (&pv)[NP], bool &ok, int n, int lane) {
-    pv[K] = K;
-    if (K < n) {
-        // first index of the maximum |A[i][K]|, i >= K: lane K scans its own column
-        double best = -1.0;
-        int bi = K;
-#pragma unroll
-        for (int i = K; i < NP; ++i)
-            if (i < n) {
-                const double v = fabs(a[i]);
-                if (v > best) { best = v; bi = i; }
-            }
-        bi = __shfl_sync(FULLMASK, bi, K);
-        best = shfl_d(best, K);
-        pv[K] = bi;
-        ok = ok && best != 0.0;                  // singular: the (non-finite) result is discarded by the caller
-        // rows K <-> bi in every column
-        const double ak = a[K];
-        double ab = ak;
-#pragma unroll
-        for (int i = K + 1; i < NP; ++i)
-            if (i == bi) { ab = a[i]; a[i] = ak; }
-        a[K] = ab;
-        const double inv = 1.0 / shfl_d(a[K], K);
-#pragma unroll
-        for (int i = K + 1; i < NP; ++i)
-            if (i < n) {
-                const double l = a[i] * inv;
-                if (lane == K) a[i] = l;
-                const double lik = shfl_d(a[i], K);
-                if (lane > K) a[i] = a[i] - lik * a[K];
-            }
-    }
-    if constexpr (K + 1 < NP) lu_reg_step<NP, K + 1>(a, pv, ok, n, lane);
-}
-
-template <int NP, int K>
-__device__ __forceinline__ void lu_reg_perm(double (&b)[NP], const int (&pv)[NP], int n) {
-    if (K < n && pv[K] != K) {
-        const double bk = b[K];
-        double bp = bk;
-#pragma unroll
-        for (int i = K + 1; i < NP; ++i)
-            if (i == pv[K]) { bp = b[i]; b[i] = bk; }
-        b[K] = bp;
-    }
-    if constexpr (K + 1 < NP) lu_reg_perm<NP, K + 1>(b, pv, n);
-}
-template <int NP, int I>
-__device__ __forceinline__ void lu_reg_fwd(const double (&a)[NP], double (&b)[NP], int n) {
-    if (I < n) {
-        double s = b[I];
-#pragma unroll
-        for (int j = 0; j < I; ++j) {
-            const double lij = shfl_d(a[I], j);
-            s = s - lij * b[j];
-        }
-        b[I] = s;
-    }
-    if constexpr (I + 1 < NP) lu_reg_fwd<NP, I + 1>(a, b, n);
-}
-template <int NP, int I>
-__device__ __forceinline__ void lu_reg_bwd(const double (&a)[NP], double (&b)[NP], int n) {
-    if (I < n) {
-        double s = b[I];
-#pragma unroll
-        for (int j = I + 1; j < NP; ++j)
-            if (j < n) {
-                const double uij = shfl_d(a[I], j);
-                s = s - uij * b[j];
-            }
-        b[I] = s / shfl_d(a[I], I);
-    }
-    if constexpr (I > 0) lu_reg_bwd<NP, I - 1>(a, b, n);
-}
-
-template <int NP>
-__device__ inline bool warp_lu_inverse_reg(int n, const double *A, double *out) {
-    const int lane = threadIdx.x & 31;
-    double a[NP];
-    int pv[NP];
-    bool ok = true;
-#pragma unroll
-    for (int i = 0; i < NP; ++i) a[i] = (i < n && lane < n) ? A[i * n + lane] : 0.0;
-    lu_reg_step<NP, 0>(a, pv, ok, n, lane);
-    // column `lane` of the inverse: P e_c, forward substitution with L (unit diagonal), back substitution with U
-    double b[NP];
-#pragma unroll
-    for (int i = 0; i < NP; ++i) b[i] = (i == lane) ? 1.0 : 0.0;
-    lu_reg_perm<NP, 0>(b, pv, n);
-    lu_reg_fwd<NP, 0>(a, b, n);
-    lu_reg_bwd<NP, NP - 1>(a, b, n);
-#pragma unroll
-    for (int i = 0; i < NP; ++i)
-        if (ok && i < n && lane < n) out[i * n + lane] = b[i];
-    return ok;
-}
-
 // M-step, part 2 (one block; the inverse on its first warp).  gathered: [nranks][MK*MK + M] dd.
 // Σ = exact_round(diag Σ_d ν + Σ_d ΔΔᵀ) / D, invΣ = inv(Σ) (src/MMCTM.jl:204-212); ll_m (:417).
-// NP: register LU for MK <= NP <= 32; NP = 0: the shared-memory LU (32 < MK <= 64).
-template <int NP>
-__global__ void __launch_bounds__(256, 1) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
+// (A register-resident, fully unrolled LU -- lane j owning column j -- was tried in round 2: 25 k straight-line SASS
+// instructions at MK = 24 run at instruction-fetch speed, 105 us against 64 us for this loop over shared memory.)
+__global__ void __launch_bounds__(256) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
                                                 double *ll_out, int *status) {
-    extern __shared__ double lu_smem[];                  // A, [B: MK x MK, piv: MK ints]
+    extern __shared__ double lu_smem[];                  // A, B: MK x MK each; piv: MK ints
     const int MK = p.MK, M = p.M, P2 = MK * MK + M;
-    double *A = lu_smem;
+    double *A = lu_smem, *B = lu_smem + MK * MK;
+    int *piv = reinterpret_cast<int *>(B + MK * MK);
     for (int i = threadIdx.x; i < P2; i += blockDim.x) {
         double hi = 0.0, lo = 0.0;
         for (int r = 0; r < nranks; ++r) {
@@ -747,14 +647,7 @@ __global__ void __launch_bounds__(256, 1) k_mstep2(MmctmDev p, const double2 *ga
     }
     __syncthreads();
     if (do_sigma && threadIdx.x < 32) {
-        bool ok;
-        if (NP > 0) {
-            ok = warp_lu_inverse_reg<(NP > 0 ? NP : 8)>(MK, A, p.invSigma);
-        } else {
-            double *B = lu_smem + MK * MK;
-            int *piv = reinterpret_cast<int *>(B + MK * MK);
-            ok = warp_lu_inverse(MK, A, B, piv, p.invSigma, nullptr);
-        }
+        const bool ok = warp_lu_inverse(MK, A, B, piv, p.invSigma, nullptr);
         if (threadIdx.x == 0) *status = ok ? 0 : 1;
     }
 }

@@ -774,7 +774,7 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
             else if (!strcmp(e, "lean4")) mm.solve_lean = p.MK <= 16 ? 4 : 8;     // 4 lanes x (> 4 coordinates) spills: 43 ms against 23 ms at sum(K) = 24
         }
     }
-    CU(allow_max_smem(h, k_mstep2<0>));
+    CU(allow_max_smem(h, k_mstep2));
     auto grid_for = [&](int nb) {
         return (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * std::max(nb, 1), (D + 7) / 8));
     };
@@ -1165,8 +1165,7 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     {
         LaunchScope ls(h, "k_mstep2");
         const size_t lus = (size_t)2 * p.MK * p.MK * sizeof(double) + p.MK * sizeof(int);
-        if (p.MK > 32) k_mstep2<0><<<1, 256, lus, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
-        else MK_DISPATCH(p.MK, (k_mstep2<MKP><<<1, 256, lus, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status)));
+        k_mstep2<<<1, 256, lus, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
     }
     mm.estep_done = true;
     return 0;
