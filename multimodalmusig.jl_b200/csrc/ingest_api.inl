@@ -214,6 +214,7 @@ extern "C" int32_t mmsig_mmctm_set_data_dense(mmsig_handle *h, int64_t D, int64_
     for (int m = 0; m < M && e == cudaSuccess; ++m) {
         e = cudaMemcpyAsync(mm.cb[m].rowptr, jobs[m].rowptr, (D + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream);
         dense_fill(h, jobs[m], D, V[m], elem_bytes, layout, mm.cb[m].rowptr, mm.cb[m].rec, 1);
+        densify_launch(h, mm.cb[m], 0, D);
     }
     if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
     if (e == cudaSuccess) e = cudaGetLastError();

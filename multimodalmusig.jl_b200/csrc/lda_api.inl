@@ -1,5 +1,11 @@
 // lda_api.inl -- host side of the LDA entry points (included by mmsig_api.cu)
 
+#define LDA_TILE_DISPATCH(K, V, DENSE_RT, EXPR)                                                          \
+    do {                                                                                                 \
+        if (DENSE_RT) { constexpr bool DENSE = true; THETA_DISPATCH(K, TILE_DISPATCH_NW(V, EXPR)); }     \
+        else { constexpr bool DENSE = false; THETA_DISPATCH(K, TILE_DISPATCH_NW(V, EXPR)); }             \
+    } while (0)
+
 template <typename F>
 static int pick_lda_plan(mmsig_handle *h, F kernel, int KV /* V * (KP + 2) */, long long D, int *W_out, int *grid_out,
                          size_t *smem_out) {
@@ -36,6 +42,33 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
     if (K > 32) return fail(h, MMSIG_ELIMIT, "K <= 32 supported");
     if (V > 65535) return fail(h, MMSIG_ELIMIT, "V <= 65535 supported");
     CU(cudaSetDevice(h->device));
+    // same shape as what is resident (a repeated fit! on the same corpus, e.g. every mmsig_lda_fit_host call of a
+    // session): keep every allocation and launch plan, only the counts travel again
+    {
+        const long long nnz_in = job ? job->nnz : rowptr[D];
+        LdaHost &L0 = h->lda;
+        if (L0.has_data && !L0.p.factored && L0.p.K == K && L0.p.V == V && L0.p.D == D && L0.p.D_total == D_total && L0.cb.nnz == nnz_in) {
+            L0.has_data = false;
+            L0.has_state = false;
+            L0.iterated = false;
+            double *dN0 = const_cast<double *>(L0.p.N);
+            long long ntot0 = 0;
+            int rc0;
+            if (job) {
+                CU(cudaMemcpyAsync(dN0, job_N, (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                CU(cudaMemcpyAsync(L0.cb.rowptr, job->rowptr, (D + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
+                dense_fill(h, *job, D, V, elem_bytes, layout, L0.cb.rowptr, L0.cb.rec, 1);
+                densify_launch(h, L0.cb, 0, D);
+                CU(cudaStreamSynchronize(h->stream));
+                CU(cudaGetLastError());
+                ntot0 = job->total;
+            } else if ((rc0 = upload_counts(h, h->allocs_lda, L0.cb, D, V, 1, 0, rowptr, term, count, dN0, &ntot0, 1))) return rc0;
+            if ((rc0 = allsum_ll(h, &ntot0, 1))) return rc0;
+            L0.p.Ntot = (double)ntot0;
+            L0.has_data = true;
+            return 0;
+        }
+    }
     free_pool(h->allocs_lda);
     h->lda = LdaHost();
     LdaHost &L = h->lda;
@@ -50,10 +83,11 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
     p.N = dN;
     long long ntot = 0;
     if (job) {
-        if ((rc = ensure_countbuf(h, h->allocs_lda, L.cb, D, job->nnz))) return rc;
+        if ((rc = ensure_countbuf(h, h->allocs_lda, L.cb, D, job->nnz, V))) return rc;
         CU(cudaMemcpyAsync(dN, job_N, (size_t)D * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
         CU(cudaMemcpyAsync(L.cb.rowptr, job->rowptr, (D + 1) * sizeof(long long), cudaMemcpyDeviceToDevice, h->stream));
         dense_fill(h, *job, D, V, elem_bytes, layout, L.cb.rowptr, L.cb.rec, 1);
+        densify_launch(h, L.cb, 0, D);
         CU(cudaStreamSynchronize(h->stream));
         CU(cudaGetLastError());
         ntot = job->total;
@@ -100,15 +134,20 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
         int KPv = 0;
         THETA_DISPATCH(K, KPv = KP);
         const int VP = V | 1, NW = (V + 31) / 32;
-        L.smem_t32 = ((size_t)V * KPv + (size_t)LDA_TS * VP + (size_t)LDA_TS * KPv + LDA_TS + 4) * sizeof(double);
-        L.smem_llt = ((size_t)LDA_TS * VP + (size_t)LDA_TS * KPv + LDA_TS + (size_t)NW * 32 + 4) * sizeof(double);
+        const bool dn = L.cb.cnt != nullptr;
+        {
+            const size_t b1 = (size_t)V * KPv + (size_t)LDA_TS * VP + (size_t)LDA_TS * KPv + LDA_TS;
+            const size_t b2 = (size_t)LDA_TS * VP + (size_t)LDA_TS * KPv + LDA_TS + (size_t)NW * 32;
+            L.smem_t32 = (dn ? tile_stage_offset(b1) + tile_stage_doubles(V) : b1 + 4) * sizeof(double);
+            L.smem_llt = (dn ? tile_stage_offset(b2) + tile_stage_doubles(V) : b2 + 4) * sizeof(double);
+        }
         L.t32 = V <= 1024 && KPv <= 24 && L.smem_t32 <= h->smem_optin && !(e && (!strcmp(e, "row") || !strcmp(e, "tile96")));
         if (L.t32) {
             int nb = 0, nb2 = 0;
-            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(allow_max_smem(h, k_lda_estep_t32<KP, NWT>))));
-            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_estep_t32<KP, NWT>, NW * 32, L.smem_t32))));
-            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(allow_max_smem(h, k_lda_ll_tile<KP, NWT>))));
-            THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lda_ll_tile<KP, NWT>, NW * 32, L.smem_llt))));
+            LDA_TILE_DISPATCH(K, V, dn, CU(allow_max_smem(h, k_lda_estep_t32<KP, NWT, DENSE>)));
+            LDA_TILE_DISPATCH(K, V, dn, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_estep_t32<KP, NWT, DENSE>, NW * 32, L.smem_t32)));
+            LDA_TILE_DISPATCH(K, V, dn, CU(allow_max_smem(h, k_lda_ll_tile<KP, NWT, DENSE>)));
+            LDA_TILE_DISPATCH(K, V, dn, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lda_ll_tile<KP, NWT, DENSE>, NW * 32, L.smem_llt)));
             if (nb < 1 || nb2 < 1) L.t32 = false;
             else {
                 const long long ntiles = (D + LDA_TS - 1) / LDA_TS;
@@ -117,6 +156,7 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
                 L.grid = std::max(L.grid, L.grid_t32);
             }
         }
+        p.cnt = L.t32 ? L.cb.cnt : nullptr;
     }
     {
         int nb = 0;
@@ -201,8 +241,8 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     if (L.t32) {
         LaunchScope ls(h, "k_lda_estep_t32");
         const int nthr = 32 * ((p.V + 31) / 32);
-        THETA_DISPATCH(p.K, TILE_DISPATCH_NW(p.V, (k_lda_estep_t32<KP, NWT><<<L.grid_t32, nthr, L.smem_t32, h->stream>>>(
-                                                      p, L.part, unsm ? p.beta : p.expElnbeta, !freeze))));
+        LDA_TILE_DISPATCH(p.K, p.V, p.cnt != nullptr, (k_lda_estep_t32<KP, NWT, DENSE><<<L.grid_t32, nthr, L.smem_t32, h->stream>>>(
+                                                          p, L.part, unsm ? p.beta : p.expElnbeta, !freeze)));
         nparts = L.grid_t32;
     } else if (L.tile) {
         LaunchScope ls(h, "k_lda_estep_tile");
@@ -235,7 +275,7 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     if (L.t32) {
         LaunchScope ls(h, "k_lda_ll_tile");
         const int nthr = 32 * ((p.V + 31) / 32);
-        THETA_DISPATCH(p.K, TILE_DISPATCH_NW(p.V, (k_lda_ll_tile<KP, NWT><<<L.grid_llt, nthr, L.smem_llt, h->stream>>>(p, L.part_ll))));
+        LDA_TILE_DISPATCH(p.K, p.V, p.cnt != nullptr, (k_lda_ll_tile<KP, NWT, DENSE><<<L.grid_llt, nthr, L.smem_llt, h->stream>>>(p, L.part_ll)));
     } else {
         LaunchScope ls(h, "k_lda_ll");
         k_lda_ll<<<L.grid_ll, 256, L.smem_ll, h->stream>>>(p, L.part_ll);

@@ -20,6 +20,7 @@ struct LdaDev {
     long long D, D_total;
     const long long *rowptr;
     const int2 *rec;
+    const int *cnt;              // dense count tiles (tile_stage.cuh) when the corpus is dense and the t32 kernels run, else null
     const double *N;             // D
     double Ntot;                 // Σ_d N_d over all ranks
     double alpha, eta;

@@ -12,9 +12,10 @@ namespace mmsig {
 
 constexpr int LDA_TS = 32;
 
-template <int KP, int NWT>
+// DENSE: dense count tiles staged by bulk copies (tile_stage.cuh), as in k_theta_tile
+template <int KP, int NWT, bool DENSE>
 __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *partial, const double *Etab, int want_stats) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int K = p.K, V = p.V, VP = V | 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     double *Evk = smem;                       // [v][KP]
@@ -22,6 +23,9 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
     double *et = rt + LDA_TS * VP;            // [t][KP]  γ, then e^{Elnθ}
     double *ssum = et + LDA_TS * KP;          // [t]      ψ(Σ_k γ)
     long long *rp = reinterpret_cast<long long *>(ssum + LDA_TS);
+    double *stg = smem + tile_stage_offset((size_t)(ssum - smem) + LDA_TS);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(stg);
+    int *nt = reinterpret_cast<int *>(stg + 2);                        // [t][V]
     const int v = tid;
     const bool vok = v < V;
     for (int i = tid; i < V * KP; i += blockDim.x) {
@@ -36,16 +40,23 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
         acc[k] = 0.0;
     }
     const long long ntiles = (p.D + LDA_TS - 1) / LDA_TS;
+    unsigned parity = 0;
+    if (DENSE) {
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < ntiles) stage_tile(p.cnt, blockIdx.x, V, nt, mbar);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long d0 = tile * LDA_TS;
-        // ---- phase 1: clear the tile, γ rows, scatter the counts, Elnθ (src/LDA.jl:78-80) and e^{Elnθ}
-        for (int i = tid; i < LDA_TS * VP; i += blockDim.x) rt[i] = 0.0;
+        // ---- phase 1: γ rows, Elnθ (src/LDA.jl:78-80) and e^{Elnθ}; CSR: clear the tile, scatter the counts
+        if (!DENSE)
+            for (int i = tid; i < LDA_TS * VP; i += blockDim.x) rt[i] = 0.0;
         for (int i = tid; i < LDA_TS * KP; i += blockDim.x) {
             const int t = i / KP, k = i % KP;
             const long long d = d0 + t;
             et[i] = (k < K && d < p.D) ? p.gamma[d * K + k] : 0.0;
         }
-        if (tid == 0) {
+        if (!DENSE && tid == 0) {
             rp[0] = p.rowptr[d0];
             rp[1] = p.rowptr[min(d0 + LDA_TS, p.D)];
             const long long dn = min(d0 + (long long)gridDim.x * LDA_TS, p.D);      // this block's next tile
@@ -53,10 +64,12 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
             rp[3] = p.rowptr[min(dn + LDA_TS, p.D)];
         }
         __syncthreads();
+        if (!DENSE) {
 #pragma unroll 4
-        for (long long w = rp[0] + tid; w < rp[1]; w += blockDim.x) {
-            const int2 r = p.rec[w];
-            rt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;
+            for (long long w = rp[0] + tid; w < rp[1]; w += blockDim.x) {
+                const int2 r = p.rec[w];
+                rt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;
+            }
         }
         if (tid < LDA_TS) {
             double s = 0.0;
@@ -69,11 +82,17 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
             et[i] = (k < K && d0 + t < p.D) ? det_exp(det_digamma(et[i]) - ssum[t]) : 0.0;
         }
         __syncthreads();
-        prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);    // next tile's records towards L2
+        if (DENSE) {
+            mbar_wait(mbar, parity);                 // this tile's counts have landed in nt
+            parity ^= 1u;
+        } else {
+            prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);    // next tile's records towards L2
+        }
         // ---- phase 2: Z, R and the statistics, lane <-> term
         if (vok) {
             for (int t = 0; t < LDA_TS; ++t) {
-                const double n = rt[t * VP + v];
+                const double n = DENSE ? (double)nt[t * V + v] : rt[t * VP + v];
+                if (DENSE && !(n > 0.0)) rt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
                 if (n > 0.0) {
                     const double2 *e2 = reinterpret_cast<const double2 *>(et + t * KP);
                     double ek[KP];
@@ -101,6 +120,7 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
             }
         }
         __syncthreads();
+        if (DENSE && tid == 0 && tile + gridDim.x < ntiles) stage_tile(p.cnt, tile + gridDim.x, V, nt, mbar);   // flies during phase 3
         // ---- phase 3: γ_{t+1} = α + e^{Elnθ} ∘ (R Eᵀ), thread <-> (sample, four consecutive k)
         {
             const int t = lane;
@@ -140,9 +160,9 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
 
 // log-likelihood pass (src/LDA.jl:174-188) with θ_t = γ_t / Σγ_t and the new β, over the same tiles.
 // partial: [gridDim.x] double2.
-template <int KP, int NWT>
+template <int KP, int NWT, bool DENSE>
 __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *partial) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int K = p.K, V = p.V, VP = V | 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     double *xt = smem;                        // [t][VP]  n, then n log(θ·β)
@@ -150,6 +170,9 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
     double *ssum = pt + LDA_TS * KP;          // [t]
     double *bsum = ssum + LDA_TS;             // [NW][32]
     long long *rp = reinterpret_cast<long long *>(bsum + NW * 32);
+    double *stg = smem + tile_stage_offset((size_t)(bsum - smem) + NW * 32);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(stg);
+    int *nt = reinterpret_cast<int *>(stg + 2);                        // [t][V]
     const int v = tid;
     const bool vok = v < V;
     double Breg[KP];
@@ -157,15 +180,22 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
     for (int k = 0; k < KP; ++k) Breg[k] = (vok && k < K) ? p.beta[k * V + v] : 0.0;
     double ahi = 0.0, alo = 0.0;
     const long long ntiles = (p.D + LDA_TS - 1) / LDA_TS;
+    unsigned parity = 0;
+    if (DENSE) {
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < ntiles) stage_tile(p.cnt, blockIdx.x, V, nt, mbar);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long d0 = tile * LDA_TS;
-        for (int i = tid; i < LDA_TS * VP; i += blockDim.x) xt[i] = 0.0;
+        if (!DENSE)
+            for (int i = tid; i < LDA_TS * VP; i += blockDim.x) xt[i] = 0.0;
         for (int i = tid; i < LDA_TS * KP; i += blockDim.x) {
             const int t = i / KP, k = i % KP;
             const long long d = d0 + t;
             pt[i] = (k < K && d < p.D) ? p.gamma[d * K + k] : 0.0;
         }
-        if (tid == 0) {
+        if (!DENSE && tid == 0) {
             rp[0] = p.rowptr[d0];
             rp[1] = p.rowptr[min(d0 + LDA_TS, p.D)];
             const long long dn = min(d0 + (long long)gridDim.x * LDA_TS, p.D);      // this block's next tile
@@ -173,10 +203,12 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
             rp[3] = p.rowptr[min(dn + LDA_TS, p.D)];
         }
         __syncthreads();
+        if (!DENSE) {
 #pragma unroll 4
-        for (long long w = rp[0] + tid; w < rp[1]; w += blockDim.x) {
-            const int2 r = p.rec[w];
-            xt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;
+            for (long long w = rp[0] + tid; w < rp[1]; w += blockDim.x) {
+                const int2 r = p.rec[w];
+                xt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;
+            }
         }
         if (tid < LDA_TS) {
             double s = 0.0;
@@ -189,10 +221,16 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
             if (k < K && d0 + t < p.D) pt[i] = pt[i] / ssum[t];
         }
         __syncthreads();
-        prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);
+        if (DENSE) {
+            mbar_wait(mbar, parity);                 // this tile's counts have landed in nt
+            parity ^= 1u;
+        } else {
+            prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);
+        }
         if (vok) {
             for (int t = 0; t < LDA_TS; ++t) {
-                const double n = xt[t * VP + v];
+                const double n = DENSE ? (double)nt[t * V + v] : xt[t * VP + v];
+                if (DENSE && !(n > 0.0)) xt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
                 if (n > 0.0) {
                     const double2 *p2 = reinterpret_cast<const double2 *>(pt + t * KP);
                     double dot = 0.0;
@@ -207,6 +245,7 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
             }
         }
         __syncthreads();
+        if (DENSE && tid == 0 && tile + gridDim.x < ntiles) stage_tile(p.cnt, tile + gridDim.x, V, nt, mbar);   // flies during the row sums
         {
             const double *row = xt + lane * VP;
             const int vb = 32 * warp, ve = min(V, vb + 32);

@@ -32,6 +32,7 @@ struct MmctmDev {
     int K[MAXM], V[MAXM], koff[MAXM + 1], goff[MAXM + 1];
     const long long *rowptr[MAXM];
     const int2 *rec[MAXM];        // (term, count) per nonzero
+    const int *cnt[MAXM];         // dense count tiles [ceil(D / 32)][32][V] of a dense modality (tile_stage.cuh), else null
     const double *N;              // D x M
     double Ntot[MAXM];            // Σ_d N_dm over ALL ranks
     double *lam, *lam_prev, *nu, *zeta, *sumtheta;
@@ -513,9 +514,14 @@ __global__ void __launch_bounds__(256) k_moments(MmctmDev p, double2 *partial) {
 #pragma unroll
     for (int i = 0; i < MKP; ++i) { mhi[i] = 0.0; mlo[i] = 0.0; }
     const long long nw = (long long)gridDim.x * 8;
-    for (long long d = (long long)blockIdx.x * 8 + warp; d < p.D; d += nw) {
-        const double lam = active ? p.lam[d * MK + lane] : 0.0;
-        const double diff = lam - muj;
+    // the next sample's λ is loaded while the current one is accumulated (the load was 20 % of the kernel's stall
+    // samples, profiles/r02e_summary.md); same samples in the same order per warp
+    long long d = (long long)blockIdx.x * 8 + warp;
+    double lam_next = (active && d < p.D) ? p.lam[d * MK + lane] : 0.0;
+    for (; d < p.D; d += nw) {
+        const double diff = lam_next - muj;
+        const long long dn = d + nw;
+        lam_next = (active && dn < p.D) ? p.lam[dn * MK + lane] : 0.0;
 #pragma unroll
         for (int i = 0; i < MKP; ++i) {
             const double di = shfl_d(diff, i);

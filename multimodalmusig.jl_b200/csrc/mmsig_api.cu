@@ -79,6 +79,8 @@ struct CountBuf {
     int2 *rec = nullptr;
     int *term = nullptr, *count = nullptr;      // staging for the packing kernel
     int *flags = nullptr;                       // [0] flags, [2..3] 8 bytes: sum of counts
+    int *cnt = nullptr;                         // dense tiles [ceil(D / 32) * 32][V] when the modality is dense (tile_stage.cuh)
+    int V = 0;
 };
 
 struct MmctmHost {
@@ -483,9 +485,10 @@ static int allsum_ll(mmsig_handle *h, long long *vals, int n) {
 // flags: bit0 term out of range, bit1 count <= 0, bit2 terms of a row not strictly ascending
 // tag != 0 (MMCTM): bits 16..20 of rec.x carry (tag_base + d) mod 32, the sample's slot in its
 // 32-sample tile, so that the tile kernels scatter a record without searching the row pointers
+// cnt != nullptr (a dense modality, tile_stage.cuh): the row is also written as V dense int32 cells
 __global__ void k_pack_rows(const long long *rowptr, const int *term, const int *count, long long D, int V,
                             int2 *rec, double *N, int M, int m, int *flags, unsigned long long *ntot, int tag,
-                            long long tag_base) {
+                            long long tag_base, int *cnt) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const long long nw = (long long)gridDim.x * (blockDim.x >> 5);
     int bad = 0;
@@ -493,6 +496,10 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
     for (long long d = (long long)blockIdx.x * (blockDim.x >> 5) + warp; d < D; d += nw) {
         const long long beg = rowptr[d], end = rowptr[d + 1];
         long long s = 0;
+        if (cnt) {
+            for (int v = lane; v < V; v += 32) cnt[d * V + v] = 0;
+            __syncwarp();
+        }
         for (long long w = beg + lane; w < end; w += 32) {
             // count == nullptr: term[] holds packed records (bits 0-9 term, bits 10-31 count: mmsig_pack_records)
             int t = term[w], c;
@@ -510,6 +517,7 @@ __global__ void k_pack_rows(const long long *rowptr, const int *term, const int 
             if (t < 0 || t >= V) { bad |= 1; t = 0; c = 0; }
             if (c <= 0) { bad |= 2; c = 0; }
             rec[w] = make_int2(tag ? (t | (int)(((tag_base + d) & 31) << 16)) : t, c);
+            if (cnt && c > 0) cnt[d * V + t] = c;
             s += c;
         }
         for (int off = 16; off >= 1; off >>= 1) s += __shfl_xor_sync(FULLMASK, s, off);
@@ -526,17 +534,42 @@ static int check_rowptr(mmsig_handle *h, const int64_t *rowptr, long long D) {
     return 0;
 }
 // (re)allocate the device side of one modality's counts when its shape changed
-static int ensure_countbuf(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, long long nnz) {
-    if (cb.D == D && cb.nnz == nnz) return 0;
+// does a modality of this shape keep dense count tiles?  MMSIG_TILES=csr | dense overrides the density rule (A/B)
+static bool want_dense_tiles(long long D, long long nnz, int V) {
+    const char *e = getenv("MMSIG_TILES");
+    if (e && !strcmp(e, "csr")) return false;
+    if (V < 1 || V > 1024) return false;
+    if (e && !strcmp(e, "dense")) return true;
+    return (double)nnz >= kDenseFrac * (double)D * (double)V;
+}
+// (re)allocate the device side of one modality's counts when its shape changed
+static int ensure_countbuf(mmsig_handle *h, std::vector<void *> &pool, CountBuf &cb, long long D, long long nnz, int V = 0) {
+    if (cb.D == D && cb.nnz == nnz && cb.V == V) return 0;
     int rc;
     if ((rc = dev_alloc(h, pool, &cb.rowptr, D + 1))) return rc;
     if ((rc = dev_alloc(h, pool, &cb.rec, nnz))) return rc;
     if ((rc = dev_alloc(h, pool, &cb.term, nnz))) return rc;
     if ((rc = dev_alloc(h, pool, &cb.count, nnz))) return rc;
     if ((rc = dev_alloc(h, pool, &cb.flags, (size_t)4))) return rc;
+    cb.cnt = nullptr;
+    if (V > 0 && want_dense_tiles(D, nnz, V)) {
+        const size_t cells = (size_t)((D + 31) / 32) * 32 * V;
+        if ((rc = dev_alloc(h, pool, &cb.cnt, cells))) return rc;
+        CU(cudaMemsetAsync(cb.cnt, 0, cells * sizeof(int), h->stream));      // the padding rows of the last tile stay zero
+    }
     cb.D = D;
     cb.nnz = nnz;
+    cb.V = V;
     return 0;
+}
+// records of rows [d0, d1) -> the dense tiles of a dense modality
+static void densify_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d1) {
+    if (!cb.cnt || d1 <= d0) return;
+    cudaMemsetAsync(cb.cnt + (size_t)d0 * cb.V, 0, (size_t)(d1 - d0) * cb.V * sizeof(int), h->stream);
+    LaunchScope ls(h, "k_densify");
+    const long long Dc = d1 - d0;
+    const int grid = (int)std::max<long long>(1, std::min<long long>((Dc + 7) / 8, (long long)h->numSM * 8));
+    k_densify<<<grid, 256, 0, h->stream>>>(cb.rowptr + d0, cb.rec, Dc, cb.V, cb.cnt + (size_t)d0 * cb.V);
 }
 // rows [d0, d1) of one modality: validation, (term, count) -> records, row totals
 static void pack_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d1, int V, int M, int m, double *d_N,
@@ -545,7 +578,13 @@ static void pack_launch(mmsig_handle *h, CountBuf &cb, long long d0, long long d
     const long long Dc = d1 - d0;
     int grid = (int)std::min<long long>((Dc + 7) / 8, (long long)h->numSM * 8);
     k_pack_rows<<<std::max(grid, 1), 256, 0, h->stream>>>(cb.rowptr + d0, cb.term, packed ? nullptr : cb.count, Dc, V, cb.rec, d_N + d0 * M, M, m,
-                                                           cb.flags, (unsigned long long *)(cb.flags + 2), tag, d0);
+                                                           cb.flags, (unsigned long long *)(cb.flags + 2), tag, d0,
+                                                           cb.cnt ? cb.cnt + (size_t)d0 * cb.V : nullptr);
+}
+// packing also writes the dense rows of a dense modality
+static void pack_and_densify(mmsig_handle *h, CountBuf &cb, long long d0, long long d1, int V, int M, int m, double *d_N,
+                             int tag = 0, bool packed = false) {
+    pack_launch(h, cb, d0, d1, V, M, m, d_N, tag, packed);
 }
 static int flags_verdict(mmsig_handle *h, const int *hf, long long *ntot_out) {
     if (hf[0] & 1) return fail(h, MMSIG_EINVAL, "term index out of range [0, V)");
@@ -564,14 +603,14 @@ static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &c
     if ((rc = check_rowptr(h, rowptr, D))) return rc;
     const long long nnz = rowptr[D];
     NEED(nnz == 0 || (term && count), "null term / count");
-    if ((rc = ensure_countbuf(h, pool, cb, D, nnz))) return rc;
+    if ((rc = ensure_countbuf(h, pool, cb, D, nnz, tag ? V : 0))) return rc;
     CU(cudaMemsetAsync(cb.flags, 0, 4 * sizeof(int), h->stream));
     CU(cudaMemcpyAsync(cb.rowptr, rowptr, (D + 1) * sizeof(long long), cudaMemcpyHostToDevice, h->stream));
     if (nnz) {
         CU(cudaMemcpyAsync(cb.term, term, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
         CU(cudaMemcpyAsync(cb.count, count, nnz * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     }
-    pack_launch(h, cb, 0, D, V, M, m, d_N, tag);
+    pack_and_densify(h, cb, 0, D, V, M, m, d_N, tag);
     int hf[4] = {0, 0, 0, 0};
     CU(cudaMemcpyAsync(hf, cb.flags, sizeof(hf), cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
@@ -584,9 +623,10 @@ static int upload_counts(mmsig_handle *h, std::vector<void *> &pool, CountBuf &c
 // ===========================================================================================
 // launch plan of k_theta_tile for one modality: one thread per term, tiles of TILE_S samples
 template <typename F>
-static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, int V, long long D, int *grid_out, size_t *smem_out) {
+static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, bool dense, int V, long long D, int *grid_out, size_t *smem_out) {
     const int VP = V | 1, NW = (V + 31) / 32;
-    const size_t smem = ((size_t)V * KP + (ereg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP + TILE_S + 2) * sizeof(double);
+    const size_t base = (size_t)V * KP + (ereg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP;
+    const size_t smem = (dense ? tile_stage_offset(base) + tile_stage_doubles(V) : base + TILE_S + 2) * sizeof(double);
     if (smem > h->smem_optin) return fail(h, MMSIG_ELIMIT, "V too large for the theta tile (shared memory)");
     CU(allow_max_smem(h, kernel));
     int nb = 0;
@@ -608,9 +648,10 @@ static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, int V, l
         else { constexpr int KP = 32, NP = 32; EXPR; }            \
     } while (0)
 template <typename F>
-static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, int V, long long D, int *grid_out, size_t *smem_out) {
+static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, bool dense, int V, long long D, int *grid_out, size_t *smem_out) {
     const int VP = V | 1, NW = (V + 31) / 32;
-    const size_t smem = ((preg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP + TILE_S + (size_t)NW * 32 + TILE_S + 2) * sizeof(double);
+    const size_t base = (preg ? 0 : (size_t)KP * VP) + (size_t)TILE_S * VP + (size_t)TILE_S * KP + TILE_S + (size_t)NW * 32;
+    const size_t smem = (dense ? tile_stage_offset(base) + tile_stage_doubles(V) : base + TILE_S + 2) * sizeof(double);
     if (smem > h->smem_optin) return fail(h, MMSIG_ELIMIT, "V too large for the log-likelihood tile (shared memory)");
     CU(allow_max_smem(h, kernel));
     int nb = 0;
@@ -637,6 +678,12 @@ static int pick_ll_plan(mmsig_handle *h, F kernel, int KP, bool preg, int V, lon
         else if ((K) <= 16) { constexpr int KP = 16; constexpr bool EREG = true; TILE_DISPATCH_NW(V, EXPR); }  \
         else if ((K) <= 24) { constexpr int KP = 24; constexpr bool EREG = false; TILE_DISPATCH_NW(V, EXPR); } \
         else { constexpr int KP = 32; constexpr bool EREG = false; TILE_DISPATCH_NW(V, EXPR); }                \
+    } while (0)
+// ... and DENSE (the modality keeps dense count tiles)
+#define TILE_DISPATCH_D(K, V, DENSE_RT, EXPR)                                                  \
+    do {                                                                                       \
+        if (DENSE_RT) { constexpr bool DENSE = true; TILE_DISPATCH(K, V, EXPR); }              \
+        else { constexpr bool DENSE = false; TILE_DISPATCH(K, V, EXPR); }                      \
     } while (0)
 #define MK_DISPATCH(MK, EXPR)                                     \
     do {                                                          \
@@ -716,9 +763,10 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     p.N = dN;
     mm.nnz.resize(M);
     for (int m = 0; m < M; ++m) {
-        if ((rc = ensure_countbuf(h, h->allocs_mm, mm.cb[m], D, nnz[m]))) return rc;
+        if ((rc = ensure_countbuf(h, h->allocs_mm, mm.cb[m], D, nnz[m], V[m]))) return rc;
         p.rowptr[m] = mm.cb[m].rowptr;
         p.rec[m] = mm.cb[m].rec;
+        p.cnt[m] = mm.cb[m].cnt;
         mm.nnz[m] = mm.cb[m].nnz;
     }
     const size_t DMK = (size_t)D * p.MK;
@@ -750,11 +798,12 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     for (int m = 0; m < M; ++m) {
         const int KV = K[m] * V[m];
         if (V[m] > 1024) return fail(h, MMSIG_ELIMIT, "V[m] <= 1024 supported");
-        TILE_DISPATCH(K[m], V[m], rc = pick_tile_plan(h, k_theta_tile<KP, EREG, NWT>, KP, EREG, V[m], D, &mm.grid_theta[m],
-                                                      &mm.smem_theta[m]));
+        const bool dn = mm.cb[m].cnt != nullptr;
+        TILE_DISPATCH_D(K[m], V[m], dn, rc = pick_tile_plan(h, k_theta_tile<KP, EREG, NWT, DENSE>, KP, EREG, DENSE, V[m], D, &mm.grid_theta[m],
+                                                            &mm.smem_theta[m]));
         if (rc) return rc;
         mm.W_theta[m] = TILE_S;
-        TILE_DISPATCH(K[m], V[m], rc = pick_ll_plan(h, k_loglik_tile<KP, EREG, NWT>, KP, EREG, V[m], D, &mm.grid_ll[m], &mm.smem_ll[m]));
+        TILE_DISPATCH_D(K[m], V[m], dn, rc = pick_ll_plan(h, k_loglik_tile<KP, EREG, NWT, DENSE>, KP, EREG, DENSE, V[m], D, &mm.grid_ll[m], &mm.smem_ll[m]));
         if (rc) return rc;
         if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
         CU(cudaMemsetAsync(mm.part_theta[m], 0, (size_t)mm.grid_theta[m] * KV * sizeof(double2), h->stream));
@@ -1038,7 +1087,10 @@ extern "C" int32_t mmsig_mmctm_get_alpha(mmsig_handle *h, double *alpha_out) {
 static MmctmDev chunk_view(const MmctmDev &p, long long d0, long long d1, int accum) {
     MmctmDev q = p;
     q.D = d1 - d0;
-    for (int m = 0; m < p.M; ++m) q.rowptr[m] = p.rowptr[m] + d0;
+    for (int m = 0; m < p.M; ++m) {
+        q.rowptr[m] = p.rowptr[m] + d0;
+        if (p.cnt[m]) q.cnt[m] = p.cnt[m] + (size_t)d0 * p.V[m];        // d0 is a multiple of 32: the chunk's tiles are the shard's
+    }
     q.N = p.N + d0 * p.M;
     q.lam = p.lam + d0 * p.MK;
     q.lam_prev = p.lam_prev + d0 * p.MK;
@@ -1059,7 +1111,7 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
     for (int m = 0; m < q.M; ++m) {
         LaunchScope ls(h, "k_theta_tile");
         const int nthr = 32 * ((q.V[m] + 31) / 32);
-        TILE_DISPATCH(q.K[m], q.V[m], (k_theta_tile<KP, EREG, NWT><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
+        TILE_DISPATCH_D(q.K[m], q.V[m], q.cnt[m] != nullptr, (k_theta_tile<KP, EREG, NWT, DENSE><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
                                           q, m, mm.part_theta[m], unsm, !freeze_topics)));
     }
     cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);      // the solve kernels draw samples from this counter
@@ -1138,7 +1190,7 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     for (int m = 0; m < p.M; ++m) {
         LaunchScope ls(h, "k_loglik_tile");
         const int nthr = 32 * ((p.V[m] + 31) / 32);
-        TILE_DISPATCH(p.K[m], p.V[m], (k_loglik_tile<KP, EREG, NWT><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
+        TILE_DISPATCH_D(p.K[m], p.V[m], p.cnt[m] != nullptr, (k_loglik_tile<KP, EREG, NWT, DENSE><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
                                           p, m, mm.part_post + p.MK * p.MK + m, P2)));
     }
     {
@@ -1488,7 +1540,7 @@ static int mmctm_fit_host_impl(mmsig_handle *h, int64_t D, int64_t D_total, int3
         if (nu) CU(cudaMemcpyAsync(p.nu + d0 * MK, nu + d0 * MK, n, cudaMemcpyHostToDevice, h->s_in));
         CU(cudaEventRecord(ev_in[c], h->s_in));
         CU(cudaStreamWaitEvent(h->stream, ev_in[c], 0));
-        for (int m = 0; m < M; ++m) pack_launch(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N), 1, packed);
+        for (int m = 0; m < M; ++m) pack_and_densify(h, mm.cb[m], d0, d1, V[m], M, m, const_cast<double *>(p.N), 1, packed);
         mmctm_estep_launch(h, chunk_view(p, d0, d1, C > 1), flags);
         if (maxiter == 1) CU(after_chunk(c));
     }

@@ -14,6 +14,7 @@
 // by roundings only; DESIGN.md section 2 (pinned arithmetic) states this form.
 #pragma once
 #include "mmctm_kernels.cuh"
+#include "tile_stage.cuh"
 
 namespace mmsig {
 
@@ -28,18 +29,28 @@ __device__ __forceinline__ void prefetch_records(const int2 *rec, long long beg,
         asm volatile("prefetch.global.L2 [%0];" ::"l"(q));
 }
 
+// doubles of shared memory in front of the staging area of the DENSE variants (mbarrier, then the 32 x V int32 counts)
+__host__ __device__ inline size_t tile_stage_offset(size_t doubles_before) { return (doubles_before + 1) & ~(size_t)1; }
+__host__ __device__ inline size_t tile_stage_doubles(int V) { return 2 + (size_t)TILE_S * V / 2; }
+
 // EREG: the thread's column of E in registers (K <= 16); else read from shared memory [k][v].
 // NWT: upper bound of the block's warp count (one thread per term: blockDim = 32 ceil(V / 32)).
-template <int KP, bool EREG, int NWT>
+// DENSE: the modality keeps dense count tiles (tile_stage.cuh): the next tile's counts arrive by one bulk copy while
+// this tile computes; no clear / scatter of records.
+template <int KP, bool EREG, int NWT, bool DENSE>
 __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, double2 *partial, int unsmoothed, int want_stats) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     double *Evk = smem;                        // [v][KP]  phase 3 (a sample's thread walks v, reads a row of k)
     double *Ekv = Evk + V * KP;                // [k][VP]  phase 2 when !EREG
     double *rt = Ekv + (EREG ? 0 : KP * VP);   // [t][VP]  n, then R
     double *et = rt + TILE_S * VP;             // [t][KP]  L
-    long long *rp = reinterpret_cast<long long *>(et + TILE_S * KP);   // [TILE_S + 1] row pointers of the tile
+    long long *rp = reinterpret_cast<long long *>(et + TILE_S * KP);   // [TILE_S + 1] row pointers of the tile (CSR variant)
+    double *stg = smem + tile_stage_offset((size_t)(et - smem) + TILE_S * KP);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(stg);                // DENSE: the staging barrier, then the counts
+    int *nt = reinterpret_cast<int *>(stg + 2);                        // [t][V]
+    const int *cnt = p.cnt[m];
     const int v = tid;
     const bool vok = v < V;
     const double *Eg = (unsmoothed ? p.phi : p.Elnphi) + p.goff[m];
@@ -62,16 +73,23 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
     const long long *rowptr = p.rowptr[m];
     const int2 *rec = p.rec[m];
     const long long ntiles = (p.D + TILE_S - 1) / TILE_S;
+    unsigned parity = 0;
+    if (DENSE) {
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < ntiles) stage_tile(cnt, blockIdx.x, V, nt, mbar);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long d0 = tile * TILE_S;
-        // ---- phase 1: clear the count tile, L = exp(λ) (thread <-> (sample, k)), the tile's row pointers
-        for (int i = tid; i < TILE_S * VP; i += blockDim.x) rt[i] = 0.0;
+        // ---- phase 1: L = exp(λ) (thread <-> (sample, k)); CSR: clear the count tile, the tile's row pointers
+        if (!DENSE)
+            for (int i = tid; i < TILE_S * VP; i += blockDim.x) rt[i] = 0.0;
         for (int i = tid; i < TILE_S * KP; i += blockDim.x) {
             const int t = i / KP, k = i % KP;
             const long long d = d0 + t;
             et[i] = (k < K && d < p.D) ? det_exp(p.lam_prev[d * p.MK + off + k]) : 0.0;
         }
-        if (tid == 0) {
+        if (!DENSE && tid == 0) {
             rp[0] = rowptr[d0];
             rp[TILE_S] = rowptr[min(d0 + TILE_S, p.D)];
             const long long dn = min(d0 + (long long)gridDim.x * TILE_S, p.D);      // this block's next tile
@@ -79,19 +97,25 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
             rp[2] = rowptr[min(dn + TILE_S, p.D)];
         }
         __syncthreads();
-        // scatter: the tile's records are one contiguous range of rec, streamed by all threads (every
-        // thread has its loads in flight at once); a record carries its sample's slot in the tile
+        if (DENSE) {
+            mbar_wait(mbar, parity);                 // this tile's counts have landed in nt
+            parity ^= 1u;
+        } else {
+            // scatter: the tile's records are one contiguous range of rec, streamed by all threads (every
+            // thread has its loads in flight at once); a record carries its sample's slot in the tile
 #pragma unroll 4
-        for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
-            const int2 r = rec[w];
-            rt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;        // slot tag | term (k_pack_rows)
+            for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
+                const int2 r = rec[w];
+                rt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;        // slot tag | term (k_pack_rows)
+            }
+            __syncthreads();
+            prefetch_records(rec, rp[1], rp[2], tid, blockDim.x);
         }
-        __syncthreads();
-        prefetch_records(rec, rp[1], rp[2], tid, blockDim.x);
         // ---- phase 2: Z, R and the statistics, lane <-> term
         if (vok) {
             for (int t = 0; t < TILE_S; ++t) {
-                const double n = rt[t * VP + v];
+                const double n = DENSE ? (double)nt[t * V + v] : rt[t * VP + v];
+                if (DENSE && !(n > 0.0)) rt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
                 if (n > 0.0) {
                     const double2 *e2 = reinterpret_cast<const double2 *>(et + t * KP);
                     double ek[KP];
@@ -117,6 +141,7 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
             }
         }
         __syncthreads();
+        if (DENSE && tid == 0 && tile + gridDim.x < ntiles) stage_tile(cnt, tile + gridDim.x, V, nt, mbar);   // flies during phase 3
         // ---- phase 3: sumθ, thread <-> (sample t, four consecutive k): per term one load of R, two 128-bit
         // loads of E, four DFMAs.  Warp kq takes the k-quads kq, kq + NW, ...
         {
@@ -171,9 +196,9 @@ namespace mmsig {
 // the sums.  One double-double per sample slot, reduced once per block at the end.
 // partial[blockIdx.x * pstride] receives the block's sum.
 // ------------------------------------------------------------------------------------------
-template <int KP, bool PREG, int NWT>
+template <int KP, bool PREG, int NWT, bool DENSE>
 __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, double2 *partial, int pstride) {
-    extern __shared__ double smem[];
+    extern __shared__ __align__(16) double smem[];
     const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1, M = p.M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
     double *Pkv = smem;                              // [k][VP] when !PREG
@@ -182,6 +207,10 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
     double *ssum = pt + TILE_S * KP;                 // [t]
     double *bsum = ssum + TILE_S;                    // [NW][32]
     long long *rp = reinterpret_cast<long long *>(bsum + NW * 32);
+    double *stg = smem + tile_stage_offset((size_t)(bsum - smem) + NW * 32);
+    uint64_t *mbar = reinterpret_cast<uint64_t *>(stg);
+    int *nt = reinterpret_cast<int *>(stg + 2);                        // [t][V]
+    const int *cnt = p.cnt[m];
     const int v = tid;
     const bool vok = v < V;
     const double *ph = p.phi + p.goff[m];
@@ -201,15 +230,22 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
     const long long *rowptr = p.rowptr[m];
     const int2 *rec = p.rec[m];
     const long long ntiles = (p.D + TILE_S - 1) / TILE_S;
+    unsigned parity = 0;
+    if (DENSE) {
+        if (tid == 0) mbar_init(mbar, 1);
+        __syncthreads();
+        if (tid == 0 && blockIdx.x < ntiles) stage_tile(cnt, blockIdx.x, V, nt, mbar);
+    }
     for (long long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
         const long long d0 = tile * TILE_S;
-        for (int i = tid; i < TILE_S * VP; i += blockDim.x) xt[i] = 0.0;
+        if (!DENSE)
+            for (int i = tid; i < TILE_S * VP; i += blockDim.x) xt[i] = 0.0;
         for (int i = tid; i < TILE_S * KP; i += blockDim.x) {
             const int t = i / KP, k = i % KP;
             const long long d = d0 + t;
             pt[i] = (k < K && d < p.D) ? det_exp(p.lam[d * p.MK + off + k]) : 0.0;
         }
-        if (tid == 0) {
+        if (!DENSE && tid == 0) {
             rp[0] = rowptr[d0];
             rp[TILE_S] = rowptr[min(d0 + TILE_S, p.D)];
             const long long dn = min(d0 + (long long)gridDim.x * TILE_S, p.D);      // this block's next tile
@@ -217,10 +253,12 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
             rp[2] = rowptr[min(dn + TILE_S, p.D)];
         }
         __syncthreads();
+        if (!DENSE) {
 #pragma unroll 4
-        for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
-            const int2 r = rec[w];
-            xt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;        // slot tag | term (k_pack_rows)
+            for (long long w = rp[0] + tid; w < rp[TILE_S]; w += blockDim.x) {
+                const int2 r = rec[w];
+                xt[(r.x >> 16) * VP + (r.x & 0xffff)] = (double)r.y;        // slot tag | term (k_pack_rows)
+            }
         }
         if (tid < TILE_S) {
             double s = 0.0;
@@ -233,10 +271,16 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
             if (k < K && d0 + t < p.D) pt[i] = pt[i] / ssum[t];
         }
         __syncthreads();
-        prefetch_records(rec, rp[1], rp[2], tid, blockDim.x);
+        if (DENSE) {
+            mbar_wait(mbar, parity);                 // this tile's counts have landed in nt
+            parity ^= 1u;
+        } else {
+            prefetch_records(rec, rp[1], rp[2], tid, blockDim.x);
+        }
         if (vok) {
             for (int t = 0; t < TILE_S; ++t) {
-                const double n = xt[t * VP + v];
+                const double n = DENSE ? (double)nt[t * V + v] : xt[t * VP + v];
+                if (DENSE && !(n > 0.0)) xt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
                 if (n > 0.0) {
                     const double2 *p2 = reinterpret_cast<const double2 *>(pt + t * KP);
                     double pw = 0.0;
@@ -251,6 +295,7 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
             }
         }
         __syncthreads();
+        if (DENSE && tid == 0 && tile + gridDim.x < ntiles) stage_tile(cnt, tile + gridDim.x, V, nt, mbar);   // flies during the row sums
         {
             const double *row = xt + lane * VP;
             const int vb = 32 * warp, ve = min(V, vb + 32);
