@@ -240,6 +240,9 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-pageable", action="store_true")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"],
+                    help="fp32: the optional FP32 mode of the tile passes (mmsig_config.precision); the headline is always fp64")
+    ap.add_argument("--no-fast", action="store_true", help="skip the extra FP32-mode measurement of the default line")
     ap.add_argument("--e2e-unpipelined", action="store_true", help="e2e through set_data/set_state/iterate/get_state")
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -313,11 +316,12 @@ def bench_mmctm(args, cfg):
         counts_p.append(tuple(trip))
 
     if grouped:
-        model = mmsig.MMCTMGroup(K_CFG, ALPHA, counts_p, list(range(ngpu)), V=V_CFG, gamma0=g0, profile=False)
+        model = mmsig.MMCTMGroup(K_CFG, ALPHA, counts_p, list(range(ngpu)), V=V_CFG, gamma0=g0, profile=False, precision=args.precision)
         stream = None
     else:
         stream = torch.cuda.Stream()
-        model = mmsig.MMCTM(K_CFG, ALPHA, counts_p, V=V_CFG, gamma0=g0, device=local, profile=False, comm=comm, D_total=D)
+        model = mmsig.MMCTM(K_CFG, ALPHA, counts_p, V=V_CFG, gamma0=g0, device=local, profile=False, comm=comm, D_total=D,
+                            precision=args.precision)
         model.h.set_stream(stream.cuda_stream)
 
     def barrier():
@@ -388,6 +392,33 @@ def bench_mmctm(args, cfg):
             ms_prof = p0.elapsed_time(p1) / args.steps
         ktimes = model.h.kernel_times(reset=True)
         model.h.set_profile(False)
+    # the optional FP32 mode of the tile passes on the same workload, reported beside the headline, never as it
+    fp32_mode = None
+    if world == 1 and not grouped and args.precision == "fp64" and not args.no_fast:
+        m32 = mmsig.MMCTM(K_CFG, ALPHA, counts_p, V=V_CFG, gamma0=g0, device=local, profile=False, precision="fp32")
+        m32.h.set_stream(stream.cuda_stream)
+        with torch.cuda.stream(stream):
+            for _ in range(args.warmup):
+                m32.iterate()
+            torch.cuda.synchronize()
+            f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            f0.record(stream)
+            ll32 = m32.fit(maxiter=args.steps, tol=0.0, verbose=False, elbo=False)[-1]
+            f1.record(stream)
+            torch.cuda.synchronize()
+            ms32 = f0.elapsed_time(f1) / args.steps
+            m32.h.set_profile(True)
+            m32.h.kernel_times(reset=True)
+            m32.fit(maxiter=args.steps, tol=0.0, verbose=False, elbo=False)
+            torch.cuda.synchronize()
+            k32 = m32.h.kernel_times(reset=True)
+        fp32_mode = {"ms_per_step": ms32, "value": 1000.0 / ms32, "unit": UNIT, "ll": [float(x) for x in ll32],
+                     "ll_rel_diff_to_fp64": float(np.max(np.abs((np.asarray(ll32) - np.asarray(ll)) / np.asarray(ll)))),
+                     "kernels": {k: {"ms_per_step": v[0] / args.steps} for k, v in k32.items() if v[1] > 0},
+                     "what": "mmsig_config.precision = MMSIG_PRECISION_FP32: theta / log-likelihood tile passes in float, sums over samples, "
+                             "LD_MMA solves and M-step in double; same warm-up and step count from the same constructor state"}
+        m32.close()
+        del m32
     # a timed region shorter than ~1.5 s can fall between two nvidia-smi samples: keep the identical
     # load running, untimed, on every rank (same count everywhere: the iterations are collective)
     # ms is already the max over ranks; ms_prof is this rank's own clock, so it must not enter a count of collective calls
@@ -542,7 +573,10 @@ def bench_mmctm(args, cfg):
             "gpu_launches": int(n_launch),
             "kernels": per_kernel,
             "roofline": roof,
-            "roofline_fp64": roof64}
+            "roofline_fp64": roof64,
+            "fp32_mode": fp32_mode}
+    if args.precision == "fp32":
+        line["dtype"] = "f32 tile passes, f64 solves and sums (optional FP32 mode; not the headline)"
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(cfg, D, os.cpu_count() or 1, steps=min(max(args.steps, 1), 3), warmup=min(args.warmup, 3),
                                             budget_s=args.cpu_budget_s, max_samples=args.cpu_samples)
@@ -571,7 +605,8 @@ def bench_lda(args, cfg):
     csr = mmsig.synth.generate(D, [K], [V], lo=lo, hi=hi)[0]
     nnz_local = int(csr[0][-1])
     stream = torch.cuda.Stream()
-    m = mmsig.LDA(K, 0.1, 0.1, csr, V=V, lambda0=mmsig.synth.init_lda_lambda(K, V), device=local, comm=comm, D_total=D)
+    m = mmsig.LDA(K, 0.1, 0.1, csr, V=V, lambda0=mmsig.synth.init_lda_lambda(K, V), device=local, comm=comm, D_total=D,
+                  precision=args.precision)
     m.h.set_stream(stream.cuda_stream)
     sampler = ClockSampler(local)
     sampler.start()
@@ -653,6 +688,8 @@ def bench_lda(args, cfg):
                          "unit": "GB/s", "frac": alg / (ms_step * 1e-3) / 1e9 / peak, "traffic": None,
                          "algorithmic_bytes_per_launch": alg, "dominant_kernel": dom,
                          "dominant_kernel_gbs": alg_local / (per_kernel[dom]["ms_per_step"] * 1e-3) / 1e9}}
+    if args.precision == "fp32":
+        line["dtype"] = "f32 tile passes, f64 sums over samples (optional FP32 mode; not the headline)"
     if not args.no_cpu:
         line["cpu_baseline"] = cpu_baseline(cfg, D, os.cpu_count() or 1, steps=3, warmup=1, budget_s=args.cpu_budget_s,
                                             max_samples=args.cpu_samples)

@@ -53,11 +53,21 @@ extern "C" {
 
 typedef struct mmsig_handle mmsig_handle;
 
+/* Arithmetic of the tile passes (θ / log-likelihood pass of the MMCTM and IMMCTM, E / log-likelihood pass of the LDA
+ * and ILDA).  FP64 (default) matches Julia's Float64 and the pinned oracle bit for bit.  FP32 is the optional fast
+ * mode: float arithmetic per nonzero, sums over samples in double, the LD_MMA solves and the M-step tables stay FP64;
+ * state keeps its FP64 layout.  Its tolerance against the FP64 path from the same state: one iteration 1e-5 on ϕ / β,
+ * 1e-6 on the log-likelihood; a 20-iteration fit 1e-6 (LDA) / 1e-3 (MMCTM: LD_MMA's stop decisions amplify any
+ * perturbation) on the log-likelihood (tests/test_gpu_fp32.py). */
+#define MMSIG_PRECISION_FP64 0
+#define MMSIG_PRECISION_FP32 1
+
 typedef struct {
     int32_t device;        /* CUDA device ordinal                                          */
     int32_t stop_rule;     /* MMSIG_STOP_*: which NLopt x-tolerance rule LD_MMA follows    */
     int32_t profile;       /* != 0: time every kernel with CUDA events (mmsig_kernel_times) */
-    int32_t reserved[5];   /* must be 0                                                    */
+    int32_t precision;     /* MMSIG_PRECISION_*                                            */
+    int32_t reserved[4];   /* must be 0                                                    */
 } mmsig_config;
 
 int32_t     mmsig_version(void);

@@ -20,7 +20,8 @@ struct MmsigConfig
     device::Int32
     stop_rule::Int32
     profile::Int32
-    reserved::NTuple{5,Int32}
+    precision::Int32
+    reserved::NTuple{4,Int32}
 end
 
 function check(h::Ptr{Cvoid}, rc::Int32)
@@ -30,8 +31,9 @@ function check(h::Ptr{Cvoid}, rc::Int32)
     end
 end
 
-function create(; device=0, stop_rule=0)
-    cfg = Ref(MmsigConfig(Int32(device), Int32(stop_rule), Int32(0), ntuple(_ -> Int32(0), 5)))
+# precision: 0 = FP64 (default, Julia's Float64), 1 = FP32 tile passes (include/mmsig.h MMSIG_PRECISION_FP32)
+function create(; device=0, stop_rule=0, precision=0)
+    cfg = Ref(MmsigConfig(Int32(device), Int32(stop_rule), Int32(0), Int32(precision), ntuple(_ -> Int32(0), 4)))
     h = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:mmsig_create, LIB), Int32, (Ref{MmsigConfig}, Ref{Ptr{Cvoid}}), cfg, h)
     check(C_NULL, rc)
@@ -114,9 +116,9 @@ function gcheck(g::Ptr{Cvoid}, rc::Int32)
     end
 end
 
-function create_group(devices; stop_rule=0)
+function create_group(devices; stop_rule=0, precision=0)
     ids = Int32.(collect(devices))
-    cfg = Ref(MmsigConfig(ids[1], Int32(stop_rule), Int32(0), ntuple(_ -> Int32(0), 5)))
+    cfg = Ref(MmsigConfig(ids[1], Int32(stop_rule), Int32(0), Int32(precision), ntuple(_ -> Int32(0), 4)))
     g = Ref{Ptr{Cvoid}}(C_NULL)
     rc = ccall((:mmsig_group_create, LIB), Int32, (Ref{MmsigConfig}, Int32, Ptr{Int32}, Ref{Ptr{Cvoid}}), cfg, length(ids), ids, g)
     gcheck(C_NULL, rc)

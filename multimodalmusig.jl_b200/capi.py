@@ -17,12 +17,20 @@ c_u32p = C.POINTER(C.c_uint32)
 
 FLAG_UPDATE_SIGMA, FLAG_FREEZE_TOPICS, FLAG_FREEZE_MU, FLAG_UNSMOOTHED, FLAG_AUTO_ALPHA = 1, 2, 4, 8, 16
 STOP_NLOPT27, STOP_NLOPT26 = 0, 1
+PRECISION_FP64, PRECISION_FP32 = 0, 1          # mmsig_config.precision (include/mmsig.h)
+
+
+def _precision(p):
+    """0 / 1, or "fp64" / "fp32"."""
+    if isinstance(p, str):
+        return {"fp64": PRECISION_FP64, "f64": PRECISION_FP64, "fp32": PRECISION_FP32, "f32": PRECISION_FP32}[p.lower()]
+    return int(p)
 DENSE_TERM_MAJOR, DENSE_SAMPLE_MAJOR = 0, 1
 
 
 class Config(C.Structure):
-    _fields_ = [("device", C.c_int32), ("stop_rule", C.c_int32), ("profile", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+    _fields_ = [("device", C.c_int32), ("stop_rule", C.c_int32), ("profile", C.c_int32), ("precision", C.c_int32),
+                ("reserved", C.c_int32 * 4)]
 
 
 class MmsigError(RuntimeError):
@@ -169,9 +177,9 @@ def f64(a, n=None):
 class Handle:
     """Owns one mmsig_handle (one GPU)."""
 
-    def __init__(self, device=0, stop_rule=STOP_NLOPT27, profile=False):
+    def __init__(self, device=0, stop_rule=STOP_NLOPT27, profile=False, precision=PRECISION_FP64):
         self.lib = load()
-        cfg = Config(device=device, stop_rule=stop_rule, profile=int(profile))
+        cfg = Config(device=device, stop_rule=stop_rule, profile=int(profile), precision=_precision(precision))
         hp = C.c_void_p()
         rc = self.lib.mmsig_create(C.byref(cfg), C.byref(hp))
         if rc != 0:
@@ -223,10 +231,10 @@ class Handle:
 class Group:
     """Owns one mmsig_group: several GPUs driven from this process (include/mmsig.h)."""
 
-    def __init__(self, devices, stop_rule=STOP_NLOPT27, profile=False):
+    def __init__(self, devices, stop_rule=STOP_NLOPT27, profile=False, precision=PRECISION_FP64):
         self.lib = load()
         self.devices = [int(d) for d in devices]
-        cfg = Config(device=self.devices[0], stop_rule=stop_rule, profile=int(profile))
+        cfg = Config(device=self.devices[0], stop_rule=stop_rule, profile=int(profile), precision=_precision(precision))
         ids = np.asarray(self.devices, np.int32)
         gp = C.c_void_p()
         rc = self.lib.mmsig_group_create(C.byref(cfg), len(self.devices), ids.ctypes.data_as(c_i32p), C.byref(gp))

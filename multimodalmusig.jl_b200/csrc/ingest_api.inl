@@ -265,7 +265,12 @@ static int tsv_scan(const char *path, long long *V, long long *D, std::vector<in
                 if (x > 2147483647LL) { err = "a count exceeds 2^31-1 in row " + std::to_string(rows + 1); return MMSIG_ELIMIT; }
                 ++p;
             }
-            if (out) (*out)[(size_t)rows * ncol + c] = (int32_t)(neg ? -x : x);
+            if (out) {
+                // the buffer was sized from an earlier scan of the same path: never write past it if the file changed
+                const size_t at = (size_t)rows * ncol + c;
+                if (c >= ncol || at >= out->size()) { err = "the file changed between the sizing scan and the read"; return MMSIG_EINVAL; }
+                (*out)[at] = (int32_t)(neg ? -x : x);
+            }
             ++c;
         }
         if (p < end && *p == '\r') ++p;

@@ -141,13 +141,26 @@ static int lda_set_data_impl(mmsig_handle *h, int64_t D, int64_t D_total, int32_
             L.smem_t32 = (dn ? tile_stage_offset(b1) + tile_stage_doubles(V) : b1 + 4) * sizeof(double);
             L.smem_llt = (dn ? tile_stage_offset(b2) + tile_stage_doubles(V) : b2 + 4) * sizeof(double);
         }
-        L.t32 = V <= 1024 && KPv <= 24 && L.smem_t32 <= h->smem_optin && !(e && (!strcmp(e, "row") || !strcmp(e, "tile96")));
+        if (h->precision) {
+            L.smem_t32 = f32_theta_smem(KPv, V);          // the LDA's FP32 E pass has the θ pass's layout
+            L.smem_llt = f32_ll_smem(KPv, V);
+            if (!(V <= 1024 && KPv <= 24 && L.smem_t32 <= h->smem_optin && dn))
+                return fail(h, MMSIG_ELIMIT, "the FP32 mode of the LDA needs V <= 1024, K <= 24 and a tile that fits shared memory");
+        }
+        L.t32 = V <= 1024 && KPv <= 24 && L.smem_t32 <= h->smem_optin && (h->precision || !(e && (!strcmp(e, "row") || !strcmp(e, "tile96"))));
         if (L.t32) {
             int nb = 0, nb2 = 0;
+            if (h->precision) {
+                THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(allow_max_smem(h, k_lda_estep_f32<KP, NWT>))));
+                THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_estep_f32<KP, NWT>, NW * 32, L.smem_t32))));
+                THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(allow_max_smem(h, k_lda_ll_f32<KP, NWT>))));
+                THETA_DISPATCH(K, TILE_DISPATCH_NW(V, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lda_ll_f32<KP, NWT>, NW * 32, L.smem_llt))));
+            } else {
             LDA_TILE_DISPATCH(K, V, dn, CU(allow_max_smem(h, k_lda_estep_t32<KP, NWT, DENSE>)));
             LDA_TILE_DISPATCH(K, V, dn, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_lda_estep_t32<KP, NWT, DENSE>, NW * 32, L.smem_t32)));
             LDA_TILE_DISPATCH(K, V, dn, CU(allow_max_smem(h, k_lda_ll_tile<KP, NWT, DENSE>)));
             LDA_TILE_DISPATCH(K, V, dn, CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_lda_ll_tile<KP, NWT, DENSE>, NW * 32, L.smem_llt)));
+            }
             if (nb < 1 || nb2 < 1) L.t32 = false;
             else {
                 const long long ntiles = (D + LDA_TS - 1) / LDA_TS;
@@ -241,6 +254,10 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     if (L.t32) {
         LaunchScope ls(h, "k_lda_estep_t32");
         const int nthr = 32 * ((p.V + 31) / 32);
+        if (h->precision)
+            THETA_DISPATCH(p.K, TILE_DISPATCH_NW(p.V, (k_lda_estep_f32<KP, NWT><<<L.grid_t32, nthr, L.smem_t32, h->stream>>>(
+                                                          p, L.part, unsm ? p.beta : p.expElnbeta, !freeze))));
+        else
         LDA_TILE_DISPATCH(p.K, p.V, p.cnt != nullptr, (k_lda_estep_t32<KP, NWT, DENSE><<<L.grid_t32, nthr, L.smem_t32, h->stream>>>(
                                                           p, L.part, unsm ? p.beta : p.expElnbeta, !freeze)));
         nparts = L.grid_t32;
@@ -275,6 +292,9 @@ static int lda_iterate_async(mmsig_handle *h, uint32_t flags) {
     if (L.t32) {
         LaunchScope ls(h, "k_lda_ll_tile");
         const int nthr = 32 * ((p.V + 31) / 32);
+        if (h->precision)
+            THETA_DISPATCH(p.K, TILE_DISPATCH_NW(p.V, (k_lda_ll_f32<KP, NWT><<<L.grid_llt, nthr, L.smem_llt, h->stream>>>(p, L.part_ll))));
+        else
         LDA_TILE_DISPATCH(p.K, p.V, p.cnt != nullptr, (k_lda_ll_tile<KP, NWT, DENSE><<<L.grid_llt, nthr, L.smem_llt, h->stream>>>(p, L.part_ll)));
     } else {
         LaunchScope ls(h, "k_lda_ll");

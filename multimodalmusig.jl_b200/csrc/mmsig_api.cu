@@ -24,6 +24,7 @@
 #include "elbo_kernels.cuh"
 #include "lda_kernels.cuh"
 #include "lda_tile.cuh"
+#include "tile_f32.cuh"
 #include "ingest_kernels.cuh"
 
 using namespace mmsig;
@@ -161,6 +162,7 @@ struct mmsig_handle {
     bool own_stream = false;
     std::string err;
     int stop_rule = 0;
+    int precision = 0;                                 // MMSIG_PRECISION_*: 1 = the tile passes in float (tile_f32.cuh)
     bool profile = false;
     int numSM = 0;
     size_t smem_optin = 0;
@@ -325,6 +327,8 @@ extern "C" int32_t mmsig_create(const mmsig_config *cfg, mmsig_handle **out) {
         return fail(nullptr, MMSIG_ENODEV, std::string("no CUDA device (there is no CPU fallback): ") +
                                                (e != cudaSuccess ? cudaGetErrorString(e) : "device count 0"));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, MMSIG_EINVAL, "mmsig_create: bad device ordinal");
+    if (cfg->precision != MMSIG_PRECISION_FP64 && cfg->precision != MMSIG_PRECISION_FP32)
+        return fail(nullptr, MMSIG_EINVAL, "mmsig_create: precision must be MMSIG_PRECISION_FP64 or MMSIG_PRECISION_FP32");
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess) return fail(nullptr, MMSIG_ECUDA, "cudaGetDeviceProperties failed");
     if (prop.major < 10)
@@ -332,6 +336,7 @@ extern "C" int32_t mmsig_create(const mmsig_config *cfg, mmsig_handle **out) {
     h = new mmsig_handle();
     h->device = cfg->device;
     h->stop_rule = cfg->stop_rule == MMSIG_STOP_NLOPT26 ? 1 : 0;
+    h->precision = cfg->precision == MMSIG_PRECISION_FP32 ? 1 : 0;
     h->profile = cfg->profile != 0;
     h->numSM = prop.multiProcessorCount;
     h->smem_optin = prop.sharedMemPerBlockOptin;
@@ -535,10 +540,11 @@ static int check_rowptr(mmsig_handle *h, const int64_t *rowptr, long long D) {
 }
 // (re)allocate the device side of one modality's counts when its shape changed
 // does a modality of this shape keep dense count tiles?  MMSIG_TILES=csr | dense overrides the density rule (A/B)
-static bool want_dense_tiles(long long D, long long nnz, int V) {
+static bool want_dense_tiles(const mmsig_handle *h, long long D, long long nnz, int V) {
     const char *e = getenv("MMSIG_TILES");
-    if (e && !strcmp(e, "csr")) return false;
     if (V < 1 || V > 1024) return false;
+    if (h->precision) return true;                  // the FP32 kernels read dense tiles only
+    if (e && !strcmp(e, "csr")) return false;
     if (e && !strcmp(e, "dense")) return true;
     return (double)nnz >= kDenseFrac * (double)D * (double)V;
 }
@@ -552,7 +558,7 @@ static int ensure_countbuf(mmsig_handle *h, std::vector<void *> &pool, CountBuf 
     if ((rc = dev_alloc(h, pool, &cb.count, nnz))) return rc;
     if ((rc = dev_alloc(h, pool, &cb.flags, (size_t)4))) return rc;
     cb.cnt = nullptr;
-    if (V > 0 && want_dense_tiles(D, nnz, V)) {
+    if (V > 0 && want_dense_tiles(h, D, nnz, V)) {
         const size_t cells = (size_t)((D + 31) / 32) * 32 * V;
         if ((rc = dev_alloc(h, pool, &cb.cnt, cells))) return rc;
         CU(cudaMemsetAsync(cb.cnt, 0, cells * sizeof(int), h->stream));      // the padding rows of the last tile stay zero
@@ -632,6 +638,21 @@ static int pick_tile_plan(mmsig_handle *h, F kernel, int KP, bool ereg, bool den
     int nb = 0;
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NW * 32, smem));
     if (nb < 1) return fail(h, MMSIG_ELIMIT, "theta tile kernel does not fit on an SM for this K, V");
+    *smem_out = smem;
+    const long long ntiles = (D + TILE_S - 1) / TILE_S;
+    *grid_out = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * nb, ntiles));
+    return 0;
+}
+
+// launch plan of an FP32 tile kernel (tile_f32.cuh): one thread per term, tiles of TILE_S samples
+template <typename F>
+static int pick_f32_plan(mmsig_handle *h, F kernel, size_t smem, int V, long long D, int *grid_out, size_t *smem_out) {
+    const int NW = (V + 31) / 32;
+    if (smem > h->smem_optin) return fail(h, MMSIG_ELIMIT, "V too large for the FP32 tile kernels (shared memory)");
+    CU(allow_max_smem(h, kernel));
+    int nb = 0;
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kernel, NW * 32, smem));
+    if (nb < 1) return fail(h, MMSIG_ELIMIT, "FP32 tile kernel does not fit on an SM for this K, V");
     *smem_out = smem;
     const long long ntiles = (D + TILE_S - 1) / TILE_S;
     *grid_out = (int)std::max<long long>(1, std::min<long long>((long long)h->numSM * nb, ntiles));
@@ -799,12 +820,21 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
         const int KV = K[m] * V[m];
         if (V[m] > 1024) return fail(h, MMSIG_ELIMIT, "V[m] <= 1024 supported");
         const bool dn = mm.cb[m].cnt != nullptr;
-        TILE_DISPATCH_D(K[m], V[m], dn, rc = pick_tile_plan(h, k_theta_tile<KP, EREG, NWT, DENSE>, KP, EREG, DENSE, V[m], D, &mm.grid_theta[m],
-                                                            &mm.smem_theta[m]));
-        if (rc) return rc;
+        if (h->precision) {
+            TILE_DISPATCH(K[m], V[m], rc = pick_f32_plan(h, k_theta_tile_f32<KP, NWT>, f32_theta_smem(KP, V[m]), V[m], D, &mm.grid_theta[m],
+                                                         &mm.smem_theta[m]));
+            if (rc) return rc;
+            TILE_DISPATCH(K[m], V[m], rc = pick_f32_plan(h, k_loglik_tile_f32<KP, NWT>, f32_ll_smem(KP, V[m]), V[m], D, &mm.grid_ll[m],
+                                                         &mm.smem_ll[m]));
+            if (rc) return rc;
+        } else {
+            TILE_DISPATCH_D(K[m], V[m], dn, rc = pick_tile_plan(h, k_theta_tile<KP, EREG, NWT, DENSE>, KP, EREG, DENSE, V[m], D, &mm.grid_theta[m],
+                                                                &mm.smem_theta[m]));
+            if (rc) return rc;
+            TILE_DISPATCH_D(K[m], V[m], dn, rc = pick_ll_plan(h, k_loglik_tile<KP, EREG, NWT, DENSE>, KP, EREG, DENSE, V[m], D, &mm.grid_ll[m], &mm.smem_ll[m]));
+            if (rc) return rc;
+        }
         mm.W_theta[m] = TILE_S;
-        TILE_DISPATCH_D(K[m], V[m], dn, rc = pick_ll_plan(h, k_loglik_tile<KP, EREG, NWT, DENSE>, KP, EREG, DENSE, V[m], D, &mm.grid_ll[m], &mm.smem_ll[m]));
-        if (rc) return rc;
         if ((rc = dev_alloc(h, h->allocs_mm, &mm.part_theta[m], (size_t)mm.grid_theta[m] * KV))) return rc;
         CU(cudaMemsetAsync(mm.part_theta[m], 0, (size_t)mm.grid_theta[m] * KV * sizeof(double2), h->stream));
     }
@@ -1111,6 +1141,10 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
     for (int m = 0; m < q.M; ++m) {
         LaunchScope ls(h, "k_theta_tile");
         const int nthr = 32 * ((q.V[m] + 31) / 32);
+        if (h->precision)
+            TILE_DISPATCH(q.K[m], q.V[m], (k_theta_tile_f32<KP, NWT><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
+                                              q, m, mm.part_theta[m], unsm, !freeze_topics)));
+        else
         TILE_DISPATCH_D(q.K[m], q.V[m], q.cnt[m] != nullptr, (k_theta_tile<KP, EREG, NWT, DENSE><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
                                           q, m, mm.part_theta[m], unsm, !freeze_topics)));
     }
@@ -1190,6 +1224,10 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     for (int m = 0; m < p.M; ++m) {
         LaunchScope ls(h, "k_loglik_tile");
         const int nthr = 32 * ((p.V[m] + 31) / 32);
+        if (h->precision)
+            TILE_DISPATCH(p.K[m], p.V[m], (k_loglik_tile_f32<KP, NWT><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
+                                              p, m, mm.part_post + p.MK * p.MK + m, P2)));
+        else
         TILE_DISPATCH_D(p.K[m], p.V[m], p.cnt[m] != nullptr, (k_loglik_tile<KP, EREG, NWT, DENSE><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
                                           p, m, mm.part_post + p.MK * p.MK + m, P2)));
     }
@@ -1878,7 +1916,7 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
             snaps[i].copy = mm.snap[i];
         }
     std::vector<double> hist((size_t)maxiter * p.M);
-    std::vector<double> alpha = mm.alpha_host, alphaf = mm.alphaf_host;
+    std::vector<double> alpha = mm.alpha_host, alphaf = mm.alphaf_host, best_alpha = alpha, best_alphaf = alphaf;
     HostTrace trace;
     trace.mark("restarts: snapshot buffers");
     int best_r = -1;
@@ -1903,13 +1941,22 @@ extern "C" int32_t mmsig_mmctm_restarts(mmsig_handle *h, int32_t R, const double
         if (best_r < 0 || e > best_e || best_e != best_e) {           // arg-max ELBO, first wins ties
             best_r = r;
             best_e = e;
+            best_alpha = mm.alpha_host;                               // autoα: every restart re-optimises α from the caller's
+            best_alphaf = mm.alphaf_host;
             if (R > 1)
                 for (auto &s : snaps)
                     cudaMemcpyAsync(s.copy, *s.live, s.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
         }
     }
-    if (!rc && R > 1 && best_r != R - 1)
+    if (!rc && R > 1 && best_r != R - 1) {
         for (auto &s : snaps) cudaMemcpyAsync(*s.live, s.copy, s.n * sizeof(double), cudaMemcpyDeviceToDevice, h->stream);
+        // ... and the best restart's α with its tables (mmsig_mmctm_get_alpha / _elbo / _iterate afterwards)
+        mm.alpha_host = best_alpha;
+        mm.alphaf_host = best_alphaf;
+        if (!best_alpha.empty()) cudaMemcpyAsync(p.alpha, mm.alpha_host.data(), std::min<size_t>(best_alpha.size(), p.M) * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+        if (p.factored && p.alphaf && !best_alphaf.empty())
+            cudaMemcpyAsync(p.alphaf, mm.alphaf_host.data(), best_alphaf.size() * sizeof(double), cudaMemcpyHostToDevice, h->stream);
+    }
     cudaStreamSynchronize(h->stream);
     trace.mark("restarts: best state restored");
     if (rc) return rc;

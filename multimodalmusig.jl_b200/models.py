@@ -24,7 +24,7 @@ class MMCTM:
 
     def __init__(self, K, alpha, counts, V=None, gamma0=None, rng=None, device=0,
                  stop_rule=capi.STOP_NLOPT27, profile=False, comm=None, D_total=None, dense=None,
-                 dense_layout=capi.DENSE_TERM_MAJOR):
+                 dense_layout=capi.DENSE_TERM_MAJOR, precision=capi.PRECISION_FP64):
         """counts: CSR triples per modality (format_counts_mmctm); or counts=None and dense = list of
         dense integer matrices ((V_m, D) term-major as the TSV files, or (D, V_m) with
         dense_layout=DENSE_SAMPLE_MAJOR), turned into CSR on the GPU (mmsig_mmctm_set_data_dense)."""
@@ -51,7 +51,7 @@ class MMCTM:
         if gamma0 is None:                                                  # init=:random, :59-63
             rng = np.random.default_rng() if rng is None else rng
             gamma0 = rng.integers(1, 101, size=self.G).astype(np.float64)
-        self.h = capi.Handle(device=device, stop_rule=stop_rule, profile=profile)
+        self.h = capi.Handle(device=device, stop_rule=stop_rule, profile=profile, precision=precision)   # "fp32": the optional fast mode
         if comm is not None:
             uid, rank, nranks = comm
             self.h.comm_init(uid, rank, nranks)
@@ -146,11 +146,18 @@ class MMCTM:
         new.ll_history = new._loop(flags, maxiter, tol, verbose)
         return new
 
-    def predict_modality_eta(self, counts_obs, m, maxiter=100, device=0):
+    def predict_modality_eta(self, counts_obs, m, maxiter=100, device=0, esteps=None):
         """predict_modality_η(Xobs, m, model; maxiter=100) (src/MMCTM.jl:588-634): fit λ on the observed
         modalities with everything else frozen, then η_u = μ_u + Σ_uo invΣ[o,o] (λ - μ_o).
-        The reference's stopping test reads `props` it never computes (undefined values, :609-618),
-        so this runs exactly `maxiter` E-steps."""
+
+        How many E-steps: the reference's stopping test (:609-618) reads `props` it never computes -- uninitialised
+        but CONSTANT memory (:47-50) -- so its log-likelihood is constant and `length(ll) > 10 && check_convergence`
+        fires at iteration 11 whenever that garbage is finite (the usual case), and never when it is NaN / Inf.
+        LD_MMA stops early (xtol 1e-4), so λ after 11 sweeps differs from λ after 100.  `esteps` states the count:
+        default min(maxiter, 11), the reference's usual behaviour; esteps=maxiter is its behaviour when the
+        uninitialised values are not finite."""
+        if esteps is None:
+            esteps = min(maxiter, 11)
         s = self.state(props=False)
         obsM = [i for i in range(self.M) if i != m]
         ko = np.cumsum([0] + self.K)
@@ -161,7 +168,7 @@ class MMCTM:
         om = MMCTM([self.K[i] for i in obsM], self.alpha[obsM], counts_obs, V=[self.V[i] for i in obsM],
                    gamma0=g_obs, device=device)
         om.set_state(g_obs, mu=s["mu"][ob], Sigma=s["Sigma"][np.ix_(ob, ob)], invSigma=s["invSigma"][np.ix_(ob, ob)])
-        for _ in range(maxiter):
+        for _ in range(esteps):
             om.iterate(flags=capi.FLAG_FREEZE_TOPICS | capi.FLAG_FREEZE_MU)
         lam = om.lam
         om.close()
@@ -393,10 +400,12 @@ class IMMCTM(MMCTM):
         a = np.cumsum([0] + self.I)
         return t, a
 
-    def predict_modality_eta(self, counts_obs, m, maxiter=100, device=0):
+    def predict_modality_eta(self, counts_obs, m, maxiter=100, device=0, esteps=None):
         """predict_modality_η(Xobs, m, model::IMMCTM; maxiter=100) (src/IMMCTM.jl:581-627): fit λ on the
         observed modalities with their feature tables and the Gaussian prior frozen, then
-        η_u = μ_u + Σ_uo invΣ[o,o] (λ - μ_o).  Runs exactly `maxiter` E-steps, like the MMCTM's."""
+        η_u = μ_u + Σ_uo invΣ[o,o] (λ - μ_o).  `esteps` as for the MMCTM's (default min(maxiter, 11))."""
+        if esteps is None:
+            esteps = min(maxiter, 11)
         s, t = self.state(props=False), self.tables()
         obsM = [i for i in range(self.M) if i != m]
         ko = np.cumsum([0] + self.K)
@@ -407,7 +416,7 @@ class IMMCTM(MMCTM):
         om = IMMCTM([self.K[i] for i in obsM], [t["alphaf"][asl[i]:asl[i + 1]] for i in obsM],
                     [self.features[i] for i in obsM], counts_obs, gammaf0=g_obs, device=device)
         om.set_state(g_obs, mu=s["mu"][ob], Sigma=s["Sigma"][np.ix_(ob, ob)], invSigma=s["invSigma"][np.ix_(ob, ob)])
-        for _ in range(maxiter):
+        for _ in range(esteps):
             om.iterate(flags=capi.FLAG_FREEZE_TOPICS | capi.FLAG_FREEZE_MU)
         lam = om.lam
         om.close()
@@ -424,7 +433,7 @@ class LDA:
     """src/LDA.jl:1-67.  counts: (rowptr, term0, count)."""
 
     def __init__(self, K, alpha, eta, counts, V=None, lambda0=None, rng=None, device=0, profile=False,
-                 comm=None, D_total=None, dense=None, dense_layout=capi.DENSE_TERM_MAJOR):
+                 comm=None, D_total=None, dense=None, dense_layout=capi.DENSE_TERM_MAJOR, precision=capi.PRECISION_FP64):
         """counts: CSR triple (format_counts_lda); or counts=None and dense = the (V, D) term-major
         (or (D, V) sample-major) integer matrix, turned into CSR on the GPU (mmsig_lda_set_data_dense)."""
         self.K = int(K)
@@ -443,7 +452,7 @@ class LDA:
         if lambda0 is None:                                                       # src/LDA.jl:36
             rng = np.random.default_rng() if rng is None else rng
             lambda0 = rng.integers(1, 101, size=self.K * self.V).astype(np.float64)
-        self.h = capi.Handle(device=device, profile=profile)
+        self.h = capi.Handle(device=device, profile=profile, precision=precision)
         if comm is not None:
             uid, rank, nranks = comm
             self.h.comm_init(uid, rank, nranks)
@@ -638,7 +647,8 @@ class MMCTMGroup:
     Same arrays as MMCTM for the whole corpus; the library shards the samples (contiguous, balanced by
     nonzeros) and every device ends each iteration with bit-identical tables."""
 
-    def __init__(self, K, alpha, counts, devices, V=None, gamma0=None, rng=None, stop_rule=capi.STOP_NLOPT27, profile=False):
+    def __init__(self, K, alpha, counts, devices, V=None, gamma0=None, rng=None, stop_rule=capi.STOP_NLOPT27, profile=False,
+                 precision=capi.PRECISION_FP64):
         self.K = [int(k) for k in K]
         self.M = len(self.K)
         self.alpha = np.asarray(alpha, dtype=np.float64).copy()
@@ -649,7 +659,7 @@ class MMCTMGroup:
         if gamma0 is None:
             rng = np.random.default_rng() if rng is None else rng
             gamma0 = rng.integers(1, 101, size=self.G).astype(np.float64)
-        self.grp = capi.Group(devices, stop_rule=stop_rule, profile=profile)
+        self.grp = capi.Group(devices, stop_rule=stop_rule, profile=profile, precision=precision)
         self._csr(counts)
         lib = self.grp.lib
         self.grp.check(lib.mmsig_group_mmctm_set_data(self.grp.g, self.D, self.M, *self._kv, *self._ptrs))
