@@ -172,8 +172,9 @@ end
 
 # fit!(model; ...) (src/MMCTM.jl:457-494).  Extra keywords: `device` (one GPU), or `devices=0:7` (the samples of this
 # fit sharded over several GPUs of this process, bit-identical results), `materialize_θ=true` to fill model.θ.
+# `precision=:fp32` selects the optional FP32 mode of the tile passes (include/mmsig.h MMSIG_PRECISION_FP32; default Float64).
 function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, updateΣ=true,
-              device=0, devices=nothing, stop_rule=0, materialize_θ=false)
+              device=0, devices=nothing, stop_rule=0, materialize_θ=false, precision=:fp64)
     D, M, MK = model.D, model.M, sum(model.K)
     rowptr, term, count = flatten_counts(model.X, M)
     K32, V32 = Int32.(model.K), Int32.(model.V)
@@ -181,8 +182,9 @@ function fit!(model::MMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, u
     γ = flat_tables(model.γ)
     Σ, invΣ = collect(transpose(model.Σ)), collect(transpose(model.invΣ))               # row-major
     grouped = devices !== nothing && length(devices) > 1
-    h = grouped ? create_group(devices; stop_rule=stop_rule) :
-                  create(device=(devices === nothing ? device : first(devices)), stop_rule=stop_rule)
+    prec = precision == :fp32 ? 1 : 0
+    h = grouped ? create_group(devices; stop_rule=stop_rule, precision=prec) :
+                  create(device=(devices === nothing ? device : first(devices)), stop_rule=stop_rule, precision=prec)
     chk = grouped ? gcheck : check
     ll = Vector{Float64}[]
     try
@@ -519,7 +521,7 @@ function fit!(model::IMMCTM; maxiter=100, tol=1e-4, verbose=true, autoα=false, 
     return ll
 end
 
-function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
+function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0, precision=:fp64)
     D, K, V = model.D, model.K, model.V
     rowptr = zeros(Int64, D + 1)
     for d in 1:D rowptr[d + 1] = rowptr[d] + size(model.X[d], 1) end
@@ -529,7 +531,7 @@ function fit!(model::LDA; maxiter=1000, tol=1e-4, verbose=true, device=0)
         term[r] .= model.X[d][:, 1] .- 1; count[r] .= model.X[d][:, 2]
     end
     λ = Float64.(vec(model.λ))            # V x K column-major == [k][v]
-    h = create(device=device)
+    h = create(device=device, precision=(precision == :fp32 ? 1 : 0))
     ll = Float64[]
     try
         check(h, ccall((:mmsig_lda_set_data, LIB), Int32,
