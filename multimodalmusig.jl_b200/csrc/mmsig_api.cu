@@ -155,6 +155,11 @@ struct mmsig_handle {
     int device = 0;
     cudaStream_t stream = nullptr;
     cudaStream_t s_in = nullptr, s_out = nullptr;      // copy streams of mmsig_mmctm_fit_host
+    // second half of the M-step (moments, log-likelihood pass, their exchange, Σ / invΣ) of iteration t on a side stream,
+    // concurrent with the θ pass of iteration t + 1 (which needs none of its results) inside the sync-free loop of fit
+    cudaStream_t s_aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    bool aux_pending = false;                          // the solve of the next E-step has to wait for ev_join
     long long *allsum_buf = nullptr;                   // scratch of allsum_ll (multi-rank totals)
     double *ll_pinned = nullptr;                       // page-locked landing zone of the log-likelihoods of the sync-free iterations
     int2 *fmt_rec = nullptr;                           // records of the last mmsig_format_counts
@@ -281,11 +286,11 @@ __global__ void k_group_push(const double2 *__restrict__ src, size_t n, PeerSlot
 
 static int group_gather(mmsig_handle *h, const double2 *rank_buf, size_t n, const double2 **out);
 
-static int gather(mmsig_handle *h, const double2 *rank_buf, double2 *gath_buf, size_t n, const double2 **out) {
+static int gather(mmsig_handle *h, const double2 *rank_buf, double2 *gath_buf, size_t n, const double2 **out, cudaStream_t st = nullptr) {
     if (h->nranks == 1) { *out = rank_buf; return 0; }
     if (h->grp) return group_gather(h, rank_buf, n, out);
     LaunchScope ls(h, "ncclAllGather");
-    int rc = g_nccl.AllGather(rank_buf, gath_buf, n * 2, kNcclFloat64, h->comm, h->stream);
+    int rc = g_nccl.AllGather(rank_buf, gath_buf, n * 2, kNcclFloat64, h->comm, st ? st : h->stream);
     if (rc != 0)
         return fail(h, MMSIG_ENCCL, std::string("ncclAllGather: ") + (g_nccl.GetErrorString ? g_nccl.GetErrorString(rc) : "?"));
     *out = gath_buf;
@@ -370,6 +375,9 @@ extern "C" int32_t mmsig_destroy(mmsig_handle *h) {
     if (h->ll_pinned) cudaFreeHost(h->ll_pinned);
     if (h->s_in) cudaStreamDestroy(h->s_in);
     if (h->s_out) cudaStreamDestroy(h->s_out);
+    if (h->s_aux) cudaStreamDestroy(h->s_aux);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return 0;
 }
@@ -1148,6 +1156,10 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         TILE_DISPATCH_D(q.K[m], q.V[m], q.cnt[m] != nullptr, (k_theta_tile<KP, EREG, NWT, DENSE><<<cap(mm.grid_theta[m], TILE_S), nthr, mm.smem_theta[m], h->stream>>>(
                                           q, m, mm.part_theta[m], unsm, !freeze_topics)));
     }
+    if (h->aux_pending) {                  // Σ, invΣ of the previous iteration come from the side stream (mmctm_mstep_launch)
+        cudaStreamWaitEvent(h->stream, h->ev_join, 0);
+        h->aux_pending = false;
+    }
     cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);      // the solve kernels draw samples from this counter
     {
         LaunchScope ls(h, "k_solve");
@@ -1166,19 +1178,19 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
     }
 }
 
-static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags);
+static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags, bool overlap = false);
 
-static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags) {
+static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags, bool overlap = false) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     mm.last_unsmoothed = (flags & MMSIG_FLAG_UNSMOOTHED) != 0;
     std::swap(p.lam, p.lam_prev);              // lam_prev = λ of the previous iteration (what θ uses)
     mmctm_estep_launch(h, p, flags);
-    return mmctm_mstep_launch(h, flags);
+    return mmctm_mstep_launch(h, flags, overlap);
 }
 
 // everything after the per-sample E-step: combine, exchange, μ, γ, Elnϕ, ϕ, [α], [Σ, invΣ], props / LL
-static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
+static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags, bool overlap) {
     MmctmHost &mm = h->mm;
     MmctmDev &p = mm.p;
     const int do_sigma = (flags & MMSIG_FLAG_UPDATE_SIGMA) ? 1 : 0;
@@ -1210,25 +1222,41 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
     }
     if ((flags & MMSIG_FLAG_AUTO_ALPHA) && !freeze_topics)       // src/MMCTM.jl:472-474, after update_γ!
         if ((rc = mmctm_update_alpha(h))) return rc;
+    // From here on nothing feeds the next θ pass (it reads λ and the Elnϕ that k_mstep1 just wrote): inside fit's
+    // sync-free loop this half runs on a side stream, so that its serial chain combine -> exchange -> LU (0.15 ms that
+    // every rank repeats) hides behind the next iteration's θ pass; the next solve waits for ev_join.  Not with
+    // per-kernel event timing (events are recorded on the main stream) and not inside a single-process group (its
+    // exchange protocol is ordered on the main stream).
+    cudaStream_t st = h->stream;
+    if (overlap && !h->profile && !h->grp && !(flags & MMSIG_FLAG_AUTO_ALPHA)) {
+        if (!h->s_aux) {
+            CU(cudaStreamCreateWithFlags(&h->s_aux, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+        }
+        CU(cudaEventRecord(h->ev_fork, h->stream));
+        CU(cudaStreamWaitEvent(h->s_aux, h->ev_fork, 0));
+        st = h->s_aux;
+    }
     if (do_sigma) {
         if (mm.wide) {
             for (int r0 = 0; r0 < p.MK; r0 += 16) {
                 LaunchScope ls(h, "k_moments");
-                k_moments_wide<<<mm.grid_mom, 256, 0, h->stream>>>(p, mm.part_mom, r0);
+                k_moments_wide<<<mm.grid_mom, 256, 0, st>>>(p, mm.part_mom, r0);
             }
         } else {
             LaunchScope ls(h, "k_moments");
-            MK_DISPATCH(p.MK, (k_moments<MKP><<<mm.grid_mom, 256, mm.smem_post, h->stream>>>(p, mm.part_mom)));
+            MK_DISPATCH(p.MK, (k_moments<MKP><<<mm.grid_mom, 256, mm.smem_post, st>>>(p, mm.part_mom)));
         }
     }
     for (int m = 0; m < p.M; ++m) {
         LaunchScope ls(h, "k_loglik_tile");
         const int nthr = 32 * ((p.V[m] + 31) / 32);
         if (h->precision)
-            TILE_DISPATCH(p.K[m], p.V[m], (k_loglik_tile_f32<KP, NWT><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
+            TILE_DISPATCH(p.K[m], p.V[m], (k_loglik_tile_f32<KP, NWT><<<mm.grid_ll[m], nthr, mm.smem_ll[m], st>>>(
                                               p, m, mm.part_post + p.MK * p.MK + m, P2)));
         else
-        TILE_DISPATCH_D(p.K[m], p.V[m], p.cnt[m] != nullptr, (k_loglik_tile<KP, EREG, NWT, DENSE><<<mm.grid_ll[m], nthr, mm.smem_ll[m], h->stream>>>(
+        TILE_DISPATCH_D(p.K[m], p.V[m], p.cnt[m] != nullptr, (k_loglik_tile<KP, EREG, NWT, DENSE><<<mm.grid_ll[m], nthr, mm.smem_ll[m], st>>>(
                                           p, m, mm.part_post + p.MK * p.MK + m, P2)));
     }
     {
@@ -1248,14 +1276,18 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags) {
             s.stride[1 + m] = P2;
         }
         LaunchScope ls(h, "k_combine");
-        k_combine<<<(P2 + 7) / 8, 256, 0, h->stream>>>(s, mm.rank_p2);
+        k_combine<<<(P2 + 7) / 8, 256, 0, st>>>(s, mm.rank_p2);
     }
     const double2 *g2 = nullptr;
-    if ((rc = gather(h, mm.rank_p2, mm.gath_p2, P2, &g2))) return rc;
+    if ((rc = gather(h, mm.rank_p2, mm.gath_p2, P2, &g2, st))) return rc;
     {
         LaunchScope ls(h, "k_mstep2");
         const size_t lus = (size_t)2 * p.MK * p.MK * sizeof(double) + p.MK * sizeof(int);
-        k_mstep2<<<1, 256, lus, h->stream>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
+        k_mstep2<<<1, 256, lus, st>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
+    }
+    if (st != h->stream) {
+        CU(cudaEventRecord(h->ev_join, st));
+        h->aux_pending = true;
     }
     mm.estep_done = true;
     return 0;
@@ -1304,12 +1336,15 @@ static int mmctm_run_iterations(mmsig_handle *h, int first, int32_t maxiter, dou
         if (nfree > 1) {
             int *status = reinterpret_cast<int *>(h->ll_pinned + (size_t)12 * MAXM);
             for (int i = 0; i < nfree; ++i) {
-                int rc = mmctm_iterate_async(h, flags);
+                int rc = mmctm_iterate_async(h, flags, true);
                 if (rc) return rc;
-                CU(cudaMemcpyAsync(h->ll_pinned + (size_t)i * MAXM, mm.d_ll, M * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                CU(cudaMemcpyAsync(status + i, mm.d_status, sizeof(int), cudaMemcpyDeviceToHost, h->stream));
+                cudaStream_t cs = h->aux_pending ? h->s_aux : h->stream;       // the stream that ran k_mstep2
+                CU(cudaMemcpyAsync(h->ll_pinned + (size_t)i * MAXM, mm.d_ll, M * sizeof(double), cudaMemcpyDeviceToHost, cs));
+                CU(cudaMemcpyAsync(status + i, mm.d_status, sizeof(int), cudaMemcpyDeviceToHost, cs));
             }
             CU(cudaStreamSynchronize(h->stream));
+            if (h->s_aux) CU(cudaStreamSynchronize(h->s_aux));
+            h->aux_pending = false;
             CU(cudaGetLastError());
             for (int i = 0; i < nfree; ++i) {
                 if (status[i]) return fail(h, MMSIG_EINVAL, "Sigma is singular (inv failed)");
