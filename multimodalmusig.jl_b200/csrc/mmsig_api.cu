@@ -1167,6 +1167,8 @@ static void mmctm_estep_launch(mmsig_handle *h, const MmctmDev &q, uint32_t flag
         else if (mm.solve_lean) {
             // ν for every sample, then λ (which reads the new ν and the ζ the first kernel stored)
             const int gs = cap(mm.grid_solve, 4 * (32 / mm.solve_lean));
+            // (Handing the samples out longest-first -- a counting sort by the previous iteration's evaluation counts -- was
+            // measured in round 2 and bought nothing: 2.703 against 2.707 ms at D = 125000, profiles/notes/r02k_order_ab.txt.)
             LEAN_DISPATCH(mm.solve_lean, q.MK, PH_NU, (k_solve_lean<LG, LC, LP, LF><<<gs, 128, lean_smem_doubles<LG, LC, LP>() * sizeof(double), h->stream>>>(q, mm.part_solve)));
             cudaMemsetAsync(q.work, 0, sizeof(unsigned long long), h->stream);
             h->launches++;

@@ -331,6 +331,44 @@ def test_solver_layouts_are_bit_identical(monkeypatch, variant):
     g.close()
 
 
+@pytest.mark.parametrize("tiles", ["csr", "dense"])
+def test_count_tile_formats_are_bit_identical(monkeypatch, tiles):
+    """MMSIG_TILES selects what the tile kernels read: the CSR records (clear + scatter per tile) or the dense count
+    tiles staged by cp.async.bulk + mbarrier (csrc/tile_stage.cuh; the default above 40 % density).  Same counts, same
+    arithmetic: both are bit-identical to the oracle, on dense and on sparse data, with a ragged last tile (D not a
+    multiple of 32), empty rows, one-warp (V <= 32) and multi-warp blocks, and through the chunked fit_host."""
+    monkeypatch.setenv("MMSIG_TILES", tiles)
+    for K, V, D, sparsify in (([10, 8, 6], [96, 32, 83], 715, 0.0), ([7, 7], [96, 48], 333, 0.8), ([3, 2], [10, 6], 67, 0.0),
+                              ([12, 5], [130, 20], 97, 0.5)):
+        counts = small_synth(D, K, V, empty_frac=0.05)
+        if sparsify:                                   # drop most cells: the density rule alone would pick CSR here
+            rng = np.random.default_rng(3)
+            out = []
+            for (rp, t, c), v in zip(counts, V):
+                dense = np.zeros((D, v), dtype=np.int64)
+                for d in range(D):
+                    dense[d, t[rp[d]:rp[d + 1]]] = c[rp[d]:rp[d + 1]]
+                dense[rng.random(dense.shape) < sparsify] = 0
+                out.append(mmsig.counts.make_count_csr(dense.T))
+            counts = out
+        g0 = mmsig.synth.init_gamma(K, V)
+        o, g = _pair(K, [0.1] * len(K), V, counts, g0)
+        for _ in range(3):
+            ll_o, ll_g = o.iterate(), g.iterate()
+            _check_iteration(o, g, ll_o, ll_g)
+        g.close()
+    monkeypatch.setenv("MMSIG_PIPE_CHUNKS", "3")
+    K, V, D = [10, 8, 6], [96, 32, 83], 1000
+    counts = small_synth(D, K, V, empty_frac=0.05)
+    g0 = mmsig.synth.init_gamma(K, V)
+    o = oracle_mmctm(K, [0.1] * 3, V, counts, g0)
+    llo = o.fit(maxiter=3, tol=1e-4)
+    g = mmsig.MMCTM(K, [0.1] * 3, counts, V=V, gamma0=g0)
+    hist, s = g.fit_host(counts, g0, maxiter=3)
+    assert np.array_equal(hist, np.asarray(llo)) and np.array_equal(s["lam"], o.lam) and np.array_equal(s["phi"], o.phi)
+    g.close()
+
+
 @pytest.mark.parametrize("maxiter,chunks", [(1, 1), (1, 3), (4, 3), (14, 5)])
 def test_fit_host_equals_the_four_calls(monkeypatch, maxiter, chunks):
     """mmsig_mmctm_fit_host (transfers pipelined behind the E-step, chunked launches accumulating
