@@ -89,7 +89,42 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_estep_t32(LdaDev p, double2 *p
             prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);    // next tile's records towards L2
         }
         // ---- phase 2: Z, R and the statistics, lane <-> term
-        if (vok) {
+        if (DENSE && vok) {
+            // Dense counts: two samples per trip, no branch on n: eight independent Z chains, two reciprocals and two runs
+            // of K independent fmas interleave (the kernel sat at 29 % of the FP64 pipe with one chain of work per thread)
+#pragma unroll 1
+            for (int t = 0; t < LDA_TS; t += 2) {
+                const int n0 = nt[t * V + v], n1 = nt[(t + 1) * V + v];
+                const double2 *a2 = reinterpret_cast<const double2 *>(et + t * KP), *b2 = a2 + KP / 2;
+                double z0 = 0.0, z1 = 0.0, z2 = 0.0, z3 = 0.0, y0 = 0.0, y1 = 0.0, y2 = 0.0, y3 = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 4) {
+                    const double2 xa = a2[k / 2], xb = a2[k / 2 + 1], ya = b2[k / 2], yb = b2[k / 2 + 1];
+                    z0 = fma(xa.x, Ereg[k], z0);
+                    y0 = fma(ya.x, Ereg[k], y0);
+                    z1 = fma(xa.y, Ereg[k + 1], z1);
+                    y1 = fma(ya.y, Ereg[k + 1], y1);
+                    z2 = fma(xb.x, Ereg[k + 2], z2);
+                    y2 = fma(yb.x, Ereg[k + 2], y2);
+                    z3 = fma(xb.y, Ereg[k + 3], z3);
+                    y3 = fma(yb.y, Ereg[k + 3], y3);
+                }
+                const double Z0 = (z0 + z1) + (z2 + z3), Z1 = (y0 + y1) + (y2 + y3);
+                const double r0 = n0 > 0 ? (double)n0 * (1.0 / Z0) : 0.0, r1 = n1 > 0 ? (double)n1 * (1.0 / Z1) : 0.0;
+                rt[t * VP + v] = r0;
+                rt[(t + 1) * VP + v] = r1;
+                if (want_stats) {
+#pragma unroll
+                    for (int k = 0; k < KP; k += 2) {
+                        const double2 x = a2[k / 2], y = b2[k / 2];
+                        acc[k] = fma(x.x, r0, acc[k]);
+                        acc[k + 1] = fma(x.y, r0, acc[k + 1]);
+                        acc[k] = fma(y.x, r1, acc[k]);
+                        acc[k + 1] = fma(y.y, r1, acc[k + 1]);
+                    }
+                }
+            }
+        } else if (vok) {
             for (int t = 0; t < LDA_TS; ++t) {
                 const double n = DENSE ? (double)nt[t * V + v] : rt[t * VP + v];
                 if (DENSE && !(n > 0.0)) rt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
@@ -227,7 +262,29 @@ __global__ void __launch_bounds__(32 * NWT) k_lda_ll_tile(LdaDev p, double2 *par
         } else {
             prefetch_records(p.rec, rp[2], rp[3], tid, blockDim.x);
         }
-        if (vok) {
+        if (DENSE && vok) {
+            // Dense counts: four samples per trip, no branch on n (four independent dot-product and logarithm chains)
+#pragma unroll 1
+            for (int t = 0; t < LDA_TS; t += 4) {
+                double dot[4] = {0.0, 0.0, 0.0, 0.0};
+                const double2 *p2 = reinterpret_cast<const double2 *>(pt + t * KP);
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 x = p2[j * (KP / 2) + k / 2];
+                        dot[j] += x.x * Breg[k];
+                        dot[j] += x.y * Breg[k + 1];
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ni = nt[(t + j) * V + v];
+                    const double lg = det_log(dot[j] > 0.0 ? dot[j] : 1.0);
+                    xt[(t + j) * VP + v] = ni > 0 ? (double)ni * lg : 0.0;
+                }
+            }
+        } else if (vok) {
             for (int t = 0; t < LDA_TS; ++t) {
                 const double n = DENSE ? (double)nt[t * V + v] : xt[t * VP + v];
                 if (DENSE && !(n > 0.0)) xt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written

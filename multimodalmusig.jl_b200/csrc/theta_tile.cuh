@@ -112,7 +112,40 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, doub
             prefetch_records(rec, rp[1], rp[2], tid, blockDim.x);
         }
         // ---- phase 2: Z, R and the statistics, lane <-> term
-        if (vok) {
+        if (DENSE && vok) {
+            // Dense counts: two samples per trip and no branch on n (88 % of the cells are nonzero): the two Z chains
+            // (K dependent additions each), the two reciprocals and the two runs of double-double updates are
+            // independent and interleave.  Per cell the same operations in the same order as below; a zero cell adds
+            // an exact + 0.0 to the accumulators (R = 0), so the sums keep their bits.
+#pragma unroll 1
+            for (int t = 0; t < TILE_S; t += 2) {
+                const int n0 = nt[t * V + v], n1 = nt[(t + 1) * V + v];
+                const double2 *a2 = reinterpret_cast<const double2 *>(et + t * KP), *b2 = a2 + KP / 2;
+                double Z0 = 0.0, Z1 = 0.0;
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double2 x = a2[k / 2], y = b2[k / 2];
+                    const double E0 = EREG ? Ereg[k] : Ekv[k * VP + v], E1 = EREG ? Ereg[k + 1] : Ekv[(k + 1) * VP + v];
+                    Z0 += x.x * E0;
+                    Z1 += y.x * E0;
+                    Z0 += x.y * E1;
+                    Z1 += y.y * E1;
+                }
+                const double R0 = n0 > 0 ? (double)n0 * (1.0 / Z0) : 0.0, R1 = n1 > 0 ? (double)n1 * (1.0 / Z1) : 0.0;
+                rt[t * VP + v] = R0;
+                rt[(t + 1) * VP + v] = R1;
+                if (want_stats) {
+#pragma unroll
+                    for (int k = 0; k < KP; k += 2) {
+                        const double2 x = a2[k / 2], y = b2[k / 2];
+                        dd_add(ahi[k], alo[k], x.x * R0);
+                        dd_add(ahi[k + 1], alo[k + 1], x.y * R0);
+                        dd_add(ahi[k], alo[k], y.x * R1);
+                        dd_add(ahi[k + 1], alo[k + 1], y.y * R1);
+                    }
+                }
+            }
+        } else if (vok) {
             for (int t = 0; t < TILE_S; ++t) {
                 const double n = DENSE ? (double)nt[t * V + v] : rt[t * VP + v];
                 if (DENSE && !(n > 0.0)) rt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
@@ -277,7 +310,32 @@ __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, dou
         } else {
             prefetch_records(rec, rp[1], rp[2], tid, blockDim.x);
         }
-        if (vok) {
+        if (DENSE && vok) {
+            // Dense counts: four samples per trip, no branch on n -- four independent chains (K dependent additions, then
+            // the logarithm's 30-odd dependent operations) per thread instead of one.  Per cell the same operations in
+            // the same order as below.
+#pragma unroll 1
+            for (int t = 0; t < TILE_S; t += 4) {
+                double pw[4] = {0.0, 0.0, 0.0, 0.0};
+                const double2 *p2 = reinterpret_cast<const double2 *>(pt + t * KP);
+#pragma unroll
+                for (int k = 0; k < KP; k += 2) {
+                    const double P0 = PREG ? Preg[k] : Pkv[k * VP + v], P1 = PREG ? Preg[k + 1] : Pkv[(k + 1) * VP + v];
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const double2 x = p2[j * (KP / 2) + k / 2];
+                        pw[j] += x.x * P0;
+                        pw[j] += x.y * P1;
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int ni = nt[(t + j) * V + v];
+                    const double lg = det_log(pw[j] > 0.0 ? pw[j] : 1.0);       // a padding sample's row is 0: keep the logarithm in range
+                    xt[(t + j) * VP + v] = ni > 0 ? (double)ni * lg : 0.0;
+                }
+            }
+        } else if (vok) {
             for (int t = 0; t < TILE_S; ++t) {
                 const double n = DENSE ? (double)nt[t * V + v] : xt[t * VP + v];
                 if (DENSE && !(n > 0.0)) xt[t * VP + v] = 0.0;       // the tile is not cleared: every cell is written
