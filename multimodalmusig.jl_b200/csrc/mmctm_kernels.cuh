@@ -43,6 +43,8 @@ struct MmctmDev {
     int stop_rule;
     int accum;                    // != 0: E-step kernels add their block partials to what the slot holds (chunked launches)
     unsigned long long *work;     // sample counter of the solve kernels (zeroed before each launch)
+    int *ctl;                     // [0] != 0: the convergence rule fired in an earlier iteration of the enqueued batch -- every
+                                  // kernel of an iteration returns at once; [1] last iteration k_mstep2 completed
     // IMMCTM (reference src/IMMCTM.jl): topics factorised over features.  factored != 0: Elnphi / phi
     // (K x V) are COMPOSITE tables derived from the feature tables gammaf / Elnphif ([m][k][i][j] flat)
     int factored, T, R;           // T entries, R rows (m, k, i) of the feature tables
@@ -227,6 +229,7 @@ __device__ __forceinline__ double block_sum_seq(double e, int lo, int hi, int MK
 // ------------------------------------------------------------------------------------------
 template <int MKP>
 __global__ void __launch_bounds__(256, SOLVE_MIN_BLOCKS) k_solve(MmctmDev p, double2 *partial) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     __shared__ __align__(16) double dsh_all[8][32];
     __shared__ double2 red[8][2][32];
     __shared__ __align__(16) double ST[32 * SROW_STRIDE];    // invΣ rows, zero padded: ST[j*SROW_STRIDE+i] = invΣ[j][i]
@@ -296,7 +299,8 @@ struct CombineSegs {
     int nparts[MAXM + 2], n[MAXM + 2], dst_off[MAXM + 2];
     int stride[MAXM + 2];        // distance between parts in src (0 = n)
 };
-__global__ void __launch_bounds__(256) k_combine(CombineSegs s, double2 *dst) {
+__global__ void __launch_bounds__(256) k_combine(CombineSegs s, double2 *dst, const int *ctl = nullptr) {
+    if (ctl && ctl[0]) return;
     // one warp per output entry; lanes stride over the parts, then a dd butterfly
     const int t = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), lane = threadIdx.x & 31;
     int base = 0;
@@ -336,6 +340,7 @@ __global__ void __launch_bounds__(256) k_combine(CombineSegs s, double2 *dst) {
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(1024) k_mstep1(MmctmDev p, const double2 *gathered, int nranks, int freeze_topics,
                                                  int freeze_mu, int unsmoothed) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     __shared__ double rowsum[MAXMK], rowdig[MAXMK];
     const int G = p.goff[p.M], MK = p.MK, P1 = G + 2 * MK;
     for (int i = threadIdx.x; i < P1; i += blockDim.x) {
@@ -458,6 +463,7 @@ __global__ void __launch_bounds__(1024) k_icompose(MmctmDev p) {
 // γf_k,i,j = α_i + Σ_{v: f(v,i) = j} Σ n θ_kv (ascending v), Elnϕf, the composite tables, μ.
 __global__ void __launch_bounds__(1024) k_imstep1(MmctmDev p, const double2 *gathered, int nranks, int freeze_topics,
                                                   int freeze_mu) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ double ism[];
     const int G = p.goff[p.M], MK = p.MK, P1 = G + 2 * MK;
     for (int i = threadIdx.x; i < P1; i += blockDim.x) {
@@ -504,6 +510,7 @@ __global__ void __launch_bounds__(1024) k_imstep1(MmctmDev p, const double2 *gat
 // ------------------------------------------------------------------------------------------
 template <int MKP>
 __global__ void __launch_bounds__(256) k_moments(MmctmDev p, double2 *partial) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ double smem[];
     const int MK = p.MK, M = p.M;
     double2 *red = reinterpret_cast<double2 *>(smem);      // 256 double2 = 512 doubles
@@ -626,8 +633,12 @@ __device__ inline bool warp_lu_inverse(int n, double *A, double *B, int *piv, do
 // Σ = exact_round(diag Σ_d ν + Σ_d ΔΔᵀ) / D, invΣ = inv(Σ) (src/MMCTM.jl:204-212); ll_m (:417).
 // (A register-resident, fully unrolled LU -- lane j owning column j -- was tried in round 2: 25 k straight-line SASS
 // instructions at MK = 24 run at instruction-fetch speed, 105 us against 64 us for this loop over shared memory.)
+// iter > 0: iteration `iter` of a fit whose later iterations are already enqueued: the block evaluates the reference's
+// stopping rule (src/MMCTM.jl:485, src/common.jl:48-51: more than 10 entries and max_m |ll_prev - ll| / |ll| < tol, the
+// same IEEE operations as converged_vec on the host) and raises p.ctl[0].  ll_prev: the previous iteration's vector.
 __global__ void __launch_bounds__(256) k_mstep2(MmctmDev p, const double2 *gathered, int nranks, int do_sigma,
-                                                double *ll_out, int *status) {
+                                                double *ll_out, int *status, int iter, double tol, double *ll_prev) {
+    if (p.ctl && p.ctl[0]) return;
     extern __shared__ double lu_smem[];                  // A, B: MK x MK each; piv: MK ints
     const int MK = p.MK, M = p.M, P2 = MK * MK + M;
     double *A = lu_smem, *B = lu_smem + MK * MK;
@@ -655,6 +666,18 @@ __global__ void __launch_bounds__(256) k_mstep2(MmctmDev p, const double2 *gathe
     if (do_sigma && threadIdx.x < 32) {
         const bool ok = warp_lu_inverse(MK, A, B, piv, p.invSigma, nullptr);
         if (threadIdx.x == 0) *status = ok ? 0 : 1;
+    }
+    if (threadIdx.x == 32 && ll_prev) {                  // a warp the inverse does not use
+        double r = 0.0;
+        for (int m = 0; m < M; ++m) {
+            const double v = fabs(ll_prev[m] - ll_out[m]) / fabs(ll_out[m]);
+            if (v > r || v != v) r = v;
+            ll_prev[m] = ll_out[m];
+        }
+        if (p.ctl) {
+            if (iter > 10 && r < tol) p.ctl[0] = 1;
+            if (iter > 0) p.ctl[1] = iter;
+        }
     }
 }
 

@@ -87,6 +87,7 @@ constexpr size_t lean_smem_doubles() {
 // FULL: sum(K) == G * CPL, no padding coordinate -- every "active" mask is compile-time true
 template <int G, int CPL, int PH, bool FULL>
 __global__ void __launch_bounds__(128, LEAN_MIN_BLOCKS) k_solve_lean(MmctmDev p, double2 *partial) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     constexpr bool NU = PH == PH_NU;
     constexpr int NG = 32 / G, MKP = G * CPL, STRIDE = 34, NW = 4;       // NW warps per block
     constexpr int NSTG = NU ? 3 : 5;                                     // staged inputs per coordinate: ν: λ, ν, N ; λ: λ, ν, sumθ, N, ζ

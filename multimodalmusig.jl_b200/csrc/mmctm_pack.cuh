@@ -51,6 +51,7 @@ constexpr int PH_IDLE = 0, PH_NU = 1, PH_LAM = 2;
 
 template <int G>
 __global__ void __launch_bounds__(256, 3) k_solve_pack(MmctmDev p, double2 *partial) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     constexpr int NG = 32 / G;                 // samples per warp
     constexpr int STRIDE = G + 2;              // padded invΣ row (doubles); (G+2)/2 odd -> conflict-free LDS.128
     __shared__ __align__(16) double ST[G * STRIDE];

@@ -172,6 +172,7 @@ __device__ __forceinline__ double smem_block_sum(const double *v, int lo, int hi
 }
 
 __global__ void __launch_bounds__(256) k_solve_wide(MmctmDev p, double2 *partial) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ double wsm[];
     double *ST = wsm;                                    // WMK x WSTRIDE
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(256) k_zeta_props_wide(MmctmDev p, double *pro
 
 // ΣΔΔᵀ for rows [r0, r0 + 16): lane owns columns lane, lane + 32.  partial: [gridDim.x][MK*MK + M]
 __global__ void __launch_bounds__(256) k_moments_wide(MmctmDev p, double2 *partial, int r0) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     __shared__ double dsh_all[8][WMK];
     __shared__ double2 red[8 * 32];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;

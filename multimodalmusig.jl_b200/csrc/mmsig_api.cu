@@ -105,6 +105,10 @@ struct MmctmHost {
     double *d_ll = nullptr;
     int *d_status = nullptr;
     double *lamA = nullptr, *lamB = nullptr;
+    int *d_ctl = nullptr;               // MmctmDev::ctl
+    double *d_llprev = nullptr;         // the previous iteration's log-likelihoods, for the stopping rule on the device
+    int cur_iter = 0;                   // > 0 while mmctm_run_iterations enqueues iteration cur_iter of a batch
+    double cur_tol = 0.0;
     double *snap[16] = {nullptr};       // best-restart snapshot of mmsig_mmctm_restarts, kept with the plan
     std::vector<double> alphaf_host;    // IMMCTM: per-(modality, feature) alpha
     std::vector<int> row_len_host, row_m_host;   // IMMCTM: J and modality of every feature-table row
@@ -807,6 +811,11 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_nu, (size_t)D))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_lam, (size_t)D))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.work, (size_t)2))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.d_ctl, (size_t)4))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.d_llprev, (size_t)MAXM))) return rc;
+    CU(cudaMemsetAsync(mm.d_ctl, 0, 4 * sizeof(int), h->stream));
+    CU(cudaMemsetAsync(mm.d_llprev, 0, MAXM * sizeof(double), h->stream));
+    p.ctl = mm.d_ctl;
     p.lam = mm.lamA;
     p.lam_prev = mm.lamB;
     for (double **t : {&p.gamma, &p.Elnphi, &p.Elnphi_prev, &p.phi, &p.stats})
@@ -1212,7 +1221,7 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags, bool overlap) {
         s.n[p.M] = 2 * p.MK;
         s.dst_off[p.M] = mm.G;
         LaunchScope ls(h, "k_combine");
-        k_combine<<<(P1 + 7) / 8, 256, 0, h->stream>>>(s, mm.rank_p1);
+        k_combine<<<(P1 + 7) / 8, 256, 0, h->stream>>>(s, mm.rank_p1, p.ctl);
     }
     const double2 *g1 = nullptr;
     int rc;
@@ -1278,14 +1287,14 @@ static int mmctm_mstep_launch(mmsig_handle *h, uint32_t flags, bool overlap) {
             s.stride[1 + m] = P2;
         }
         LaunchScope ls(h, "k_combine");
-        k_combine<<<(P2 + 7) / 8, 256, 0, st>>>(s, mm.rank_p2);
+        k_combine<<<(P2 + 7) / 8, 256, 0, st>>>(s, mm.rank_p2, p.ctl);
     }
     const double2 *g2 = nullptr;
     if ((rc = gather(h, mm.rank_p2, mm.gath_p2, P2, &g2, st))) return rc;
     {
         LaunchScope ls(h, "k_mstep2");
         const size_t lus = (size_t)2 * p.MK * p.MK * sizeof(double) + p.MK * sizeof(int);
-        k_mstep2<<<1, 256, lus, st>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status);
+        k_mstep2<<<1, 256, lus, st>>>(p, g2, h->nranks, do_sigma, mm.d_ll, mm.d_status, mm.cur_iter, mm.cur_tol, mm.d_llprev);
     }
     if (st != h->stream) {
         CU(cudaEventRecord(h->ev_join, st));
@@ -1356,7 +1365,50 @@ static int mmctm_run_iterations(mmsig_handle *h, int first, int32_t maxiter, dou
             it = iter - 1;
         }
     }
-    for (; iter <= maxiter; ++iter) {
+    // From iteration 11 on the rule of src/MMCTM.jl:485 can end the loop.  It is evaluated on the device (k_mstep2), so
+    // the iterations are still enqueued without host round trips, in batches of kBatch: when the rule fires in iteration
+    // j every kernel of the later iterations of the batch returns at once (MmctmDev::ctl), and the state is exactly what
+    // the reference leaves -- that of iteration j.  The host reads the log-likelihoods, the flag and the count after
+    // each batch.  (autoα updates α on the host inside every iteration: one iteration per round trip there.)
+    constexpr int kBatch = 8;
+    if (!(flags & MMSIG_FLAG_AUTO_ALPHA) && iter > 10) {
+        int *status = reinterpret_cast<int *>(h->ll_pinned + (size_t)12 * MAXM);
+        int *ctl_host = status + 16;
+        while (iter <= maxiter && !conv) {
+            const int nb = std::min<int>(kBatch, maxiter - iter + 1);
+            for (int i = 0; i < nb; ++i) {
+                mm.cur_iter = iter + i;
+                mm.cur_tol = tol;
+                int rc = mmctm_iterate_async(h, flags, true);
+                mm.cur_iter = 0;
+                if (rc) return rc;
+                cudaStream_t cs = h->aux_pending ? h->s_aux : h->stream;
+                CU(cudaMemcpyAsync(h->ll_pinned + (size_t)i * MAXM, mm.d_ll, M * sizeof(double), cudaMemcpyDeviceToHost, cs));
+                CU(cudaMemcpyAsync(status + i, mm.d_status, sizeof(int), cudaMemcpyDeviceToHost, cs));
+                if (i == nb - 1) CU(cudaMemcpyAsync(ctl_host, mm.d_ctl, 2 * sizeof(int), cudaMemcpyDeviceToHost, cs));
+            }
+            CU(cudaStreamSynchronize(h->stream));
+            if (h->s_aux) CU(cudaStreamSynchronize(h->s_aux));
+            h->aux_pending = false;
+            CU(cudaGetLastError());
+            const int done = ctl_host[0];
+            const int n_exec = done ? ctl_host[1] - (iter - 1) : nb;         // iterations of this batch that ran
+            if (n_exec < 1 || n_exec > nb) return fail(h, MMSIG_ECUDA, "internal: iteration count of a batch out of range");
+            for (int i = 0; i < n_exec; ++i) {
+                if (status[i]) return fail(h, MMSIG_EINVAL, "Sigma is singular (inv failed)");
+                memcpy(ll_hist + (size_t)(iter - 1 + i) * M, h->ll_pinned + (size_t)i * MAXM, M * sizeof(double));
+            }
+            if ((nb - n_exec) & 1) std::swap(mm.p.lam, mm.p.lam_prev);       // the skipped iterations' host-side buffer swaps
+            it = iter + n_exec - 1;
+            iter += nb;
+            if (done) {
+                conv = 1;
+                CU(cudaMemsetAsync(mm.d_ctl, 0, 2 * sizeof(int), h->stream));
+                CU(cudaStreamSynchronize(h->stream));
+            }
+        }
+    }
+    for (; iter <= maxiter && !conv; ++iter) {
         double *ll = ll_hist + (size_t)(iter - 1) * M;
         int rc = mmsig_mmctm_iterate(h, flags, ll);
         if (rc) return rc;

@@ -39,6 +39,7 @@ __host__ __device__ inline size_t tile_stage_doubles(int V) { return 2 + (size_t
 // this tile computes; no clear / scatter of records.
 template <int KP, bool EREG, int NWT, bool DENSE>
 __global__ void __launch_bounds__(32 * NWT) k_theta_tile(MmctmDev p, int m, double2 *partial, int unsmoothed, int want_stats) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ __align__(16) double smem[];
     const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
@@ -231,6 +232,7 @@ namespace mmsig {
 // ------------------------------------------------------------------------------------------
 template <int KP, bool PREG, int NWT, bool DENSE>
 __global__ void __launch_bounds__(32 * NWT) k_loglik_tile(MmctmDev p, int m, double2 *partial, int pstride) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ __align__(16) double smem[];
     const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1, M = p.M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;

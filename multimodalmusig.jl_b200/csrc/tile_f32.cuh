@@ -46,6 +46,7 @@ __host__ __device__ inline size_t f32_ll_smem(int KP, int V) {
 // ------------------------------------------------------------------------------------------------------------------
 template <int KP, int NWT>
 __global__ void __launch_bounds__(32 * NWT) k_theta_tile_f32(MmctmDev p, int m, double2 *partial, int unsmoothed, int want_stats) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(32 * NWT) k_theta_tile_f32(MmctmDev p, int m, 
 // ------------------------------------------------------------------------------------------------------------------
 template <int KP, int NWT>
 __global__ void __launch_bounds__(32 * NWT) k_loglik_tile_f32(MmctmDev p, int m, double2 *partial, int pstride) {
+    if (p.ctl && p.ctl[0]) return;        // an earlier iteration of this batch met the convergence rule (mmctm_run_iterations)
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int K = p.K[m], V = p.V[m], off = p.koff[m], VP = V | 1, M = p.M;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, NW = blockDim.x >> 5;

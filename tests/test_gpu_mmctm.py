@@ -97,6 +97,37 @@ def test_brca_fit_config1(brca):
     g.close()
 
 
+def test_fit_stops_exactly_where_the_reference_rule_fires(brca):
+    """Beyond iteration 10 the iterations of fit are enqueued in batches of 8 and the stopping rule (src/MMCTM.jl:485) is
+    evaluated on the device; when it fires in iteration j the later kernels of the batch return at once.  For tolerances
+    that make the rule fire first at different positions of a batch (odd and even numbers of skipped iterations: the
+    host-side lambda buffer swap has to be undone for an odd count) the history, the iteration count and the state are
+    the oracle's, bit for bit -- the state of iteration j, not of the last enqueued one."""
+    K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
+    g0 = mmsig.synth.init_gamma(K, V)
+    o = oracle_mmctm(K, alpha, V, brca, g0)
+    full = o.fit(maxiter=30, tol=0.0)
+    r = np.max(np.abs(full[:-1] - full[1:]) / np.abs(full[1:]), axis=1)        # r[i]: change entering iteration i + 2
+    tols = []
+    for j in (11, 12, 14, 17, 18, 19, 22):                                     # positions 0, 1, 3, 6, 7 of the first batch; 0, 3 of the second
+        rj, prev = r[j - 2], r[9:j - 2]
+        if prev.size == 0 or rj < prev.min():                                  # the change entering iteration j is a new minimum
+            tols.append((j, float(rj * 1.0000001 if prev.size == 0 else 0.5 * (rj + prev.min()))))
+    assert len(tols) >= 5, tols
+    for j, tol in tols:
+        oo = oracle_mmctm(K, alpha, V, brca, g0)
+        ho = oo.fit(maxiter=30, tol=tol)
+        assert len(ho) == j and oo.converged, (j, tol, len(ho))
+        g = mmsig.MMCTM(K, alpha, brca, V=V, gamma0=g0)
+        hg = g.fit(maxiter=30, tol=tol, verbose=False)
+        assert hg.shape == ho.shape and g.converged, (j, hg.shape, ho.shape)
+        assert np.array_equal(hg, ho)
+        _check_iteration(oo, g, ho[-1], hg[-1])
+        ll_next_o, ll_next_g = oo.iterate(), g.iterate()                       # and the handle goes on from there
+        assert np.array_equal(ll_next_g, ll_next_o)
+        g.close()
+
+
 @pytest.mark.parametrize("K,V,D,empty", [([10, 8, 6], [96, 32, 83], 1500, 0.05),     # config 4 shape
                                          ([10], [96], 1200, 0.0),                    # config 3: CTM
                                          ([7, 7], [96, 32], 800, 0.1),               # config 5 shape
