@@ -1323,6 +1323,9 @@ extern "C" int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *
 }
 
 // src/common.jl:48-51 on the last two LL vectors
+#ifndef MMSIG_DEVICE_RULE_DEFAULT
+#define MMSIG_DEVICE_RULE_DEFAULT false     // the batched loop below; MMSIG_DEVICE_RULE=1 / 0 overrides
+#endif
 static bool converged_vec(const double *prev, const double *cur, int M, double tol) {
     double r = 0.0;
     for (int i = 0; i < M; ++i) {
@@ -1371,7 +1374,9 @@ static int mmctm_run_iterations(mmsig_handle *h, int first, int32_t maxiter, dou
     // the reference leaves -- that of iteration j.  The host reads the log-likelihoods, the flag and the count after
     // each batch.  (autoα updates α on the host inside every iteration: one iteration per round trip there.)
     constexpr int kBatch = 8;
-    if (!(flags & MMSIG_FLAG_AUTO_ALPHA) && iter > 10) {
+    const char *edr = getenv("MMSIG_DEVICE_RULE");
+    const bool device_rule = edr ? atoi(edr) != 0 : MMSIG_DEVICE_RULE_DEFAULT;
+    if (device_rule && !(flags & MMSIG_FLAG_AUTO_ALPHA) && iter > 10) {
         int *status = reinterpret_cast<int *>(h->ll_pinned + (size_t)12 * MAXM);
         int *ctl_host = status + 16;
         while (iter <= maxiter && !conv) {

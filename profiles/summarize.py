@@ -32,8 +32,9 @@ if os.path.exists(lp):
     out.append("")
 
 rp = os.path.join(ROOT, "gpurun_out", "prof_%s.ncu-rep" % tag)
-if os.path.exists(rp):
-    raw = subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rc = os.path.join(ROOT, "gpurun_out", "prof_%s_raw.csv" % tag)          # written on the GPU box when the report is too large to pull
+if os.path.exists(rp) or os.path.exists(rc):
+    raw = open(rc).read() if os.path.exists(rc) else subprocess.run(["ncu", "-i", rp, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units, data = rows[0], rows[1], rows[2:]
     idx = {h: i for i, h in enumerate(hdr)}
