@@ -1324,7 +1324,7 @@ extern "C" int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *
 
 // src/common.jl:48-51 on the last two LL vectors
 #ifndef MMSIG_DEVICE_RULE_DEFAULT
-#define MMSIG_DEVICE_RULE_DEFAULT false     // the batched loop below; MMSIG_DEVICE_RULE=1 / 0 overrides
+#define MMSIG_DEVICE_RULE_DEFAULT true      // the batched loop below; MMSIG_DEVICE_RULE=0 keeps one host round trip per iteration (A/B)
 #endif
 static bool converged_vec(const double *prev, const double *cur, int M, double tol) {
     double r = 0.0;

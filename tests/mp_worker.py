@@ -51,6 +51,33 @@ def main():
             assert abs(elbo - eo) <= 1e-12 * abs(eo), (elbo, eo)
             print("MULTI-RANK PARITY OK mmctm_host world=%d D=%d" % (world, D), flush=True)
         m.close()
+    elif mode == "mmctm_fit":
+        # a whole fit!: ten iterations without host round trips, then batches with the stopping rule on the device, the
+        # second half of every M-step (and its all-gather) on the side stream; stops where the full-data oracle stops
+        K, V = [10, 8, 6], [96, 32, 83]
+        full = mmsig.synth.generate(D, K, V, key=8)
+        b = mmsig.counts.shard_rows([c[0] for c in full], world)
+        lo, hi = int(b[rank]), int(b[rank + 1])
+        shard = [mmsig.counts.slice_csr(c, lo, hi) for c in full]
+        g0 = mmsig.synth.init_gamma(K, V)
+        m = mmsig.MMCTM(K, [0.1] * 3, shard, V=V, gamma0=g0, device=local, comm=comm, D_total=D)
+        tol = float(sys.argv[3]) if len(sys.argv) > 3 else 2.5e-3       # the rule fires in iteration 15: three enqueued iterations are skipped
+        hist = m.fit(maxiter=22, tol=tol, verbose=False)
+        s = m.state()
+        parts = [None] * world
+        dist.gather_object((lo, hi, s["lam"], s["nu"]), parts if rank == 0 else None, 0)
+        if rank == 0:
+            import orc
+            o = orc.OracleMMCTM(K, [0.1] * 3, V, full, g0, arith=orc.ARITH_DET, nthreads=os.cpu_count() or 1)
+            llo = o.fit(maxiter=22, tol=tol)
+            assert np.asarray(hist).shape == llo.shape, (np.asarray(hist).shape, llo.shape)
+            assert np.array_equal(np.asarray(hist), llo)
+            assert np.array_equal(np.concatenate([p[2] for p in parts]), o.lam) and np.array_equal(np.concatenate([p[3] for p in parts]), o.nu)
+            for k in ("gamma", "mu", "Sigma", "invSigma", "phi"):
+                assert np.array_equal(s[k], getattr(o, k)), k
+            assert abs(m.elbo - o.elbo()[0]) <= 1e-12 * abs(o.elbo()[0])
+            print("MULTI-RANK PARITY OK mmctm_fit world=%d D=%d iterations=%d converged=%s" % (world, D, len(llo), o.converged), flush=True)
+        m.close()
     elif mode == "mmctm":
         K, V = [10, 8, 6], [96, 32, 83]
         full = mmsig.synth.generate(D, K, V, key=5)

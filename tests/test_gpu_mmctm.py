@@ -104,8 +104,6 @@ def test_fit_stops_exactly_where_the_reference_rule_fires(brca, monkeypatch, dev
     that make the rule fire first at different positions of a batch (odd and even numbers of skipped iterations: the
     host-side lambda buffer swap has to be undone for an odd count) the history, the iteration count and the state are
     the oracle's, bit for bit -- the state of iteration j, not of the last enqueued one."""
-    if device_rule == "1" and not os.environ.get("MMSIG_TEST_DEVICE_RULE"):
-        pytest.skip("the batched loop is switched on (and this case with it) once a GPU run has shown it green")
     monkeypatch.setenv("MMSIG_DEVICE_RULE", device_rule)
     K, alpha, V = [7, 7], [0.1, 0.1], [96, 48]
     g0 = mmsig.synth.init_gamma(K, V)
