@@ -105,6 +105,8 @@ struct MmctmHost {
     double *d_ll = nullptr;
     int *d_status = nullptr;
     double *lamA = nullptr, *lamB = nullptr;
+    double *sumtheta_alt = nullptr;     // second sumθ buffer: the θ pass of iteration t+1 may run (side-stream overlap) before
+                                        // iteration t's stopping rule is known; it must not overwrite the sumθ the ELBO reads
     int *d_ctl = nullptr;               // MmctmDev::ctl
     double *d_llprev = nullptr;         // the previous iteration's log-likelihoods, for the stopping rule on the device
     int cur_iter = 0;                   // > 0 while mmctm_run_iterations enqueues iteration cur_iter of a batch
@@ -807,6 +809,8 @@ static int mmctm_prepare(mmsig_handle *h, int64_t D, int64_t D_total, int32_t M,
     if ((rc = dev_alloc(h, h->allocs_mm, &mm.lamB, DMK))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nu, DMK))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.sumtheta, DMK))) return rc;
+    if ((rc = dev_alloc(h, h->allocs_mm, &mm.sumtheta_alt, DMK))) return rc;
+    CU(cudaMemsetAsync(mm.sumtheta_alt, 0, DMK * sizeof(double), h->stream));
     if ((rc = dev_alloc(h, h->allocs_mm, &p.zeta, (size_t)D * M))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_nu, (size_t)D))) return rc;
     if ((rc = dev_alloc(h, h->allocs_mm, &p.nev_lam, (size_t)D))) return rc;
@@ -1196,6 +1200,7 @@ static int mmctm_iterate_async(mmsig_handle *h, uint32_t flags, bool overlap = f
     MmctmDev &p = mm.p;
     mm.last_unsmoothed = (flags & MMSIG_FLAG_UNSMOOTHED) != 0;
     std::swap(p.lam, p.lam_prev);              // lam_prev = λ of the previous iteration (what θ uses)
+    std::swap(p.sumtheta, mm.sumtheta_alt);    // this iteration's θ pass writes the other buffer (see sumtheta_alt)
     mmctm_estep_launch(h, p, flags);
     return mmctm_mstep_launch(h, flags, overlap);
 }
@@ -1403,7 +1408,10 @@ static int mmctm_run_iterations(mmsig_handle *h, int first, int32_t maxiter, dou
                 if (status[i]) return fail(h, MMSIG_EINVAL, "Sigma is singular (inv failed)");
                 memcpy(ll_hist + (size_t)(iter - 1 + i) * M, h->ll_pinned + (size_t)i * MAXM, M * sizeof(double));
             }
-            if ((nb - n_exec) & 1) std::swap(mm.p.lam, mm.p.lam_prev);       // the skipped iterations' host-side buffer swaps
+            if ((nb - n_exec) & 1) {                                         // the skipped iterations' host-side buffer swaps
+                std::swap(mm.p.lam, mm.p.lam_prev);
+                std::swap(mm.p.sumtheta, mm.sumtheta_alt);
+            }
             it = iter + n_exec - 1;
             iter += nb;
             if (done) {

@@ -75,7 +75,9 @@ def main():
             assert np.array_equal(np.concatenate([p[2] for p in parts]), o.lam) and np.array_equal(np.concatenate([p[3] for p in parts]), o.nu)
             for k in ("gamma", "mu", "Sigma", "invSigma", "phi"):
                 assert np.array_equal(s[k], getattr(o, k)), k
-            assert abs(m.elbo - o.elbo()[0]) <= 1e-12 * abs(o.elbo()[0])
+            eo = o.elbo()[0]
+            print("mmctm_fit: elbo device %.17g oracle %.17g rel %.3e" % (m.elbo, eo, abs(m.elbo - eo) / abs(eo)), flush=True)
+            assert abs(m.elbo - eo) <= 1e-12 * abs(eo), (m.elbo, eo)
             print("MULTI-RANK PARITY OK mmctm_fit world=%d D=%d iterations=%d converged=%s" % (world, D, len(llo), o.converged), flush=True)
         m.close()
     elif mode == "mmctm":

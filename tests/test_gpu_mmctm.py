@@ -125,6 +125,8 @@ def test_fit_stops_exactly_where_the_reference_rule_fires(brca, monkeypatch, dev
         assert hg.shape == ho.shape and g.converged, (j, hg.shape, ho.shape)
         assert np.array_equal(hg, ho)
         _check_iteration(oo, g, ho[-1], hg[-1])
+        eo = oo.elbo()[0]                      # reads the sumθ, ζ and λ_prev of iteration j (a θ pass enqueued after it must not touch them)
+        assert abs(g.elbo - eo) <= TOL_ITER * abs(eo), (j, g.elbo, eo)
         ll_next_o, ll_next_g = oo.iterate(), g.iterate()                       # and the handle goes on from there
         assert np.array_equal(ll_next_g, ll_next_o)
         g.close()
