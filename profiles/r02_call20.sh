@@ -5,6 +5,7 @@
 # kernels and its two FP32 kernels.  Raw / source pages become CSV on the box (the reports exceed the 64 MiB pull limit).
 mkdir -p gpurun_out
 T=r02p
+timeout 900 python -m pytest tests -q -m gpu -x --timeout 300 2>&1 | tail -5 | tee gpurun_out/${T}_tests.log
 timeout 400 python bench.py > gpurun_out/${T}_bench_c4.json 2> gpurun_out/${T}_bench_c4.err
 for c in 2 3; do timeout 200 python bench.py --config $c --no-cpu > gpurun_out/${T}_bench_c$c.json 2> gpurun_out/${T}_bench_c$c.err; done
 python - <<'PY'
