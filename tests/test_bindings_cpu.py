@@ -146,3 +146,37 @@ def test_julia_shim_touches_only_fields_the_reference_structs_have():
         assert used and used <= set(ref[typ]), (m.group(1), typ, used - set(ref[typ]))
         seen += 1
     assert seen >= 7
+
+
+def test_config_struct_fields_agree():
+    """mmsig_config (passed by pointer to mmsig_create / mmsig_group_create): the same fields in the same order and
+    widths in include/mmsig.h, capi.Config and the Julia shim's MmsigConfig -- a drifted field would silently hand the
+    library a wrong `precision` or `profile`."""
+    src = open(os.path.join(ROOT, "include", "mmsig.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\}\s*mmsig_config;", src, flags=re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    hfields = []
+    for typ, name, arr in re.findall(r"(int32_t)\s+([a-z_]+)(?:\[(\d+)\])?;", body):
+        hfields.append((name, int(arr) if arr else 1))
+    assert [f[0] for f in hfields] == ["device", "stop_rule", "profile", "precision", "reserved"], hfields
+    cfields = []
+    for name, typ in mmsig.capi.Config._fields_:
+        n = typ._length_ if hasattr(typ, "_length_") else 1
+        base = typ._type_ if hasattr(typ, "_length_") else typ
+        assert base is C.c_int32, name
+        cfields.append((name, n))
+    assert cfields == hfields
+    assert C.sizeof(mmsig.capi.Config) == 4 * sum(n for _, n in hfields) == 32
+    jl = open(os.path.join(ROOT, "julia", "MMSigB200.jl")).read()
+    jbody = re.search(r"struct MmsigConfig\n(.*?)\nend", jl, flags=re.S).group(1)
+    jfields = []
+    for name, typ in re.findall(r"^\s*([a-z_]+)::(\S+)", jbody, flags=re.M):
+        m = re.match(r"NTuple\{(\d+),Int32\}", typ)
+        assert typ == "Int32" or m, (name, typ)
+        jfields.append((name, int(m.group(1)) if m else 1))
+    assert jfields == hfields
+    # every constructor call of the shim passes as many values as the struct has fields
+    for call in re.findall(r"MmsigConfig\((.*?)\)\)", jl):
+        assert call.count("Int32(") + call.count("ids[1]") >= 4 and "ntuple" in call, call
+    assert mmsig.capi.PRECISION_FP64 == 0 and mmsig.capi.PRECISION_FP32 == 1
+    assert re.search(r"#define MMSIG_PRECISION_FP32\s+1", src) and re.search(r"#define MMSIG_PRECISION_FP64\s+0", src)
