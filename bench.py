@@ -526,10 +526,12 @@ def bench_mmctm(args, cfg):
     traffic, traffic_src = None, None
     try:        # DRAM bytes of the dominant kernel from the committed ncu capture, per sample x local samples
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
-        for name, v in tj["kernels"].items():
-            if dom and name.startswith(dom):
-                traffic = v["dram_bytes_per_sample"][0] * Dl
-                traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum per launch at D=%d (%s), scaled by the local sample count" % (tj["D"], "profiles/traffic.json")
+        # the dominant kernel's own entry ("k_solve" = the two launches of the lean solver of one iteration), else the first
+        # entry that carries its name
+        pick = dom if dom in tj["kernels"] else next((n for n in tj["kernels"] if dom and n.startswith(dom)), None)
+        if pick is not None:
+            traffic = tj["kernels"][pick]["dram_bytes_per_sample"][0] * Dl
+            traffic_src = "ncu dram__bytes_read.sum + dram__bytes_write.sum of %s at D=%d (%s), scaled by the local sample count" % (pick, tj["D"], "profiles/traffic.json")
     except Exception:
         pass
     roof, roof64 = None, None

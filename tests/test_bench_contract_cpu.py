@@ -43,3 +43,34 @@ def test_product_arm_refuses_to_run_without_a_gpu():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--steps", "1", "--warmup", "0", "--samples", "2000"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def test_committed_gpu_bench_line_keeps_the_contract():
+    """The product arm needs a B200; its last line from the GPU box is committed (profiles/bench_r02p_c4_final.json).  It has
+    to carry what the driver and the judge read, with consistent arithmetic: value = 1000 / ms_per_step, roofline.frac =
+    achieved / peak with achieved = algorithmic bytes / the dominant kernel's duration, e2e with real copies, a CPU arm."""
+    j = json.load(open(os.path.join(ROOT, "profiles", "bench_r02p_c4_final.json")))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert k in j, k
+    assert j["metric"] == "mmctm_em_iterations_per_sec" and j["unit"] == "iterations/s" and j["dtype"] == "f64"
+    assert j["n_gpus"] == 1 and j["warmup"] >= 3 and j["higher_is_better"] is True and j["vs_baseline"] is None
+    assert abs(j["value"] - 1000.0 / j["ms_per_step"]) <= 1e-9 * j["value"]
+    assert "workload" in j["config"] and "model" not in j["config"] and j["config"]["samples"] == 1000000
+    r = j["roofline"]
+    assert r["bound"] == "hbm" and r["unit"] == "GB/s" and r["kernel"] == "k_solve"
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) <= 1e-12
+    assert abs(r["achieved"] - r["algorithmic_bytes_per_launch"] / (r["kernel_ms_per_launch"] * 1e-3) / 1e9) <= 1e-6 * r["achieved"]
+    assert r["kernel_ms_per_launch"] <= j["ms_per_step"] and r["traffic"] > 0
+    f = j["roofline_fp64"]
+    assert f["bound"] == "fp64_pipe" and 0 < f["frac"] < 1 and abs(f["frac"] - f["achieved"] / f["peak"]) <= 1e-12
+    e = j["e2e"]
+    assert e["unit"] == j["unit"] and e["h2d_bytes_per_step"] > 1e9 and e["d2h_bytes_per_step"] > 5e8 and 0 < e["value"] < j["value"]
+    c = j["cpu_baseline"]
+    assert c["kind"] == "port" and c["cores"] >= 1 and c["value"] > 0 and c["unit"] == j["unit"] and c["sample"]
+    assert j["clocks"]["sm_mhz"] > 0 and j["clocks"]["sm_max_mhz"] >= j["clocks"]["sm_mhz"]
+    assert not set(j["clocks"]["reasons"]) & {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    assert j["gpu_launches"] >= 13 * j["steps"]               # θ x3, solve x2, combine x2, mstep1, moments, LL x3, mstep2 per iteration
+    assert sum(v["ms_per_step"] for v in j["kernels"].values()) <= 1.05 * j["ms_per_step_with_kernel_timing"]
+    m = j["fp32_mode"]                                        # reported beside the headline, never as it
+    assert m["ms_per_step"] < j["ms_per_step"] and m["ll_rel_diff_to_fp64"] < 1e-5
