@@ -217,7 +217,9 @@ int32_t mmsig_mmctm_set_phi(mmsig_handle *h, const double *phi);
  * predict_modality_η (:604-609); adding UNSMOOTHED gives transform's (:523-538). */
 int32_t mmsig_mmctm_iterate(mmsig_handle *h, uint32_t flags, double *ll_out);
 /* fit! (src/MMCTM.jl:457-494): loop + `length(ll) > 10 && check_convergence` (src/common.jl:48-51);
- * ll_hist is maxiter x M.  The ELBO of :490 is mmsig_mmctm_elbo. */
+ * ll_hist is maxiter x M.  The ELBO of :490 is mmsig_mmctm_elbo.  The loop runs without a host round trip per
+ * iteration: the rule is evaluated on the device and the iterations are enqueued in batches; the state left behind
+ * is that of the iteration where the rule fired, as in the reference (autoα: one round trip per iteration). */
 int32_t mmsig_mmctm_fit(mmsig_handle *h, int32_t maxiter, double tol, uint32_t flags,
                         double *ll_hist, int32_t *n_iter, int32_t *converged);
 /* fit! from and to HOST buffers in one call: exactly mmsig_mmctm_set_data + _set_state + _fit +
